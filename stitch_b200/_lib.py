@@ -1,0 +1,101 @@
+"""Loads the CUDA/C-ABI library (stitch_b200/libstitch_b200.so) and declares its signatures.
+
+There is no fallback: if the library has not been built (`python -c "import __graft_entry__ as g;
+g.build()"`) importing any compute entry point fails loudly.
+"""
+import ctypes as C
+import os
+
+from ._abi import StitchChain, StitchContig, StitchOp, StitchOpts, StitchStats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstitch_b200.so")
+
+# every symbol include/stitch_b200.h declares
+EXPORTED_SYMBOLS = [
+    "stitch_create", "stitch_align_batch", "stitch_custom_batch", "stitch_custom_batch_device",
+    "stitch_results_n_reads", "stitch_results_read", "stitch_results_chains", "stitch_results_ops",
+    "stitch_free_results", "stitch_get_stats", "stitch_set_max_inflight", "stitch_destroy",
+    "stitch_last_error", "stitch_abi_version",
+]
+
+_lib = None
+
+
+def declare_results_api(lib, prefix_map):
+    """Shared by the product library and (in tests) the oracle, whose accessors have the same shape."""
+    n_reads = getattr(lib, prefix_map["n_reads"])
+    n_reads.restype = C.c_uint32
+    n_reads.argtypes = [C.c_void_p]
+    read = getattr(lib, prefix_map["read"])
+    read.restype = None
+    read.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    chains = getattr(lib, prefix_map["chains"])
+    chains.restype = C.POINTER(StitchChain)
+    chains.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    ops = getattr(lib, prefix_map["ops"])
+    ops.restype = C.POINTER(StitchOp)
+    ops.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    free = getattr(lib, prefix_map["free"])
+    free.restype = None
+    free.argtypes = [C.c_void_p]
+
+
+def read_results(lib, prefix_map, handle):
+    """-> list (per read) of lists of Alignment."""
+    from .alignment import Alignment
+    n_reads = getattr(lib, prefix_map["n_reads"])(handle)
+    n_ch, n_op = C.c_uint64(), C.c_uint64()
+    chains = getattr(lib, prefix_map["chains"])(handle, C.byref(n_ch))
+    ops = getattr(lib, prefix_map["ops"])(handle, C.byref(n_op))
+    out = []
+    first, count = C.c_uint64(), C.c_uint32()
+    for r in range(n_reads):
+        getattr(lib, prefix_map["read"])(handle, r, C.byref(first), C.byref(count))
+        lst = []
+        for k in range(first.value, first.value + count.value):
+            c = chains[k]
+            o = [(ops[t].kind, ops[t].a, ops[t].b) for t in range(c.ops_offset, c.ops_offset + c.n_ops)]
+            lst.append(Alignment(c.score, c.xstart, c.xend, c.ystart, c.yend, c.xlen, c.ylen,
+                                 c.start_contig_idx, c.end_contig_idx, c.length, o))
+        out.append(lst)
+    return out
+
+
+PRODUCT_RESULTS = {"n_reads": "stitch_results_n_reads", "read": "stitch_results_read",
+                   "chains": "stitch_results_chains", "ops": "stitch_results_ops", "free": "stitch_free_results"}
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.stitch_create.restype = C.c_int
+    lib.stitch_create.argtypes = [C.POINTER(StitchOpts), C.POINTER(StitchContig), C.c_uint32, C.c_int,
+                                  C.POINTER(C.c_void_p)]
+    for name in ("stitch_align_batch", "stitch_custom_batch"):
+        f = getattr(lib, name)
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
+                      C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.stitch_custom_batch_device.restype = C.c_int
+    lib.stitch_custom_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32,
+                                               C.POINTER(C.c_void_p)]
+    declare_results_api(lib, PRODUCT_RESULTS)
+    lib.stitch_get_stats.restype = C.c_int
+    lib.stitch_get_stats.argtypes = [C.c_void_p, C.POINTER(StitchStats)]
+    lib.stitch_set_max_inflight.restype = C.c_int
+    lib.stitch_set_max_inflight.argtypes = [C.c_void_p, C.c_uint32]
+    lib.stitch_destroy.restype = None
+    lib.stitch_destroy.argtypes = [C.c_void_p]
+    lib.stitch_last_error.restype = C.c_char_p
+    lib.stitch_last_error.argtypes = [C.c_void_p]
+    lib.stitch_abi_version.restype = C.c_uint32
+    lib.stitch_abi_version.argtypes = []
+    _lib = lib
+    return lib
