@@ -1,0 +1,111 @@
+// capi_impl.hpp — the extern "C" surface of include/stitch_b200.h over host::Aligner.
+//
+// Included exactly once per shared library after defining
+//   STITCH_API(name)            the exported symbol name (product: stitch_##name)
+//   stitch::host::Backend *stitch_make_backend(stitch::host::Aligner &, int device)
+// The product library (capi.cu) binds the CUDA backend.  The test-only emulator library binds a
+// CPU emulation backend under a different prefix; it is never linked into the product.
+#pragma once
+#include <cstdio>
+#include <string>
+
+#include "host_common.hpp"
+
+namespace stitch { namespace host { Backend *stitch_make_backend(Aligner &al, int device); } }
+
+struct stitch_ctx { stitch::host::Aligner al; };
+struct stitch_results { stitch::host::Results res; };
+
+static thread_local std::string g_create_error;
+
+#define STITCH_GUARD_BEGIN try {
+#define STITCH_GUARD_END(ctx)                                                         \
+    } catch (const stitch::host::Error &e) {                                          \
+        (ctx)->al.last_error = e.what(); return e.code;                               \
+    } catch (const std::bad_alloc &) {                                                \
+        (ctx)->al.last_error = "out of host memory"; return STITCH_ERR_NOMEM;         \
+    } catch (const std::exception &e) {                                               \
+        (ctx)->al.last_error = e.what(); return STITCH_ERR_INTERNAL;                  \
+    }
+
+extern "C" {
+
+int STITCH_API(create)(const stitch_opts *opts, const stitch_contig *contigs, uint32_t n_contigs, int device,
+                       stitch_ctx **out) {
+    if (!opts || !contigs || !out) { g_create_error = "null argument"; return STITCH_ERR_INVALID; }
+    stitch_ctx *ctx = nullptr;
+    try {
+        ctx = new stitch_ctx();
+        ctx->al.init(*opts, contigs, n_contigs);
+        ctx->al.backend.reset(stitch::host::stitch_make_backend(ctx->al, device));
+        *out = ctx;
+        return STITCH_OK;
+    } catch (const stitch::host::Error &e) {
+        g_create_error = e.what(); delete ctx; return e.code;
+    } catch (const std::exception &e) {
+        g_create_error = e.what(); delete ctx; return STITCH_ERR_INTERNAL;
+    }
+}
+
+static int run_batch(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
+                     const uint32_t *subset_words, uint32_t subset_stride, stitch_results **out, bool raw) {
+    if (!ctx) return STITCH_ERR_INVALID;
+    STITCH_GUARD_BEGIN
+    if (!out || (n_reads && (!bases || !offsets))) throw stitch::host::Error(STITCH_ERR_INVALID, "null argument");
+    for (uint32_t r = 0; r < n_reads; ++r)
+        if (offsets[r + 1] < offsets[r]) throw stitch::host::Error(STITCH_ERR_INVALID, "offsets not monotone");
+    std::unique_ptr<stitch_results> r(new stitch_results());
+    ctx->al.backend->stats.reset();
+    if (raw) ctx->al.custom_batch(bases, offsets, n_reads, subset_words, subset_stride, r->res);
+    else ctx->al.align_batch(bases, offsets, n_reads, subset_words, subset_stride, r->res);
+    *out = r.release();
+    return STITCH_OK;
+    STITCH_GUARD_END(ctx)
+}
+
+int STITCH_API(align_batch)(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
+                            const uint32_t *subset_words, uint32_t subset_stride, stitch_results **out) {
+    return run_batch(ctx, bases, offsets, n_reads, subset_words, subset_stride, out, false);
+}
+
+int STITCH_API(custom_batch)(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
+                             const uint32_t *subset_words, uint32_t subset_stride, stitch_results **out) {
+    return run_batch(ctx, bases, offsets, n_reads, subset_words, subset_stride, out, true);
+}
+
+uint32_t STITCH_API(results_n_reads)(const stitch_results *r) { return (uint32_t)r->res.first.size(); }
+void STITCH_API(results_read)(const stitch_results *r, uint32_t read, uint64_t *first, uint32_t *count) {
+    *first = r->res.first[read]; *count = r->res.count[read];
+}
+const stitch_chain *STITCH_API(results_chains)(const stitch_results *r, uint64_t *n) {
+    *n = r->res.chains.size(); return r->res.chains.data();
+}
+const stitch_op *STITCH_API(results_ops)(const stitch_results *r, uint64_t *n) {
+    *n = r->res.ops.size(); return r->res.ops.data();
+}
+void STITCH_API(free_results)(stitch_results *r) { delete r; }
+
+int STITCH_API(get_stats)(const stitch_ctx *ctx, stitch_stats *out) {
+    if (!ctx || !out) return STITCH_ERR_INVALID;
+    const stitch::host::BackendStats &s = ctx->al.backend->stats;
+    out->cells = s.cells; out->fills = s.fills; out->kernel_launches = s.launches;
+    out->fill_ms = s.fill_ms; out->traceback_ms = s.tb_ms; out->total_ms = s.total_ms;
+    out->h2d_bytes = s.h2d; out->d2h_bytes = s.d2h; out->traceback_bytes = s.tb_bytes;
+    return STITCH_OK;
+}
+
+int STITCH_API(set_max_inflight)(stitch_ctx *ctx, uint32_t max_reads) {
+    if (!ctx) return STITCH_ERR_INVALID;
+    ctx->al.backend->set_max_inflight(max_reads);
+    return STITCH_OK;
+}
+
+void STITCH_API(destroy)(stitch_ctx *ctx) { delete ctx; }
+
+const char *STITCH_API(last_error)(const stitch_ctx *ctx) {
+    return ctx ? ctx->al.last_error.c_str() : g_create_error.c_str();
+}
+
+uint32_t STITCH_API(abi_version)(void) { return 1; }
+
+}  // extern "C"

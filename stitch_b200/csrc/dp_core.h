@@ -1,0 +1,745 @@
+// dp_core.h — the arithmetic of stitch's jump-aware affine-gap DP, decomposed for a GPU.
+//
+// Everything here is __host__ __device__ so that the exact same code runs inside the CUDA
+// kernels (fill_kernel.cu) and inside the CPU lane/tile emulator the tests fuzz against the
+// oracle (tests/emul/).  Citations: SCA = fg-stitch-lib/src/align/aligners/single_contig_aligner.rs,
+// MCA = .../multi_contig_aligner.rs, TB = fg-stitch-lib/src/align/traceback/mod.rs of the reference.
+//
+// Decomposition (DESIGN.md has the derivations):
+//  * one column j of one contig is cut into warp TILES of 32 lanes x STRIP consecutive rows;
+//  * pass A (per lane, no dependency inside the column): D, diagonal, jump, clips -> H' = the
+//    best S candidate that does not come from the I layer, plus "H' > A" (A = best of
+//    {start, diag, D}), which is all the S/I merge needs;
+//  * the in-column insertion chain I(i) = max_k<i H'(k)+o+e(i-k) (earliest k on ties) is an
+//    associative max-plus scan over lane aggregates (warp shuffles on the GPU);
+//  * pass B (per lane, sequential over its STRIP rows): I, S = merge(H', I), trackers, packed
+//    traceback byte;
+//  * row m of every contig doubles as the x-suffix-clip accumulator (SCA:407-429), so it is
+//    finished per contig after a reduction over rows < m ("finalize");
+//  * the per-column best cell of every contig feeds the jump selection of the next column
+//    (MCA:279-331).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SHD __host__ __device__ __forceinline__
+#else
+#define SHD inline
+#endif
+
+namespace stitch {
+
+constexpr int32_t MIN_SCORE = -858993459;   // aligners/constants.rs:7
+#ifndef STITCH_STRIP
+#define STITCH_STRIP 8
+#endif
+constexpr int STRIP = STITCH_STRIP;          // rows per lane (tests shrink it to force multi-tile contigs)
+constexpr int TILE = 32 * STRIP;             // rows per warp tile
+constexpr uint32_t MAX_STRANDS = 256;        // packed_length_cell.rs:112-114 (8-bit contig index)
+constexpr uint32_t MAX_CONTIG_LEN = 134217727u;
+
+// Reference traceback codes (TB:47-57).
+enum : uint32_t {
+    TB_START = 0, TB_INS = 1, TB_DEL = 2, TB_SUBST = 3, TB_MATCH = 4, TB_XCLIP_PREFIX = 5,
+    TB_XCLIP_SUFFIX = 6, TB_YCLIP_PREFIX = 7, TB_YCLIP_SUFFIX = 8, TB_XJUMP = 9
+};
+
+// Packed traceback byte of an interior cell (1 <= j <= n, 1 <= i <= m):
+//   bits 0-3 S move (MV_*), bit 4 D pointer is an extension, bit 5 I pointer is an extension.
+// An "open" I/D pointer is resolved at walk time as the S move of the cell it left
+// (SCA:324-325, 336-337), which is final by then except in column n (kept in LastCell).
+enum : uint32_t {
+    MV_START = 0, MV_INS = 1, MV_DEL = 2, MV_DIAG = 3, MV_JUMP = 4, MV_XCLIP_PREFIX = 5,
+    MV_XCLIP_SUFFIX = 6, MV_YCLIP_PREFIX = 7, MV_WRAP = 8
+};
+constexpr uint32_t TBB_DEXT = 16, TBB_IEXT = 32;
+
+struct Scoring {
+    int32_t match, mismatch, o, e;           // o = gap_open, e = gap_extend
+    int32_t g_same, g_opp, g_inter;
+    int32_t xp, xs, yp, ys;                  // clip penalties (AMOD:123-131)
+};
+
+// Rolling column state of one cell (what column j+1 needs from column j).
+struct CellState { int32_t S, D; uint32_t sl, dl; };
+
+struct JumpInfo { int32_t score; uint32_t len, idx, from; };
+
+// Per (contig, column) record kept for the walk.
+struct ColRec { uint32_t jidx, jfrom, lx, pad; };
+
+// Column-n cell in reference form (the end-of-read fix-up edits these, SCA:453-555).
+struct LastCell {
+    int32_t S, I;
+    uint32_t sl, il, idx, from;
+    uint8_t s_tb, i_tb, flags, pad;   // flags: bit0 I pointer is an extension
+    uint32_t pad2;
+};
+
+// y-suffix tracker of one row (Sn / Ly of SCA:432-447 plus what SCA:482-490 later reads).
+struct SnRec { int32_t sn; uint32_t len, ly, idx; };
+
+// One contig-strand of a read's layout.
+struct ContigEntry {
+    uint32_t contig_idx;   // index among all contig-strands (forward contigs, then reverse)
+    uint32_t m;
+    uint32_t tile_start, ntiles;
+    int32_t opp;           // position (in this layout) of the opposite strand, or -1
+    uint32_t seq_off;      // offset of the bases in the contig blob
+    uint32_t circular;
+    uint32_t pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Row 0 of column j (SCA:188-239).  Identical for every contig.  Sn[0]/Ly[0] never move off
+// their initial (ys, n): S(0,j) <= 0 = S(0,0) for every j.
+// ---------------------------------------------------------------------------------------------
+struct Row0 { int32_t S, D; uint32_t sl, dl; uint32_t s_tb, d_tb; };
+
+SHD Row0 row0_at(const Scoring &sc, uint32_t j, uint32_t n) {
+    Row0 r;
+    if (j == 0) { r.S = 0; r.D = MIN_SCORE; r.sl = 0; r.dl = 0; r.s_tb = TB_START; r.d_tb = TB_START; return r; }
+    if (j == 1) {
+        r.D = sc.o + sc.e; r.d_tb = TB_START; r.dl = 1;
+    } else {
+        int32_t d = sc.o + sc.e * (int32_t)j, c = sc.yp + sc.o + sc.e;
+        if (d > c) { r.D = d; r.d_tb = TB_DEL; r.dl = j; }
+        else { r.D = c; r.d_tb = TB_YCLIP_PREFIX; r.dl = 0; }
+    }
+    if (r.D > sc.yp) { r.S = r.D; r.s_tb = TB_DEL; r.sl = j; }
+    else { r.S = sc.yp; r.s_tb = TB_YCLIP_PREFIX; r.sl = 0; }
+    if (j == n && sc.ys > r.S) { r.S = sc.ys; r.s_tb = TB_YCLIP_SUFFIX; r.sl = 0; }   // Sn[0] == ys
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column 0 (SCA:97-186).
+// ---------------------------------------------------------------------------------------------
+struct Col0 { int32_t S, I; uint32_t sl, il; uint32_t s_tb, i_tb; };
+
+// Value S[.][m] holds after rows < m of column 0 (x-suffix tracker); lx = Lx[0].
+SHD void col0_tracker(const Scoring &sc, uint32_t m, int32_t &tm, uint32_t &lx) {
+    tm = MIN_SCORE; lx = 0;
+    if (m >= 2) {
+        int32_t s1 = sc.o + sc.e;               // S(1,0) = max(I(1,0), xp)
+        if (sc.xp > s1) s1 = sc.xp;
+        if (s1 + sc.xs > MIN_SCORE) { tm = s1 + sc.xs; lx = m - 1; }
+    }
+}
+
+SHD Col0 col0_at(const Scoring &sc, uint32_t i, uint32_t m) {   // i >= 1
+    Col0 c;
+    if (i == 1) { c.I = sc.o + sc.e; c.i_tb = TB_START; c.il = 1; }
+    else {
+        int32_t is = sc.o + sc.e * (int32_t)i, cs = sc.xp + sc.o + sc.e;
+        if (is > cs) { c.I = is; c.i_tb = TB_INS; c.il = i; }
+        else { c.I = cs; c.i_tb = TB_XCLIP_PREFIX; c.il = 0; }
+    }
+    c.S = MIN_SCORE; c.s_tb = TB_START; c.sl = 0;
+    if (i == m) { uint32_t lx; col0_tracker(sc, m, c.S, lx); c.s_tb = TB_XCLIP_SUFFIX; }
+    if (c.I > c.S) { c.S = c.I; c.s_tb = TB_INS; c.sl = i; }
+    if (sc.xp > c.S) { c.S = sc.xp; c.s_tb = TB_XCLIP_PREFIX; c.sl = 0; }
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Insertion-chain carry: the best candidate for I arriving at some row, with its length and
+// whether it opens from the row immediately before (the only case the I pointer is "open").
+// ---------------------------------------------------------------------------------------------
+struct ICarry { int32_t v; uint32_t il; uint32_t open; };
+
+// `a` covers earlier rows and arrives `dist` rows before `b`'s arrival row; earlier wins ties
+// (extension is preferred, SCA:321).
+SHD ICarry icarry_combine(ICarry a, uint32_t dist, int32_t e, ICarry b) {
+    int32_t av = a.v + e * (int32_t)dist;
+    if (av >= b.v) { ICarry r; r.v = av; r.il = a.il + dist; r.open = 0; return r; }
+    return b;
+}
+
+// I candidate arriving at row 1 of a contig in column j (from row 0, SCA:317-326 with i = 1).
+SHD ICarry icarry_row1(const Scoring &sc, const Row0 &r0) {
+    int32_t ext = MIN_SCORE + sc.e, open = r0.S + sc.o + sc.e;
+    ICarry c;
+    if (ext >= open) { c.v = ext; c.il = 1; c.open = 0; }
+    else { c.v = open; c.il = r0.sl + 1; c.open = 1; }
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-cell results of pass A.
+// ---------------------------------------------------------------------------------------------
+struct PassA {
+    int32_t D; uint32_t dl; uint32_t dext;
+    int32_t H; uint32_t hl; uint32_t mv;    // best non-I candidate, its length and move
+    uint32_t gtA;                            // H > best of {start, diag, D}
+    uint32_t hidx, hfrom;                    // reference (idx, from) of the S pointer if H wins
+};
+
+// Everything row m needs to be finished once the x-suffix tracker of rows < m is known.
+struct RowM {
+    int32_t diag; uint32_t dgl;
+    int32_t D; uint32_t dl, dext;
+    int32_t I; uint32_t il, iext;
+    JumpInfo jp;
+    int32_t xclip; uint32_t xclip_len;
+    int32_t yclip; uint32_t yclip_len;
+    uint32_t is_match;
+};
+
+struct ColConst {          // per column, per read
+    uint32_t j, n;
+    int32_t xclip_score;   // xp + max(yp, o + e*j)   (SCA:304-308)
+    uint32_t sl0j;         // s_len of cell (0, j)
+    uint8_t q;             // read base y[j-1]
+};
+
+SHD uint32_t col0_slen(const Scoring &sc, uint32_t i, uint32_t m) { return col0_at(sc, i, m).sl; }
+
+// D layer (SCA:329-338).
+SHD void d_layer(const Scoring &sc, const CellState &up, int32_t &D, uint32_t &dl, uint32_t &dext) {
+    int32_t ext = up.D + sc.e, open = up.S + sc.o + sc.e;
+    if (ext >= open) { D = ext; dl = up.dl + 1; dext = 1; }
+    else { D = open; dl = up.sl + 1; dext = 0; }
+}
+
+// Jump candidate of a cell (SCA:242-290): J + substitution score, with the circular zero-cost
+// wrap from row m of the previous column at i == 1.
+SHD JumpInfo jump_for_cell(JumpInfo J, int32_t addend, bool wrap_ok, int32_t Sm_prev, uint32_t slm_prev,
+                           uint32_t self_idx, uint32_t m, uint32_t &is_wrap) {
+    J.score += addend;
+    is_wrap = 0;
+    if (wrap_ok) {
+        int32_t w = Sm_prev + addend;
+        if (!(J.score > w)) {
+            uint32_t wl = slm_prev + 1;
+            if (!(w == J.score && wl <= J.len)) {
+                J.score = w; J.len = wl; J.idx = self_idx; J.from = m; is_wrap = 1;
+            }
+        }
+    }
+    return J;
+}
+
+// Pass A for a row i < m (SCA:340-399 without the I layer).
+//   up   = state of (i, j-1);  dg = state of (i-1, j-1)
+SHD PassA pass_a(const Scoring &sc, const ColConst &cc, const CellState &up, int32_t dgS, uint32_t dgsl,
+                 uint8_t p, JumpInfo J, bool wrap_ok, int32_t Sm_prev, uint32_t slm_prev,
+                 uint32_t self_idx, uint32_t i, uint32_t m) {
+    PassA r;
+    d_layer(sc, up, r.D, r.dl, r.dext);
+    const bool eq = (p == cc.q);
+    const int32_t addend = eq ? sc.match : sc.mismatch;
+    const int32_t diag = dgS + addend;
+    const uint32_t dgl = dgsl + 1;
+    int32_t best = MIN_SCORE; uint32_t mv = MV_XCLIP_SUFFIX, len = 0, idx = 0, from = 0;
+    bool is_diag = false;
+    if (diag >= best) { best = diag; mv = MV_DIAG; len = dgl; idx = self_idx; from = i - 1; is_diag = true; }
+    if (r.D > best) { best = r.D; mv = MV_DEL; len = r.dl; idx = self_idx; from = i; is_diag = false; }
+    const int32_t A = best;
+    uint32_t is_wrap;
+    JumpInfo jp = jump_for_cell(J, addend, wrap_ok, Sm_prev, slm_prev, self_idx, m, is_wrap);
+    if (jp.score > best || (jp.score == best && is_diag && jp.len > dgl)) {
+        best = jp.score; mv = is_wrap ? MV_WRAP : MV_JUMP; len = jp.len; idx = jp.idx; from = jp.from;
+    }
+    if (cc.xclip_score > best) { best = cc.xclip_score; mv = MV_XCLIP_PREFIX; len = cc.sl0j; idx = self_idx; from = 0; }
+    const int32_t yclip = sc.yp + sc.o + sc.e * (int32_t)i;
+    if (yclip > best) { best = yclip; mv = MV_YCLIP_PREFIX; len = col0_slen(sc, i, m); idx = self_idx; from = i; }
+    r.H = best; r.hl = len; r.mv = mv; r.gtA = best > A; r.hidx = idx; r.hfrom = from;
+    return r;
+}
+
+// Candidates of row m (everything except the start value, which is the tracker).
+SHD RowM pass_a_rowm(const Scoring &sc, const ColConst &cc, const CellState &up, int32_t dgS, uint32_t dgsl,
+                     uint8_t p, JumpInfo J, bool wrap_ok, int32_t Sm_prev, uint32_t slm_prev,
+                     uint32_t self_idx, uint32_t m) {
+    RowM r;
+    d_layer(sc, up, r.D, r.dl, r.dext);
+    const bool eq = (p == cc.q);
+    const int32_t addend = eq ? sc.match : sc.mismatch;
+    r.is_match = eq;
+    r.diag = dgS + addend; r.dgl = dgsl + 1;
+    uint32_t is_wrap;
+    r.jp = jump_for_cell(J, addend, wrap_ok, Sm_prev, slm_prev, self_idx, m, is_wrap);
+    if (is_wrap) r.jp.idx |= 0x80000000u;   // remember it is the wrap (for the packed move)
+    r.xclip = cc.xclip_score; r.xclip_len = cc.sl0j;
+    r.yclip = sc.yp + sc.o + sc.e * (int32_t)m; r.yclip_len = 0;   // filled lazily below
+    r.I = MIN_SCORE; r.il = 0; r.iext = 0;
+    return r;
+}
+
+// S/I merge for a row < m (see header comment); returns the packed move.
+struct CellOut { int32_t S; uint32_t sl, mv, idx, from; };
+
+SHD CellOut merge_si(const PassA &a, int32_t I, uint32_t il, uint32_t self_idx, uint32_t i) {
+    CellOut c;
+    if (I > a.H || (I == a.H && a.gtA)) { c.S = I; c.sl = il; c.mv = MV_INS; c.idx = self_idx; c.from = i - 1; }
+    else { c.S = a.H; c.sl = a.hl; c.mv = a.mv; c.idx = a.hidx; c.from = a.hfrom; }
+    return c;
+}
+
+// Next row's I from this row's final S (SCA:317-326).
+SHD void i_step(const Scoring &sc, int32_t S, uint32_t sl, int32_t &I, uint32_t &il, uint32_t &iext) {
+    int32_t ext = I + sc.e, open = S + sc.o + sc.e;
+    if (ext >= open) { I = ext; il = il + 1; iext = 1; }
+    else { I = open; il = sl + 1; iext = 0; }
+}
+
+// x-suffix tracker partial over rows < m of one contig in one column (SCA:407-429):
+// maximal (t, len), FIRST row on full ties.  Start state: (MIN_SCORE, 0) with no row.
+struct XsPart { int32_t t; uint32_t len, row; };   // row == 0: nothing beat the start state
+SHD void xs_init(XsPart &p) { p.t = MIN_SCORE; p.len = 0; p.row = 0; }
+SHD void xs_add(XsPart &p, int32_t t, uint32_t len, uint32_t row) {     // rows arrive in increasing order
+    if (t > p.t || (t == p.t && len > p.len)) { p.t = t; p.len = len; p.row = row; }
+}
+SHD XsPart xs_merge(const XsPart &a, const XsPart &b) {                 // order-independent
+    if (a.row == 0) return b;
+    if (b.row == 0) return a;
+    if (a.t != b.t) return a.t > b.t ? a : b;
+    if (a.len != b.len) return a.len > b.len ? a : b;
+    return a.row < b.row ? a : b;
+}
+
+// Column-best partial for the next column's jump (SCA:677-697): max S, FIRST row on ties.
+struct CmPart { int32_t S; uint32_t row, sl; uint32_t valid; };
+SHD void cm_init(CmPart &p) { p.S = 0; p.row = 0; p.sl = 0; p.valid = 0; }
+SHD void cm_add(CmPart &p, int32_t S, uint32_t sl, uint32_t row) {      // rows in increasing order
+    if (!p.valid || S > p.S) { p.S = S; p.row = row; p.sl = sl; p.valid = 1; }
+}
+SHD CmPart cm_merge(const CmPart &a, const CmPart &b) {
+    if (!a.valid) return b;
+    if (!b.valid) return a;
+    if (a.S != b.S) return a.S > b.S ? a : b;
+    return a.row < b.row ? a : b;
+}
+
+// y-suffix tracker update of one row (SCA:432-447).  The tie-break compares with the s_len of
+// cell (i, n), which is still the zero of Traceback::init whenever this runs.
+SHD void sn_update(const Scoring &sc, SnRec &r, int32_t S, uint32_t sl, uint32_t idx, uint32_t j, uint32_t n) {
+    int32_t u = S + sc.ys;
+    if (u > r.sn || (u == r.sn && sl > 0)) { r.sn = u; r.ly = n - j; r.len = sl; r.idx = idx; }
+}
+
+SHD SnRec sn_init(const Scoring &sc, int32_t S0, uint32_t sl0, uint32_t self_idx, uint32_t n) {   // SCA:179-183
+    SnRec r; r.sn = MIN_SCORE; r.ly = 0; r.len = 0; r.idx = 0;
+    if (S0 + sc.ys > MIN_SCORE) { r.sn = S0 + sc.ys; r.ly = n; r.len = sl0; r.idx = self_idx; }
+    return r;
+}
+
+// Finishes row m of a contig in column j given the tracker over rows < m (SCA:350-429 at i == m).
+struct RowMOut { CellOut c; uint32_t lx; uint32_t s_tb; };
+SHD RowMOut finish_rowm(const Scoring &sc, const RowM &r, const XsPart &tr, uint32_t self_idx, uint32_t m) {
+    RowMOut o;
+    int32_t best = tr.t; uint32_t mv = MV_XCLIP_SUFFIX, len = tr.len, idx = 0, from = 0;
+    bool is_diag = false;
+    if (r.diag >= best) { best = r.diag; mv = MV_DIAG; len = r.dgl; idx = self_idx; from = m - 1; is_diag = true; }
+    if (r.D > best) { best = r.D; mv = MV_DEL; len = r.dl; idx = self_idx; from = m; is_diag = false; }
+    if (r.I > best) { best = r.I; mv = MV_INS; len = r.il; idx = self_idx; from = m - 1; is_diag = false; }
+    const bool wrap = (r.jp.idx & 0x80000000u) != 0;
+    const uint32_t jidx = r.jp.idx & 0x7fffffffu;
+    if (r.jp.score > best || (r.jp.score == best && is_diag && best == r.diag && r.jp.len > r.dgl)) {
+        best = r.jp.score; mv = wrap ? MV_WRAP : MV_JUMP; len = r.jp.len; idx = jidx; from = r.jp.from;
+    }
+    if (r.xclip > best) { best = r.xclip; mv = MV_XCLIP_PREFIX; len = r.xclip_len; idx = self_idx; from = 0; }
+    if (r.yclip > best) { best = r.yclip; mv = MV_YCLIP_PREFIX; len = col0_slen(sc, m, m); idx = self_idx; from = m; }
+    o.c.S = best; o.c.sl = len; o.c.mv = mv; o.c.idx = idx; o.c.from = from;
+    // tracker step at i == m compares the new cell with the stored tracker cell (SCA:407-429)
+    uint32_t lx = tr.row ? (m - tr.row) : 0;
+    if (sc.xs == 0 && len > tr.len) lx = 0;
+    o.lx = lx;
+    o.s_tb = (mv == MV_DIAG || mv == MV_JUMP || mv == MV_WRAP) ? (r.is_match ? TB_MATCH : TB_SUBST) : mv;
+    return o;
+}
+
+// Reference TB code of a packed move.
+SHD uint32_t tb_of_move(uint32_t mv, bool is_match) {
+    if (mv == MV_DIAG || mv == MV_JUMP || mv == MV_WRAP) return is_match ? TB_MATCH : TB_SUBST;
+    return mv;   // MV_START..MV_DEL and the clip codes share the reference's numbering
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jump selection for one contig of the layout (MCA:279-331).  cm/len/from: per layout position,
+// the column best of the previous column (score WITHOUT the jump cost).
+// ---------------------------------------------------------------------------------------------
+SHD JumpInfo select_jump(const Scoring &sc, const ContigEntry *ent, uint32_t C, uint32_t a,
+                         const int32_t *cm, const uint32_t *cml, const uint32_t *cmk) {
+    JumpInfo best;
+    best.score = cm[a] + sc.g_same; best.len = cml[a] + 1; best.idx = ent[a].contig_idx; best.from = cmk[a];
+    const int32_t opp = ent[a].opp;
+    if (opp >= 0) {
+        int32_t s = cm[opp] + sc.g_opp;
+        if (s > best.score) { best.score = s; best.len = cml[opp] + 1; best.idx = ent[opp].contig_idx; best.from = cmk[opp]; }
+    }
+    bool have = false; int32_t is = 0; uint32_t il = 0, ib = 0;
+    for (uint32_t b = 0; b < C; ++b) {
+        if (b == a || (int32_t)b == opp) continue;
+        int32_t s = cm[b] + sc.g_inter; uint32_t l = cml[b] + 1;
+        if (!have || s > is || (s == is && l >= il)) { have = true; is = s; il = l; ib = b; }   // last max wins
+    }
+    if (have && is > best.score) { best.score = is; best.len = il; best.idx = ent[ib].contig_idx; best.from = cmk[ib]; }
+    return best;
+}
+
+
+// =============================================================================================
+// Lane-level passes over one strip of STRIP consecutive rows of one contig in one column.
+// Index math: padded cell p = tile*TILE + r (r = row-1 within the contig's tiles).  The rolling
+// state is stored tile-transposed (k*32 + lane) so that a warp's loads are 512 contiguous bytes.
+// =============================================================================================
+SHD uint32_t state_index(uint32_t tile, uint32_t lane, uint32_t k) { return tile * TILE + k * 32 + lane; }
+SHD uint32_t cell_index(uint32_t tile, uint32_t lane, uint32_t k) { return tile * TILE + lane * STRIP + k; }
+
+struct TileCtx {          // per tile, per column (uniform over the warp)
+    uint32_t a;           // layout position of the contig
+    uint32_t self_idx;    // its contig index
+    uint32_t m;
+    uint32_t tile;        // global tile index
+    uint32_t tile_in_contig;
+    JumpInfo J;           // best jump into this contig for this column (MCA:319-330)
+    bool circular;
+    bool wrap_src_ok;     // s_tb(m, j-1) != XCLIP_SUFFIX   (SCA:263-267)
+    int32_t Sm_prev; uint32_t slm_prev;   // S / s_len of (m, j-1)
+};
+
+struct LaneA {
+    PassA a[STRIP];
+    ICarry agg;           // I candidate leaving this strip (arrives at the row after it)
+    RowM rowm;            // valid iff has_m
+    uint32_t has_m;
+    uint32_t nbelow;      // rows of this strip that are < m
+};
+
+// Pass A of one lane.  `up[k]` = state of row (row0+k) at column j-1; (dgS, dgsl) = S, s_len of
+// row (row0-1) at column j-1.
+SHD void lane_pass_a(const Scoring &sc, const ColConst &cc, const TileCtx &tc, uint32_t row0,
+                     const CellState *up, int32_t dgS, uint32_t dgsl, const uint8_t *x, LaneA &out) {
+    out.has_m = 0; out.nbelow = 0;
+    out.agg.v = MIN_SCORE; out.agg.il = 0; out.agg.open = 0;
+    bool first = true;
+    for (int k = 0; k < STRIP; ++k) {
+        const uint32_t i = row0 + (uint32_t)k;
+        if (i > tc.m) break;
+        const bool wrap_ok = tc.circular && i == 1 && tc.wrap_src_ok;
+        if (i < tc.m) {
+            PassA pa = pass_a(sc, cc, up[k], dgS, dgsl, x[k], tc.J, wrap_ok, tc.Sm_prev, tc.slm_prev, tc.self_idx, i, tc.m);
+            out.a[k] = pa;
+            out.nbelow = (uint32_t)k + 1;
+            const int32_t open = pa.H + sc.o + sc.e;
+            if (first) { out.agg.v = open; out.agg.il = pa.hl + 1; out.agg.open = 1; first = false; }
+            else {
+                const int32_t ext = out.agg.v + sc.e;
+                if (ext >= open) { out.agg.v = ext; out.agg.il += 1; out.agg.open = 0; }
+                else { out.agg.v = open; out.agg.il = pa.hl + 1; out.agg.open = 1; }
+            }
+        } else {
+            out.rowm = pass_a_rowm(sc, cc, up[k], dgS, dgsl, x[k], tc.J, wrap_ok, tc.Sm_prev, tc.slm_prev, tc.self_idx, tc.m);
+            out.has_m = 1;
+        }
+        dgS = up[k].S; dgsl = up[k].sl;
+    }
+}
+
+struct LaneB {
+    XsPart xs;            // x-suffix tracker partial over this strip's rows < m
+    CmPart cm;            // column-best partial over this strip's rows < m
+};
+
+// Pass B of one lane.  `cin` = I arriving at row0.  Writes the new rolling state, the packed
+// traceback bytes and (optionally) the y-suffix trackers / column-n records.
+SHD void lane_pass_b(const Scoring &sc, const ColConst &cc, const TileCtx &tc, uint32_t row0, uint32_t lane,
+                     LaneA &la, ICarry cin, CellState *state_curr, uint8_t *tb_col, bool track, SnRec *sn,
+                     bool lastcol, LastCell *last, const uint8_t *x, LaneB &out) {
+    xs_init(out.xs); cm_init(out.cm);
+    int32_t I = cin.v; uint32_t il = cin.il; uint32_t iext = cin.open ? 0u : 1u;
+    for (int k = 0; k < STRIP; ++k) {
+        const uint32_t i = row0 + (uint32_t)k;
+        if (i > tc.m) break;
+        if (i == tc.m) { la.rowm.I = I; la.rowm.il = il; la.rowm.iext = iext; break; }
+        const PassA &pa = la.a[k];
+        CellOut c = merge_si(pa, I, il, tc.self_idx, i);
+        CellState st; st.S = c.S; st.D = pa.D; st.sl = c.sl; st.dl = pa.dl;
+        state_curr[state_index(tc.tile, lane, (uint32_t)k)] = st;
+        const uint32_t p = cell_index(tc.tile, lane, (uint32_t)k);
+        tb_col[p] = (uint8_t)(c.mv | (pa.dext ? TBB_DEXT : 0u) | (iext ? TBB_IEXT : 0u));
+        xs_add(out.xs, c.S + sc.xs, c.sl, i);
+        cm_add(out.cm, c.S, c.sl, i);
+        if (track) sn_update(sc, sn[p], c.S, c.sl, c.idx, cc.j, cc.n);
+        if (lastcol) {
+            LastCell lc; lc.S = c.S; lc.I = I; lc.sl = c.sl; lc.il = il; lc.idx = c.idx; lc.from = c.from;
+            lc.s_tb = (uint8_t)tb_of_move(c.mv, x[k] == cc.q); lc.i_tb = 0; lc.flags = (uint8_t)(iext ? 1 : 0); lc.pad = 0; lc.pad2 = 0;
+            last[p] = lc;
+        }
+        i_step(sc, c.S, c.sl, I, il, iext);
+    }
+}
+
+// Per-contig end of column: finishes row m, returns the column best (for the next jump).
+struct ContigColOut { CmPart cm; int32_t Sm; uint32_t slm; uint32_t s_tb_m; };
+SHD ContigColOut contig_finalize(const Scoring &sc, const ColConst &cc, const ContigEntry &en, uint32_t a, uint32_t C,
+                                 const RowM &rm, XsPart xs, CmPart cm_rows, const Row0 &r0, JumpInfo J,
+                                 CellState *state_curr, uint8_t *tb_col, ColRec *colrec_col, bool track, SnRec *sn,
+                                 bool lastcol, LastCell *last) {
+    (void)C;
+    RowMOut ro = finish_rowm(sc, rm, xs, en.contig_idx, en.m);
+    const uint32_t r = en.m - 1;
+    const uint32_t tile = en.tile_start + r / TILE, lane = (r % TILE) / STRIP, k = r % STRIP;
+    CellState st; st.S = ro.c.S; st.D = rm.D; st.sl = ro.c.sl; st.dl = rm.dl;
+    state_curr[state_index(tile, lane, k)] = st;
+    const uint32_t p = cell_index(tile, lane, k);
+    tb_col[p] = (uint8_t)(ro.c.mv | (rm.dext ? TBB_DEXT : 0u) | (rm.iext ? TBB_IEXT : 0u));
+    ColRec cr; cr.jidx = J.idx; cr.jfrom = J.from; cr.lx = ro.lx; cr.pad = 0;
+    colrec_col[a] = cr;
+    if (track) sn_update(sc, sn[p], ro.c.S, ro.c.sl, ro.c.idx, cc.j, cc.n);
+    if (lastcol) {
+        LastCell lc; lc.S = ro.c.S; lc.I = rm.I; lc.sl = ro.c.sl; lc.il = rm.il; lc.idx = ro.c.idx; lc.from = ro.c.from;
+        lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0; lc.flags = (uint8_t)(rm.iext ? 1 : 0); lc.pad = 0; lc.pad2 = 0;
+        last[p] = lc;
+    }
+    // column best over rows 0..m, first row on ties (SCA:680-687)
+    CmPart cm; cm_init(cm);
+    cm_add(cm, r0.S, r0.sl, 0);
+    cm = cm_merge(cm, cm_rows);
+    CmPart top; top.S = ro.c.S; top.row = en.m; top.sl = ro.c.sl; top.valid = 1;
+    cm = cm_merge(cm, top);
+    ContigColOut o; o.cm = cm; o.Sm = ro.c.S; o.slm = ro.c.sl; o.s_tb_m = ro.s_tb;
+    return o;
+}
+
+// =============================================================================================
+// End-of-read fix-up of one contig (SCA:453-555) on the column-n records.
+// =============================================================================================
+SHD void fixup_contig(const Scoring &sc, const ContigEntry &en, uint32_t n, LastCell *last /* base of the read */,
+                      const SnRec *sn, uint32_t *lx_n) {
+    const uint32_t base = en.tile_start * TILE;   // row i -> last[base + i - 1]
+    const uint32_t m = en.m;
+    const Row0 r0 = row0_at(sc, n, n);
+    LastCell row0c; row0c.S = r0.S; row0c.I = MIN_SCORE; row0c.sl = r0.sl; row0c.il = 0; row0c.idx = en.contig_idx;
+    row0c.from = 0; row0c.s_tb = (uint8_t)r0.s_tb; row0c.i_tb = TB_START; row0c.flags = 0; row0c.pad = 0; row0c.pad2 = 0;
+    // resolve the open I pointers against the S moves as they were when the column was filled
+    {
+        uint8_t prev_tb = row0c.s_tb;
+        for (uint32_t i = 1; i <= m; ++i) {
+            LastCell &c = last[base + i - 1];
+            c.i_tb = (c.flags & 1) ? (uint8_t)TB_INS : prev_tb;
+            prev_tb = c.s_tb;
+        }
+    }
+    LastCell &cm_ = last[base + m - 1];
+    for (uint32_t i = 0; i <= m; ++i) {
+        LastCell &c = (i == 0) ? row0c : last[base + i - 1];
+        if (c.S + sc.g_same > cm_.S) {                                   // SCA:460-466
+            cm_.S = c.S + sc.g_same;
+            uint32_t l = c.sl, ix = c.idx;
+            cm_.s_tb = TB_XJUMP; cm_.sl = l; cm_.idx = ix; cm_.from = i;
+        }
+        SnRec s;
+        if (i == 0) { s.sn = sc.ys; s.ly = n; s.len = 0; s.idx = en.contig_idx; }
+        else s = sn[base + i - 1];
+        if (s.sn > c.S) {                                                // SCA:469-491
+            c.S = s.sn;
+            c.s_tb = TB_YCLIP_SUFFIX; c.sl = s.len; c.idx = s.idx; c.from = i;
+        }
+        {                                                                // SCA:494-516
+            const int32_t t = c.S + sc.xs;
+            if (t > cm_.S || (t == cm_.S && c.sl > cm_.sl)) {
+                cm_.S = t; *lx_n = m - i;
+                uint32_t l = c.sl, ix = c.idx;
+                cm_.s_tb = TB_XCLIP_SUFFIX; cm_.sl = l; cm_.idx = ix; cm_.from = i;
+            }
+        }
+    }
+    for (uint32_t i = 1; i <= m; ++i) {                                  // SCA:521-554
+        LastCell &pc = (i == 1) ? row0c : last[base + i - 2];
+        LastCell &c = last[base + i - 1];
+        const int32_t is = pc.S + sc.o + sc.e;
+        if (is > c.I) { c.I = is; c.i_tb = pc.s_tb; c.il = pc.sl + 1; }
+        if (is > c.S) {
+            c.S = is;
+            const uint32_t pl = c.il;
+            c.s_tb = TB_INS; c.sl = pl; c.idx = en.contig_idx; c.from = i - 1;
+            if (c.S + sc.xs > cm_.S) {
+                cm_.S = c.S + sc.xs; *lx_n = m - i;
+                cm_.s_tb = TB_XCLIP_SUFFIX; cm_.sl = pl; cm_.idx = en.contig_idx; cm_.from = i;
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Traceback walk (TB:219-373) over a virtual reference-cell view of the packed stores.
+// =============================================================================================
+struct OutOp { uint32_t kind, a, b; };   // same layout as stitch_op
+enum : uint32_t { OP_MATCH = 0, OP_SUBST = 1, OP_DEL = 2, OP_INS = 3, OP_XCLIP = 4, OP_YCLIP = 5, OP_XJUMP = 6, OP_YJUMP = 7 };
+
+struct ChainHdr {
+    int32_t score;
+    uint32_t xstart, xend, ystart, yend, xlen, ylen, start_contig_idx, end_contig_idx, length, n_ops, status;
+};
+enum : uint32_t { WALK_OK = 0, WALK_NONE = 1, WALK_OVERFLOW = 2, WALK_PANIC = 3 };
+
+struct ReadView {
+    Scoring sc;
+    const ContigEntry *ent; uint32_t C; uint32_t n; uint32_t PM;
+    const uint8_t *tb;          // dense: column j (1..n) at tb + (j-1)*PM
+    const ColRec *colrec;       // [(j)*C + a], j = 0..n
+    const LastCell *last;       // [PM]
+    const SnRec *sn;            // [PM]
+    const uint8_t *contig_bases;
+    const uint8_t *read;
+    const int16_t *pos_of;      // contig_idx -> layout position or -1 (MAX_STRANDS entries)
+
+    SHD uint32_t pidx(uint32_t a, uint32_t i) const { return ent[a].tile_start * TILE + i - 1; }
+    SHD bool is_match(uint32_t a, uint32_t i, uint32_t j) const {
+        return contig_bases[ent[a].seq_off + i - 1] == read[j - 1];
+    }
+    SHD uint32_t s_tb(uint32_t a, uint32_t i, uint32_t j) const {
+        if (i == 0) return row0_at(sc, j, n).s_tb;
+        if (j == 0) return col0_at(sc, i, ent[a].m).s_tb;
+        if (j == n) return last[pidx(a, i)].s_tb;
+        return tb_of_move(tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & 15u, is_match(a, i, j));
+    }
+    SHD uint32_t i_tb(uint32_t a, uint32_t i, uint32_t j) const {
+        if (i == 0) return TB_START;
+        if (j == 0) return col0_at(sc, i, ent[a].m).i_tb;
+        if (j == n) return last[pidx(a, i)].i_tb;
+        return (tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & TBB_IEXT) ? (uint32_t)TB_INS : s_tb(a, i - 1, j);
+    }
+    SHD uint32_t d_tb(uint32_t a, uint32_t i, uint32_t j) const {
+        if (i == 0) return row0_at(sc, j, n).d_tb;
+        if (j == 0) return TB_START;
+        return (tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & TBB_DEXT) ? (uint32_t)TB_DEL : s_tb(a, i, j - 1);
+    }
+    // (idx, from) of the S pointer of a MATCH/SUBST cell
+    SHD void s_ptr(uint32_t a, uint32_t i, uint32_t j, uint32_t &idx, uint32_t &from) const {
+        if (j == n) { const LastCell &c = last[pidx(a, i)]; idx = c.idx; from = c.from; return; }
+        const uint32_t mv = tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & 15u;
+        if (mv == MV_JUMP) { const ColRec &r = colrec[(uint64_t)j * C + a]; idx = r.jidx; from = r.jfrom; }
+        else if (mv == MV_WRAP) { idx = ent[a].contig_idx; from = ent[a].m; }
+        else { idx = ent[a].contig_idx; from = i - 1; }
+    }
+    SHD uint32_t lx(uint32_t a, uint32_t j) const {
+        if (j == 0) { int32_t t; uint32_t l; col0_tracker(sc, ent[a].m, t, l); return l; }
+        return colrec[(uint64_t)j * C + a].lx;
+    }
+    SHD uint32_t ly(uint32_t a, uint32_t i) const { return i == 0 ? n : sn[pidx(a, i)].ly; }
+};
+
+struct OpWriter {
+    OutOp *ops; uint32_t cap, n; bool overflow;
+    uint32_t first_kind;   // kind of the first op pushed (operations.first() in the reference)
+    uint32_t n_pushed;     // un-encoded count
+    bool only_special;
+    SHD void init(OutOp *o, uint32_t c) { ops = o; cap = c; n = 0; overflow = false; first_kind = 0xff; n_pushed = 0; only_special = true; }
+    SHD void push(uint32_t kind, uint32_t a, uint32_t b) {
+        if (n_pushed == 0) first_kind = kind;
+        ++n_pushed;
+        if (kind <= OP_INS) {
+            only_special = false;
+            if (n > 0 && ops[n - 1].kind == kind) { ops[n - 1].a += 1; return; }
+            a = 1; b = 0;
+        }
+        if (n >= cap) { overflow = true; return; }
+        ops[n].kind = kind; ops[n].a = a; ops[n].b = b; ++n;
+    }
+};
+
+// Walks back from (m_c, n) of layout position `a_end`; ops come out in reverse order and are
+// reversed in place at the end.
+SHD void walk_chain(const ReadView &v, uint32_t a_end, OutOp *ops, uint32_t cap, ChainHdr &h) {
+    OpWriter w; w.init(ops, cap);
+    const uint32_t n = v.n;
+    uint32_t a = a_end;
+    uint32_t j = n, i = v.ent[a].m;
+    uint32_t xstart = 0, ystart = 0, yend = n, xend = v.ent[a].m;
+    const LastCell &endc = v.last[v.pidx(a, i)];
+    h.score = endc.S; h.length = endc.sl; h.end_contig_idx = v.ent[a].contig_idx; h.xlen = v.ent[a].m; h.ylen = n;
+    uint32_t cur_idx = v.ent[a].contig_idx;
+    uint32_t layer = v.s_tb(a, i, j);
+    h.status = WALK_OK;
+    for (;;) {
+        if (w.overflow) { h.status = WALK_OVERFLOW; break; }
+        uint32_t next;
+        if (layer == TB_START) break;
+        if (layer == TB_INS) {
+            w.push(OP_INS, 0, 0);
+            next = v.i_tb(a, i, j);
+            if (i == 0) { h.status = WALK_PANIC; break; }
+            i -= 1;
+        } else if (layer == TB_DEL) {
+            w.push(OP_DEL, 0, 0);
+            next = v.d_tb(a, i, j);
+            if (j == 0) { h.status = WALK_PANIC; break; }
+            j -= 1;
+        } else if (layer == TB_MATCH || layer == TB_SUBST) {
+            w.push(layer == TB_MATCH ? OP_MATCH : OP_SUBST, 0, 0);
+            if (i == 0 || j == 0) { h.status = WALK_PANIC; break; }
+            uint32_t sidx, sfrom;
+            v.s_ptr(a, i, j, sidx, sfrom);
+            if (sidx != cur_idx || sfrom != i - 1) {
+                w.push(OP_XJUMP, cur_idx, i - 1);
+                cur_idx = sidx;
+                const int16_t na = sidx < MAX_STRANDS ? v.pos_of[sidx] : (int16_t)-1;
+                if (na < 0) { h.status = WALK_NONE; break; }
+                a = (uint32_t)na;
+            }
+            i = sfrom; j -= 1;
+            if (i > v.ent[a].m) { h.status = WALK_PANIC; break; }
+            next = v.s_tb(a, i, j);
+        } else if (layer == TB_XCLIP_PREFIX) {
+            next = v.s_tb(a, 0, j);
+            if (next == TB_START || next == TB_YCLIP_PREFIX) { w.push(OP_XCLIP, i, 0); xstart = i; }
+            i = 0;
+        } else if (layer == TB_XCLIP_SUFFIX) {
+            const uint32_t l = v.lx(a, j);
+            if (w.n_pushed == 0 || w.first_kind == OP_YCLIP) { w.push(OP_XCLIP, l, 0); xend = i - l; }
+            if (l > i) { h.status = WALK_PANIC; break; }
+            i -= l;
+            next = v.s_tb(a, i, j);
+        } else if (layer == TB_YCLIP_PREFIX) {
+            w.push(OP_YCLIP, j, 0);
+            ystart = j; j = 0;
+            next = v.s_tb(a, i, 0);
+        } else if (layer == TB_YCLIP_SUFFIX) {
+            const uint32_t l = v.ly(a, i);
+            w.push(OP_YCLIP, l, 0);
+            const uint32_t sfrom = (i == 0) ? 0u : v.last[v.pidx(a, i)].from;   // only column n holds this move
+            if (l > j) { h.status = WALK_PANIC; break; }
+            j -= l;
+            if (sfrom != i) { w.push(OP_XJUMP, cur_idx, i); i = sfrom; }
+            yend = j;
+            next = v.s_tb(a, i, j);
+        } else if (layer == TB_XJUMP) {
+            const LastCell &c = v.last[v.pidx(a, i)];                              // only (m, n) holds this move
+            w.push(OP_XJUMP, cur_idx, i);
+            cur_idx = c.idx;
+            const int16_t na = c.idx < MAX_STRANDS ? v.pos_of[c.idx] : (int16_t)-1;
+            if (na < 0) { h.status = WALK_NONE; break; }
+            a = (uint32_t)na;
+            i = c.from;
+            if (i > v.ent[a].m) { h.status = WALK_PANIC; break; }
+            next = v.s_tb(a, i, j);
+        } else { h.status = WALK_PANIC; break; }
+        layer = next;
+    }
+    if (w.overflow && h.status == WALK_OK) h.status = WALK_OVERFLOW;
+    // reverse in place
+    for (uint32_t l = 0; l < w.n / 2; ++l) {
+        OutOp t = ops[l]; ops[l] = ops[w.n - 1 - l]; ops[w.n - 1 - l] = t;
+    }
+    if (w.only_special) { xstart = 0; xend = 0; ystart = 0; yend = 0; }
+    h.xstart = xstart; h.xend = xend; h.ystart = ystart; h.yend = yend;
+    h.start_contig_idx = cur_idx; h.n_ops = w.n;
+}
+
+// End contig of the best chain (TB:129-150): max S[m_c], then longer length, else first.
+// `skip` (optional, by layout position): contigs to leave out (traceback_all's seen / not-considered).
+SHD uint32_t pick_end(const ReadView &v, const uint8_t *skip) {
+    uint32_t off = 0; int32_t score = MIN_SCORE; uint32_t alen = 0;
+    for (uint32_t a = 0; a < v.C; ++a) {
+        if (skip && skip[a]) continue;
+        const LastCell &c = v.last[v.pidx(a, v.ent[a].m)];
+        if (c.S > score || (c.S == score && c.sl > alen)) { off = a; score = c.S; alen = c.sl; }
+    }
+    return off;
+}
+
+}  // namespace stitch
