@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define SHD __host__ __device__ __forceinline__
+#define STITCH_UNROLL _Pragma("unroll")
 #else
 #define SHD inline
+#define STITCH_UNROLL
 #endif
 
 namespace stitch {
@@ -169,11 +171,26 @@ SHD ICarry icarry_row1(const Scoring &sc, const Row0 &r0) {
 // Per-cell results of pass A.
 // ---------------------------------------------------------------------------------------------
 struct PassA {
-    int32_t D; uint32_t dl; uint32_t dext;
-    int32_t H; uint32_t hl; uint32_t mv;    // best non-I candidate, its length and move
-    uint32_t gtA;                            // H > best of {start, diag, D}
-    uint32_t hidx, hfrom;                    // reference (idx, from) of the S pointer if H wins
+    int32_t D; uint32_t dl;
+    int32_t H; uint32_t hl;                  // best non-I candidate and its length
+    uint32_t fl;                             // bits 0-3 move of H, bit 4 D is an extension,
+                                             // bit 6 "H > best of {start, diag, D}"
 };
+constexpr uint32_t PA_GTA = 64;
+
+// Reference (idx, from) fields of the S pointer a packed move stands for (SCA:360-398); the
+// untouched start value keeps the zeros of Cell::default().
+SHD void ptr_of_move(uint32_t mv, uint32_t self_idx, uint32_t i, uint32_t m, const JumpInfo &J,
+                     uint32_t &idx, uint32_t &from) {
+    switch (mv) {
+    case MV_JUMP: idx = J.idx; from = J.from; break;
+    case MV_WRAP: idx = self_idx; from = m; break;
+    case MV_DEL: case MV_YCLIP_PREFIX: idx = self_idx; from = i; break;
+    case MV_XCLIP_PREFIX: idx = self_idx; from = 0; break;
+    case MV_XCLIP_SUFFIX: idx = 0; from = 0; break;
+    default: idx = self_idx; from = i - 1; break;   // MV_DIAG, MV_INS
+    }
+}
 
 // Everything row m needs to be finished once the x-suffix tracker of rows < m is known.
 struct RowM {
@@ -226,25 +243,26 @@ SHD PassA pass_a(const Scoring &sc, const ColConst &cc, const CellState &up, int
                  uint8_t p, JumpInfo J, bool wrap_ok, int32_t Sm_prev, uint32_t slm_prev,
                  uint32_t self_idx, uint32_t i, uint32_t m) {
     PassA r;
-    d_layer(sc, up, r.D, r.dl, r.dext);
+    uint32_t dext;
+    d_layer(sc, up, r.D, r.dl, dext);
     const bool eq = (p == cc.q);
     const int32_t addend = eq ? sc.match : sc.mismatch;
     const int32_t diag = dgS + addend;
     const uint32_t dgl = dgsl + 1;
-    int32_t best = MIN_SCORE; uint32_t mv = MV_XCLIP_SUFFIX, len = 0, idx = 0, from = 0;
+    int32_t best = MIN_SCORE; uint32_t mv = MV_XCLIP_SUFFIX, len = 0;
     bool is_diag = false;
-    if (diag >= best) { best = diag; mv = MV_DIAG; len = dgl; idx = self_idx; from = i - 1; is_diag = true; }
-    if (r.D > best) { best = r.D; mv = MV_DEL; len = r.dl; idx = self_idx; from = i; is_diag = false; }
+    if (diag >= best) { best = diag; mv = MV_DIAG; len = dgl; is_diag = true; }
+    if (r.D > best) { best = r.D; mv = MV_DEL; len = r.dl; is_diag = false; }
     const int32_t A = best;
     uint32_t is_wrap;
     JumpInfo jp = jump_for_cell(J, addend, wrap_ok, Sm_prev, slm_prev, self_idx, m, is_wrap);
     if (jp.score > best || (jp.score == best && is_diag && jp.len > dgl)) {
-        best = jp.score; mv = is_wrap ? MV_WRAP : MV_JUMP; len = jp.len; idx = jp.idx; from = jp.from;
+        best = jp.score; mv = is_wrap ? MV_WRAP : MV_JUMP; len = jp.len;
     }
-    if (cc.xclip_score > best) { best = cc.xclip_score; mv = MV_XCLIP_PREFIX; len = cc.sl0j; idx = self_idx; from = 0; }
+    if (cc.xclip_score > best) { best = cc.xclip_score; mv = MV_XCLIP_PREFIX; len = cc.sl0j; }
     const int32_t yclip = sc.yp + sc.o + sc.e * (int32_t)i;
-    if (yclip > best) { best = yclip; mv = MV_YCLIP_PREFIX; len = col0_slen(sc, i, m); idx = self_idx; from = i; }
-    r.H = best; r.hl = len; r.mv = mv; r.gtA = best > A; r.hidx = idx; r.hfrom = from;
+    if (yclip > best) { best = yclip; mv = MV_YCLIP_PREFIX; len = col0_slen(sc, i, m); }
+    r.H = best; r.hl = len; r.fl = mv | (dext ? TBB_DEXT : 0u) | (best > A ? PA_GTA : 0u);
     return r;
 }
 
@@ -268,13 +286,11 @@ SHD RowM pass_a_rowm(const Scoring &sc, const ColConst &cc, const CellState &up,
 }
 
 // S/I merge for a row < m (see header comment); returns the packed move.
-struct CellOut { int32_t S; uint32_t sl, mv, idx, from; };
+struct CellOut { int32_t S; uint32_t sl, mv, idx, from; };   // idx/from only filled by finish_rowm
 
-SHD CellOut merge_si(const PassA &a, int32_t I, uint32_t il, uint32_t self_idx, uint32_t i) {
-    CellOut c;
-    if (I > a.H || (I == a.H && a.gtA)) { c.S = I; c.sl = il; c.mv = MV_INS; c.idx = self_idx; c.from = i - 1; }
-    else { c.S = a.H; c.sl = a.hl; c.mv = a.mv; c.idx = a.hidx; c.from = a.hfrom; }
-    return c;
+SHD void merge_si(const PassA &a, int32_t I, uint32_t il, int32_t &S, uint32_t &sl, uint32_t &mv) {
+    if (I > a.H || (I == a.H && (a.fl & PA_GTA))) { S = I; sl = il; mv = MV_INS; }
+    else { S = a.H; sl = a.hl; mv = a.fl & 15u; }
 }
 
 // Next row's I from this row's final S (SCA:317-326).
@@ -387,6 +403,13 @@ SHD JumpInfo select_jump(const Scoring &sc, const ContigEntry *ent, uint32_t C, 
 // =============================================================================================
 SHD uint32_t state_index(uint32_t tile, uint32_t lane, uint32_t k) { return tile * TILE + k * 32 + lane; }
 SHD uint32_t cell_index(uint32_t tile, uint32_t lane, uint32_t k) { return tile * TILE + lane * STRIP + k; }
+// row i (1-based) of a contig -> tile-transposed index (rolling state, SnRec, LastCell)
+SHD uint32_t row_index(const ContigEntry &en, uint32_t i) {
+    const uint32_t r = i - 1;
+    return state_index(en.tile_start + r / TILE, (r % TILE) / STRIP, r % STRIP);
+}
+// row i -> linear index (packed traceback bytes)
+SHD uint32_t row_linear(const ContigEntry &en, uint32_t i) { return en.tile_start * TILE + i - 1; }
 
 struct TileCtx {          // per tile, per column (uniform over the warp)
     uint32_t a;           // layout position of the contig
@@ -403,35 +426,31 @@ struct TileCtx {          // per tile, per column (uniform over the warp)
 struct LaneA {
     PassA a[STRIP];
     ICarry agg;           // I candidate leaving this strip (arrives at the row after it)
-    RowM rowm;            // valid iff has_m
-    uint32_t has_m;
-    uint32_t nbelow;      // rows of this strip that are < m
+    uint32_t has_m;       // row m is in this strip (its candidates went to *rowm)
 };
 
 // Pass A of one lane.  `up[k]` = state of row (row0+k) at column j-1; (dgS, dgsl) = S, s_len of
-// row (row0-1) at column j-1.
+// row (row0-1) at column j-1.  Row m's candidates are written to *rowm (shared memory on the GPU).
 SHD void lane_pass_a(const Scoring &sc, const ColConst &cc, const TileCtx &tc, uint32_t row0,
-                     const CellState *up, int32_t dgS, uint32_t dgsl, const uint8_t *x, LaneA &out) {
-    out.has_m = 0; out.nbelow = 0;
+                     const CellState *up, int32_t dgS, uint32_t dgsl, const uint8_t *x, LaneA &out, RowM *rowm) {
+    out.has_m = 0;
     out.agg.v = MIN_SCORE; out.agg.il = 0; out.agg.open = 0;
-    bool first = true;
+    STITCH_UNROLL
     for (int k = 0; k < STRIP; ++k) {
         const uint32_t i = row0 + (uint32_t)k;
-        if (i > tc.m) break;
         const bool wrap_ok = tc.circular && i == 1 && tc.wrap_src_ok;
         if (i < tc.m) {
             PassA pa = pass_a(sc, cc, up[k], dgS, dgsl, x[k], tc.J, wrap_ok, tc.Sm_prev, tc.slm_prev, tc.self_idx, i, tc.m);
             out.a[k] = pa;
-            out.nbelow = (uint32_t)k + 1;
             const int32_t open = pa.H + sc.o + sc.e;
-            if (first) { out.agg.v = open; out.agg.il = pa.hl + 1; out.agg.open = 1; first = false; }
+            if (k == 0) { out.agg.v = open; out.agg.il = pa.hl + 1; out.agg.open = 1; }
             else {
                 const int32_t ext = out.agg.v + sc.e;
                 if (ext >= open) { out.agg.v = ext; out.agg.il += 1; out.agg.open = 0; }
                 else { out.agg.v = open; out.agg.il = pa.hl + 1; out.agg.open = 1; }
             }
-        } else {
-            out.rowm = pass_a_rowm(sc, cc, up[k], dgS, dgsl, x[k], tc.J, wrap_ok, tc.Sm_prev, tc.slm_prev, tc.self_idx, tc.m);
+        } else if (i == tc.m) {
+            *rowm = pass_a_rowm(sc, cc, up[k], dgS, dgsl, x[k], tc.J, wrap_ok, tc.Sm_prev, tc.slm_prev, tc.self_idx, tc.m);
             out.has_m = 1;
         }
         dgS = up[k].S; dgsl = up[k].sl;
@@ -446,29 +465,36 @@ struct LaneB {
 // Pass B of one lane.  `cin` = I arriving at row0.  Writes the new rolling state, the packed
 // traceback bytes and (optionally) the y-suffix trackers / column-n records.
 SHD void lane_pass_b(const Scoring &sc, const ColConst &cc, const TileCtx &tc, uint32_t row0, uint32_t lane,
-                     LaneA &la, ICarry cin, CellState *state_curr, uint8_t *tb_col, bool track, SnRec *sn,
-                     bool lastcol, LastCell *last, const uint8_t *x, LaneB &out) {
+                     const LaneA &la, ICarry cin, CellState *state_curr, uint8_t *tb_col, bool track, SnRec *sn,
+                     bool lastcol, LastCell *last, const uint8_t *x, LaneB &out, RowM *rowm) {
     xs_init(out.xs); cm_init(out.cm);
     int32_t I = cin.v; uint32_t il = cin.il; uint32_t iext = cin.open ? 0u : 1u;
+    STITCH_UNROLL
     for (int k = 0; k < STRIP; ++k) {
         const uint32_t i = row0 + (uint32_t)k;
-        if (i > tc.m) break;
-        if (i == tc.m) { la.rowm.I = I; la.rowm.il = il; la.rowm.iext = iext; break; }
-        const PassA &pa = la.a[k];
-        CellOut c = merge_si(pa, I, il, tc.self_idx, i);
-        CellState st; st.S = c.S; st.D = pa.D; st.sl = c.sl; st.dl = pa.dl;
-        state_curr[state_index(tc.tile, lane, (uint32_t)k)] = st;
-        const uint32_t p = cell_index(tc.tile, lane, (uint32_t)k);
-        tb_col[p] = (uint8_t)(c.mv | (pa.dext ? TBB_DEXT : 0u) | (iext ? TBB_IEXT : 0u));
-        xs_add(out.xs, c.S + sc.xs, c.sl, i);
-        cm_add(out.cm, c.S, c.sl, i);
-        if (track) sn_update(sc, sn[p], c.S, c.sl, c.idx, cc.j, cc.n);
-        if (lastcol) {
-            LastCell lc; lc.S = c.S; lc.I = I; lc.sl = c.sl; lc.il = il; lc.idx = c.idx; lc.from = c.from;
-            lc.s_tb = (uint8_t)tb_of_move(c.mv, x[k] == cc.q); lc.i_tb = 0; lc.flags = (uint8_t)(iext ? 1 : 0); lc.pad = 0; lc.pad2 = 0;
-            last[p] = lc;
+        if (i == tc.m) { rowm->I = I; rowm->il = il; rowm->iext = iext; }
+        if (i < tc.m) {
+            const PassA &pa = la.a[k];
+            int32_t S; uint32_t sl, mv;
+            merge_si(pa, I, il, S, sl, mv);
+            CellState st; st.S = S; st.D = pa.D; st.sl = sl; st.dl = pa.dl;
+            const uint32_t si = state_index(tc.tile, lane, (uint32_t)k);
+            state_curr[si] = st;
+            tb_col[cell_index(tc.tile, lane, (uint32_t)k)] = (uint8_t)(mv | (pa.fl & TBB_DEXT) | (iext ? TBB_IEXT : 0u));
+            xs_add(out.xs, S + sc.xs, sl, i);
+            cm_add(out.cm, S, sl, i);
+            if (track || lastcol) {
+                uint32_t idx, from;
+                ptr_of_move(mv, tc.self_idx, i, tc.m, tc.J, idx, from);
+                if (track) sn_update(sc, sn[si], S, sl, idx, cc.j, cc.n);
+                if (lastcol) {
+                    LastCell lc; lc.S = S; lc.I = I; lc.sl = sl; lc.il = il; lc.idx = idx; lc.from = from;
+                    lc.s_tb = (uint8_t)tb_of_move(mv, x[k] == cc.q); lc.i_tb = 0; lc.flags = (uint8_t)(iext ? 1 : 0); lc.pad = 0; lc.pad2 = 0;
+                    last[si] = lc;
+                }
+            }
+            i_step(sc, S, sl, I, il, iext);
         }
-        i_step(sc, c.S, c.sl, I, il, iext);
     }
 }
 
@@ -484,8 +510,8 @@ SHD ContigColOut contig_finalize(const Scoring &sc, const ColConst &cc, const Co
     const uint32_t tile = en.tile_start + r / TILE, lane = (r % TILE) / STRIP, k = r % STRIP;
     CellState st; st.S = ro.c.S; st.D = rm.D; st.sl = ro.c.sl; st.dl = rm.dl;
     state_curr[state_index(tile, lane, k)] = st;
-    const uint32_t p = cell_index(tile, lane, k);
-    tb_col[p] = (uint8_t)(ro.c.mv | (rm.dext ? TBB_DEXT : 0u) | (rm.iext ? TBB_IEXT : 0u));
+    const uint32_t p = state_index(tile, lane, k);
+    tb_col[cell_index(tile, lane, k)] = (uint8_t)(ro.c.mv | (rm.dext ? TBB_DEXT : 0u) | (rm.iext ? TBB_IEXT : 0u));
     ColRec cr; cr.jidx = J.idx; cr.jfrom = J.from; cr.lx = ro.lx; cr.pad = 0;
     colrec_col[a] = cr;
     if (track) sn_update(sc, sn[p], ro.c.S, ro.c.sl, ro.c.idx, cc.j, cc.n);
@@ -507,10 +533,12 @@ SHD ContigColOut contig_finalize(const Scoring &sc, const ColConst &cc, const Co
 // =============================================================================================
 // End-of-read fix-up of one contig (SCA:453-555) on the column-n records.
 // =============================================================================================
+// `track` false: the y-suffix trackers were not kept (ys == MIN_SCORE: Sn = S + MIN can never
+// exceed S(i, n) inside the score range the API accepts), so Sn reads as MIN_SCORE.
 SHD void fixup_contig(const Scoring &sc, const ContigEntry &en, uint32_t n, LastCell *last /* base of the read */,
-                      const SnRec *sn, uint32_t *lx_n) {
-    const uint32_t base = en.tile_start * TILE;   // row i -> last[base + i - 1]
+                      const SnRec *sn, bool track, uint32_t *lx_n) {
     const uint32_t m = en.m;
+    #define ROWIDX(i) row_index(en, (i))
     const Row0 r0 = row0_at(sc, n, n);
     LastCell row0c; row0c.S = r0.S; row0c.I = MIN_SCORE; row0c.sl = r0.sl; row0c.il = 0; row0c.idx = en.contig_idx;
     row0c.from = 0; row0c.s_tb = (uint8_t)r0.s_tb; row0c.i_tb = TB_START; row0c.flags = 0; row0c.pad = 0; row0c.pad2 = 0;
@@ -518,22 +546,21 @@ SHD void fixup_contig(const Scoring &sc, const ContigEntry &en, uint32_t n, Last
     {
         uint8_t prev_tb = row0c.s_tb;
         for (uint32_t i = 1; i <= m; ++i) {
-            LastCell &c = last[base + i - 1];
+            LastCell &c = last[ROWIDX(i)];
             c.i_tb = (c.flags & 1) ? (uint8_t)TB_INS : prev_tb;
             prev_tb = c.s_tb;
         }
     }
-    LastCell &cm_ = last[base + m - 1];
-    for (uint32_t i = 0; i <= m; ++i) {
-        LastCell &c = (i == 0) ? row0c : last[base + i - 1];
+    LastCell &cm_ = last[ROWIDX(m)];
+    // One row of SCA:455-517.  Row 0 lives in a local record, rows >= 1 in global memory; the two
+    // cases are kept as separate calls (a pointer select between the address spaces made nvcc
+    // 12.9 drop the `from` store of the selected record).
+    auto row_step = [&](LastCell &c, const SnRec &s, uint32_t i) {
         if (c.S + sc.g_same > cm_.S) {                                   // SCA:460-466
             cm_.S = c.S + sc.g_same;
-            uint32_t l = c.sl, ix = c.idx;
+            const uint32_t l = c.sl, ix = c.idx;
             cm_.s_tb = TB_XJUMP; cm_.sl = l; cm_.idx = ix; cm_.from = i;
         }
-        SnRec s;
-        if (i == 0) { s.sn = sc.ys; s.ly = n; s.len = 0; s.idx = en.contig_idx; }
-        else s = sn[base + i - 1];
         if (s.sn > c.S) {                                                // SCA:469-491
             c.S = s.sn;
             c.s_tb = TB_YCLIP_SUFFIX; c.sl = s.len; c.idx = s.idx; c.from = i;
@@ -542,16 +569,28 @@ SHD void fixup_contig(const Scoring &sc, const ContigEntry &en, uint32_t n, Last
             const int32_t t = c.S + sc.xs;
             if (t > cm_.S || (t == cm_.S && c.sl > cm_.sl)) {
                 cm_.S = t; *lx_n = m - i;
-                uint32_t l = c.sl, ix = c.idx;
+                const uint32_t l = c.sl, ix = c.idx;
                 cm_.s_tb = TB_XCLIP_SUFFIX; cm_.sl = l; cm_.idx = ix; cm_.from = i;
             }
         }
+    };
+    {
+        SnRec s0; s0.sn = sc.ys; s0.ly = n; s0.len = 0; s0.idx = en.contig_idx;
+        row_step(row0c, s0, 0);
+    }
+    for (uint32_t i = 1; i <= m; ++i) {
+        SnRec s;
+        if (track) s = sn[ROWIDX(i)];
+        else { s.sn = MIN_SCORE; s.len = 0; s.ly = 0; s.idx = 0; }
+        row_step(last[ROWIDX(i)], s, i);
     }
     for (uint32_t i = 1; i <= m; ++i) {                                  // SCA:521-554
-        LastCell &pc = (i == 1) ? row0c : last[base + i - 2];
-        LastCell &c = last[base + i - 1];
-        const int32_t is = pc.S + sc.o + sc.e;
-        if (is > c.I) { c.I = is; c.i_tb = pc.s_tb; c.il = pc.sl + 1; }
+        int32_t pS; uint32_t psl; uint8_t ptb;
+        if (i == 1) { pS = row0c.S; psl = row0c.sl; ptb = row0c.s_tb; }
+        else { const LastCell &pc = last[ROWIDX(i - 1)]; pS = pc.S; psl = pc.sl; ptb = pc.s_tb; }
+        LastCell &c = last[ROWIDX(i)];
+        const int32_t is = pS + sc.o + sc.e;
+        if (is > c.I) { c.I = is; c.i_tb = ptb; c.il = psl + 1; }
         if (is > c.S) {
             c.S = is;
             const uint32_t pl = c.il;
@@ -562,6 +601,7 @@ SHD void fixup_contig(const Scoring &sc, const ContigEntry &en, uint32_t n, Last
             }
         }
     }
+    #undef ROWIDX
 }
 
 // =============================================================================================
@@ -587,7 +627,8 @@ struct ReadView {
     const uint8_t *read;
     const int16_t *pos_of;      // contig_idx -> layout position or -1 (MAX_STRANDS entries)
 
-    SHD uint32_t pidx(uint32_t a, uint32_t i) const { return ent[a].tile_start * TILE + i - 1; }
+    SHD uint32_t pidx(uint32_t a, uint32_t i) const { return row_index(ent[a], i); }      // state order
+    SHD uint32_t plin(uint32_t a, uint32_t i) const { return row_linear(ent[a], i); }     // tb byte order
     SHD bool is_match(uint32_t a, uint32_t i, uint32_t j) const {
         return contig_bases[ent[a].seq_off + i - 1] == read[j - 1];
     }
@@ -595,23 +636,23 @@ struct ReadView {
         if (i == 0) return row0_at(sc, j, n).s_tb;
         if (j == 0) return col0_at(sc, i, ent[a].m).s_tb;
         if (j == n) return last[pidx(a, i)].s_tb;
-        return tb_of_move(tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & 15u, is_match(a, i, j));
+        return tb_of_move(tb[(uint64_t)(j - 1) * PM + plin(a, i)] & 15u, is_match(a, i, j));
     }
     SHD uint32_t i_tb(uint32_t a, uint32_t i, uint32_t j) const {
         if (i == 0) return TB_START;
         if (j == 0) return col0_at(sc, i, ent[a].m).i_tb;
         if (j == n) return last[pidx(a, i)].i_tb;
-        return (tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & TBB_IEXT) ? (uint32_t)TB_INS : s_tb(a, i - 1, j);
+        return (tb[(uint64_t)(j - 1) * PM + plin(a, i)] & TBB_IEXT) ? (uint32_t)TB_INS : s_tb(a, i - 1, j);
     }
     SHD uint32_t d_tb(uint32_t a, uint32_t i, uint32_t j) const {
         if (i == 0) return row0_at(sc, j, n).d_tb;
         if (j == 0) return TB_START;
-        return (tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & TBB_DEXT) ? (uint32_t)TB_DEL : s_tb(a, i, j - 1);
+        return (tb[(uint64_t)(j - 1) * PM + plin(a, i)] & TBB_DEXT) ? (uint32_t)TB_DEL : s_tb(a, i, j - 1);
     }
     // (idx, from) of the S pointer of a MATCH/SUBST cell
     SHD void s_ptr(uint32_t a, uint32_t i, uint32_t j, uint32_t &idx, uint32_t &from) const {
         if (j == n) { const LastCell &c = last[pidx(a, i)]; idx = c.idx; from = c.from; return; }
-        const uint32_t mv = tb[(uint64_t)(j - 1) * PM + pidx(a, i)] & 15u;
+        const uint32_t mv = tb[(uint64_t)(j - 1) * PM + plin(a, i)] & 15u;
         if (mv == MV_JUMP) { const ColRec &r = colrec[(uint64_t)j * C + a]; idx = r.jidx; from = r.jfrom; }
         else if (mv == MV_WRAP) { idx = ent[a].contig_idx; from = ent[a].m; }
         else { idx = ent[a].contig_idx; from = i - 1; }

@@ -12,6 +12,8 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -109,6 +111,7 @@ struct Contigs {
             for (auto &b : fwd[k]) if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);   // target_seq.rs:111-115
         }
         auto add = [&](const std::vector<uint8_t> &s) {
+            while (blob.size() % 16) blob.push_back(0);   // aligned vector loads of a lane's bases
             seq_off.push_back((uint32_t)blob.size());
             len.push_back((uint32_t)s.size());
             blob.insert(blob.end(), s.begin(), s.end());
@@ -195,6 +198,19 @@ struct Backend {
     virtual void set_max_inflight(uint32_t) {}
     BackendStats stats;
 };
+
+// Debugging aid (STITCH_DUMP_DIR): raw per-job records, same format from every backend.
+inline void dump_job(const char *dir, uint32_t seq, const std::vector<LastCell> &last, const std::vector<SnRec> &sn,
+                     const std::vector<ColRec> &colrec, const std::vector<uint8_t> &tb) {
+    auto wr = [&](const char *name, const void *p, size_t bytes) {
+        std::string fn = std::string(dir) + "/job" + std::to_string(seq) + "." + name;
+        if (FILE *f = std::fopen(fn.c_str(), "wb")) { std::fwrite(p, 1, bytes, f); std::fclose(f); }
+    };
+    wr("last", last.data(), last.size() * sizeof(LastCell));
+    wr("sn", sn.data(), sn.size() * sizeof(SnRec));
+    wr("colrec", colrec.data(), colrec.size() * sizeof(ColRec));
+    wr("tb", tb.data(), tb.size());
+}
 
 // ---------------------------------------------------------------------------------------------
 // Host alignment record with expanded operations
@@ -347,7 +363,7 @@ struct Aligner {
         // i32 headroom: the reference's scores are sums of at most (n + m) per-step scores on top
         // of MIN_SCORE; outside this range the reference itself overflows.
         const int64_t span = (int64_t)std::max<uint64_t>(max_n, contigs.max_len) + 2;
-        if (max_abs_score(opts.sc) * span > 1000000000ll)
+        if (max_abs_score(opts.sc) * span > 400000000ll)
             throw Error(STITCH_ERR_INVALID, "scores x sequence length exceed the i32 range of the reference's DP");
         if (max_n > MAX_CONTIG_LEN) throw Error(STITCH_ERR_LIMIT, "read longer than 2^27-1");
     }

@@ -17,6 +17,7 @@ namespace host {
 
 struct EmulBackend : Backend {
     Aligner &al;
+    uint32_t dump_seq = 0;
     explicit EmulBackend(Aligner &a) : al(a) {}
 
     void run_one(const Job &job, JobResult &res) {
@@ -31,7 +32,7 @@ struct EmulBackend : Backend {
         std::vector<uint8_t> tb((size_t)std::max<uint32_t>(n, 1) * PM, 0);
         std::vector<ColRec> colrec((size_t)(n + 1) * C, ColRec{0, 0, 0, 0});
         std::vector<LastCell> last(PM);
-        std::vector<SnRec> sn(PM, SnRec{MIN_SCORE, 0, 0, 0});
+        std::vector<SnRec> sn(PM, SnRec{track ? MIN_SCORE : 0x3fffffff, 7, 7, 7});
         stats.cells += (uint64_t)L.cells_per_col * n;
         stats.fills += 1;
 
@@ -46,12 +47,12 @@ struct EmulBackend : Backend {
                 Col0 c0 = col0_at(sc, i, en.m);
                 const uint32_t r = i - 1, tile = en.tile_start + r / TILE, lane = (r % TILE) / STRIP, k = r % STRIP;
                 st[0][state_index(tile, lane, k)] = CellState{c0.S, MIN_SCORE, c0.sl, 0};
-                sn[cell_index(tile, lane, k)] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n);
+                sn[state_index(tile, lane, k)] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n);
                 cm_add(part, c0.S, c0.sl, i);
                 if (n == 0) {   // column 0 is also column n
                     LastCell lc{}; lc.S = c0.S; lc.I = c0.I; lc.sl = c0.sl; lc.il = c0.il; lc.idx = en.contig_idx; lc.from = 0;
                     lc.s_tb = (uint8_t)c0.s_tb; lc.i_tb = (uint8_t)c0.i_tb; lc.flags = 0x80;
-                    last[cell_index(tile, lane, k)] = lc;
+                    last[state_index(tile, lane, k)] = lc;
                 }
             }
             if (!(part.S == 0 && part.row == 0)) throw Error(STITCH_ERR_INTERNAL, "emul: column-0 best is not (0, row 0)");
@@ -99,7 +100,7 @@ struct EmulBackend : Backend {
                     for (uint32_t lane = 0; lane < 32; ++lane) {
                         const uint32_t row0 = tc.tile_in_contig * TILE + lane * STRIP + 1;
                         LaneA &out = la[(size_t)w * 32 + lane];
-                        out.has_m = 0; out.nbelow = 0; out.agg = ICarry{MIN_SCORE, 0, 0};
+                        out.has_m = 0; out.agg = ICarry{MIN_SCORE, 0, 0};
                         if (row0 > en.m) continue;
                         CellState up[STRIP]; uint8_t x[STRIP];
                         for (int k = 0; k < STRIP; ++k) {
@@ -113,7 +114,7 @@ struct EmulBackend : Backend {
                             const uint32_t r = row0 - 2, pt = en.tile_start + r / TILE, pl = (r % TILE) / STRIP, pk = r % STRIP;
                             dgS = prev[state_index(pt, pl, pk)].S; dgsl = prev[state_index(pt, pl, pk)].sl;
                         }
-                        lane_pass_a(sc, cc, tc, row0, up, dgS, dgsl, x, out);
+                        lane_pass_a(sc, cc, tc, row0, up, dgS, dgsl, x, out, &rowm[a]);
                     }
                     // warp scan (Hillis-Steele over lane aggregates, as the kernel does with shuffles)
                     ICarry cur[32];
@@ -161,10 +162,9 @@ struct EmulBackend : Backend {
                         }
                         LaneB lb;
                         lane_pass_b(sc, cc, tc, row0, lane, a_, cin, curr.data(), tb_col, track, sn.data(), j == n,
-                                    last.data(), x, lb);
+                                    last.data(), x, lb, &rowm[tc.a]);
                         xs[tc.a] = xs_merge(xs[tc.a], lb.xs);
                         cmp[tc.a] = cm_merge(cmp[tc.a], lb.cm);
-                        if (a_.has_m) rowm[tc.a] = a_.rowm;
                     }
                 }
             }
@@ -178,7 +178,8 @@ struct EmulBackend : Backend {
         }
         // end-of-read fix-up, then the walks
         for (uint32_t a = 0; a < C; ++a)
-            fixup_contig(sc, L.ent[a], n, last.data(), sn.data(), &colrec[(size_t)n * C + a].lx);
+            fixup_contig(sc, L.ent[a], n, last.data(), sn.data(), track, &colrec[(size_t)n * C + a].lx);
+        if (const char *dump = std::getenv("STITCH_DUMP_DIR")) dump_job(dump, dump_seq++, last, sn, colrec, tb);
         ReadView v;
         v.sc = sc; v.ent = L.ent.data(); v.C = C; v.n = n; v.PM = PM; v.tb = tb.data(); v.colrec = colrec.data();
         v.last = last.data(); v.sn = sn.data(); v.contig_bases = bases; v.read = job.read; v.pos_of = L.pos_of.data();

@@ -1,0 +1,159 @@
+"""GPU tier: the CUDA path, called through the C ABI, must reproduce the oracle bit for bit
+(scores, coordinates, contigs, lengths, every operation) on the same seeded inputs; plus
+size-independent properties at larger sizes."""
+import json
+import os
+import random
+
+import pytest
+
+import gen
+from stitch_b200._abi import make_opts
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu_aligners(kw, named, max_inflight=0):
+    import stitch_b200
+    targets = [stitch_b200.TargetSeq(n, s) for n, s in named]
+    al = stitch_b200.Builder(**kw).build_aligners(targets, device=0)
+    if max_inflight:
+        al.set_max_inflight(max_inflight)
+    return al
+
+
+def compare(got, exp, ctx):
+    assert len(got) == len(exp)
+    for r, (la, lb) in enumerate(zip(got, exp)):
+        assert len(la) == len(lb), f"{ctx} read {r}: chain count {len(la)} vs {len(lb)}"
+        for k, (a, b) in enumerate(zip(la, lb)):
+            assert a.key() == b.key(), f"{ctx} read {r} chain {k}:\n  gpu    {a}\n  oracle {b}"
+
+
+def run_both(oracle, kw, contigs, reads, raw, subsets=None, max_inflight=0):
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    exp, _ = oracle.OracleAligners(make_opts(**kw), named).batch(reads, subsets=subsets, raw=raw)
+    al = gpu_aligners(kw, named, max_inflight)
+    got = al.custom_batch(reads, subsets) if raw else al.align_batch(reads, subsets)
+    al.close()
+    return got, exp
+
+
+def test_reference_kats_on_gpu(oracle):
+    """The reference's own single- and multi-contig known-answer tests through the CUDA path."""
+    for c in json.load(open(os.path.join(GOLD, "sca_kats.json"))):
+        kw = dict(mode=c["mode"], match_score=c["match"], mismatch_score=c["mismatch"], gap_open=c["gap_open"],
+                  gap_extend=c["gap_extend"], default_jump_score=c["jump"], circular=c["circular"])
+        got, exp = run_both(oracle, kw, [c["x"].encode()], [c["y"].encode()], raw=True)
+        compare(got, exp, c["name"])
+        a = got[0][0]
+        e = c["expect"]
+        assert (a.score, a.length) == (e["score"], e["length"]), c["name"]
+        if c["mode"] == 3:   # global: no clip ops are filtered by the mode wrapper, so the cigar is comparable
+            assert (a.xstart, a.xend, a.ystart, a.yend, oracle.cigar_of(a)) == (e["xstart"], e["xend"], e["ystart"], e["yend"], e["cigar"])
+    api = json.load(open(os.path.join(GOLD, "api_kats.json")))[0]
+    al = gpu_aligners({}, [(c["name"], c["seq"].encode()) for c in api["contigs"]])
+    chains = al.align_batch([api["read"].lower().encode()])[0]
+    assert len(chains) == 1 and chains[0].length == 25 and chains[0].cigar() == "25="
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_custom_small(oracle, block):
+    """Random small cases, all modes / strands / circular, low-complexity alphabets to force ties.
+    Many reads per batch so the persistent-CTA queue is exercised."""
+    for seed in range(block * 50, block * 50 + 50):
+        alphabet = [b"ACGT", b"AC", b"A", b"ACGTN"][seed % 4]
+        contigs, reads = gen.fuzz_case(seed, alphabet=alphabet)
+        kw = gen.fuzz_opts(seed)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=True)
+        compare(got, exp, f"seed {seed} {kw}")
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzz_align_small(oracle, block):
+    for seed in range(1000 + block * 40, 1000 + block * 40 + 40):
+        alphabet = [b"ACGT", b"AC", b"ACG"][seed % 3]
+        contigs, reads = gen.fuzz_case(seed, max_contigs=4, max_len=80, max_read=80, alphabet=alphabet)
+        kw = gen.fuzz_opts(seed)
+        rng = random.Random(seed)
+        kw["suboptimal"] = rng.random() < 0.5
+        kw["suboptimal_pct"] = rng.choice([0.0, 20.0, 90.0])
+        got, exp = run_both(oracle, kw, contigs, reads, raw=False)
+        compare(got, exp, f"seed {seed} {kw}")
+
+
+def test_fuzz_subsets(oracle):
+    for seed in range(3000, 3040):
+        rng = random.Random(seed)
+        contigs, reads = gen.fuzz_case(seed, max_contigs=5)
+        kw = gen.fuzz_opts(seed)
+        ns = len(contigs) * (2 if kw["double_strand"] else 1)
+        subsets = []
+        for _ in reads:
+            sub = [c for c in range(ns) if rng.random() < 0.6]
+            subsets.append(sub or [rng.randrange(ns)])
+        got, exp = run_both(oracle, kw, contigs, reads, raw=rng.random() < 0.5, subsets=subsets)
+        compare(got, exp, f"seed {seed} {kw} {subsets}")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_multi_tile_contigs(oracle, seed):
+    """Contigs spanning several 256-row warp tiles and several rounds of the CTA (the cross-warp
+    insertion-chain carry, per-contig reductions), low-complexity so that long gaps and ties occur."""
+    rng = random.Random(100 + seed)
+    alphabet = [b"ACGT", b"AC", b"ACGT"][seed % 3]
+    lens = [rng.randint(200, 2600) for _ in range(rng.randint(2, 5))] + [257, 256, 255][: seed % 3 + 1]
+    contigs = [gen.rand_seq(rng, l, alphabet) for l in lens]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(150, 500), rng.randint(1, 4), strands=True, wrap=True,
+                               alphabet=alphabet) for _ in range(5)]
+    kw = gen.fuzz_opts(seed)
+    kw["double_strand"] = seed % 2 == 0
+    if seed == 3:   # long insertions across tile boundaries: cheap gaps
+        kw.update(gap_open=-1, gap_extend=0, mismatch_score=-6)
+    got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 2 == 1))
+    compare(got, exp, f"seed {seed} {kw}")
+
+
+def test_config1_shape_downscaled(oracle):
+    """BASELINE config 1/2 shapes, down-scaled so the oracle finishes in seconds: 20 plasmid-like
+    contigs, chimeric noisy reads, default CLI scoring; single strand and -d -C."""
+    rng = random.Random(20241)
+    contigs = [gen.rand_seq(rng, rng.randint(700, 900)) for _ in range(20)]
+    reads = [gen.chimeric_read(rng, contigs, 1000, rng.randint(3, 6)) for _ in range(6)]
+    got, exp = run_both(oracle, {}, contigs, reads, raw=False)
+    compare(got, exp, "config1")
+    rng = random.Random(20242)
+    reads = [gen.chimeric_read(rng, contigs, 1000, rng.randint(3, 6), strands=True, wrap=True) for _ in range(4)]
+    got, exp = run_both(oracle, dict(double_strand=True, circular=True), contigs, reads, raw=False)
+    compare(got, exp, "config2")
+    # same batch split into chunks of 2 reads in flight: identical answers
+    got2, _ = run_both(oracle, dict(double_strand=True, circular=True), contigs, reads, raw=False, max_inflight=2)
+    compare(got2, exp, "config2 chunked")
+
+
+def test_full_size_properties():
+    """Config-1 sizes (10 kb reads vs 20 x ~8 kb contigs), no oracle: size-independent properties.
+    A read that is an exact concatenation of contig substrings must score
+    sum(len) + jumps * jump_score in local mode, its chain must validate, and the alignment of the
+    read's reverse complement under --double-strand must have the same score."""
+    import stitch_b200
+    rng = random.Random(5)
+    contigs = [gen.rand_seq(rng, rng.randint(7000, 9000)) for _ in range(20)]
+    segs = []
+    for _ in range(4):
+        c = rng.randrange(20)
+        s = rng.randrange(0, len(contigs[c]) - 2500)
+        segs.append(contigs[c][s:s + 2500])
+    read = b"".join(segs)
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    al = gpu_aligners(dict(double_strand=True), named)
+    chains = al.align_batch([read, gen.revcomp(read)])
+    fwd, rev = chains[0][0], chains[1][0]
+    assert fwd.score == 10000 - 3 * 10
+    assert rev.score == fwd.score
+    assert fwd.length == 10000 and fwd.ystart == 0 and fwd.yend == 10000
+    fwd.validate(); rev.validate()
+    assert sum(1 for k, _, _ in fwd.ops if k == 6) == 3
+    st = al.stats()
+    assert st.cells == 2 * 10000 * 2 * sum(len(c) for c in contigs)
