@@ -149,6 +149,10 @@ void stitch_destroy(stitch_ctx *ctx);
 /* Message of the last failure on this ctx (or of stitch_create when ctx is NULL). */
 const char *stitch_last_error(const stitch_ctx *ctx);
 
+/* Diagnostic for the roofline: sustained INT32 add+max issue rate of the device, in giga
+ * operations per second, an add followed by a max counted as two operations. */
+int stitch_measure_int32_peak(int device, double *gops);
+
 /* ABI version of this header. */
 uint32_t stitch_abi_version(void);
 

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "stitch_create", "stitch_align_batch", "stitch_custom_batch", "stitch_custom_batch_device",
     "stitch_results_n_reads", "stitch_results_read", "stitch_results_chains", "stitch_results_ops",
     "stitch_free_results", "stitch_get_stats", "stitch_set_max_inflight", "stitch_destroy",
-    "stitch_last_error", "stitch_abi_version",
+    "stitch_last_error", "stitch_abi_version", "stitch_measure_int32_peak",
 ]
 
 _lib = None
@@ -95,6 +95,8 @@ def load():
     lib.stitch_destroy.argtypes = [C.c_void_p]
     lib.stitch_last_error.restype = C.c_char_p
     lib.stitch_last_error.argtypes = [C.c_void_p]
+    lib.stitch_measure_int32_peak.restype = C.c_int
+    lib.stitch_measure_int32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.stitch_abi_version.restype = C.c_uint32
     lib.stitch_abi_version.argtypes = []
     _lib = lib

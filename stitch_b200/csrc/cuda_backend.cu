@@ -667,3 +667,53 @@ extern "C" int stitch_custom_batch_device(stitch_ctx *ctx, const uint8_t *d_base
     return STITCH_OK;
     STITCH_GUARD_END(ctx)
 }
+
+// ---------------------------------------------------------------------------------------------
+// INT32 add+max issue-rate microbenchmark (the roofline denominator of the fill kernel)
+// ---------------------------------------------------------------------------------------------
+namespace stitch { namespace gpu {
+__global__ void __launch_bounds__(256) int32_peak_kernel(int32_t *out, int iters, int32_t c, int32_t w) {
+    int32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (int32_t)(threadIdx.x * 16 + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = max(v[k] + c, w + k);   // one add + one max per element
+        }
+    }
+    int32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc ^= v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+}}  // namespace stitch::gpu
+
+extern "C" int stitch_measure_int32_peak(int device, double *gops) {
+    if (!gops) return STITCH_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return STITCH_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return STITCH_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STITCH_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    int32_t *d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(int32_t)) != cudaSuccess) return STITCH_ERR_NOMEM;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        stitch::gpu::int32_peak_kernel<<<blocks, threads>>>(d, iters, -3, -1000000 + rep);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return STITCH_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double ops = 2.0 * 16 * 4 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *gops = best;
+    return STITCH_OK;
+}

@@ -67,14 +67,18 @@ struct CellState { int32_t S, D; uint32_t sl, dl; };
 
 struct JumpInfo { int32_t score; uint32_t len, idx, from; };
 
-// Per (contig, column) record kept for the walk.
-struct ColRec { uint32_t jidx, jfrom, lx, pad; };
+// Per (contig, column) record: the jump selected for the column (so that one contig can be
+// re-filled alone from a checkpoint) and Lx[j] of the x-suffix tracker (walk).
+struct ColRec { int32_t jscore; uint32_t jlen, jidx, jfrom, lx, pad0, pad1, pad2; };
+
+// What a re-fill needs about row m of a contig at a checkpoint column.
+struct CkSum { int32_t Sm; uint32_t slm, tbm, pad; };
 
 // Column-n cell in reference form (the end-of-read fix-up edits these, SCA:453-555).
 struct LastCell {
     int32_t S, I;
     uint32_t sl, il, idx, from;
-    uint8_t s_tb, i_tb, flags, pad;   // flags: bit0 I pointer is an extension
+    uint8_t s_tb, i_tb, flags, pad;   // flags: bit0 I pointer is an extension, bit1 D pointer is an extension
     uint32_t pad2;
 };
 
@@ -341,6 +345,24 @@ SHD SnRec sn_init(const Scoring &sc, int32_t S0, uint32_t sl0, uint32_t self_idx
     return r;
 }
 
+// Windowed y-suffix tracking: with G(j) = best cell of column j over all
+// contigs, every row i >= 1 ends with Sn(i) - ys >= Gmax - W', W' = max(match, mismatch, 0) - min jump
+// score - min(match, mismatch), because every cell of column j+1 can be entered by a jump from the
+// best cell of column j.  Columns with G(j) < Gmax - W' therefore never hold the final (Sn, Ly) of any
+// row; the trackers only need the columns from the first candidate on (column 0 is their start value).
+SHD uint32_t first_candidate_column(const Scoring &sc, const int32_t *gcol, uint32_t n) {
+    int32_t gmax = gcol[0];
+    for (uint32_t j = 1; j <= n; ++j) gmax = gcol[j] > gmax ? gcol[j] : gmax;
+    int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
+    if (submax < 0) submax = 0;
+    const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+    int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+    gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+    const int32_t thr = gmax - (submax - gmin - submin);
+    for (uint32_t j = 1; j <= n; ++j) if (gcol[j] >= thr) return j;
+    return n + 1;
+}
+
 // Finishes row m of a contig in column j given the tracker over rows < m (SCA:350-429 at i == m).
 struct RowMOut { CellOut c; uint32_t lx; uint32_t s_tb; };
 SHD RowMOut finish_rowm(const Scoring &sc, const RowM &r, const XsPart &tr, uint32_t self_idx, uint32_t m) {
@@ -465,8 +487,8 @@ struct LaneB {
 // Pass B of one lane.  `cin` = I arriving at row0.  Writes the new rolling state, the packed
 // traceback bytes and (optionally) the y-suffix trackers / column-n records.
 SHD void lane_pass_b(const Scoring &sc, const ColConst &cc, const TileCtx &tc, uint32_t row0, uint32_t lane,
-                     const LaneA &la, ICarry cin, CellState *state_curr, uint8_t *tb_col, bool track, SnRec *sn,
-                     bool lastcol, LastCell *last, const uint8_t *x, LaneB &out, RowM *rowm) {
+                     const LaneA &la, ICarry cin, CellState *state_curr, CellState *ck_state, uint8_t *tb_col,
+                     bool track, SnRec *sn, bool lastcol, LastCell *last, const uint8_t *x, LaneB &out, RowM *rowm) {
     xs_init(out.xs); cm_init(out.cm);
     int32_t I = cin.v; uint32_t il = cin.il; uint32_t iext = cin.open ? 0u : 1u;
     STITCH_UNROLL
@@ -480,7 +502,8 @@ SHD void lane_pass_b(const Scoring &sc, const ColConst &cc, const TileCtx &tc, u
             CellState st; st.S = S; st.D = pa.D; st.sl = sl; st.dl = pa.dl;
             const uint32_t si = state_index(tc.tile, lane, (uint32_t)k);
             state_curr[si] = st;
-            tb_col[cell_index(tc.tile, lane, (uint32_t)k)] = (uint8_t)(mv | (pa.fl & TBB_DEXT) | (iext ? TBB_IEXT : 0u));
+            if (ck_state) ck_state[si] = st;
+            if (tb_col) tb_col[cell_index(tc.tile, lane, (uint32_t)k)] = (uint8_t)(mv | (pa.fl & TBB_DEXT) | (iext ? TBB_IEXT : 0u));
             xs_add(out.xs, S + sc.xs, sl, i);
             cm_add(out.cm, S, sl, i);
             if (track || lastcol) {
@@ -489,7 +512,8 @@ SHD void lane_pass_b(const Scoring &sc, const ColConst &cc, const TileCtx &tc, u
                 if (track) sn_update(sc, sn[si], S, sl, idx, cc.j, cc.n);
                 if (lastcol) {
                     LastCell lc; lc.S = S; lc.I = I; lc.sl = sl; lc.il = il; lc.idx = idx; lc.from = from;
-                    lc.s_tb = (uint8_t)tb_of_move(mv, x[k] == cc.q); lc.i_tb = 0; lc.flags = (uint8_t)(iext ? 1 : 0); lc.pad = 0; lc.pad2 = 0;
+                    lc.s_tb = (uint8_t)tb_of_move(mv, x[k] == cc.q); lc.i_tb = 0;
+                    lc.flags = (uint8_t)((iext ? 1 : 0) | ((pa.fl & TBB_DEXT) ? 2 : 0)); lc.pad = 0; lc.pad2 = 0;
                     last[si] = lc;
                 }
             }
@@ -502,22 +526,26 @@ SHD void lane_pass_b(const Scoring &sc, const ColConst &cc, const TileCtx &tc, u
 struct ContigColOut { CmPart cm; int32_t Sm; uint32_t slm; uint32_t s_tb_m; };
 SHD ContigColOut contig_finalize(const Scoring &sc, const ColConst &cc, const ContigEntry &en, uint32_t a, uint32_t C,
                                  const RowM &rm, XsPart xs, CmPart cm_rows, const Row0 &r0, JumpInfo J,
-                                 CellState *state_curr, uint8_t *tb_col, ColRec *colrec_col, bool track, SnRec *sn,
-                                 bool lastcol, LastCell *last) {
+                                 CellState *state_curr, CellState *ck_state, uint8_t *tb_col, ColRec *colrec_col,
+                                 bool track, SnRec *sn, bool lastcol, LastCell *last) {
     (void)C;
     RowMOut ro = finish_rowm(sc, rm, xs, en.contig_idx, en.m);
     const uint32_t r = en.m - 1;
     const uint32_t tile = en.tile_start + r / TILE, lane = (r % TILE) / STRIP, k = r % STRIP;
     CellState st; st.S = ro.c.S; st.D = rm.D; st.sl = ro.c.sl; st.dl = rm.dl;
-    state_curr[state_index(tile, lane, k)] = st;
     const uint32_t p = state_index(tile, lane, k);
-    tb_col[cell_index(tile, lane, k)] = (uint8_t)(ro.c.mv | (rm.dext ? TBB_DEXT : 0u) | (rm.iext ? TBB_IEXT : 0u));
-    ColRec cr; cr.jidx = J.idx; cr.jfrom = J.from; cr.lx = ro.lx; cr.pad = 0;
-    colrec_col[a] = cr;
+    state_curr[p] = st;
+    if (ck_state) ck_state[p] = st;
+    if (tb_col) tb_col[cell_index(tile, lane, k)] = (uint8_t)(ro.c.mv | (rm.dext ? TBB_DEXT : 0u) | (rm.iext ? TBB_IEXT : 0u));
+    if (colrec_col) {
+        ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from; cr.lx = ro.lx;
+        cr.pad0 = cr.pad1 = cr.pad2 = 0;
+        colrec_col[a] = cr;
+    }
     if (track) sn_update(sc, sn[p], ro.c.S, ro.c.sl, ro.c.idx, cc.j, cc.n);
     if (lastcol) {
         LastCell lc; lc.S = ro.c.S; lc.I = rm.I; lc.sl = ro.c.sl; lc.il = rm.il; lc.idx = ro.c.idx; lc.from = ro.c.from;
-        lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0; lc.flags = (uint8_t)(rm.iext ? 1 : 0); lc.pad = 0; lc.pad2 = 0;
+        lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0; lc.flags = (uint8_t)((rm.iext ? 1 : 0) | (rm.dext ? 2 : 0)); lc.pad = 0; lc.pad2 = 0;
         last[p] = lc;
     }
     // column best over rows 0..m, first row on ties (SCA:680-687)
@@ -616,43 +644,43 @@ struct ChainHdr {
 };
 enum : uint32_t { WALK_OK = 0, WALK_NONE = 1, WALK_OVERFLOW = 2, WALK_PANIC = 3 };
 
+// The packed traceback bytes of ONE contig over one block of columns (jb, je], re-filled from
+// a column-state checkpoint when the walk needs them (checkpoint-and-recompute).
+struct TbUnit {
+    const uint8_t *bytes;   // column j (jb < j <= je), row i (1..m): bytes[(j - jb - 1) * pm + i - 1]
+    uint32_t a;             // layout position; 0xffffffff = nothing loaded
+    uint32_t jb, je, pm;
+    SHD bool has(uint32_t a_, uint32_t j) const { return a == a_ && j > jb && j <= je; }
+    SHD uint32_t at(uint32_t i, uint32_t j) const { return bytes[(uint64_t)(j - jb - 1) * pm + (i - 1)]; }
+};
+
 struct ReadView {
     Scoring sc;
-    const ContigEntry *ent; uint32_t C; uint32_t n; uint32_t PM;
-    const uint8_t *tb;          // dense: column j (1..n) at tb + (j-1)*PM
+    const ContigEntry *ent; uint32_t C; uint32_t n;
     const ColRec *colrec;       // [(j)*C + a], j = 0..n
-    const LastCell *last;       // [PM]
-    const SnRec *sn;            // [PM]
+    const LastCell *last;       // column n, tile-transposed order
+    const SnRec *sn;            // tile-transposed order
     const uint8_t *contig_bases;
     const uint8_t *read;
     const int16_t *pos_of;      // contig_idx -> layout position or -1 (MAX_STRANDS entries)
+    TbUnit unit;
 
-    SHD uint32_t pidx(uint32_t a, uint32_t i) const { return row_index(ent[a], i); }      // state order
-    SHD uint32_t plin(uint32_t a, uint32_t i) const { return row_linear(ent[a], i); }     // tb byte order
+    SHD uint32_t pidx(uint32_t a, uint32_t i) const { return row_index(ent[a], i); }
     SHD bool is_match(uint32_t a, uint32_t i, uint32_t j) const {
         return contig_bases[ent[a].seq_off + i - 1] == read[j - 1];
     }
+    SHD bool interior(uint32_t i, uint32_t j) const { return i >= 1 && j >= 1 && j < n; }
+    // S move of a cell as a reference TB code (interior cells need the loaded unit)
     SHD uint32_t s_tb(uint32_t a, uint32_t i, uint32_t j) const {
         if (i == 0) return row0_at(sc, j, n).s_tb;
         if (j == 0) return col0_at(sc, i, ent[a].m).s_tb;
         if (j == n) return last[pidx(a, i)].s_tb;
-        return tb_of_move(tb[(uint64_t)(j - 1) * PM + plin(a, i)] & 15u, is_match(a, i, j));
-    }
-    SHD uint32_t i_tb(uint32_t a, uint32_t i, uint32_t j) const {
-        if (i == 0) return TB_START;
-        if (j == 0) return col0_at(sc, i, ent[a].m).i_tb;
-        if (j == n) return last[pidx(a, i)].i_tb;
-        return (tb[(uint64_t)(j - 1) * PM + plin(a, i)] & TBB_IEXT) ? (uint32_t)TB_INS : s_tb(a, i - 1, j);
-    }
-    SHD uint32_t d_tb(uint32_t a, uint32_t i, uint32_t j) const {
-        if (i == 0) return row0_at(sc, j, n).d_tb;
-        if (j == 0) return TB_START;
-        return (tb[(uint64_t)(j - 1) * PM + plin(a, i)] & TBB_DEXT) ? (uint32_t)TB_DEL : s_tb(a, i, j - 1);
+        return tb_of_move(unit.at(i, j) & 15u, is_match(a, i, j));
     }
     // (idx, from) of the S pointer of a MATCH/SUBST cell
     SHD void s_ptr(uint32_t a, uint32_t i, uint32_t j, uint32_t &idx, uint32_t &from) const {
         if (j == n) { const LastCell &c = last[pidx(a, i)]; idx = c.idx; from = c.from; return; }
-        const uint32_t mv = tb[(uint64_t)(j - 1) * PM + plin(a, i)] & 15u;
+        const uint32_t mv = unit.at(i, j) & 15u;
         if (mv == MV_JUMP) { const ColRec &r = colrec[(uint64_t)j * C + a]; idx = r.jidx; from = r.jfrom; }
         else if (mv == MV_WRAP) { idx = ent[a].contig_idx; from = ent[a].m; }
         else { idx = ent[a].contig_idx; from = i - 1; }
@@ -683,92 +711,116 @@ struct OpWriter {
     }
 };
 
-// Walks back from (m_c, n) of layout position `a_end`; ops come out in reverse order and are
-// reversed in place at the end.
-SHD void walk_chain(const ReadView &v, uint32_t a_end, OutOp *ops, uint32_t cap, ChainHdr &h) {
-    OpWriter w; w.init(ops, cap);
-    const uint32_t n = v.n;
-    uint32_t a = a_end;
-    uint32_t j = n, i = v.ent[a].m;
-    uint32_t xstart = 0, ystart = 0, yend = n, xend = v.ent[a].m;
-    const LastCell &endc = v.last[v.pidx(a, i)];
-    h.score = endc.S; h.length = endc.sl; h.end_contig_idx = v.ent[a].contig_idx; h.xlen = v.ent[a].m; h.ylen = n;
-    uint32_t cur_idx = v.ent[a].contig_idx;
-    uint32_t layer = v.s_tb(a, i, j);
+// Resumable walk (TB:219-373): runs until the chain is complete or the packed bytes of a
+// (contig, column block) that is not loaded are needed (WALK_NEED_UNIT: load the unit holding
+// column st.j of layout position st.a and call walk_run again).
+constexpr uint32_t WL_LOOKUP = 0xffu;   // "S move of the current cell", resolved lazily
+struct WalkState {
+    uint32_t a, i, j, layer, cur_idx;
+    uint32_t xstart, ystart, yend, xend;
+    OpWriter w;
+};
+enum : uint32_t { WALK_NEED_UNIT = 4 };
+
+SHD void walk_begin(const ReadView &v, uint32_t a_end, OutOp *ops, uint32_t cap, WalkState &st, ChainHdr &h) {
+    st.w.init(ops, cap);
+    st.a = a_end; st.j = v.n; st.i = v.ent[a_end].m;
+    st.xstart = 0; st.ystart = 0; st.yend = v.n; st.xend = v.ent[a_end].m;
+    const LastCell &endc = v.last[v.pidx(a_end, st.i)];
+    h.score = endc.S; h.length = endc.sl; h.end_contig_idx = v.ent[a_end].contig_idx; h.xlen = v.ent[a_end].m; h.ylen = v.n;
+    st.cur_idx = v.ent[a_end].contig_idx;
+    st.layer = WL_LOOKUP;
     h.status = WALK_OK;
+}
+
+SHD uint32_t walk_run(const ReadView &v, WalkState &st, ChainHdr &h) {
+    const uint32_t n = v.n;
+    OpWriter &w = st.w;
+    uint32_t a = st.a, i = st.i, j = st.j, layer = st.layer, cur_idx = st.cur_idx;
+    uint32_t status = WALK_OK;
     for (;;) {
-        if (w.overflow) { h.status = WALK_OVERFLOW; break; }
-        uint32_t next;
+        if (w.overflow) { status = WALK_OVERFLOW; break; }
+        if (v.interior(i, j) && !v.unit.has(a, j) &&
+            (layer == WL_LOOKUP || layer == TB_INS || layer == TB_DEL || layer == TB_MATCH || layer == TB_SUBST)) {
+            st.a = a; st.i = i; st.j = j; st.layer = layer; st.cur_idx = cur_idx;
+            return WALK_NEED_UNIT;
+        }
+        if (layer == WL_LOOKUP) { layer = v.s_tb(a, i, j); continue; }
         if (layer == TB_START) break;
         if (layer == TB_INS) {
             w.push(OP_INS, 0, 0);
-            next = v.i_tb(a, i, j);
-            if (i == 0) { h.status = WALK_PANIC; break; }
-            i -= 1;
+            uint32_t next;
+            if (i == 0) next = TB_START;
+            else if (j == 0) next = col0_at(v.sc, i, v.ent[a].m).i_tb;
+            else if (j == n) next = v.last[v.pidx(a, i)].i_tb;
+            else next = (v.unit.at(i, j) & TBB_IEXT) ? (uint32_t)TB_INS : WL_LOOKUP;
+            if (i == 0) { status = WALK_PANIC; break; }
+            i -= 1; layer = next;
         } else if (layer == TB_DEL) {
             w.push(OP_DEL, 0, 0);
-            next = v.d_tb(a, i, j);
-            if (j == 0) { h.status = WALK_PANIC; break; }
-            j -= 1;
+            uint32_t next;
+            if (i == 0) next = row0_at(v.sc, j, n).d_tb;
+            else if (j == 0) next = TB_START;
+            else if (j == n) next = (v.last[v.pidx(a, i)].flags & 2) ? (uint32_t)TB_DEL : WL_LOOKUP;
+            else next = (v.unit.at(i, j) & TBB_DEXT) ? (uint32_t)TB_DEL : WL_LOOKUP;
+            if (j == 0) { status = WALK_PANIC; break; }
+            j -= 1; layer = next;
         } else if (layer == TB_MATCH || layer == TB_SUBST) {
             w.push(layer == TB_MATCH ? OP_MATCH : OP_SUBST, 0, 0);
-            if (i == 0 || j == 0) { h.status = WALK_PANIC; break; }
+            if (i == 0 || j == 0) { status = WALK_PANIC; break; }
             uint32_t sidx, sfrom;
             v.s_ptr(a, i, j, sidx, sfrom);
             if (sidx != cur_idx || sfrom != i - 1) {
                 w.push(OP_XJUMP, cur_idx, i - 1);
                 cur_idx = sidx;
                 const int16_t na = sidx < MAX_STRANDS ? v.pos_of[sidx] : (int16_t)-1;
-                if (na < 0) { h.status = WALK_NONE; break; }
+                if (na < 0) { status = WALK_NONE; break; }
                 a = (uint32_t)na;
             }
             i = sfrom; j -= 1;
-            if (i > v.ent[a].m) { h.status = WALK_PANIC; break; }
-            next = v.s_tb(a, i, j);
+            if (i > v.ent[a].m) { status = WALK_PANIC; break; }
+            layer = WL_LOOKUP;
         } else if (layer == TB_XCLIP_PREFIX) {
-            next = v.s_tb(a, 0, j);
-            if (next == TB_START || next == TB_YCLIP_PREFIX) { w.push(OP_XCLIP, i, 0); xstart = i; }
-            i = 0;
+            const uint32_t next = v.s_tb(a, 0, j);
+            if (next == TB_START || next == TB_YCLIP_PREFIX) { w.push(OP_XCLIP, i, 0); st.xstart = i; }
+            i = 0; layer = next;
         } else if (layer == TB_XCLIP_SUFFIX) {
             const uint32_t l = v.lx(a, j);
-            if (w.n_pushed == 0 || w.first_kind == OP_YCLIP) { w.push(OP_XCLIP, l, 0); xend = i - l; }
-            if (l > i) { h.status = WALK_PANIC; break; }
-            i -= l;
-            next = v.s_tb(a, i, j);
+            if (w.n_pushed == 0 || w.first_kind == OP_YCLIP) { w.push(OP_XCLIP, l, 0); st.xend = i - l; }
+            if (l > i) { status = WALK_PANIC; break; }
+            if (l == 0) { status = WALK_PANIC; break; }   // the reference would spin forever on the same cell
+            i -= l; layer = WL_LOOKUP;
         } else if (layer == TB_YCLIP_PREFIX) {
             w.push(OP_YCLIP, j, 0);
-            ystart = j; j = 0;
-            next = v.s_tb(a, i, 0);
+            st.ystart = j; j = 0; layer = WL_LOOKUP;
         } else if (layer == TB_YCLIP_SUFFIX) {
             const uint32_t l = v.ly(a, i);
             w.push(OP_YCLIP, l, 0);
             const uint32_t sfrom = (i == 0) ? 0u : v.last[v.pidx(a, i)].from;   // only column n holds this move
-            if (l > j) { h.status = WALK_PANIC; break; }
+            if (l > j) { status = WALK_PANIC; break; }
             j -= l;
             if (sfrom != i) { w.push(OP_XJUMP, cur_idx, i); i = sfrom; }
-            yend = j;
-            next = v.s_tb(a, i, j);
+            st.yend = j; layer = WL_LOOKUP;
         } else if (layer == TB_XJUMP) {
             const LastCell &c = v.last[v.pidx(a, i)];                              // only (m, n) holds this move
             w.push(OP_XJUMP, cur_idx, i);
             cur_idx = c.idx;
             const int16_t na = c.idx < MAX_STRANDS ? v.pos_of[c.idx] : (int16_t)-1;
-            if (na < 0) { h.status = WALK_NONE; break; }
+            if (na < 0) { status = WALK_NONE; break; }
             a = (uint32_t)na;
             i = c.from;
-            if (i > v.ent[a].m) { h.status = WALK_PANIC; break; }
-            next = v.s_tb(a, i, j);
-        } else { h.status = WALK_PANIC; break; }
-        layer = next;
+            if (i > v.ent[a].m) { status = WALK_PANIC; break; }
+            layer = WL_LOOKUP;
+        } else { status = WALK_PANIC; break; }
     }
-    if (w.overflow && h.status == WALK_OK) h.status = WALK_OVERFLOW;
-    // reverse in place
+    if (w.overflow && status == WALK_OK) status = WALK_OVERFLOW;
     for (uint32_t l = 0; l < w.n / 2; ++l) {
-        OutOp t = ops[l]; ops[l] = ops[w.n - 1 - l]; ops[w.n - 1 - l] = t;
+        OutOp t = w.ops[l]; w.ops[l] = w.ops[w.n - 1 - l]; w.ops[w.n - 1 - l] = t;
     }
-    if (w.only_special) { xstart = 0; xend = 0; ystart = 0; yend = 0; }
-    h.xstart = xstart; h.xend = xend; h.ystart = ystart; h.yend = yend;
-    h.start_contig_idx = cur_idx; h.n_ops = w.n;
+    if (w.only_special) { st.xstart = 0; st.xend = 0; st.ystart = 0; st.yend = 0; }
+    h.xstart = st.xstart; h.xend = st.xend; h.ystart = st.ystart; h.yend = st.yend;
+    h.start_contig_idx = cur_idx; h.n_ops = w.n; h.status = status;
+    return status;
 }
 
 // End contig of the best chain (TB:129-150): max S[m_c], then longer length, else first.
