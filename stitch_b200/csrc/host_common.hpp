@@ -185,7 +185,7 @@ struct RawChain { ChainHdr h{}; std::vector<OutOp> ops; };
 struct JobResult { std::vector<RawChain> chains; };
 
 struct BackendStats {
-    uint64_t cells = 0, fills = 0, launches = 0, h2d = 0, d2h = 0, tb_bytes = 0;
+    uint64_t cells = 0, fills = 0, launches = 0, h2d = 0, d2h = 0, tb_bytes = 0, refills = 0;
     double fill_ms = 0, tb_ms = 0, total_ms = 0;
     void reset() { *this = BackendStats(); }
 };

@@ -20,7 +20,7 @@ def lib():
 
 def test_exports_every_declared_symbol(lib):
     header = open(os.path.join(ROOT, "include", "stitch_b200.h")).read()
-    declared = set(re.findall(r"\b(stitch_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(stitch_[a-z0-9_]+)\s*\(", header))
     from stitch_b200 import _lib
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:

@@ -14,10 +14,23 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def gpu_aligners(kw, named, max_inflight=0):
+# Small checkpoint spacing / tracking window so that tiny fuzz reads still span several checkpoint
+# blocks, re-filled units and window re-runs (the library reads these when a context is created).
+TUNING = {"STITCH_CK_EVERY": "7", "STITCH_TRACK_WINDOW": "6"}
+
+
+def gpu_aligners(kw, named, max_inflight=0, tuning=None):
     import stitch_b200
     targets = [stitch_b200.TargetSeq(n, s) for n, s in named]
-    al = stitch_b200.Builder(**kw).build_aligners(targets, device=0)
+    for k in TUNING:
+        os.environ.pop(k, None)
+    if tuning:
+        os.environ.update(tuning)
+    try:
+        al = stitch_b200.Builder(**kw).build_aligners(targets, device=0)
+    finally:
+        for k in TUNING:
+            os.environ.pop(k, None)
     if max_inflight:
         al.set_max_inflight(max_inflight)
     return al
@@ -31,10 +44,10 @@ def compare(got, exp, ctx):
             assert a.key() == b.key(), f"{ctx} read {r} chain {k}:\n  gpu    {a}\n  oracle {b}"
 
 
-def run_both(oracle, kw, contigs, reads, raw, subsets=None, max_inflight=0):
+def run_both(oracle, kw, contigs, reads, raw, subsets=None, max_inflight=0, tuning=None):
     named = [(f"c{k}", s) for k, s in enumerate(contigs)]
     exp, _ = oracle.OracleAligners(make_opts(**kw), named).batch(reads, subsets=subsets, raw=raw)
-    al = gpu_aligners(kw, named, max_inflight)
+    al = gpu_aligners(kw, named, max_inflight, tuning)
     got = al.custom_batch(reads, subsets) if raw else al.align_batch(reads, subsets)
     al.close()
     return got, exp
@@ -66,7 +79,7 @@ def test_fuzz_custom_small(oracle, block):
         alphabet = [b"ACGT", b"AC", b"A", b"ACGTN"][seed % 4]
         contigs, reads = gen.fuzz_case(seed, alphabet=alphabet)
         kw = gen.fuzz_opts(seed)
-        got, exp = run_both(oracle, kw, contigs, reads, raw=True)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=True, tuning=TUNING if seed % 2 else None)
         compare(got, exp, f"seed {seed} {kw}")
 
 
@@ -79,7 +92,7 @@ def test_fuzz_align_small(oracle, block):
         rng = random.Random(seed)
         kw["suboptimal"] = rng.random() < 0.5
         kw["suboptimal_pct"] = rng.choice([0.0, 20.0, 90.0])
-        got, exp = run_both(oracle, kw, contigs, reads, raw=False)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=False, tuning=TUNING if seed % 2 else None)
         compare(got, exp, f"seed {seed} {kw}")
 
 
@@ -93,7 +106,8 @@ def test_fuzz_subsets(oracle):
         for _ in reads:
             sub = [c for c in range(ns) if rng.random() < 0.6]
             subsets.append(sub or [rng.randrange(ns)])
-        got, exp = run_both(oracle, kw, contigs, reads, raw=rng.random() < 0.5, subsets=subsets)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=rng.random() < 0.5, subsets=subsets,
+                            tuning=TUNING if seed % 2 else None)
         compare(got, exp, f"seed {seed} {kw} {subsets}")
 
 
@@ -111,7 +125,8 @@ def test_multi_tile_contigs(oracle, seed):
     kw["double_strand"] = seed % 2 == 0
     if seed == 3:   # long insertions across tile boundaries: cheap gaps
         kw.update(gap_open=-1, gap_extend=0, mismatch_score=-6)
-    got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 2 == 1))
+    got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 2 == 1),
+                        tuning={"STITCH_CK_EVERY": "50", "STITCH_TRACK_WINDOW": "40"} if seed >= 3 else None)
     compare(got, exp, f"seed {seed} {kw}")
 
 
