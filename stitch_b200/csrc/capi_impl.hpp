@@ -91,6 +91,8 @@ int STITCH_API(get_stats)(const stitch_ctx *ctx, stitch_stats *out) {
     out->cells = s.cells; out->fills = s.fills; out->kernel_launches = s.launches;
     out->fill_ms = s.fill_ms; out->traceback_ms = s.tb_ms; out->total_ms = s.total_ms;
     out->h2d_bytes = s.h2d; out->d2h_bytes = s.d2h; out->traceback_bytes = s.tb_bytes;
+    out->packed_fill_ms = s.packed_ms; out->wide_fill_ms = s.wide_ms; out->redo_fill_ms = s.redo_ms;
+    out->packed_cells = s.packed_cells; out->redo_fills = s.refills;
     return STITCH_OK;
 }
 
@@ -106,6 +108,6 @@ const char *STITCH_API(last_error)(const stitch_ctx *ctx) {
     return ctx ? ctx->al.last_error.c_str() : g_create_error.c_str();
 }
 
-uint32_t STITCH_API(abi_version)(void) { return 1; }
+uint32_t STITCH_API(abi_version)(void) { return 2; }
 
 }  // extern "C"

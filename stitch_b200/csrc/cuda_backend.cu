@@ -19,6 +19,7 @@
 #define STITCH_API(name) stitch_##name
 #include "capi_impl.hpp"
 #include "kernels_wide.cuh"
+#include "kernels_packed.cuh"
 
 namespace stitch {
 namespace gpu {
@@ -34,6 +35,7 @@ using host::Error;
     } while (0)
 
 constexpr int FILL_WARPS = 8;
+constexpr int PACK_WARPS = 16;
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -77,7 +79,9 @@ struct CudaBackend : host::Backend {
     host::Aligner &al;
     int device;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[16] = {};
+    int marks[16] = {}; int n_marks = 0;
+    enum { T_H2D = 0, T_PACKED, T_WIDE, T_FIXUP, T_REDO, T_WALK, T_D2H, T_END };
     int num_sms = 0;
     uint32_t max_inflight = 0;
     size_t uploaded_layouts = 0;
@@ -93,7 +97,10 @@ struct CudaBackend : host::Backend {
     DevBuf<LayoutDesc> d_layouts;
     DevBuf<JobDesc> d_jobs;
     DevBuf<uint32_t> d_order;
-    DevBuf<CellState> d_state, d_ck;
+    DevBuf<CellState> d_state, d_ck, d_hand;
+    DevBuf<CkSum> d_handsum;
+    DevBuf<int32_t> d_pstate;
+    uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
     DevBuf<ColRec> d_colrec;
@@ -105,7 +112,8 @@ struct CudaBackend : host::Backend {
     DevBuf<uint32_t> d_counter;
     PinBuf<uint8_t> h_reads;
     PinBuf<JobDesc> h_jobs;
-    PinBuf<uint32_t> h_order;
+    PinBuf<uint32_t> h_order, h_redo;
+    DevBuf<uint32_t> d_redo;
     PinBuf<OutOp> h_ops;
     PinBuf<ChainHdr> h_chains;
     PinBuf<JobOut> h_jobout;
@@ -123,11 +131,12 @@ struct CudaBackend : host::Backend {
         num_sms = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
-        d_contigs.reserve(al.contigs.blob.size() + 64);
+        d_contigs.reserve(al.contigs.blob.size() + 1024);   // strips of the last tile over-read
         CUDA_CHECK(cudaMemcpy(d_contigs.p, al.contigs.blob.data(), al.contigs.blob.size(), cudaMemcpyHostToDevice));
         d_counter.reserve(4);
         K = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K));
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
+        use_packed = env_u32("STITCH_PACKED", 1);
     }
     ~CudaBackend() override {
         cudaSetDevice(device);
@@ -168,7 +177,7 @@ struct CudaBackend : host::Backend {
         const host::Layout &L = al.layouts.layouts[j.layout];
         const uint64_t C = L.ent.size(), PM = L.PM(), nb = blocks_of(j.n);
         return (nb - 1) * (PM * sizeof(CellState) + C * sizeof(CkSum)) + (uint64_t)(j.n + 1) * (C * sizeof(ColRec) + 4) +
-               PM * (sizeof(LastCell) + sizeof(SnRec)) + (uint64_t)(2 * j.n + 4 * C + 64) * sizeof(OutOp) + 4096;
+               PM * (sizeof(LastCell) + sizeof(SnRec) + sizeof(CellState)) + (uint64_t)(2 * j.n + 4 * C + 64) * sizeof(OutOp) + 4096;
     }
 
     void run(const std::vector<host::Job> &jobs, std::vector<host::JobResult> &out) override {
@@ -205,10 +214,11 @@ struct CudaBackend : host::Backend {
     void run_chunk(const std::vector<host::Job> &jobs, size_t begin, size_t end, std::vector<host::JobResult> &out) {
         const uint32_t nj = (uint32_t)(end - begin);
         const auto &Ls = al.layouts.layouts;
-        h_jobs.reserve(nj); h_order.reserve(2 * (size_t)nj);
+        h_jobs.reserve(nj); h_order.reserve(3 * (size_t)nj);
         const bool tracked = al.opts.sc.ys != MIN_SCORE;
         uint64_t reads_b = 0, colrec_n = 0, cell_n = 0, ck_n = 0, cksum_n = 0, gcol_n = 0, ops_n = 0, chains_n = 0, pm_max = 0,
-                 unit_max = 0, cells = 0;
+                 unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0;
+        uint32_t n_packed = 0, ntmax = 1;
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
             const host::Layout &L = Ls[j.layout];
@@ -223,6 +233,15 @@ struct CudaBackend : host::Backend {
             d.ops_cap = per_chain * (j.walk == host::WALK_ALL ? std::min<uint32_t>(C, 8) : 1) * ops_scale;
             d.chain_first = (uint32_t)chains_n;
             d.track_from = tracked ? (j.n > WINDOW ? j.n - WINDOW + 1 : 1) : j.n + 1;
+            d.hand_off = cell_n; d.handsum_off = handsum_n;
+            {
+                uint32_t m_max = 0;
+                for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
+                d.LB = use_packed ? pk_plan(al.opts.sc, j.n, m_max) : 0;
+                d.j0 = (d.LB && j.n > WINDOW + 1 && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) <= 200 * 1024) ? j.n - WINDOW : 0;
+                if (d.j0) { stats.packed_cells += L.cells_per_col * d.j0; ++n_packed; ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM()); }
+            }
+            handsum_n += C;
             h_jobs.p[k] = d;
             reads_b += round_up(j.n, 16);
             colrec_n += (uint64_t)(j.n + 1) * C; cell_n += L.PM(); ck_n += (nb - 1) * L.PM(); cksum_n += (nb - 1) * C;
@@ -240,15 +259,19 @@ struct CudaBackend : host::Backend {
         });
         const int ctas_per_sm = 2;
         const uint32_t grid = std::min<uint32_t>(nj, (uint32_t)(num_sms * ctas_per_sm));
-        d_jobs.reserve(nj); d_order.reserve(2 * (size_t)nj); d_colrec.reserve(colrec_n); d_last.reserve(cell_n);
+        d_jobs.reserve(nj); d_order.reserve(3 * (size_t)nj); d_colrec.reserve(colrec_n); d_last.reserve(cell_n);
         d_sn.reserve(cell_n); d_ck.reserve(ck_n); d_cksum.reserve(cksum_n); d_gcol.reserve(gcol_n);
         d_ops.reserve(ops_n); d_chains.reserve(chains_n); d_jobout.reserve(nj);
         d_state.reserve((uint64_t)grid * 2 * pm_max);
+        d_hand.reserve(cell_n); d_handsum.reserve(handsum_n);
+        const uint32_t pgrid = std::min<uint32_t>(n_packed, (uint32_t)num_sms);
+        d_pstate.reserve((uint64_t)pgrid * 2 * ppm_max + 64);
         d_unit.reserve((uint64_t)grid * round_up(unit_max, 256));
         if (!device_reads) { d_reads.reserve(reads_b); h_reads.reserve(reads_b); }
         h_ops.reserve(ops_n); h_chains.reserve(chains_n); h_jobout.reserve(nj);
 
-        CUDA_CHECK(cudaEventRecord(ev[0], stream));
+        n_marks = 0;
+        mark(T_H2D);
         if (!device_reads) {
             for (uint32_t k = 0; k < nj; ++k)
                 std::memcpy(h_reads.p + h_jobs.p[k].read_off, jobs[begin + k].read, jobs[begin + k].n);
@@ -269,41 +292,60 @@ struct CudaBackend : host::Backend {
         P.colrec = d_colrec.p; P.last = d_last.p; P.sn = d_sn.p; P.ck_state = d_ck.p; P.ck_sum = d_cksum.p; P.gcol = d_gcol.p;
         P.ops = d_ops.p; P.chains = d_chains.p; P.job_out = d_jobout.p; P.counter = d_counter.p;
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
+        P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
+        P.ntmax = ntmax;
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
         set_smem(fill_wide_kernel<FILL_WARPS>, smem);
-        CUDA_CHECK(cudaEventRecord(ev[1], stream));
+        mark(T_PACKED);
+        if (n_packed) {
+            // the order list of the packed kernel: jobs with j0 > 0, largest first
+            uint32_t *po = h_order.p + 2 * (size_t)nj;
+            uint32_t c = 0;
+            for (uint32_t k = 0; k < nj; ++k) if (h_jobs.p[h_order.p[k]].j0) po[c++] = h_order.p[k];
+            CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj, po, c * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            Params Q = P; Q.order = d_order.p + 2 * (size_t)nj; Q.n_jobs = c; Q.counter = d_counter.p + 3;
+            const size_t psmem = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
+            set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
+            fill_packed_kernel<PACK_WARPS><<<pgrid, PACK_WARPS * 32, psmem, stream>>>(Q);
+            CUDA_CHECK(cudaGetLastError());
+            stats.launches += 1;
+        }
+        mark(T_WIDE);
         fill_wide_kernel<FILL_WARPS><<<grid, FILL_WARPS * 32, smem, stream>>>(P);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaEventRecord(ev[2], stream));
+        mark(T_FIXUP);
         fixup_kernel<<<nj, 64, 0, stream>>>(P);
         CUDA_CHECK(cudaGetLastError());
         stats.launches += 2; stats.fills += nj; stats.cells += cells;
-        float ms_fill = 0, ms_tb = 0, ms_total = 0, ms = 0;
         if (tracked) {
             // reads whose tracking window was too narrow are filled again with full tracking
             CUDA_CHECK(cudaMemcpyAsync(h_jobout.p, d_jobout.p, nj * sizeof(JobOut), cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaEventRecord(ev[3], stream));
+            mark(T_END);
             sync("fill");
-            cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_fill += ms;
-            cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_tb += ms;
+            collect_marks();
             uint32_t n_redo = 0;
+            h_redo.reserve(nj); d_redo.reserve(nj);
             for (uint32_t k = 0; k < nj; ++k) if (h_jobout.p[k].status == JOB_NEED_FULL_TRACK) {
                 h_order.p[nj + n_redo++] = k;
-                stats.cells += Ls[jobs[begin + k].layout].cells_per_col * jobs[begin + k].n;
+                const uint32_t first = h_jobout.p[k].n_chains;   // first column that may hold a final y-suffix tracker
+                h_redo.p[k] = first > 0 ? ((first - 1) / K) * K : 0;
+                stats.cells += Ls[jobs[begin + k].layout].cells_per_col * (jobs[begin + k].n - h_redo.p[k]);
             }
-            CUDA_CHECK(cudaEventRecord(ev[1], stream));
+            mark(T_REDO);
             if (n_redo) {
                 CUDA_CHECK(cudaMemcpyAsync(d_order.p + nj, h_order.p + nj, n_redo * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                CUDA_CHECK(cudaMemcpyAsync(d_redo.p, h_redo.p, nj * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
                 Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_redo; Q.force_full = 1; Q.counter = d_counter.p + 1;
+                Q.redo_j0 = d_redo.p;
                 fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_redo, grid), FILL_WARPS * 32, smem, stream>>>(Q);
                 CUDA_CHECK(cudaGetLastError());
                 fixup_kernel<<<n_redo, 64, 0, stream>>>(Q);
                 CUDA_CHECK(cudaGetLastError());
                 stats.launches += 2; stats.fills += n_redo; stats.refills += n_redo;
             }
-            CUDA_CHECK(cudaEventRecord(ev[2], stream));
         }
+        mark(T_WALK);
         {
             Params Wp = P; Wp.counter = d_counter.p + 2;
             const size_t wsmem = WideSmem<FILL_WARPS>::bytes(1);
@@ -311,16 +353,13 @@ struct CudaBackend : host::Backend {
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
-        CUDA_CHECK(cudaEventRecord(ev[3], stream));
+        mark(T_D2H);
         CUDA_CHECK(cudaMemcpyAsync(h_jobout.p, d_jobout.p, nj * sizeof(JobOut), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaMemcpyAsync(h_chains.p, d_chains.p, chains_n * sizeof(ChainHdr), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaMemcpyAsync(h_ops.p, d_ops.p, ops_n * sizeof(OutOp), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaEventRecord(ev[4], stream));
+        mark(T_END);
         sync("walk");
-        cudaEventElapsedTime(&ms, ev[1], ev[2]); ms_fill += ms;
-        cudaEventElapsedTime(&ms, ev[2], ev[3]); ms_tb += ms;
-        cudaEventElapsedTime(&ms_total, ev[0], ev[4]);
-        stats.fill_ms += ms_fill; stats.tb_ms += ms_tb; stats.total_ms += ms_total;
+        collect_marks();
         stats.tb_bytes += ck_n * sizeof(CellState) + colrec_n * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);
 
@@ -349,6 +388,27 @@ struct CudaBackend : host::Backend {
                 out[begin + k].chains.push_back(std::move(rc));
             }
         }
+    }
+    void mark(int tag) {
+        if (n_marks >= 16) return;
+        CUDA_CHECK(cudaEventRecord(ev[n_marks], stream));
+        marks[n_marks++] = tag;
+    }
+    // durations between consecutive marks, credited to the earlier mark's phase (call after a stream sync)
+    void collect_marks() {
+        for (int k = 0; k + 1 < n_marks; ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+            switch (marks[k]) {
+            case T_PACKED: stats.packed_ms += ms; stats.fill_ms += ms; break;
+            case T_WIDE: stats.wide_ms += ms; stats.fill_ms += ms; break;
+            case T_REDO: stats.redo_ms += ms; stats.fill_ms += ms; break;
+            case T_FIXUP: case T_WALK: stats.tb_ms += ms; break;
+            default: break;
+            }
+            stats.total_ms += ms;
+        }
+        n_marks = 0;
     }
     void sync(const char *what) {
         cudaError_t se = cudaStreamSynchronize(stream);

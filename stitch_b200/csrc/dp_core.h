@@ -648,6 +648,7 @@ enum : uint32_t { WALK_OK = 0, WALK_NONE = 1, WALK_OVERFLOW = 2, WALK_PANIC = 3 
 // a column-state checkpoint when the walk needs them (checkpoint-and-recompute).
 struct TbUnit {
     const uint8_t *bytes;   // column j (jb < j <= je), row i (1..m): bytes[(j - jb - 1) * pm + i - 1]
+    const ColRec *cr;       // per column of the unit: cr[j - jb - 1].lx = Lx[j] of this contig (SCA:407-429)
     uint32_t a;             // layout position; 0xffffffff = nothing loaded
     uint32_t jb, je, pm;
     SHD bool has(uint32_t a_, uint32_t j) const { return a == a_ && j > jb && j <= je; }
@@ -657,7 +658,7 @@ struct TbUnit {
 struct ReadView {
     Scoring sc;
     const ContigEntry *ent; uint32_t C; uint32_t n;
-    const ColRec *colrec;       // [(j)*C + a], j = 0..n
+    const ColRec *colrec;       // [(j)*C + a], j = 0..n: jump sources; lx only for j = n
     const LastCell *last;       // column n, tile-transposed order
     const SnRec *sn;            // tile-transposed order
     const uint8_t *contig_bases;
@@ -687,7 +688,8 @@ struct ReadView {
     }
     SHD uint32_t lx(uint32_t a, uint32_t j) const {
         if (j == 0) { int32_t t; uint32_t l; col0_tracker(sc, ent[a].m, t, l); return l; }
-        return colrec[(uint64_t)j * C + a].lx;
+        if (j == n) return colrec[(uint64_t)j * C + a].lx;
+        return unit.cr[j - unit.jb - 1].lx;   // interior columns: from the re-filled unit
     }
     SHD uint32_t ly(uint32_t a, uint32_t i) const { return i == 0 ? n : sn[pidx(a, i)].ly; }
 };
@@ -741,7 +743,8 @@ SHD uint32_t walk_run(const ReadView &v, WalkState &st, ChainHdr &h) {
     for (;;) {
         if (w.overflow) { status = WALK_OVERFLOW; break; }
         if (v.interior(i, j) && !v.unit.has(a, j) &&
-            (layer == WL_LOOKUP || layer == TB_INS || layer == TB_DEL || layer == TB_MATCH || layer == TB_SUBST)) {
+            (layer == WL_LOOKUP || layer == TB_INS || layer == TB_DEL || layer == TB_MATCH || layer == TB_SUBST ||
+             layer == TB_XCLIP_SUFFIX)) {
             st.a = a; st.i = i; st.j = j; st.layer = layer; st.cur_idx = cur_idx;
             return WALK_NEED_UNIT;
         }

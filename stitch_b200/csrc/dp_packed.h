@@ -1,0 +1,269 @@
+// dp_packed.h — the fast arithmetic of the fill: one 32-bit key per DP value.
+//
+//   key = [ relative score | 4-bit priority | alignment length ]      (signed 32-bit compare)
+//           32-SH bits        bits LB..LB+3    LB bits        SH = LB + 4
+//
+// The reference (SCA = single_contig_aligner.rs, MCA = multi_contig_aligner.rs) keeps every DP
+// value as an i32 score plus a 27-bit alignment length and decides every cell by a fixed sequence
+// of "replace if strictly greater" comparisons (SCA:350-399) with two length tie-breaks
+// (SCA:373-377 jump vs diagonal, SCA:272-281 circular wrap vs jump).  Packing (score, priority,
+// length) into one integer turns that sequence into plain integer max operations:
+//   * a candidate that must WIN score ties gets the higher priority, so max() reproduces the
+//     "strictly greater" order diag > D > I > jump > x-clip > y-clip;
+//   * the jump candidate inherits the diagonal's priority when (and only when) the running best is
+//     the diagonal, so that exactly then the longer alignment wins an equal score (SCA:373-377);
+//   * lengths ride along in the low bits: one integer add updates score and length together.
+// Scores are stored relative to the best cell of the previous column (B_j = G(j-1), MCA:279-331
+// makes a jump from that cell available to every cell, so every live value lies in a band of
+// width max(match,mismatch,0) - min(match,mismatch) - min(jump scores) below B_j + max(...)); the
+// change of base is folded into the per-column add constants.  Values below the band (they exist
+// only in column 0 and in D of column 1) are clamped to NEG; a clamped value can never win or tie
+// against the jump candidate, so its exact value never matters.
+//
+// The in-column insertion chain I(i) = max_{k<i} H'(k) + o + e(i-k) (SCA:317-326) has a bounded
+// reach R = floor(band/|e|) + 1 rows: a source further back is strictly worse than opening from
+// row i-1.  When R <= STRIP a lane's chain needs nothing beyond the previous lane's strip, so the
+// cross-lane dependency is ONE warp shuffle (no scan); the host only selects this path for such
+// scorings (pk_plan) and everything else runs on the exact wide kernels.
+//
+// Everything here is __host__ __device__: the CUDA kernels (kernels_packed.cuh) and the CPU
+// emulator the tests fuzz against the oracle run the same code.
+#pragma once
+#include "dp_core.h"
+
+namespace stitch {
+
+enum : int32_t { PP_YC = 1, PP_XC = 2, PP_JMP = 3, PP_INC = 4, PP_ICARRY = 5, PP_D = 6, PP_DIAG = 11, PP_DIAGBIT = 8 };
+
+struct PK {                 // per job
+    int32_t LB, SH;
+    int32_t NEG;            // lowest relative score kept exactly
+    int32_t NEGKEY;         // NEG << SH
+    int32_t LMASK, NPM;     // (1 << LB) - 1,  ~(15 << LB)
+    int32_t PD6, PI4, PI5, PB8, P1;
+};
+
+SHD int32_t pk_band(const Scoring &sc) {
+    int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
+    if (submax < 0) submax = 0;
+    const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+    int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+    gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+    return submax - submin - gmin;
+}
+SHD int32_t pk_submax0(const Scoring &sc) {
+    int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
+    return submax < 0 ? 0 : submax;
+}
+SHD int32_t pk_neg(const Scoring &sc) {
+    // every live D is >= (gmin + submin) + o + e - submax0 relative to its column base
+    return -(pk_band(sc) - sc.o - sc.e + 2 * pk_submax0(sc) + 2);
+}
+
+// Can the packed path run this (scoring, read length, longest contig)?  Returns LB or 0.
+SHD uint32_t pk_plan(const Scoring &sc, uint32_t n, uint32_t m_max) {
+    if (sc.e >= 0) return 0;
+    const int32_t band = pk_band(sc), ae = -sc.e;
+    if (band / ae + 1 > STRIP) return 0;                       // insertion-chain reach
+    const int64_t submax0 = pk_submax0(sc);
+    int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+    if (submin > 0) submin = 0;
+    int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+    gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+    // y-prefix clip (SCA:391-399) can only win in the first warp tile of a contig
+    if (sc.yp != MIN_SCORE && sc.xp == MIN_SCORE && sc.o + sc.e * (int64_t)(TILE + 1) > (int64_t)gmin + submin) return 0;
+    // length field: any cell's alignment length is at most j + #insertions, and a path that stays
+    // inside the band cannot afford more than j*submax0/|e| + const insertions
+    const int64_t len_bound = (int64_t)n * (2 + (submax0 + ae - 1) / ae) + (int64_t)(-gmin) - sc.o - submin + 64;
+    int64_t need = len_bound > (int64_t)m_max + 2 ? len_bound : (int64_t)m_max + 2;
+    uint32_t LB = 4;
+    while (((int64_t)1 << LB) <= need) ++LB;
+    if (LB > 24) return 0;
+    const uint32_t SB = 32 - 4 - LB;                           // score bits
+    const int64_t lim = 2 * ((int64_t)-pk_neg(sc) + band + submax0 - submin - sc.o + (int64_t)(STRIP + 1) * ae) + 16;
+    if (SB < 4 || lim >= ((int64_t)1 << (SB - 1))) return 0;
+    return LB;
+}
+
+SHD PK pk_make(const Scoring &sc, uint32_t LB) {
+    PK p;
+    p.LB = (int32_t)LB; p.SH = (int32_t)LB + 4;
+    p.NEG = pk_neg(sc);
+    p.NEGKEY = (int32_t)((uint32_t)p.NEG << p.SH);
+    p.LMASK = (int32_t)((1u << LB) - 1u);
+    p.NPM = (int32_t)~(15u << LB);
+    p.PD6 = PP_D << LB; p.PI4 = PP_INC << LB; p.PI5 = PP_ICARRY << LB; p.PB8 = PP_DIAGBIT << LB; p.P1 = 1 << LB;
+    return p;
+}
+SHD int32_t pk_shl(const PK &p, int32_t v) { return (int32_t)((uint32_t)v << p.SH); }   // v * 2^SH, wrap-around
+SHD int32_t pk_key(const PK &p, int64_t rel, int32_t prio, uint32_t len) {
+    if (rel < p.NEG) rel = p.NEG;
+    return pk_shl(p, (int32_t)rel) + (prio << p.LB) + (int32_t)(len & (uint32_t)p.LMASK);
+}
+SHD int32_t pk_rel(const PK &p, int32_t key) { return key >> p.SH; }
+SHD uint32_t pk_len(const PK &p, int32_t key) { return (uint32_t)(key & p.LMASK); }
+SHD uint32_t pk_prio(const PK &p, int32_t key) { return (uint32_t)(key >> p.LB) & 15u; }
+SHD int32_t pk_max(int32_t a, int32_t b) { return a > b ? a : b; }
+#if defined(__CUDA_ARCH__)
+// DPX instructions of sm_90+/sm_100: VIMNMX3 and VIADDMNMX (one issue slot each)
+SHD int32_t pk_max3(int32_t a, int32_t b, int32_t c) { return __vimax3_s32(a, b, c); }
+SHD int32_t pk_addmax(int32_t a, int32_t b, int32_t c) { return __viaddmax_s32(a, b, c); }   // max(a + b, c)
+#else
+SHD int32_t pk_max3(int32_t a, int32_t b, int32_t c) { return pk_max(pk_max(a, b), c); }
+SHD int32_t pk_addmax(int32_t a, int32_t b, int32_t c) { return pk_max((int32_t)((uint32_t)a + (uint32_t)b), c); }
+#endif
+
+struct PCol {               // per column of a read (uniform over the CTA)
+    int32_t cM, cX;         // diagonal add (match / mismatch), includes the change of base, PP_DIAG and len+1
+    int32_t cE, cOE;        // D layer: extension of a stored D (PP_D -> 1) / open from a stored S (-> 0)
+    int32_t cEi, cOEi;      // in-column chain: extension (keeps PP_INC) / open from a clean H (-> PP_JMP)
+    int32_t XC;             // x-prefix clip candidate (PP_XC) or NEGKEY
+    int32_t B, delta;       // base of this column, B_j - B_{j-1}
+    uint8_t q;              // read base y[j-1]
+};
+
+SHD PCol pk_col(const PK &p, const Scoring &sc, int32_t B, int32_t Bprev, uint32_t j, uint32_t n, uint8_t q) {
+    PCol c;
+    c.B = B; c.delta = B - Bprev; c.q = q;
+    c.cM = pk_shl(p, sc.match - c.delta) + (PP_DIAG << p.LB) + 1;
+    c.cX = pk_shl(p, sc.mismatch - c.delta) + (PP_DIAG << p.LB) + 1;
+    c.cE = pk_shl(p, sc.e - c.delta) + (1 - PP_D) * (1 << p.LB) + 1;
+    c.cOE = pk_shl(p, sc.o + sc.e - c.delta) + 1;
+    c.cEi = pk_shl(p, sc.e) + 1;
+    c.cOEi = pk_shl(p, sc.o + sc.e) + (PP_JMP << p.LB) + 1;
+    if (sc.xp != MIN_SCORE) {   // SCA:304-308: xp + max(yp, o + e*j), length = s_len(0, j)
+        const int64_t dj = (int64_t)sc.o + (int64_t)sc.e * j;
+        const int64_t xs = (int64_t)sc.xp + ((int64_t)sc.yp > dj ? (int64_t)sc.yp : dj);
+        c.XC = pk_key(p, xs - B, PP_XC, row0_at(sc, j, n).sl);
+    } else c.XC = p.NEGKEY;
+    return c;
+}
+
+// Jump candidate of a contig for this column, pre-adjusted so that jp = Jc + (cM | cX).
+SHD int32_t pk_jc(const PK &p, const PCol &c, int32_t jscore_abs, uint32_t jlen) {
+    return pk_key(p, (int64_t)jscore_abs - c.B, PP_JMP, jlen) + pk_shl(p, c.delta) - (PP_DIAG << p.LB) - 1;
+}
+// Circular wrap source (SCA:263-281): S(m, j-1) as stored (relative to B_{j-1}, priority 0).
+SHD int32_t pk_wbase(const PK &p, int32_t sm_prev_key) { return sm_prev_key - p.PB8; }
+
+struct PStrip {             // a lane's working set between pass 1 and pass 2
+    int32_t A[STRIP];       // best of {diag, D}             (row m: the diagonal candidate alone)
+    int32_t jp[STRIP];      // jump candidate, PP_JMP
+    int32_t D6[STRIP];      // D of the cell, PP_D (what is stored)
+    int32_t Inc[STRIP];     // chain value arriving at row k from the strip's own rows (no carry-in), PP_INC
+    int32_t YC[STRIP];      // y-prefix clip candidates (special tiles only)
+    int32_t exit;           // chain value leaving the strip, PP_INC
+    uint32_t fl[STRIP];     // traceback variant: bit0 D is an extension, bit1 Inc[k] is an extension, bit2 wrap won
+    uint32_t exit_open;     // traceback variant: exit opens from the strip's last row
+};
+
+// Pass 1 of one lane: everything that does not depend on the insertion chain of earlier lanes.
+//   Sup/Dup[k] : stored S / D keys of row (row0+k) at column j-1;  Sdg0 : S key of row (row0-1) at j-1
+//   SPECIAL    : first or last tile of a contig (rows >= nv are not ordinary cells; row m at index nv
+//                when has_m; wrap / y-clip candidates are live)
+template <bool SPECIAL, bool TB>
+SHD void pk_pass1(const PK &p, const PCol &c, const int32_t *Sup, const int32_t *Dup, int32_t Sdg0, const uint8_t *x,
+                  int32_t Jc, bool wrap0, int32_t wbase, int nv, bool has_m, PStrip &o) {
+    int32_t Iacc = p.NEGKEY + p.PI4;
+    uint32_t iacc_ext = 0;
+    int32_t Sdg = Sdg0;
+    STITCH_UNROLL
+    for (int k = 0; k < STRIP; ++k) {
+        const bool ordinary = !SPECIAL || k < nv;
+        const bool rowm = SPECIAL && has_m && k == nv;
+        if (ordinary || rowm) {
+            const int32_t cc = (x[k] == c.q) ? c.cM : c.cX;
+            const int32_t ext = pk_addmax(Dup[k], c.cE, p.NEGKEY);
+            const int32_t Dp = pk_addmax(Sup[k], c.cOE, ext);
+            const int32_t D6 = (Dp & p.NPM) | p.PD6;
+            int32_t jp = Jc + cc;
+            uint32_t fl = 0;
+            if (TB) fl = (Dp & p.P1) ? 1u : 0u;
+            if (SPECIAL && k == 0 && wrap0) {
+                const int32_t w = wbase + cc;
+                if (w > jp) { jp = w; if (TB) fl |= 4u; }
+            }
+            o.D6[k] = D6; o.jp[k] = jp;
+            o.Inc[k] = Iacc;
+            if (TB) { fl |= iacc_ext ? 2u : 0u; o.fl[k] = fl; }
+            if (ordinary) {
+                const int32_t A = pk_addmax(Sdg, cc, D6);
+                o.A[k] = A;
+                int32_t H = pk_max3(A, jp | (A & p.PB8), c.XC);
+                if (SPECIAL) H = pk_max(H, o.YC[k]);
+                const int32_t Hc = H & p.NPM;
+                const int32_t exti = pk_addmax(Iacc, c.cEi, p.NEGKEY + p.PI4);
+                const int32_t Ip = pk_addmax(Hc, c.cOEi, exti);
+                if (TB) iacc_ext = ((Ip >> p.LB) & 15) == PP_INC ? 1u : 0u;
+                Iacc = (Ip & p.NPM) | p.PI4;
+            } else {
+                o.A[k] = Sdg + cc;   // row m: the diagonal candidate; finished per contig
+            }
+        }
+        Sdg = Sup[k];
+    }
+    o.exit = Iacc;
+    if (TB) o.exit_open = iacc_ext ? 0u : 1u;
+}
+
+// Pass 2 of one lane.  `cin` = chain value arriving at the strip's first row from earlier rows
+// (PP_ICARRY), `cin_open` = it opens from the row just before (traceback variant).
+// Outputs: S[k] clean keys of the ordinary rows, their running max in `colmax`, packed traceback
+// bytes (TB), and for row m the insertion candidate arriving at it.
+template <bool SPECIAL, bool TB>
+SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint32_t cin_open, int nv, bool has_m,
+                  int32_t *S, int32_t &colmax, uint8_t *tb, int32_t &I_m, uint32_t &iext_m) {
+    int32_t cx = cin;
+    STITCH_UNROLL
+    for (int k = 0; k < STRIP; ++k) {
+        const bool ordinary = !SPECIAL || k < nv;
+        const bool rowm = SPECIAL && has_m && k == nv;
+        if (ordinary) {
+            const int32_t T1 = pk_max3(s.A[k], s.Inc[k], cx);
+            const int32_t jT = s.jp[k] | (T1 & p.PB8);
+            int32_t Sp = pk_max3(T1, jT, c.XC);
+            if (SPECIAL) Sp = pk_max(Sp, s.YC[k]);
+            const int32_t Sc = Sp & p.NPM;
+            S[k] = Sc;
+            colmax = pk_max(colmax, Sc);
+            if (TB) {
+                const uint32_t pr = (uint32_t)(Sp >> p.LB) & 15u;
+                uint32_t mv;
+                if (pr == PP_DIAG) mv = (Sp == jT && jT != T1) ? ((s.fl[k] & 4u) ? MV_WRAP : MV_JUMP) : MV_DIAG;
+                else if (pr == PP_D) mv = MV_DEL;
+                else if (pr == PP_INC || pr == PP_ICARRY) mv = MV_INS;
+                else if (pr == PP_JMP) mv = (s.fl[k] & 4u) ? MV_WRAP : MV_JUMP;
+                else if (pr == PP_XC) mv = MV_XCLIP_PREFIX;
+                else mv = MV_YCLIP_PREFIX;
+                // the I pointer of this cell: the carried value wins ties against the strip's own chain
+                const bool from_carry = (cx >> p.SH) >= (s.Inc[k] >> p.SH);
+                const uint32_t iext = from_carry ? ((k == 0) ? (cin_open ? 0u : 1u) : 1u) : ((s.fl[k] & 2u) ? 1u : 0u);
+                tb[k] = (uint8_t)(mv | ((s.fl[k] & 1u) ? TBB_DEXT : 0u) | (iext ? TBB_IEXT : 0u));
+            }
+        } else if (rowm) {
+            const bool from_carry = (cx >> p.SH) >= (s.Inc[k] >> p.SH);
+            I_m = from_carry ? cx : s.Inc[k];
+            iext_m = from_carry ? ((k == 0) ? (cin_open ? 0u : 1u) : 1u) : ((s.fl[k] & 2u) ? 1u : 0u);
+        }
+        cx = pk_addmax(cx, c.cEi, p.NEGKEY + p.PI5);
+    }
+}
+
+// Carry into a lane from the previous lane's exit (PP_INC -> PP_ICARRY).
+SHD int32_t pk_carry_from_exit(const PK &p, int32_t exit_key) { return exit_key + p.P1; }
+
+// Carry arriving at row 1 of a contig from row 0 (SCA:317-326 with i = 1): always the open from S(0, j).
+SHD int32_t pk_carry_row1(const PK &p, const PCol &c, const Scoring &sc, const Row0 &r0) {
+    return pk_key(p, (int64_t)r0.S - c.B + sc.o + sc.e, PP_ICARRY, r0.sl + 1);
+}
+
+// Wide <-> packed state conversion (checkpoints, hand-over to the wide tail, row m).
+SHD int32_t pk_from_wide(const PK &p, int32_t B, int32_t score_abs, uint32_t len, int32_t prio) {
+    return pk_key(p, (int64_t)score_abs - B, prio, len);
+}
+SHD int32_t pk_abs(const PK &p, int32_t B, int32_t key) {
+    const int32_t r = pk_rel(p, key);
+    return r <= p.NEG ? MIN_SCORE : B + r;   // a clamped value stands for "far below everything live"
+}
+
+}  // namespace stitch

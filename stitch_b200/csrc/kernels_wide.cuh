@@ -31,6 +31,9 @@ struct JobDesc {
     uint64_t cksum_off;    // CkSum records [(nb-1) * C]
     uint64_t gcol_off;     // int32 [n+1]
     uint64_t ops_off;      // OutOp records
+    uint64_t hand_off;     // CellState records [PM]: wide state at column j0 (packed -> wide hand-over)
+    uint64_t handsum_off;  // CkSum records [C]
+    uint32_t j0, LB;       // columns [1, j0] run on the packed kernel (0: none); LB = length bits of its keys
     uint32_t n, layout;
     uint32_t walk, from_contig;
     uint32_t ops_cap, chain_first, max_chains, track_from;
@@ -62,6 +65,11 @@ struct Params {
     SnRec *sn;
     CellState *ck_state;
     CkSum *ck_sum;
+    CellState *hand_state;
+    CkSum *hand_sum;
+    int32_t *pstate;         // packed kernel, per CTA: S keys then D keys
+    uint64_t pstate_stride, pstate_half;
+    uint32_t ntmax;          // largest tile count among the packed jobs
     int32_t *gcol;
     OutOp *ops;
     ChainHdr *chains;
@@ -69,7 +77,8 @@ struct Params {
     uint32_t *counter;
     uint32_t K;              // checkpoint spacing (columns)
     int tracked_mode;        // ys != MIN_SCORE
-    int force_full;          // re-run: track from column 1
+    int force_full;          // re-run of reads whose tracking window was too narrow
+    const uint32_t *redo_j0; // force_full: per job, the checkpointed column the re-run starts from (multiple of K, 0 = column 0)
 };
 
 __device__ __forceinline__ ICarry shfl_up_ic(ICarry c, int d) {
@@ -248,7 +257,7 @@ __device__ void column_wide(const Scoring &sc, const ColWide &A, WideSmem<W> &S)
 // Column 0 of every contig of the layout into `st` (SCA:97-186), row-m summaries and column best.
 template <int W>
 __device__ void column0_wide(const Scoring &sc, const ContigEntry *ent, const uint16_t *owner, uint32_t C, uint32_t NT,
-                             CellState *st, WideSmem<W> &S, bool init_sn, SnRec *sn, uint32_t n) {
+                             CellState *st, WideSmem<W> &S, bool init_sn, SnRec *sn, uint32_t n, bool write_state = true) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr uint32_t T = W * 32;
     for (uint32_t tile = warp; tile < NT; tile += W) {
@@ -262,7 +271,7 @@ __device__ void column0_wide(const Scoring &sc, const ContigEntry *ent, const ui
                 const Col0 c0 = col0_at(sc, i, en.m);
                 CellState s; s.S = c0.S; s.D = MIN_SCORE; s.sl = c0.sl; s.dl = 0;
                 const uint32_t si = state_index(tile, lane, (uint32_t)k);
-                st[si] = s;
+                if (write_state) st[si] = s;
                 if (init_sn) sn[si] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n);
             }
         }
@@ -304,22 +313,43 @@ __global__ void __launch_bounds__(W * 32) fill_wide_kernel(const Params P) {
         SnRec *sn = P.sn + jd.cell_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;
-        const uint32_t track_from = P.tracked_mode ? (P.force_full ? 1u : jd.track_from) : n + 1;
+        // columns [1, j0] are already filled: by the packed kernel (hand-over state) or, in a re-run, up to a checkpoint
+        const uint32_t j0 = P.force_full ? P.redo_j0[P.order[sJob]] : jd.j0;
+        const uint32_t track_from = P.tracked_mode ? (P.force_full ? 1u : (jd.track_from > j0 ? jd.track_from : j0 + 1)) : n + 1;
 
-        column0_wide<W>(sc, ent, owner, C, NT, st0, S, track_from <= n, sn, n);
+        column0_wide<W>(sc, ent, owner, C, NT, st0, S, track_from <= n, sn, n, j0 == 0);
         for (uint32_t a = tid; a < C; a += T) {
             int32_t t; uint32_t lx; col0_tracker(sc, ent[a].m, t, lx);
             ColRec cr; cr.jscore = 0; cr.jlen = 0; cr.jidx = 0; cr.jfrom = 0; cr.lx = lx; cr.pad0 = cr.pad1 = cr.pad2 = 0;
             colrec[a] = cr;
         }
+        if (j0 > 0) {   // hand-over: wide state and row-m summaries of column j0
+            __syncthreads();
+            const CellState *hs = P.force_full ? P.ck_state + jd.ck_off + (uint64_t)(j0 / K - 1) * PM : P.hand_state + jd.hand_off;
+            const CkSum *hsum = P.force_full ? P.ck_sum + jd.cksum_off + (uint64_t)(j0 / K - 1) * C : P.hand_sum + jd.handsum_off;
+            CellState *dst = (j0 & 1u) ? st1 : st0;
+            for (uint32_t p = tid; p < PM; p += T) dst[p] = hs[p];
+            for (uint32_t a = tid; a < C; a += T) {
+                const CkSum cs = hsum[a];
+                S.Sm[a] = cs.Sm; S.slm[a] = cs.slm; S.tbm[a] = cs.tbm;
+            }
+        }
         __syncthreads();
 
-        for (uint32_t j = 1; j <= n; ++j) {
-            for (uint32_t a = tid; a < C; a += T) S.J[a] = select_jump(sc, ent, C, a, S.cm, S.cml, S.cmk);
-            if (tid == 0) {
-                int32_t g = S.cm[0];
-                for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-                gcol[j - 1] = g;
+        for (uint32_t j = j0 + 1; j <= n; ++j) {
+            if (j == j0 + 1 && j0 > 0) {   // the jump of the first wide column was selected by the packed kernel
+                for (uint32_t a = tid; a < C; a += T) {
+                    const ColRec cr = colrec[(uint64_t)j * C + a];
+                    JumpInfo J; J.score = cr.jscore; J.len = cr.jlen; J.idx = cr.jidx; J.from = cr.jfrom;
+                    S.J[a] = J;
+                }
+            } else {
+                for (uint32_t a = tid; a < C; a += T) S.J[a] = select_jump(sc, ent, C, a, S.cm, S.cml, S.cmk);
+                if (tid == 0) {
+                    int32_t g = S.cm[0];
+                    for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
+                    gcol[j - 1] = g;
+                }
             }
             const bool ck = (j % K == 0) && j < n;
             ColWide A;
@@ -355,7 +385,8 @@ __global__ void fixup_kernel(const Params P) {
     __shared__ int32_t s_gmax;
     __shared__ uint32_t s_first;
     // Was the y-suffix tracking window wide enough?  (dp_core.h: first_candidate_column)
-    const bool windowed = P.tracked_mode && !P.force_full && jd.track_from > 1;
+    const uint32_t eff_track_from = jd.track_from > jd.j0 ? jd.track_from : jd.j0 + 1;
+    const bool windowed = P.tracked_mode && !P.force_full && eff_track_from > 1;
     if (windowed) {
         const int32_t *gcol = P.gcol + jd.gcol_off;
         if (threadIdx.x == 0) { s_gmax = gcol[0]; s_first = n + 1; }
@@ -375,8 +406,8 @@ __global__ void fixup_kernel(const Params P) {
         for (uint32_t j = 1 + threadIdx.x; j <= n; j += blockDim.x) if (gcol[j] >= thr) { first = j; break; }
         atomicMin(&s_first, first);
         __syncthreads();
-        if (s_first < jd.track_from) {
-            if (threadIdx.x == 0) { JobOut o; o.n_chains = 0; o.status = JOB_NEED_FULL_TRACK; P.job_out[job] = o; }
+        if (s_first < eff_track_from) {
+            if (threadIdx.x == 0) { JobOut o; o.n_chains = s_first; o.status = JOB_NEED_FULL_TRACK; P.job_out[job] = o; }
             return;
         }
     }

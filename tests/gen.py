@@ -83,3 +83,23 @@ def fuzz_opts(seed):
                   jump_score_inter_contig=-rng.randint(0, 3))
     kw["circular_slop"] = rng.choice([0, 2, 5, 20])
     return kw
+
+
+def fuzz_opts_packed(seed, strip=8):
+    """Scorings inside the packed kernel's regime (stitch_b200/csrc/dp_packed.h: insertion-chain reach
+    <= strip rows, e < 0), all modes / strands / circular, with score ties made likely."""
+    rng = random.Random(seed * 104729 + 7)
+    kw = dict(mode=rng.randint(0, 3), double_strand=rng.random() < 0.5, circular=rng.random() < 0.5)
+    if rng.random() < 0.3 and strip >= 8:
+        pass   # reference CLI defaults
+    else:
+        match = rng.randint(0, 2)
+        mismatch = -rng.randint(0, 4) if rng.random() < 0.9 else rng.randint(0, 1)
+        jumps = [-rng.randint(0, 8) for _ in range(3)]
+        band = max(match, mismatch, 0) - min(match, mismatch) - min(jumps)
+        ext = band // strip + 1 + (rng.randint(0, 2) if rng.random() < 0.5 else 0)
+        kw.update(match_score=match, mismatch_score=mismatch, gap_open=-rng.randint(0, 6), gap_extend=-ext,
+                  jump_score_same_contig_and_strand=jumps[0], jump_score_same_contig_opposite_strand=jumps[1],
+                  jump_score_inter_contig=jumps[2])
+    kw["circular_slop"] = rng.choice([0, 2, 5, 20])
+    return kw

@@ -172,3 +172,35 @@ def test_full_size_properties():
     assert sum(1 for k, _, _ in fwd.ops if k == 6) == 3
     st = al.stats()
     assert st.cells == 2 * 10000 * 2 * sum(len(c) for c in contigs)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_packed_small(oracle, block):
+    """Scorings inside the packed kernel's regime (dp_packed.h), tiny checkpoint spacing / wide tail so that
+    small reads run through packed columns, the hand-over, wide re-filled units and the walk."""
+    for seed in range(block * 50, block * 50 + 50):
+        alphabet = [b"ACGT", b"AC", b"A", b"ACGTN"][seed % 4]
+        contigs, reads = gen.fuzz_case(seed + 7000, max_contigs=5, max_len=90, max_read=70, alphabet=alphabet)
+        kw = gen.fuzz_opts_packed(seed, 8)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 3 != 0), tuning=TUNING)
+        compare(got, exp, f"seed {seed} {kw}")
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_packed_multi_tile(oracle, block):
+    """Contigs spanning several 256-row tiles and all 16 warp chunks of the packed kernel (halo strips),
+    reads long enough for several checkpoint blocks and for the column base to drift."""
+    for seed in range(block * 6, block * 6 + 6):
+        rng = random.Random(9000 + seed * 31)
+        alphabet = [b"ACGT", b"AC", b"ACG"][seed % 3]
+        lens = [rng.randint(1, 2600) for _ in range(rng.randint(1, 6))] + [257, 256, 255][: seed % 4]
+        if seed % 5 == 0:
+            lens.append(9000)          # 36 tiles: every warp chunk of the CTA starts inside this contig
+        contigs = [gen.rand_seq(rng, l, alphabet) for l in lens]
+        reads = [gen.chimeric_read(rng, contigs, rng.randint(20, 300), rng.randint(1, 4), strands=True,
+                                   wrap=rng.random() < 0.5, noise=rng.random() < 0.8, alphabet=alphabet) for _ in range(4)]
+        reads = [r if r else b"A" for r in reads]
+        kw = gen.fuzz_opts_packed(seed + 100 * block, 8)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 2 == 0),
+                            tuning={"STITCH_CK_EVERY": "50", "STITCH_TRACK_WINDOW": "8"})
+        compare(got, exp, f"seed {seed} {kw}")
