@@ -109,6 +109,7 @@ typedef struct stitch_stats {
     double redo_fill_ms;          /* of fill_ms: re-runs of reads whose tracking window was too narrow */
     uint64_t packed_cells;        /* cell updates done by the packed-key kernel                */
     uint64_t redo_fills;          /* number of such re-runs                                    */
+    double tail_fill_ms;          /* of fill_ms: the packed tail (last columns again, with trackers)  */
 } stitch_stats;
 
 typedef struct stitch_ctx stitch_ctx;

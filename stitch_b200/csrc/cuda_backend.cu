@@ -20,6 +20,7 @@
 #include "capi_impl.hpp"
 #include "kernels_wide.cuh"
 #include "kernels_packed.cuh"
+#include "kernels_walk.cuh"
 
 namespace stitch {
 namespace gpu {
@@ -81,7 +82,7 @@ struct CudaBackend : host::Backend {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[16] = {};
     int marks[16] = {}; int n_marks = 0;
-    enum { T_H2D = 0, T_PACKED, T_WIDE, T_FIXUP, T_REDO, T_WALK, T_D2H, T_END };
+    enum { T_H2D = 0, T_PACKED, T_TAIL, T_WIDE, T_FIXUP, T_REDO, T_WALK, T_D2H, T_END };
     int num_sms = 0;
     uint32_t max_inflight = 0;
     size_t uploaded_layouts = 0;
@@ -99,7 +100,9 @@ struct CudaBackend : host::Backend {
     DevBuf<uint32_t> d_order;
     DevBuf<CellState> d_state, d_ck, d_hand;
     DevBuf<CkSum> d_handsum;
-    DevBuf<int32_t> d_pstate;
+    DevBuf<int32_t> d_pstate, d_wpstate;
+    DevBuf<uint32_t> d_tailj0;
+    DevBuf<ColRec> d_ucr;
     uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
@@ -133,7 +136,7 @@ struct CudaBackend : host::Backend {
         for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
         d_contigs.reserve(al.contigs.blob.size() + 1024);   // strips of the last tile over-read
         CUDA_CHECK(cudaMemcpy(d_contigs.p, al.contigs.blob.data(), al.contigs.blob.size(), cudaMemcpyHostToDevice));
-        d_counter.reserve(4);
+        d_counter.reserve(8);
         K = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K));
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
         use_packed = env_u32("STITCH_PACKED", 1);
@@ -218,7 +221,7 @@ struct CudaBackend : host::Backend {
         const bool tracked = al.opts.sc.ys != MIN_SCORE;
         uint64_t reads_b = 0, colrec_n = 0, cell_n = 0, ck_n = 0, cksum_n = 0, gcol_n = 0, ops_n = 0, chains_n = 0, pm_max = 0,
                  unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0;
-        uint32_t n_packed = 0, ntmax = 1;
+        uint32_t n_packed = 0, ntmax = 1, max_ctiles = 1;
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
             const host::Layout &L = Ls[j.layout];
@@ -238,8 +241,10 @@ struct CudaBackend : host::Backend {
                 uint32_t m_max = 0;
                 for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
                 d.LB = use_packed ? pk_plan(al.opts.sc, j.n, m_max) : 0;
-                d.j0 = (d.LB && j.n > WINDOW + 1 && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) <= 200 * 1024) ? j.n - WINDOW : 0;
-                if (d.j0) { stats.packed_cells += L.cells_per_col * d.j0; ++n_packed; ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM()); }
+                if (d.LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) > 200 * 1024) d.LB = 0;   // tile table must fit shared memory
+                d.j0 = 0;
+                if (d.LB) { stats.packed_cells += L.cells_per_col * j.n; ++n_packed; ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM()); }
+                max_ctiles = std::max(max_ctiles, m_max / (uint32_t)TILE + 1);
             }
             handsum_n += C;
             h_jobs.p[k] = d;
@@ -266,6 +271,10 @@ struct CudaBackend : host::Backend {
         d_hand.reserve(cell_n); d_handsum.reserve(handsum_n);
         const uint32_t pgrid = std::min<uint32_t>(n_packed, (uint32_t)num_sms);
         d_pstate.reserve((uint64_t)pgrid * 2 * ppm_max + 64);
+        d_tailj0.reserve(nj);
+        const uint64_t wps_half = (uint64_t)max_ctiles * TILE;
+        d_wpstate.reserve((uint64_t)grid * 2 * wps_half + 64);
+        d_ucr.reserve((uint64_t)grid * K + 64);
         d_unit.reserve((uint64_t)grid * round_up(unit_max, 256));
         if (!device_reads) { d_reads.reserve(reads_b); h_reads.reserve(reads_b); }
         h_ops.reserve(ops_n); h_chains.reserve(chains_n); h_jobout.reserve(nj);
@@ -281,7 +290,7 @@ struct CudaBackend : host::Backend {
         CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, h_jobs.p, nj * sizeof(JobDesc), cudaMemcpyHostToDevice, stream));
         CUDA_CHECK(cudaMemcpyAsync(d_order.p, h_order.p, nj * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         stats.h2d += nj * (sizeof(JobDesc) + sizeof(uint32_t));
-        CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 4 * sizeof(uint32_t), stream));
+        CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 8 * sizeof(uint32_t), stream));
 
         Params P{};
         P.sc = al.opts.sc; P.jobs = d_jobs.p; P.order = d_order.p; P.n_jobs = nj; P.cmax = cmax;
@@ -293,33 +302,49 @@ struct CudaBackend : host::Backend {
         P.ops = d_ops.p; P.chains = d_chains.p; P.job_out = d_jobout.p; P.counter = d_counter.p;
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
-        P.ntmax = ntmax;
+        P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
+        P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles;
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
         set_smem(fill_wide_kernel<FILL_WARPS>, smem);
         mark(T_PACKED);
+        const uint32_t n_wide = nj - n_packed;
         if (n_packed) {
-            // the order list of the packed kernel: jobs with j0 > 0, largest first
+            // the order list of the packed kernels: jobs on the packed path, largest first
             uint32_t *po = h_order.p + 2 * (size_t)nj;
             uint32_t c = 0;
-            for (uint32_t k = 0; k < nj; ++k) if (h_jobs.p[h_order.p[k]].j0) po[c++] = h_order.p[k];
+            for (uint32_t k = 0; k < nj; ++k) if (h_jobs.p[h_order.p[k]].LB) po[c++] = h_order.p[k];
             CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj, po, c * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
             Params Q = P; Q.order = d_order.p + 2 * (size_t)nj; Q.n_jobs = c; Q.counter = d_counter.p + 3;
             const size_t psmem = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
             set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
+            set_smem(tail_packed_kernel<PACK_WARPS>, psmem);
             fill_packed_kernel<PACK_WARPS><<<pgrid, PACK_WARPS * 32, psmem, stream>>>(Q);
+            CUDA_CHECK(cudaGetLastError());
+            mark(T_TAIL);
+            Q.counter = d_counter.p + 4;
+            tail_packed_kernel<PACK_WARPS><<<pgrid, PACK_WARPS * 32, psmem, stream>>>(Q);
+            CUDA_CHECK(cudaGetLastError());
+            stats.launches += 2;
+        }
+        mark(T_WIDE);
+        if (n_wide) {
+            // jobs outside the packed regime run on the wide kernel (order list: the rest, largest first)
+            uint32_t *wo = h_order.p + 2 * (size_t)nj + n_packed;
+            uint32_t c = 0;
+            for (uint32_t k = 0; k < nj; ++k) if (!h_jobs.p[h_order.p[k]].LB) wo[c++] = h_order.p[k];
+            CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj + n_packed, wo, c * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            Params Q = P; Q.order = d_order.p + 2 * (size_t)nj + n_packed; Q.n_jobs = c;
+            fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(c, grid), FILL_WARPS * 32, smem, stream>>>(Q);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
-        mark(T_WIDE);
-        fill_wide_kernel<FILL_WARPS><<<grid, FILL_WARPS * 32, smem, stream>>>(P);
-        CUDA_CHECK(cudaGetLastError());
         mark(T_FIXUP);
         fixup_kernel<<<nj, 64, 0, stream>>>(P);
         CUDA_CHECK(cudaGetLastError());
-        stats.launches += 2; stats.fills += nj; stats.cells += cells;
-        if (tracked) {
-            // reads whose tracking window was too narrow are filled again with full tracking
+        stats.launches += 1; stats.fills += nj; stats.cells += cells;
+        if (tracked && n_wide) {
+            // wide-path reads whose tracking window was too narrow are filled again from an earlier checkpoint
             CUDA_CHECK(cudaMemcpyAsync(h_jobout.p, d_jobout.p, nj * sizeof(JobOut), cudaMemcpyDeviceToHost, stream));
             mark(T_END);
             sync("fill");
@@ -348,7 +373,8 @@ struct CudaBackend : host::Backend {
         mark(T_WALK);
         {
             Params Wp = P; Wp.counter = d_counter.p + 2;
-            const size_t wsmem = WideSmem<FILL_WARPS>::bytes(1);
+            const size_t wsmem = std::max(WideSmem<FILL_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, FILL_WARPS));
+            set_smem(walk_kernel<FILL_WARPS>, wsmem);
             walk_kernel<FILL_WARPS><<<grid, FILL_WARPS * 32, wsmem, stream>>>(Wp);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
@@ -401,6 +427,7 @@ struct CudaBackend : host::Backend {
             cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
             switch (marks[k]) {
             case T_PACKED: stats.packed_ms += ms; stats.fill_ms += ms; break;
+            case T_TAIL: stats.tail_ms += ms; stats.fill_ms += ms; break;
             case T_WIDE: stats.wide_ms += ms; stats.fill_ms += ms; break;
             case T_REDO: stats.redo_ms += ms; stats.fill_ms += ms; break;
             case T_FIXUP: case T_WALK: stats.tb_ms += ms; break;

@@ -113,6 +113,15 @@ SHD int32_t pk_max3(int32_t a, int32_t b, int32_t c) { return pk_max(pk_max(a, b
 SHD int32_t pk_addmax(int32_t a, int32_t b, int32_t c) { return pk_max((int32_t)((uint32_t)a + (uint32_t)b), c); }
 #endif
 
+// Wide <-> packed state conversion (checkpoints, hand-over to the wide tail, row m).
+SHD int32_t pk_from_wide(const PK &p, int32_t B, int32_t score_abs, uint32_t len, int32_t prio) {
+    return pk_key(p, (int64_t)score_abs - B, prio, len);
+}
+SHD int32_t pk_abs(const PK &p, int32_t B, int32_t key) {
+    const int32_t r = pk_rel(p, key);
+    return r <= p.NEG ? MIN_SCORE : B + r;   // a clamped value stands for "far below everything live"
+}
+
 struct PCol {               // per column of a read (uniform over the CTA)
     int32_t cM, cX;         // diagonal add (match / mismatch), includes the change of base, PP_DIAG and len+1
     int32_t cE, cOE;        // D layer: extension of a stored D (PP_D -> 1) / open from a stored S (-> 0)
@@ -212,7 +221,7 @@ SHD void pk_pass1(const PK &p, const PCol &c, const int32_t *Sup, const int32_t 
 // bytes (TB), and for row m the insertion candidate arriving at it.
 template <bool SPECIAL, bool TB>
 SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint32_t cin_open, int nv, bool has_m,
-                  int32_t *S, int32_t &colmax, uint8_t *tb, int32_t &I_m, uint32_t &iext_m) {
+                  int32_t *S, int32_t &colmax, uint8_t *tb, int32_t *Iarr, int32_t &I_m, uint32_t &iext_m) {
     int32_t cx = cin;
     STITCH_UNROLL
     for (int k = 0; k < STRIP; ++k) {
@@ -239,6 +248,7 @@ SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint
                 const bool from_carry = (cx >> p.SH) >= (s.Inc[k] >> p.SH);
                 const uint32_t iext = from_carry ? ((k == 0) ? (cin_open ? 0u : 1u) : 1u) : ((s.fl[k] & 2u) ? 1u : 0u);
                 tb[k] = (uint8_t)(mv | ((s.fl[k] & 1u) ? TBB_DEXT : 0u) | (iext ? TBB_IEXT : 0u));
+                Iarr[k] = from_carry ? cx : s.Inc[k];
             }
         } else if (rowm) {
             const bool from_carry = (cx >> p.SH) >= (s.Inc[k] >> p.SH);
@@ -249,21 +259,55 @@ SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint
     }
 }
 
+// The wide records (dp_core.h) of one ordinary cell of the traceback variant: y-suffix tracker update
+// (SCA:432-447) and the column-n record the end-of-read fix-up edits (SCA:453-555).
+SHD void pk_cell_records(const PK &p, const PCol &c, const Scoring &sc, int32_t Skey, int32_t Ikey, uint32_t tbbyte, bool is_match,
+                         uint32_t self_idx, uint32_t i, uint32_t m, const JumpInfo &J, uint32_t j, uint32_t n,
+                         SnRec *sn_rec, LastCell *last_rec) {
+    const uint32_t mv = tbbyte & 15u;
+    const int32_t S = pk_abs(p, c.B, Skey);
+    const uint32_t sl = pk_len(p, Skey);
+    uint32_t idx, from;
+    ptr_of_move(mv, self_idx, i, m, J, idx, from);
+    if (sn_rec) sn_update(sc, *sn_rec, S, sl, idx, j, n);
+    if (last_rec) {
+        LastCell lc; lc.S = S; lc.I = pk_abs(p, c.B, Ikey); lc.sl = sl; lc.il = pk_len(p, Ikey); lc.idx = idx; lc.from = from;
+        lc.s_tb = (uint8_t)tb_of_move(mv, is_match); lc.i_tb = 0;
+        lc.flags = (uint8_t)(((tbbyte & TBB_IEXT) ? 1 : 0) | ((tbbyte & TBB_DEXT) ? 2 : 0)); lc.pad = 0; lc.pad2 = 0;
+        *last_rec = lc;
+    }
+}
+
+// Row m of a contig, finished from the packed candidates once the tracker over rows < m is known
+// (the same finish_rowm as the wide path).  stash = {diagonal, D6, jump, I arriving} keys.
+struct PkRowM { int32_t diag, D6, jp, I; uint32_t fl, iext; };   // fl: bit0 dext, bit2 wrap won
+struct PkRowMOut { RowMOut ro; int32_t skey; uint32_t tbbyte; };
+SHD PkRowMOut pk_finish_rowm(const PK &p, const PCol &c, const Scoring &sc, const PkRowM &st, const XsPart &tr, const Row0 &r0,
+                             const JumpInfo &J, bool is_match, uint32_t self_idx, uint32_t m, uint32_t j) {
+    RowM rm;
+    rm.diag = pk_abs(p, c.B, st.diag); rm.dgl = pk_len(p, st.diag);
+    rm.D = pk_abs(p, c.B, st.D6); rm.dl = pk_len(p, st.D6); rm.dext = st.fl & 1u;
+    rm.I = pk_abs(p, c.B, st.I); rm.il = pk_len(p, st.I); rm.iext = st.iext;
+    rm.jp.score = pk_abs(p, c.B, st.jp); rm.jp.len = pk_len(p, st.jp);
+    if (st.fl & 4u) { rm.jp.idx = self_idx | 0x80000000u; rm.jp.from = m; }
+    else { rm.jp.idx = J.idx; rm.jp.from = J.from; }
+    { const int32_t dj = sc.o + sc.e * (int32_t)j; rm.xclip = sc.xp + (sc.yp > dj ? sc.yp : dj); }
+    rm.xclip_len = r0.sl;
+    rm.yclip = sc.yp + sc.o + sc.e * (int32_t)m; rm.yclip_len = 0;
+    rm.is_match = is_match ? 1u : 0u;
+    PkRowMOut o;
+    o.ro = finish_rowm(sc, rm, tr, self_idx, m);
+    o.skey = pk_from_wide(p, c.B, o.ro.c.S, o.ro.c.sl, 0);
+    o.tbbyte = o.ro.c.mv | (rm.dext ? TBB_DEXT : 0u) | (rm.iext ? TBB_IEXT : 0u);
+    return o;
+}
+
 // Carry into a lane from the previous lane's exit (PP_INC -> PP_ICARRY).
 SHD int32_t pk_carry_from_exit(const PK &p, int32_t exit_key) { return exit_key + p.P1; }
 
 // Carry arriving at row 1 of a contig from row 0 (SCA:317-326 with i = 1): always the open from S(0, j).
 SHD int32_t pk_carry_row1(const PK &p, const PCol &c, const Scoring &sc, const Row0 &r0) {
     return pk_key(p, (int64_t)r0.S - c.B + sc.o + sc.e, PP_ICARRY, r0.sl + 1);
-}
-
-// Wide <-> packed state conversion (checkpoints, hand-over to the wide tail, row m).
-SHD int32_t pk_from_wide(const PK &p, int32_t B, int32_t score_abs, uint32_t len, int32_t prio) {
-    return pk_key(p, (int64_t)score_abs - B, prio, len);
-}
-SHD int32_t pk_abs(const PK &p, int32_t B, int32_t key) {
-    const int32_t r = pk_rel(p, key);
-    return r <= p.NEG ? MIN_SCORE : B + r;   // a clamped value stands for "far below everything live"
 }
 
 }  // namespace stitch

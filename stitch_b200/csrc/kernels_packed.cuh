@@ -1,10 +1,19 @@
-// kernels_packed.cuh — the fast fill: columns [1, j1] of a read over all its contig-strands in the
-// packed-key arithmetic of dp_packed.h.  Replaces the body of MCA::custom's column loop
-// (multi_contig_aligner.rs:270-347 = SCA:188-239 + 292-451 + 677-697 of the reference) for the
-// scorings pk_plan accepts; leaves wide checkpoints, the per-column jump records and the wide
-// hand-over state from which fill_wide_kernel finishes the last columns.
+// kernels_packed.cuh — the fast path: the DP columns of a read in the packed-key arithmetic of
+// dp_packed.h.  Replaces the body of MCA::custom's column loop (multi_contig_aligner.rs:270-347 =
+// SCA:188-239 + 292-451 + 677-697 of the reference) for the scorings pk_plan accepts.
 //
-// Structure (one CTA per read, persistent, W warps):
+//   fill_packed_kernel   bulk: all n columns over all contig-strands, no traceback output; leaves
+//                        column-state checkpoints every K columns, the jump record of every
+//                        (contig, column), the best score of every column, and the column the tail
+//                        must restart from.
+//   tail_packed_kernel   the last columns again, from a checkpoint, in the traceback variant: keeps
+//                        the y-suffix trackers of every row (SCA:432-447) for every column that can
+//                        still hold a final tracker value, and the column-n records the end-of-read
+//                        fix-up edits (SCA:453-555).
+//   pk_refill_unit       (walk kernel) packed traceback bytes of one contig over one block of
+//                        columns, re-filled from a checkpoint (checkpoint-and-recompute).
+//
+// Structure of a column (one CTA per read, W warps):
 //   * every warp owns a contiguous chunk of 256-row tiles and walks it tile by tile; a lane owns 8
 //     consecutive rows (a strip).  The rolling column state (one S key + one D key per cell) lives
 //     in global memory / L2 and is updated IN PLACE: a tile is read (column j-1) and written
@@ -24,19 +33,22 @@ namespace gpu {
 
 struct PackSmem {
     int32_t *Jc, *cm, *Sm, *SmKey, *tilemax, *haloS, *haloD;
-    uint32_t *cml, *cmk, *slm, *tbm;
-    int4 *stash;
+    uint32_t *cml, *cmk, *slm, *tbm, *haloF;
+    PkRowM *stash;
+    JumpInfo *Jw;
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W) {
-        return sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 17) + sizeof(int4) * cmax + 64;
+        return sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) + (sizeof(PkRowM) + sizeof(JumpInfo)) * cmax + 64;
     }
     __device__ void carve(unsigned char *raw, uint32_t cmax, uint32_t ntmax, int W) {
-        stash = reinterpret_cast<int4 *>(raw);
+        Jw = reinterpret_cast<JumpInfo *>(raw);
+        stash = reinterpret_cast<PkRowM *>(Jw + cmax);
         Jc = reinterpret_cast<int32_t *>(stash + cmax);
         cm = Jc + cmax; Sm = cm + cmax; SmKey = Sm + cmax;
         cml = reinterpret_cast<uint32_t *>(SmKey + cmax); cmk = cml + cmax; slm = cmk + cmax; tbm = slm + cmax;
         tilemax = reinterpret_cast<int32_t *>(tbm + cmax);
-        haloS = tilemax + ntmax;            // [2][W][9]
-        haloD = haloS + 2 * W * 9;          // [2][W][8]
+        haloS = tilemax + ntmax;                             // [2][W][9]
+        haloD = haloS + 2 * W * 9;                           // [2][W][8]
+        haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W] (unused)
     }
 };
 
@@ -44,22 +56,36 @@ __device__ __forceinline__ uint32_t pk_sidx(uint32_t tile, uint32_t lane, uint32
     return tile * TILE + (k >> 2) * 128u + lane * 4u + (k & 3u);
 }
 
-struct PackCtx {            // uniform per job
+struct PackCtx {            // uniform per (job, set of contigs)
     PK pk; Scoring sc;
-    const ContigEntry *ent; const uint16_t *owner;
+    const ContigEntry *ent; const uint16_t *owner;   // owner == nullptr: a single contig (position 0)
+    uint32_t C, NT;
     const uint8_t *bases;
     int32_t *Sst, *Dst;
     uint32_t n;
     bool yclip_mode;
 };
 
-// One tile of one column.  Returns through `prev_exit` / `prev_s7` what the next tile of the chunk needs.
-template <bool SPECIAL>
-__device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, uint32_t tile, uint32_t lane,
-                                        int32_t r0pkey, int32_t cr1key, bool chunk_start, const int32_t *hS, const int32_t *hD,
-                                        int32_t &prev_exit, int32_t &prev_s7, int32_t *outS, int32_t *outD) {
+struct PkColOut {           // traceback-variant outputs of a column (all optional)
+    uint8_t *tb_col;        // packed traceback bytes, linear rows
+    ColRec *colrec_col;     // per contig: Lx[j] (+ the jump record)
+    SnRec *sn; LastCell *last;
+    bool track, lastcol;
+};
+
+__device__ __forceinline__ void unpack8(const uint2 xb, uint8_t *x) {
+    x[0] = (uint8_t)xb.x; x[1] = (uint8_t)(xb.x >> 8); x[2] = (uint8_t)(xb.x >> 16); x[3] = (uint8_t)(xb.x >> 24);
+    x[4] = (uint8_t)xb.y; x[5] = (uint8_t)(xb.y >> 8); x[6] = (uint8_t)(xb.y >> 16); x[7] = (uint8_t)(xb.y >> 24);
+}
+
+// One tile of one column.  `prev_*` carry what the next tile of the same chunk needs.
+template <bool SPECIAL, bool TB>
+__device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, const PkColOut &O, uint32_t j, uint32_t tile,
+                                        uint32_t lane, int32_t r0pkey, int32_t cr1key, bool chunk_start, const int32_t *hS,
+                                        const int32_t *hD, int32_t &prev_exit, uint32_t &prev_exit_open, int32_t &prev_s7,
+                                        int32_t *outS, int32_t *outD) {
     const PK &pk = X.pk;
-    const uint32_t a = X.owner[tile];
+    const uint32_t a = X.owner ? X.owner[tile] : 0u;
     const ContigEntry en = X.ent[a];
     const uint32_t tic = tile - en.tile_start;
     const bool first = tic == 0;
@@ -74,12 +100,8 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
         Dup[0] = d0.x; Dup[1] = d0.y; Dup[2] = d0.z; Dup[3] = d0.w; Dup[4] = d1.x; Dup[5] = d1.y; Dup[6] = d1.z; Dup[7] = d1.w;
     }
     uint8_t x[STRIP];
-    {
-        // contig bases are 16-byte aligned per contig and a strip starts at a multiple of 8 (over-reads stay inside the blob's padding)
-        const uint2 xb = *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
-        x[0] = (uint8_t)xb.x; x[1] = (uint8_t)(xb.x >> 8); x[2] = (uint8_t)(xb.x >> 16); x[3] = (uint8_t)(xb.x >> 24);
-        x[4] = (uint8_t)xb.y; x[5] = (uint8_t)(xb.y >> 8); x[6] = (uint8_t)(xb.y >> 16); x[7] = (uint8_t)(xb.y >> 24);
-    }
+    // contig bases are 16-byte aligned per contig and a strip starts at a multiple of 8 (over-reads stay inside the blob's padding)
+    unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1)), x);
     int32_t Sdg0 = __shfl_up_sync(FULL, Sup[STRIP - 1], 1);
     if (lane == 0) Sdg0 = first ? r0pkey : (chunk_start ? hS[8] : prev_s7);
     const int32_t Jc = S.Jc[a];
@@ -97,21 +119,21 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
                 st.YC[k] = pk_key(pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e * i - pc.B, PP_YC, col0_slen(X.sc, i, en.m));
         }
         const bool wrap0 = first && lane == 0 && en.circular && S.tbm[a] != TB_XCLIP_SUFFIX;
-        pk_pass1<true, false>(pk, pc, Sup, Dup, Sdg0, x, Jc, wrap0, pk_wbase(pk, S.SmKey[a]), nv, has_m, st);
+        pk_pass1<true, TB>(pk, pc, Sup, Dup, Sdg0, x, Jc, wrap0, pk_wbase(pk, S.SmKey[a]), nv, has_m, st);
     } else {
-        pk_pass1<false, false>(pk, pc, Sup, Dup, Sdg0, x, Jc, false, 0, STRIP, false, st);
+        pk_pass1<false, TB>(pk, pc, Sup, Dup, Sdg0, x, Jc, false, 0, STRIP, false, st);
     }
     int32_t cin = pk_carry_from_exit(pk, __shfl_up_sync(FULL, st.exit, 1));
-    if (first) { if (lane == 0) cin = cr1key; }
+    uint32_t cin_open = 0;
+    if (TB) cin_open = __shfl_up_sync(FULL, st.exit_open, 1);
+    if (first) { if (lane == 0) { cin = cr1key; cin_open = 1; } }
     else if (chunk_start) {
         // halo strip: rows row0-8 .. row0-1 of the same contig, from the state the previous chunk's owner published
+        // (hS[0] = S of the row before the 8 halo rows, hS[1..8] = S of the halo rows, hD[0..7] = their D)
         PStrip h;
         uint8_t hx[STRIP];
         const uint32_t hrow0 = tic * TILE - STRIP + 1;
-        const uint2 xb = *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (hrow0 - 1));
-        hx[0] = (uint8_t)xb.x; hx[1] = (uint8_t)(xb.x >> 8); hx[2] = (uint8_t)(xb.x >> 16); hx[3] = (uint8_t)(xb.x >> 24);
-        hx[4] = (uint8_t)xb.y; hx[5] = (uint8_t)(xb.y >> 8); hx[6] = (uint8_t)(xb.y >> 16); hx[7] = (uint8_t)(xb.y >> 24);
-        // halo layout: hS[0] = S of the row before the 8 halo rows, hS[1..8] = S of the halo rows, hD[0..7] = their D
+        unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (hrow0 - 1)), hx);
         int32_t hs[STRIP], hd[STRIP];
         STITCH_UNROLL
         for (int k = 0; k < STRIP; ++k) {
@@ -120,25 +142,52 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
             if (tic == 1 && X.yclip_mode)
                 h.YC[k] = pk_key(pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e * (hrow0 + k) - pc.B, PP_YC, col0_slen(X.sc, hrow0 + k, en.m));
         }
-        pk_pass1<true, false>(pk, pc, hs, hd, hS[0], hx, Jc, false, 0, STRIP, false, h);
-        if (lane == 0) cin = pk_carry_from_exit(pk, h.exit);
-    } else if (lane == 0) cin = pk_carry_from_exit(pk, prev_exit);
+        pk_pass1<true, TB>(pk, pc, hs, hd, hS[0], hx, Jc, false, 0, STRIP, false, h);
+        if (lane == 0) { cin = pk_carry_from_exit(pk, h.exit); if (TB) cin_open = h.exit_open; }
+    } else if (lane == 0) { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }
 
-    int32_t Sn[STRIP]; int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
-    if (SPECIAL) pk_pass2<true, false>(pk, pc, st, cin, 0, nv, has_m, Sn, colmax, nullptr, I_m, iext_m);
-    else pk_pass2<false, false>(pk, pc, st, cin, 0, STRIP, false, Sn, colmax, nullptr, I_m, iext_m);
+    int32_t Sn[STRIP], Iarr[STRIP]; uint8_t tbb[STRIP];
+    int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
+    if (SPECIAL) pk_pass2<true, TB>(pk, pc, st, cin, cin_open, nv, has_m, Sn, colmax, tbb, Iarr, I_m, iext_m);
+    else pk_pass2<false, TB>(pk, pc, st, cin, cin_open, STRIP, false, Sn, colmax, tbb, Iarr, I_m, iext_m);
 
     // what the next tile of this chunk needs (before the in-place stores)
     prev_s7 = __shfl_sync(FULL, Sup[STRIP - 1], 31);
     prev_exit = __shfl_sync(FULL, st.exit, 31);
+    if (TB) prev_exit_open = __shfl_sync(FULL, st.exit_open, 31);
 
+    if (TB) {   // traceback bytes, y-suffix trackers, column-n records of the ordinary rows
+        if (O.tb_col) {
+            uint32_t lo = 0, hi = 0;
+            STITCH_UNROLL
+            for (int k = 0; k < 4; ++k) {
+                lo |= (uint32_t)((!SPECIAL || k < nv) ? tbb[k] : 0) << (8 * k);
+                hi |= (uint32_t)((!SPECIAL || k + 4 < nv) ? tbb[k + 4] : 0) << (8 * k);
+            }
+            *reinterpret_cast<uint2 *>(O.tb_col + tile * TILE + lane * STRIP) = make_uint2(lo, hi);
+        }
+        if (O.track || O.lastcol) {
+            const JumpInfo Jw = S.Jw[a];
+            STITCH_UNROLL
+            for (int k = 0; k < STRIP; ++k) {
+                if (!SPECIAL || k < nv) {
+                    const uint32_t si = state_index(tile, lane, (uint32_t)k);
+                    pk_cell_records(pk, pc, X.sc, Sn[k], Iarr[k], tbb[k], x[k] == pc.q, en.contig_idx, row0 + (uint32_t)k, en.m, Jw, j, X.n,
+                                    O.track ? O.sn + si : nullptr, O.lastcol ? O.last + si : nullptr);
+                }
+            }
+        }
+    }
     if (SPECIAL) {
         STITCH_UNROLL
         for (int k = 0; k < STRIP; ++k) {
             if (k >= nv) Sn[k] = Sup[k];                       // row m is finished per contig; padding keeps its value
             if (k > nv || (k == nv && !has_m)) st.D6[k] = Dup[k];
         }
-        if (has_m) S.stash[a] = make_int4(st.A[nv], st.D6[nv], st.jp[nv], I_m);
+        if (has_m) {
+            PkRowM rm; rm.diag = st.A[nv]; rm.D6 = st.D6[nv]; rm.jp = st.jp[nv]; rm.I = I_m; rm.fl = TB ? st.fl[nv] : 0u; rm.iext = iext_m;
+            S.stash[a] = rm;
+        }
     }
     STITCH_UNROLL
     for (int k = 0; k < STRIP; ++k) { outS[k] = Sn[k]; outD[k] = st.D6[k]; }
@@ -151,15 +200,235 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     if (lane == 0) S.tilemax[tile] = colmax;
 }
 
+// Halos of the current state into parity slot `slot` (before the first column computed from it).
+template <int W>
+__device__ void pk_init_halos(const PackCtx &X, PackSmem &S, uint32_t slot) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t Weff = X.NT < (uint32_t)W ? X.NT : (uint32_t)W;
+    if (warp >= 1 && warp < Weff && lane < 9) {
+        const uint32_t t_lo = (uint32_t)((uint64_t)X.NT * warp / Weff);
+        const uint32_t hl = lane == 0 ? 30u : 31u, hk = lane == 0 ? (uint32_t)STRIP - 1 : lane - 1;
+        const uint32_t pi = pk_sidx(t_lo - 1, hl, hk);
+        S.haloS[(slot * W + warp) * 9 + lane] = X.Sst[pi];
+        if (lane >= 1) S.haloD[(slot * W + warp) * 8 + lane - 1] = X.Dst[pi];
+    }
+}
 
+// Phases T and F of one column.  On entry S.Jc (and S.Jw for the traceback variant), S.Sm/slm/tbm/SmKey of
+// column j-1 and the halos of parity (j-1)&1 are set and the CTA is synchronised; on exit S.cm/cml/cmk,
+// S.Sm/slm/tbm/SmKey describe column j and the CTA is synchronised.
+template <int W, bool TB>
+__device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t r0pkey, int32_t cr1key, uint32_t j,
+                          const PkColOut &O) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const PK &pk = X.pk;
+    const Scoring &sc = X.sc;
+    const uint32_t NT = X.NT, C = X.C, par = j & 1u;
+    const uint32_t Weff = NT < (uint32_t)W ? NT : (uint32_t)W;
+    if (warp < Weff) {
+        const uint32_t t_lo = (uint32_t)((uint64_t)NT * warp / Weff), t_hi = (uint32_t)((uint64_t)NT * (warp + 1) / Weff);
+        const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
+        int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
+        int32_t oS[STRIP], oD[STRIP];
+        for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
+            const ContigEntry en = X.ent[X.owner ? X.owner[tile] : 0u];
+            const uint32_t tic = tile - en.tile_start;
+            if (tic == 0 || tic + 1 == en.ntiles)
+                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD);
+            else
+                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD);
+        }
+        if (warp + 1 < Weff) {   // publish the halo of the next chunk for the next column
+            int32_t *nS = S.haloS + (par * W + warp + 1) * 9, *nD = S.haloD + (par * W + warp + 1) * 8;
+            if (lane == 31) {
+                STITCH_UNROLL
+                for (int k = 0; k < STRIP; ++k) { nS[k + 1] = oS[k]; nD[k] = oD[k]; }
+            }
+            if (lane == 30) nS[0] = oS[STRIP - 1];
+        }
+    }
+    __syncthreads();
+
+    // ---- per contig: tracker + row m + column best ----
+    const Row0 r0 = row0_at(sc, j, X.n);
+    for (uint32_t a = warp; a < C; a += W) {
+        const ContigEntry en = X.ent[a];
+        int32_t kmax = pk.NEGKEY;
+        for (uint32_t t = lane; t < en.ntiles; t += 32) kmax = pk_max(kmax, S.tilemax[en.tile_start + t]);
+        STITCH_UNROLL
+        for (int d = 16; d >= 1; d >>= 1) kmax = pk_max(kmax, __shfl_xor_sync(FULL, kmax, d));
+        const int32_t smax = pk_rel(pk, kmax);
+        // first row (< m) whose S has the best score (column best, SCA:680-687) / equals the best key (tracker, SCA:411-416)
+        uint32_t frow = 0, trow = 0; int32_t fkey = 0;
+        if (en.m >= 2) {
+            STITCH_UNROLL
+            for (int pass = 0; pass < (TB ? 2 : 1); ++pass) {
+                const bool full = pass == 1;
+                uint32_t ft = 0xffffffffu;
+                for (uint32_t t = lane; t < en.ntiles; t += 32) {
+                    const int32_t tm = S.tilemax[en.tile_start + t];
+                    if (full ? tm == kmax : pk_rel(pk, tm) == smax) { ft = t; break; }
+                }
+                STITCH_UNROLL
+                for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
+                const uint32_t tile = en.tile_start + ft;
+                const int4 s0 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + lane * 4);
+                const int4 s1 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + 128 + lane * 4);
+                const int32_t sk[STRIP] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                uint32_t row = 0xffffffffu; int32_t key = 0;
+                STITCH_UNROLL
+                for (int k = STRIP - 1; k >= 0; --k) {
+                    const uint32_t i = ft * TILE + lane * STRIP + (uint32_t)k + 1;
+                    if (i < en.m && (full ? sk[k] == kmax : pk_rel(pk, sk[k]) == smax)) { row = i; key = sk[k]; }
+                }
+                uint32_t best = row;
+                STITCH_UNROLL
+                for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, best, d); best = o < best ? o : best; }
+                const uint32_t src = __ffs(__ballot_sync(FULL, row == best)) - 1;
+                key = __shfl_sync(FULL, key, src);
+                if (full) trow = best; else { frow = best; fkey = key; }
+            }
+        }
+        if (lane == 0) {
+            CmPart rows; cm_init(rows);
+            XsPart tr; xs_init(tr);
+            if (en.m >= 2) {
+                rows.S = pc.B + smax; rows.row = frow; rows.sl = pk_len(pk, fkey); rows.valid = 1;
+                if (sc.xs != MIN_SCORE) { tr.t = pc.B + smax + sc.xs; tr.len = pk_len(pk, kmax); tr.row = TB ? trow : 1u; }
+            }
+            const PkRowM stash = S.stash[a];
+            JumpInfo Jw; Jw.score = 0; Jw.len = 0; Jw.idx = 0; Jw.from = 0;
+            if (TB) Jw = S.Jw[a];
+            const PkRowMOut fo = pk_finish_rowm(pk, pc, sc, stash, tr, r0, Jw, X.bases[en.seq_off + en.m - 1] == pc.q, en.contig_idx, en.m, j);
+            const RowMOut &ro = fo.ro;
+            const uint32_t r = en.m - 1;
+            const uint32_t mt = en.tile_start + r / TILE, ml = (r % TILE) / STRIP, mk = r % STRIP;
+            X.Sst[pk_sidx(mt, ml, mk)] = fo.skey;
+            if (TB) {
+                if (O.tb_col) O.tb_col[mt * TILE + ml * STRIP + mk] = (uint8_t)fo.tbbyte;
+                if (O.colrec_col) {
+                    ColRec cr; cr.jscore = Jw.score; cr.jlen = Jw.len; cr.jidx = Jw.idx; cr.jfrom = Jw.from; cr.lx = ro.lx;
+                    cr.pad0 = cr.pad1 = cr.pad2 = 0;
+                    O.colrec_col[a] = cr;
+                }
+                const uint32_t p = state_index(mt, ml, mk);
+                if (O.track) sn_update(sc, O.sn[p], ro.c.S, ro.c.sl, ro.c.idx, j, X.n);
+                if (O.lastcol) {
+                    LastCell lc; lc.S = ro.c.S; lc.I = pk_abs(pk, pc.B, stash.I); lc.sl = ro.c.sl; lc.il = pk_len(pk, stash.I);
+                    lc.idx = ro.c.idx; lc.from = ro.c.from; lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0;
+                    lc.flags = (uint8_t)((stash.iext ? 1 : 0) | ((stash.fl & 1u) ? 2 : 0)); lc.pad = 0; lc.pad2 = 0;
+                    O.last[p] = lc;
+                }
+            }
+            CmPart cmv; cm_init(cmv);
+            cm_add(cmv, r0.S, r0.sl, 0);
+            cmv = cm_merge(cmv, rows);
+            CmPart top; top.S = ro.c.S; top.row = en.m; top.sl = ro.c.sl; top.valid = 1;
+            cmv = cm_merge(cmv, top);
+            S.cm[a] = cmv.S; S.cmk[a] = cmv.row; S.cml[a] = cmv.sl;
+            S.Sm[a] = ro.c.S; S.slm[a] = ro.c.sl; S.tbm[a] = ro.s_tb; S.SmKey[a] = fo.skey;
+        }
+    }
+    __syncthreads();
+}
+
+// Column 0 (SCA:97-186) of the contigs of X into the packed state (base B_0 = 0) + row-m summaries.
+template <int W>
+__device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr uint32_t T = W * 32;
+    const PK &pk = X.pk;
+    const uint32_t pm = X.NT * TILE;
+    for (uint32_t p = tid; p < pm; p += T) { X.Sst[p] = pk.NEGKEY; X.Dst[p] = pk.NEGKEY + pk.PD6; }
+    __syncthreads();
+    for (uint32_t tile = warp; tile < X.NT; tile += W) {
+        const ContigEntry en = X.ent[X.owner ? X.owner[tile] : 0u];
+        const uint32_t tic = tile - en.tile_start;
+        STITCH_UNROLL
+        for (int k = 0; k < STRIP; ++k) {
+            const uint32_t i = tic * TILE + lane * STRIP + (uint32_t)k + 1;
+            if (i <= en.m) {
+                const Col0 c0 = col0_at(X.sc, i, en.m);
+                X.Sst[pk_sidx(tile, lane, (uint32_t)k)] = pk_from_wide(pk, 0, c0.S, c0.sl, 0);
+            }
+        }
+    }
+    for (uint32_t a = tid; a < X.C; a += T) {
+        const ContigEntry en = X.ent[a];
+        S.cm[a] = 0; S.cml[a] = 0; S.cmk[a] = 0;
+        const Col0 cmm = col0_at(X.sc, en.m, en.m);
+        S.Sm[a] = cmm.S; S.slm[a] = cmm.sl; S.tbm[a] = cmm.s_tb;
+        S.SmKey[a] = pk_from_wide(pk, 0, cmm.S, cmm.sl, 0);
+    }
+    __syncthreads();
+}
+
+// The packed state of column j0 from a wide checkpoint (`ck` in the wide tile-transposed order, first tile of X
+// at ck[0]); Bj0 = base of column j0.
+template <int W>
+__device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const CellState *ck, const CkSum *sums, int32_t Bj0) {
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    const PK &pk = X.pk;
+    const uint32_t pm = X.NT * TILE;
+    for (uint32_t idx = tid; idx < pm; idx += T) {
+        const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
+        const CellState cs = ck[idx];
+        const uint32_t pi = pk_sidx(tile, ln, k);
+        X.Sst[pi] = pk_from_wide(pk, Bj0, cs.S, cs.sl, 0);
+        X.Dst[pi] = pk_from_wide(pk, Bj0, cs.D, cs.dl, PP_D);
+    }
+    for (uint32_t a = tid; a < X.C; a += T) {
+        const CkSum cs = sums[a];
+        S.cm[a] = 0; S.cml[a] = 0; S.cmk[a] = 0;
+        S.Sm[a] = cs.Sm; S.slm[a] = cs.slm; S.tbm[a] = cs.tbm;
+        S.SmKey[a] = pk_from_wide(pk, Bj0, cs.Sm, cs.slm, 0);
+    }
+    __syncthreads();
+}
+
+// Wide checkpoint of the current packed state (column base B).
+template <int W>
+__device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t B, CellState *dck, CkSum *dsum) {
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    const PK &pk = X.pk;
+    const uint32_t pm = X.NT * TILE;
+    for (uint32_t idx = tid; idx < pm; idx += T) {
+        const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
+        const uint32_t pi = pk_sidx(tile, ln, k);
+        const int32_t s = X.Sst[pi], d = X.Dst[pi];
+        CellState cs; cs.S = pk_abs(pk, B, s); cs.D = pk_abs(pk, B, d); cs.sl = pk_len(pk, s); cs.dl = pk_len(pk, d);
+        dck[idx] = cs;
+    }
+    for (uint32_t a = tid; a < X.C; a += T) {
+        CkSum cs; cs.Sm = S.Sm[a]; cs.slm = S.slm[a]; cs.tbm = S.tbm[a]; cs.pad = 0;
+        dsum[a] = cs;
+    }
+}
+
+struct PkColConst { PCol pc; int32_t r0pkey, cr1key; };
+__device__ __forceinline__ PkColConst pk_col_const(const PK &pk, const Scoring &sc, int32_t B, int32_t Bprev, uint32_t j, uint32_t n, uint8_t q) {
+    PkColConst c;
+    c.pc = pk_col(pk, sc, B, Bprev, j, n, q);
+    const Row0 r0 = row0_at(sc, j, n), r0p = row0_at(sc, j - 1, n);
+    c.r0pkey = pk_from_wide(pk, Bprev, r0p.S, r0p.sl, 0);
+    c.cr1key = pk_carry_row1(pk, c.pc, sc, r0);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk fill
+// ---------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
     __shared__ uint32_t sJob;
-    __shared__ PCol s_pc[2];
-    __shared__ int32_t s_r0pkey[2], s_cr1key[2];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ PkColConst s_cc[2];
+    __shared__ int32_t s_gmax;
+    __shared__ uint32_t s_first;
+    const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const Scoring sc = P.sc;
 
@@ -168,196 +437,196 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         if (tid == 0) sJob = atomicAdd(P.counter, 1u);
         __syncthreads();
         if (sJob >= P.n_jobs) break;
-        const JobDesc jd = P.jobs[P.order[sJob]];
+        const uint32_t job = P.order[sJob];
+        const JobDesc jd = P.jobs[job];
         const LayoutDesc ld = P.layouts[jd.layout];
-        const ContigEntry *ent = P.ents + ld.ent_off;
-        const uint16_t *owner = P.owners + ld.owner_off;
-        const uint32_t C = ld.C, NT = ld.n_tiles, PM = ld.PM, n = jd.n, K = P.K, j1 = jd.j0;
-        const PK pk = pk_make(sc, jd.LB);
+        const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
         PackCtx X;
-        X.pk = pk; X.sc = sc; X.ent = ent; X.owner = owner; X.bases = P.contig_bases;
+        X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
+        X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;
-        const uint32_t Weff = NT < (uint32_t)W ? NT : (uint32_t)W;
+        PkColOut O; O.tb_col = nullptr; O.colrec_col = nullptr; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false;
 
-        // ---- column 0 (SCA:97-186), base B_0 = 0 ----
-        for (uint32_t p = tid; p < PM; p += T) { X.Sst[p] = pk.NEGKEY; X.Dst[p] = pk.NEGKEY + pk.PD6; }
+        pk_state_init0<W>(X, S);
+        pk_init_halos<W>(X, S, 0);
+        if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
         __syncthreads();
-        for (uint32_t tile = warp; tile < NT; tile += W) {
-            const ContigEntry en = ent[owner[tile]];
-            const uint32_t tic = tile - en.tile_start;
-            STITCH_UNROLL
-            for (int k = 0; k < STRIP; ++k) {
-                const uint32_t i = tic * TILE + lane * STRIP + (uint32_t)k + 1;
-                if (i <= en.m) {
-                    const Col0 c0 = col0_at(sc, i, en.m);
-                    X.Sst[pk_sidx(tile, lane, (uint32_t)k)] = pk_from_wide(pk, 0, c0.S, c0.sl, 0);
-                }
-            }
-        }
-        for (uint32_t a = tid; a < C; a += T) {
-            const ContigEntry en = ent[a];
-            S.cm[a] = 0; S.cml[a] = 0; S.cmk[a] = 0;
-            const Col0 cmm = col0_at(sc, en.m, en.m);
-            S.Sm[a] = cmm.S; S.slm[a] = cmm.sl; S.tbm[a] = cmm.s_tb;
-            S.SmKey[a] = pk_from_wide(pk, 0, cmm.S, cmm.sl, 0);
-        }
-        if (tid == 0) { s_pc[0].B = 0; s_pc[0].delta = 0; }
-        __syncthreads();
-        // halos of column 0 (read by column 1 from parity slot 0): the 9 rows before every chunk
-        if (warp >= 1 && warp < Weff && lane < 9) {
-            const uint32_t t_lo = (uint32_t)((uint64_t)NT * warp / Weff);
-            const uint32_t hl = lane == 0 ? 30u : 31u, hk = lane == 0 ? (uint32_t)STRIP - 1 : lane - 1;
-            const uint32_t pi = pk_sidx(t_lo - 1, hl, hk);
-            S.haloS[(0 * W + warp) * 9 + lane] = X.Sst[pi];
-            if (lane >= 1) S.haloD[(0 * W + warp) * 8 + lane - 1] = X.Dst[pi];
-        }
 
-        for (uint32_t j = 1; j <= j1 + 1; ++j) {
+        for (uint32_t j = 1; j <= n; ++j) {
             const uint32_t par = j & 1u;
-            // ---- phase S: base of the column, jump selection (MCA:279-331), per-column constants ----
+            // ---- base of the column, jump selection (MCA:279-331), per-column constants ----
             {
-                const int32_t Bprev = s_pc[par ^ 1u].B;
+                const int32_t Bprev = s_cc[par ^ 1u].pc.B;
                 if (tid < C || tid == 0) {
                     int32_t g = S.cm[0];
                     for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
                     PCol pcl; pcl.B = g; pcl.delta = g - Bprev;
                     for (uint32_t a = tid; a < C; a += T) {
-                        const JumpInfo J = select_jump(sc, ent, C, a, S.cm, S.cml, S.cmk);
+                        const JumpInfo J = select_jump(sc, X.ent, C, a, S.cm, S.cml, S.cmk);
                         ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
                         cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
                         colrec[(uint64_t)j * C + a] = cr;
-                        S.Jc[a] = pk_jc(pk, pcl, J.score, J.len);
+                        S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
                     }
                     if (tid == 0) {
                         gcol[j - 1] = g;
-                        if (j <= j1) {
-                            s_pc[par] = pk_col(pk, sc, g, Bprev, j, n, read[j - 1]);
-                            const Row0 r0 = row0_at(sc, j, n), r0p = row0_at(sc, j - 1, n);
-                            s_r0pkey[par] = pk_from_wide(pk, Bprev, r0p.S, r0p.sl, 0);
-                            s_cr1key[par] = pk_carry_row1(pk, s_pc[par], sc, r0);
-                        }
+                        s_cc[par] = pk_col_const(X.pk, sc, g, Bprev, j, n, read[j - 1]);
                     }
                 }
             }
-            if (j == j1 + 1) break;   // only the jump records of the first wide column were needed
             __syncthreads();
-            const PCol pc = s_pc[par];
-            const int32_t r0pkey = s_r0pkey[par], cr1key = s_cr1key[par];
-
-            // ---- phase T: tiles ----
-            if (warp < Weff) {
-                const uint32_t t_lo = (uint32_t)((uint64_t)NT * warp / Weff), t_hi = (uint32_t)((uint64_t)NT * (warp + 1) / Weff);
-                const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
-                int32_t prev_exit = 0, prev_s7 = 0;
-                int32_t oS[STRIP], oD[STRIP];
-                for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
-                    const ContigEntry en = ent[owner[tile]];
-                    const uint32_t tic = tile - en.tile_start;
-                    if (tic == 0 || tic + 1 == en.ntiles)
-                        pk_tile<true>(X, pc, S, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_s7, oS, oD);
-                    else
-                        pk_tile<false>(X, pc, S, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_s7, oS, oD);
-                }
-                if (warp + 1 < Weff) {   // publish the halo of the next chunk for the next column
-                    int32_t *nS = S.haloS + (par * W + warp + 1) * 9, *nD = S.haloD + (par * W + warp + 1) * 8;
-                    if (lane == 31) {
-                        STITCH_UNROLL
-                        for (int k = 0; k < STRIP; ++k) { nS[k + 1] = oS[k]; nD[k] = oD[k]; }
-                    }
-                    if (lane == 30) nS[0] = oS[STRIP - 1];
-                }
-            }
+            const PkColConst cc = s_cc[par];
+            pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+            if ((j % K == 0) && j < n)
+                pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
+        }
+        // best score of column n; the column the tail restarts from: the last checkpoint before the first column
+        // that can hold a final y-suffix tracker (dp_core.h: first_candidate_column); column n is always in the tail
+        if (tid == 0) {
+            int32_t g = S.cm[0];
+            for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
+            gcol[n] = g;
+            s_gmax = g; s_first = n;
+        }
+        __syncthreads();
+        if (P.tracked_mode) {
+            int32_t g = gcol[n];
+            for (uint32_t jj = tid; jj < n; jj += T) g = gcol[jj] > g ? gcol[jj] : g;
+            atomicMax(&s_gmax, g);
             __syncthreads();
+            int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
+            if (submax < 0) submax = 0;
+            const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+            int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+            gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+            const int32_t thr = s_gmax - (submax - gmin - submin);
+            uint32_t first = n;
+            for (uint32_t jj = 1 + tid; jj <= n; jj += T) if (gcol[jj] >= thr) { first = jj; break; }
+            atomicMin(&s_first, first);
+            __syncthreads();
+        }
+        if (tid == 0) P.tail_j0[job] = ((s_first - 1) / K) * K;
+    }
+}
 
-            // ---- phase F: per contig, tracker + row m + column best ----
-            const Row0 r0 = row0_at(sc, j, n);
-            for (uint32_t a = warp; a < C; a += W) {
-                const ContigEntry en = ent[a];
-                int32_t kmax = pk.NEGKEY;
-                for (uint32_t t = lane; t < en.ntiles; t += 32) kmax = pk_max(kmax, S.tilemax[en.tile_start + t]);
+// ---------------------------------------------------------------------------------------------
+// tail: columns (j0, n] again in the traceback variant
+// ---------------------------------------------------------------------------------------------
+// Replays the jump records and column bases the bulk pass left (colrec, gcol).
+template <int W>
+__device__ __forceinline__ void pk_replay_consts(const PackCtx &X, PackSmem &S, const ColRec *colrec, const int32_t *gcol,
+                                                 const uint8_t *read, uint32_t j, uint32_t a_global, uint32_t Cglobal, PkColConst *s_cc) {
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    const int32_t B = gcol[j - 1], Bprev = j >= 2 ? gcol[j - 2] : 0;
+    PCol pcl; pcl.B = B; pcl.delta = B - Bprev;
+    for (uint32_t a = tid; a < X.C; a += T) {
+        const ColRec cr = colrec[(uint64_t)j * Cglobal + a_global + a];
+        JumpInfo J; J.score = cr.jscore; J.len = cr.jlen; J.idx = cr.jidx; J.from = cr.jfrom;
+        S.Jw[a] = J;
+        S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
+    }
+    if (tid == 0) *s_cc = pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, read[j - 1]);
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) tail_packed_kernel(const Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
+    __shared__ uint32_t sJob;
+    __shared__ PkColConst s_cc;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const Scoring sc = P.sc;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sJob = atomicAdd(P.counter, 1u);
+        __syncthreads();
+        if (sJob >= P.n_jobs) break;
+        const uint32_t job = P.order[sJob];
+        const JobDesc jd = P.jobs[job];
+        const LayoutDesc ld = P.layouts[jd.layout];
+        const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
+        const uint32_t j0 = P.tail_j0[job];
+        PackCtx X;
+        X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
+        X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
+        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
+        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
+        ColRec *colrec = P.colrec + jd.colrec_off;
+        const int32_t *gcol = P.gcol + jd.gcol_off;
+        const uint8_t *read = P.reads + jd.read_off;
+        SnRec *sn = P.sn + jd.cell_off;
+        const bool tracked = P.tracked_mode != 0;
+
+        if (j0 == 0) pk_state_init0<W>(X, S);
+        else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(j0 / K - 1) * PM,
+                                 P.ck_sum + jd.cksum_off + (uint64_t)(j0 / K - 1) * C, gcol[j0 - 1]);
+        if (tracked) {   // trackers start from column 0 (SCA:179-183)
+            for (uint32_t tile = warp; tile < X.NT; tile += W) {
+                const ContigEntry en = X.ent[X.owner[tile]];
+                const uint32_t tic = tile - en.tile_start;
                 STITCH_UNROLL
-                for (int d = 16; d >= 1; d >>= 1) kmax = pk_max(kmax, __shfl_xor_sync(FULL, kmax, d));
-                const int32_t smax = pk_rel(pk, kmax);
-                uint32_t frow = 0xffffffffu; int32_t fkey = 0;
-                if (en.m >= 2) {
-                    uint32_t ft = 0xffffffffu;
-                    for (uint32_t t = lane; t < en.ntiles; t += 32)
-                        if (pk_rel(pk, S.tilemax[en.tile_start + t]) == smax) { ft = t; break; }
-                    STITCH_UNROLL
-                    for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
-                    const uint32_t tile = en.tile_start + ft;
-                    const int4 s0 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + lane * 4);
-                    const int4 s1 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + 128 + lane * 4);
-                    const int32_t sk[STRIP] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                    STITCH_UNROLL
-                    for (int k = STRIP - 1; k >= 0; --k) {
-                        const uint32_t i = ft * TILE + lane * STRIP + (uint32_t)k + 1;
-                        if (i < en.m && pk_rel(pk, sk[k]) == smax) { frow = i; fkey = sk[k]; }
+                for (int k = 0; k < STRIP; ++k) {
+                    const uint32_t i = tic * TILE + lane * STRIP + (uint32_t)k + 1;
+                    if (i <= en.m) {
+                        const Col0 c0 = col0_at(sc, i, en.m);
+                        sn[state_index(tile, lane, (uint32_t)k)] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n);
                     }
-                    uint32_t best = frow;
-                    STITCH_UNROLL
-                    for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, best, d); best = o < best ? o : best; }
-                    const uint32_t src = __ffs(__ballot_sync(FULL, frow == best)) - 1;
-                    fkey = __shfl_sync(FULL, fkey, src);
-                    frow = best;
-                }
-                if (lane == 0) {
-                    CmPart rows; cm_init(rows);
-                    XsPart tr; xs_init(tr);
-                    if (en.m >= 2) {
-                        rows.S = pc.B + smax; rows.row = frow; rows.sl = pk_len(pk, fkey); rows.valid = 1;
-                        if (sc.xs != MIN_SCORE) { tr.t = pc.B + smax + sc.xs; tr.len = pk_len(pk, kmax); tr.row = 1; }
-                    }
-                    const int4 sm_ = S.stash[a];
-                    RowM rm;
-                    rm.diag = pk_abs(pk, pc.B, sm_.x); rm.dgl = pk_len(pk, sm_.x);
-                    rm.D = pk_abs(pk, pc.B, sm_.y); rm.dl = pk_len(pk, sm_.y); rm.dext = 0;
-                    rm.I = pk_abs(pk, pc.B, sm_.w); rm.il = pk_len(pk, sm_.w); rm.iext = 0;
-                    rm.jp.score = pk_abs(pk, pc.B, sm_.z); rm.jp.len = pk_len(pk, sm_.z); rm.jp.idx = 0; rm.jp.from = 0;
-                    { const int32_t dj = sc.o + sc.e * (int32_t)j; rm.xclip = sc.xp + (sc.yp > dj ? sc.yp : dj); }
-                    rm.xclip_len = r0.sl;
-                    rm.yclip = sc.yp + sc.o + sc.e * (int32_t)en.m; rm.yclip_len = 0;
-                    rm.is_match = P.contig_bases[en.seq_off + en.m - 1] == pc.q;
-                    const RowMOut ro = finish_rowm(sc, rm, tr, en.contig_idx, en.m);
-                    const uint32_t r = en.m - 1;
-                    const int32_t skey = pk_from_wide(pk, pc.B, ro.c.S, ro.c.sl, 0);
-                    X.Sst[pk_sidx(en.tile_start + r / TILE, (r % TILE) / STRIP, r % STRIP)] = skey;
-                    CmPart cmv; cm_init(cmv);
-                    cm_add(cmv, r0.S, r0.sl, 0);
-                    cmv = cm_merge(cmv, rows);
-                    CmPart top; top.S = ro.c.S; top.row = en.m; top.sl = ro.c.sl; top.valid = 1;
-                    cmv = cm_merge(cmv, top);
-                    S.cm[a] = cmv.S; S.cmk[a] = cmv.row; S.cml[a] = cmv.sl;
-                    S.Sm[a] = ro.c.S; S.slm[a] = ro.c.sl; S.tbm[a] = ro.s_tb; S.SmKey[a] = skey;
-                }
-            }
-            __syncthreads();
-
-            // ---- wide checkpoints (every K columns) and the hand-over state at column j1 ----
-            const bool ck = (j % K == 0) && j < n;
-            if (ck || j == j1) {
-                CellState *dck = ck ? P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM : nullptr;
-                CellState *dh = (j == j1) ? P.hand_state + jd.hand_off : nullptr;
-                for (uint32_t idx = tid; idx < PM; idx += T) {
-                    const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
-                    const uint32_t pi = pk_sidx(tile, ln, k);
-                    const int32_t s = X.Sst[pi], d = X.Dst[pi];
-                    CellState cs; cs.S = pk_abs(pk, pc.B, s); cs.D = pk_abs(pk, pc.B, d); cs.sl = pk_len(pk, s); cs.dl = pk_len(pk, d);
-                    if (dck) dck[idx] = cs;
-                    if (dh) dh[idx] = cs;
-                }
-                for (uint32_t a = tid; a < C; a += T) {
-                    CkSum cs; cs.Sm = S.Sm[a]; cs.slm = S.slm[a]; cs.tbm = S.tbm[a]; cs.pad = 0;
-                    if (ck) P.ck_sum[jd.cksum_off + (uint64_t)(j / K - 1) * C + a] = cs;
-                    if (j == j1) P.hand_sum[jd.handsum_off + a] = cs;
                 }
             }
         }
+        pk_init_halos<W>(X, S, j0 & 1u);
+        __syncthreads();
+        for (uint32_t j = j0 + 1; j <= n; ++j) {
+            pk_replay_consts<W>(X, S, colrec, gcol, read, j, 0, C, &s_cc);
+            __syncthreads();
+            const PkColConst cc = s_cc;
+            PkColOut O; O.tb_col = nullptr; O.colrec_col = colrec + (uint64_t)j * C; O.sn = sn; O.last = P.last + jd.cell_off;
+            O.track = tracked; O.lastcol = j == n;
+            pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+        }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// walk: packed re-fill of one unit (contig `a`, the block of K columns holding column j)
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc &ld, PackSmem &S, ContigEntry *s_en, PkColConst *s_cc,
+                               uint32_t a, uint32_t j, int32_t *pstate, uint64_t pstate_half, uint8_t *bytes, ColRec *ucr, TbUnit *unit_out) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
+    const uint32_t b = (j - 1) / K, jb = b * K, je = (jb + K < n) ? jb + K : n;
+    const ContigEntry gen = P.ents[ld.ent_off + a];
+    const uint32_t pm = gen.ntiles * TILE, gbase = gen.tile_start * TILE;
+    if (tid == 0) { *s_en = gen; s_en->tile_start = 0; }
+    __syncthreads();
+    PackCtx X;
+    X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = P.contig_bases;
+    X.Sst = pstate; X.Dst = pstate + pstate_half; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
+    const int32_t *gcol = P.gcol + jd.gcol_off;
+    const ColRec *colrec = P.colrec + jd.colrec_off;
+    const uint8_t *read = P.reads + jd.read_off;
+    if (b == 0) pk_state_init0<W>(X, S);
+    else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(b - 1) * PM + gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
+                             gcol[jb - 1]);
+    pk_init_halos<W>(X, S, jb & 1u);
+    __syncthreads();
+    for (uint32_t jj = jb + 1; jj <= je; ++jj) {
+        pk_replay_consts<W>(X, S, colrec, gcol, read, jj, a, C, s_cc);
+        __syncthreads();
+        const PkColConst cc = *s_cc;
+        PkColOut O; O.tb_col = bytes + (uint64_t)(jj - jb - 1) * pm; O.colrec_col = ucr + (jj - jb - 1); O.sn = nullptr; O.last = nullptr;
+        O.track = false; O.lastcol = false;
+        pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, jj, O);
+    }
+    if (tid == 0) { unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; }
+    __syncthreads();
 }
 
 }  // namespace gpu

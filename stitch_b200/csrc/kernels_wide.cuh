@@ -70,6 +70,11 @@ struct Params {
     int32_t *pstate;         // packed kernel, per CTA: S keys then D keys
     uint64_t pstate_stride, pstate_half;
     uint32_t ntmax;          // largest tile count among the packed jobs
+    uint32_t *tail_j0;       // per job: the checkpointed column the packed tail restarts from
+    int32_t *wpstate;        // walk kernel, per CTA: packed state of one contig (S keys then D keys)
+    uint64_t wpstate_stride, wpstate_half;
+    ColRec *unit_cr;         // walk kernel, per CTA: K per-column records of the loaded unit
+    uint32_t max_ctiles;     // most tiles of any single contig (walk kernel shared memory)
     int32_t *gcol;
     OutOp *ops;
     ChainHdr *chains;
@@ -386,7 +391,7 @@ __global__ void fixup_kernel(const Params P) {
     __shared__ uint32_t s_first;
     // Was the y-suffix tracking window wide enough?  (dp_core.h: first_candidate_column)
     const uint32_t eff_track_from = jd.track_from > jd.j0 ? jd.track_from : jd.j0 + 1;
-    const bool windowed = P.tracked_mode && !P.force_full && eff_track_from > 1;
+    const bool windowed = P.tracked_mode && !P.force_full && eff_track_from > 1 && jd.LB == 0;   // the packed tail tracks by construction
     if (windowed) {
         const int32_t *gcol = P.gcol + jd.gcol_off;
         if (threadIdx.x == 0) { s_gmax = gcol[0]; s_first = n + 1; }
@@ -422,7 +427,7 @@ __global__ void fixup_kernel(const Params P) {
 // ---------------------------------------------------------------------------------------------
 template <int W>
 __device__ void refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc &ld, WideSmem<W> &S, ContigEntry *s_en,
-                            uint32_t a, uint32_t j, CellState *st0, CellState *st1, uint8_t *bytes, TbUnit *unit_out) {
+                            uint32_t a, uint32_t j, CellState *st0, CellState *st1, uint8_t *bytes, ColRec *ucr, TbUnit *unit_out) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const Scoring sc = P.sc;
@@ -455,97 +460,16 @@ __device__ void refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc
         ColWide A;
         A.ent = s_en; A.owner = nullptr; A.C = 1; A.NT = gen.ntiles; A.bases = P.contig_bases;
         A.prev = ((jj - 1) & 1u) ? st1 : st0; A.curr = (jj & 1u) ? st1 : st0; A.ck = nullptr;
-        A.tb_col = bytes + (uint64_t)(jj - jb - 1) * pm; A.colrec_col = nullptr;
+        A.tb_col = bytes + (uint64_t)(jj - jb - 1) * pm; A.colrec_col = ucr + (jj - jb - 1);
         A.sn = nullptr; A.last = nullptr; A.j = jj; A.n = n; A.q = read[jj - 1];
         A.track = false; A.lastcol = false;
         column_wide<W>(sc, A, S);
     }
-    if (tid == 0) { unit_out->bytes = bytes; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; }
+    if (tid == 0) { unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; }
     __syncthreads();
 }
 
 enum : uint32_t { WCMD_DONE = 0, WCMD_UNIT = 1 };
-
-template <int W>
-__global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WideSmem<W> S; S.carve(smem_raw, 1);
-    __shared__ uint32_t sJob, sCmd, sUa, sUj;
-    __shared__ ContigEntry s_en;
-    __shared__ TbUnit s_unit;
-    __shared__ uint8_t s_seen[MAX_STRANDS];
-    const uint32_t tid = threadIdx.x;
-    CellState *st0 = P.state + (uint64_t)blockIdx.x * P.state_stride;
-    CellState *st1 = st0 + P.state_half;
-    uint8_t *ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) sJob = atomicAdd(P.counter, 1u);
-        __syncthreads();
-        if (sJob >= P.n_jobs) break;
-        const uint32_t job = P.order[sJob];
-        const JobDesc jd = P.jobs[job];
-        const LayoutDesc ld = P.layouts[jd.layout];
-
-        // thread-0 state
-        ReadView v; WalkState ws; ChainHdr h;
-        uint32_t used = 0, n_chains = 0, status = WALK_OK, n_seen = 0, a_cur = 0;
-        bool walking = false, finished = false;
-        OutOp *ops = P.ops + jd.ops_off;
-        ChainHdr *hdr = P.chains + jd.chain_first;
-        if (tid == 0) {
-            v.sc = P.sc; v.ent = P.ents + ld.ent_off; v.C = ld.C; v.n = jd.n;
-            v.colrec = P.colrec + jd.colrec_off; v.last = P.last + jd.cell_off; v.sn = P.sn + jd.cell_off;
-            v.contig_bases = P.contig_bases; v.read = P.reads + jd.read_off; v.pos_of = P.posof + ld.posof_off;
-            v.unit.bytes = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
-            if (jd.walk == host::WALK_ALL) for (uint32_t a = 0; a < ld.C; ++a) s_seen[a] = 0;
-        }
-        for (;;) {
-            if (tid == 0) {
-                sCmd = WCMD_DONE;
-                while (!finished) {
-                    if (!walking) {   // choose the next chain to walk
-                        int a_end = -1;
-                        if (jd.walk == host::WALK_BEST) { if (n_chains == 0 && used == 0) a_end = (int)pick_end(v, nullptr); }
-                        else if (jd.walk == host::WALK_FROM) {
-                            if (n_chains == 0 && used == 0) a_end = jd.from_contig < MAX_STRANDS ? v.pos_of[jd.from_contig] : -1;
-                        } else if (n_seen < ld.C) a_end = (int)pick_end(v, s_seen);
-                        if (a_end < 0) { finished = true; break; }
-                        a_cur = (uint32_t)a_end;
-                        walk_begin(v, a_cur, ops + used, jd.ops_cap - used, ws, h);
-                        walking = true;
-                    }
-                    const uint32_t s = walk_run(v, ws, h);
-                    if (s == WALK_NEED_UNIT) { sCmd = WCMD_UNIT; sUa = ws.a; sUj = ws.j; break; }
-                    walking = false;
-                    auto mark = [&](uint32_t idx) {
-                        const int p = idx < MAX_STRANDS ? v.pos_of[idx] : -1;
-                        if (p >= 0 && !s_seen[p]) { s_seen[p] = 1; ++n_seen; }
-                    };
-                    if (jd.walk == host::WALK_ALL) {
-                        if (s == WALK_NONE) { mark(v.ent[a_cur].contig_idx); continue; }
-                        if (s != WALK_OK) { status = s; finished = true; break; }
-                        mark(h.start_contig_idx); mark(h.end_contig_idx);
-                        for (uint32_t k = 0; k < h.n_ops; ++k) if (ops[used + k].kind == OP_XJUMP) mark(ops[used + k].a);
-                        if (n_chains >= jd.max_chains) { status = WALK_OVERFLOW; finished = true; break; }
-                        hdr[n_chains++] = h;
-                        used += h.n_ops;
-                    } else {
-                        if (s == WALK_OK) { hdr[0] = h; n_chains = 1; }
-                        else if (s != WALK_NONE) status = s;
-                        finished = true;
-                    }
-                }
-            }
-            __syncthreads();
-            if (sCmd == WCMD_DONE) break;
-            refill_unit<W>(P, jd, ld, S, &s_en, sUa, sUj, st0, st1, ubytes, &s_unit);
-            if (tid == 0) v.unit = s_unit;
-        }
-        if (tid == 0) { JobOut o; o.n_chains = n_chains; o.status = status; P.job_out[job] = o; }
-    }
-}
 
 }  // namespace gpu
 }  // namespace stitch

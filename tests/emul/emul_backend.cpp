@@ -221,206 +221,333 @@ struct EmulBackend : Backend {
         F.need_full_track = any_track && track_from > 1 && first_candidate_column(sc, F.gcol.data(), n) < track_from;
     }
 
-    // Packed columns [1, j1] (dp_packed.h) with the kernel's structure: EMUL_WARPS warps own contiguous
-    // chunks of tiles; a chunk that starts inside a contig recomputes the chain exit of the strip before it
-    // (the halo).  Leaves wide checkpoints, the wide hand-over state at column j1, colrec[1..j1+1], gcol[0..j1].
-    void fill_packed(const Job &job, const Layout &L, uint32_t LB, uint32_t j1, Fill &F) {
+    // ---- packed path (dp_packed.h) with the kernel's structure: EMUL_WARPS warps own contiguous chunks of
+    // tiles; a chunk that starts inside a contig recomputes the chain exit of the strip before it (the halo).
+    struct PkState {           // rolling packed state of a set of contigs (tile_start relative to these arrays)
+        std::vector<int32_t> S[2], D[2];
+        std::vector<int32_t> cm, Sm, SmKey; std::vector<uint32_t> cml, cmk, slm, tbm;
+    };
+    struct PkCol {
+        const ContigEntry *ent; uint32_t C, NT; const uint32_t *owner;
+        const uint8_t *read; uint32_t j, n; int32_t B, Bprev; const JumpInfo *J;
+        bool tb; uint8_t *tb_col; ColRec *colrec_col;       // traceback variant: packed bytes, Lx[j] per contig
+        bool track; SnRec *sn; bool lastcol; LastCell *last;
+    };
+
+    void pk_state_init0(const PK &pk, const ContigEntry *ent, uint32_t C, uint32_t pm, PkState &st) {
         const Scoring &sc = al.opts.sc;
-        const uint32_t C = (uint32_t)L.ent.size(), PM = L.PM(), NT = L.n_tiles, n = job.n;
-        const uint8_t *bases = al.contigs.blob.data();
-        const PK pk = pk_make(sc, LB);
-        const int W = EMUL_WARPS;
-        stats.cells += (uint64_t)L.cells_per_col * j1;
-        std::vector<int32_t> Sst[2], Dst[2];   // linear: tile * TILE + (row - 1 within the contig's tiles)
-        for (int b = 0; b < 2; ++b) { Sst[b].assign(PM, pk.NEGKEY); Dst[b].assign(PM, pk.NEGKEY + pk.PD6); }
-        std::vector<uint32_t> owner(NT);
-        for (uint32_t a = 0; a < C; ++a) for (uint32_t t = 0; t < L.ent[a].ntiles; ++t) owner[L.ent[a].tile_start + t] = a;
-        std::vector<int32_t> cm(C, 0), Sm(C);
-        std::vector<uint32_t> cml(C, 0), cmk(C, 0), slm(C), tbm(C);
-        std::vector<int32_t> SmKey(C);
-        int32_t B = 0;   // B_0 = 0
+        for (int b = 0; b < 2; ++b) { st.S[b].assign(pm, pk.NEGKEY); st.D[b].assign(pm, pk.NEGKEY + pk.PD6); }
+        st.cm.assign(C, 0); st.cml.assign(C, 0); st.cmk.assign(C, 0); st.Sm.resize(C); st.slm.resize(C); st.tbm.resize(C); st.SmKey.resize(C);
         for (uint32_t a = 0; a < C; ++a) {
-            const ContigEntry &en = L.ent[a];
-            for (uint32_t i = 1; i <= en.m; ++i) {
-                Col0 c0 = col0_at(sc, i, en.m);
-                Sst[0][row_linear(en, i)] = pk_from_wide(pk, 0, c0.S, c0.sl, 0);
-            }
+            const ContigEntry &en = ent[a];
+            for (uint32_t i = 1; i <= en.m; ++i) { Col0 c0 = col0_at(sc, i, en.m); st.S[0][row_linear(en, i)] = pk_from_wide(pk, 0, c0.S, c0.sl, 0); }
             Col0 cmm = col0_at(sc, en.m, en.m);
-            Sm[a] = cmm.S; slm[a] = cmm.sl; tbm[a] = cmm.s_tb;
-            SmKey[a] = Sst[0][row_linear(en, en.m)];
+            st.Sm[a] = cmm.S; st.slm[a] = cmm.sl; st.tbm[a] = cmm.s_tb; st.SmKey[a] = st.S[0][row_linear(en, en.m)];
         }
-        F.gcol[0] = 0;
-        std::vector<JumpInfo> J(C);
+    }
+    // from a wide checkpoint of column j0 (base Bj0); `ck` in the wide tile-transposed order of `ent_ck` positions
+    void pk_state_from_ck(const PK &pk, const ContigEntry *ent, const ContigEntry *ent_ck, uint32_t C, uint32_t pm, uint32_t j0, int32_t Bj0,
+                          const CellState *ck, const CkSum *sums, PkState &st) {
+        for (int b = 0; b < 2; ++b) { st.S[b].assign(pm, pk.NEGKEY); st.D[b].assign(pm, pk.NEGKEY + pk.PD6); }
+        st.cm.assign(C, 0); st.cml.assign(C, 0); st.cmk.assign(C, 0); st.Sm.resize(C); st.slm.resize(C); st.tbm.resize(C); st.SmKey.resize(C);
+        for (uint32_t a = 0; a < C; ++a) {
+            const ContigEntry &en = ent[a];
+            for (uint32_t i = 1; i <= en.m; ++i) {
+                const CellState &cs = ck[row_index(ent_ck[a], i)];
+                st.S[j0 & 1][row_linear(en, i)] = pk_from_wide(pk, Bj0, cs.S, cs.sl, 0);
+                st.D[j0 & 1][row_linear(en, i)] = pk_from_wide(pk, Bj0, cs.D, cs.dl, PP_D);
+            }
+            st.Sm[a] = sums[a].Sm; st.slm[a] = sums[a].slm; st.tbm[a] = sums[a].tbm;
+            st.SmKey[a] = pk_from_wide(pk, Bj0, sums[a].Sm, sums[a].slm, 0);
+        }
+    }
+
+    void packed_column(const PK &pk, const PkCol &A, PkState &st) {
+        const Scoring &sc = al.opts.sc;
+        const uint8_t *bases = al.contigs.blob.data();
+        const uint32_t C = A.C, NT = A.NT, j = A.j, n = A.n;
+        const int W = EMUL_WARPS;
+        const int32_t B = A.B;
+        const PCol pc = pk_col(pk, sc, B, A.Bprev, j, n, A.read[j - 1]);
+        const Row0 r0 = row0_at(sc, j, n), r0p = row0_at(sc, j - 1, n);
+        const int32_t *Sp = st.S[(j - 1) & 1].data(), *Dp = st.D[(j - 1) & 1].data();
+        int32_t *Sc = st.S[j & 1].data(), *Dc = st.D[j & 1].data();
         std::vector<int32_t> tilemax(NT);
-        struct RowMStash { int32_t diag, D6, jp, I; bool wrap; };
-        std::vector<RowMStash> stash(C);
-        for (uint32_t j = 1; j <= j1 + 1; ++j) {
-            int32_t g = cm[0];
-            for (uint32_t a = 1; a < C; ++a) g = std::max(g, cm[a]);
-            const int32_t Bprev = B;
-            B = g;
-            for (uint32_t a = 0; a < C; ++a) {
-                J[a] = select_jump(sc, L.ent.data(), C, a, cm.data(), cml.data(), cmk.data());
-                ColRec &cr = F.colrec[(size_t)j * C + a];
-                cr.jscore = J[a].score; cr.jlen = J[a].len; cr.jidx = J[a].idx; cr.jfrom = J[a].from;
-            }
-            if (j == j1 + 1) break;   // only the jump of the first wide column was needed
-            const PCol pc = pk_col(pk, sc, B, Bprev, j, n, job.read[j - 1]);
-            const Row0 r0 = row0_at(sc, j, n), r0p = row0_at(sc, j - 1, n);
-            const int32_t *Sp = Sst[(j - 1) & 1].data(), *Dp = Dst[(j - 1) & 1].data();
-            int32_t *Sc = Sst[j & 1].data(), *Dc = Dst[j & 1].data();
-            for (int w = 0; w < W; ++w) {
-                const uint32_t t_lo = (uint32_t)((uint64_t)NT * w / W), t_hi = (uint32_t)((uint64_t)NT * (w + 1) / W);
-                int32_t prev_exit = 0;
-                for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
-                    const uint32_t a = owner[tile];
-                    const ContigEntry &en = L.ent[a];
-                    const uint32_t tic = tile - en.tile_start;
-                    const bool first = tic == 0, lastt = tic + 1 == en.ntiles;
-                    const bool special = first || lastt;
-                    const int32_t Jc = pk_jc(pk, pc, J[a].score, J[a].len);
-                    const bool wrap0 = first && en.circular && tbm[a] != TB_XCLIP_SUFFIX;
-                    const int32_t wbase = pk_wbase(pk, SmKey[a]);
-                    PStrip strips[32];
-                    int nvs[32]; bool hasm[32];
-                    for (uint32_t lane = 0; lane < 32; ++lane) {
-                        const uint32_t row0 = tic * TILE + lane * STRIP + 1;   // 1-based row of the strip's first cell
-                        const uint32_t base = tile * TILE + lane * STRIP;
-                        int32_t Sdg0;
-                        if (row0 == 1) Sdg0 = pk_from_wide(pk, Bprev, r0p.S, r0p.sl, 0);
-                        else Sdg0 = Sp[base - 1];
-                        uint8_t x[STRIP];
-                        for (int k = 0; k < STRIP; ++k) x[k] = row0 + k <= en.m ? bases[en.seq_off + row0 + k - 1] : 0;
-                        int nv = STRIP; bool hm = false;
-                        if (special) {
-                            const int64_t left = (int64_t)en.m - (int64_t)row0;   // rows < m in this strip
-                            nv = left >= STRIP ? STRIP : (left < 0 ? 0 : (int)left);
-                            hm = left >= 0 && left < STRIP;
-                            for (int k = 0; k < STRIP; ++k) {
-                                strips[lane].YC[k] = pk.NEGKEY;
-                                const uint32_t i = row0 + (uint32_t)k;
-                                if (first && sc.yp != MIN_SCORE && sc.xp == MIN_SCORE && i <= en.m)
-                                    strips[lane].YC[k] = pk_key(pk, (int64_t)sc.yp + sc.o + (int64_t)sc.e * i - B, PP_YC, col0_slen(sc, i, en.m));
-                            }
-                        }
-                        nvs[lane] = nv; hasm[lane] = hm;
-                        if (special) pk_pass1<true, false>(pk, pc, Sp + base, Dp + base, Sdg0, x, Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
-                        else pk_pass1<false, false>(pk, pc, Sp + base, Dp + base, Sdg0, x, Jc, false, wbase, STRIP, false, strips[lane]);
+        std::vector<PkRowM> stash(C);
+        const uint32_t Weff = std::min<uint32_t>((uint32_t)W, NT);
+        const bool ycmode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
+        for (uint32_t w = 0; w < Weff; ++w) {
+            const uint32_t t_lo = (uint32_t)((uint64_t)NT * w / Weff), t_hi = (uint32_t)((uint64_t)NT * (w + 1) / Weff);
+            int32_t prev_exit = 0; uint32_t prev_exit_open = 0;
+            for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
+                const uint32_t a = A.owner[tile];
+                const ContigEntry &en = A.ent[a];
+                const uint32_t tic = tile - en.tile_start;
+                const bool first = tic == 0, lastt = tic + 1 == en.ntiles;
+                const bool special = first || lastt;
+                const int32_t Jc = pk_jc(pk, pc, A.J[a].score, A.J[a].len);
+                const bool wrap0 = first && en.circular && st.tbm[a] != TB_XCLIP_SUFFIX;
+                const int32_t wbase = pk_wbase(pk, st.SmKey[a]);
+                PStrip strips[32];
+                int nvs[32]; bool hasm[32];
+                uint8_t xs[32][STRIP];
+                auto fill_yc = [&](PStrip &ps, uint32_t row0, bool in_first) {
+                    for (int k = 0; k < STRIP; ++k) {
+                        ps.YC[k] = pk.NEGKEY;
+                        const uint32_t i = row0 + (uint32_t)k;
+                        if (in_first && ycmode && i <= en.m)
+                            ps.YC[k] = pk_key(pk, (int64_t)sc.yp + sc.o + (int64_t)sc.e * i - B, PP_YC, col0_slen(sc, i, en.m));
                     }
-                    int32_t tmax = pk.NEGKEY;
-                    for (uint32_t lane = 0; lane < 32; ++lane) {
-                        const uint32_t base = tile * TILE + lane * STRIP;
-                        int32_t cin;
-                        if (lane > 0) cin = pk_carry_from_exit(pk, strips[lane - 1].exit);
-                        else if (first) cin = pk_carry_row1(pk, pc, sc, r0);
-                        else if (tile == t_lo) {   // chunk start inside a contig: the halo strip (rows row0-8 .. row0-1)
-                            const uint32_t hb = tile * TILE - STRIP;
-                            uint8_t x[STRIP];
-                            const uint32_t hrow0 = tic * TILE - STRIP + 1;
-                            for (int k = 0; k < STRIP; ++k) x[k] = bases[en.seq_off + hrow0 + k - 1];
-                            const bool hfirst = (tic == 1);   // the halo lies in the contig's first tile
-                            PStrip h;
-                            for (int k = 0; k < STRIP; ++k) {
-                                h.YC[k] = pk.NEGKEY;
-                                const uint32_t i = hrow0 + (uint32_t)k;
-                                if (hfirst && sc.yp != MIN_SCORE && sc.xp == MIN_SCORE)
-                                    h.YC[k] = pk_key(pk, (int64_t)sc.yp + sc.o + (int64_t)sc.e * i - B, PP_YC, col0_slen(sc, i, en.m));
-                            }
-                            pk_pass1<true, false>(pk, pc, Sp + hb, Dp + hb, Sp[hb - 1], x, Jc, false, wbase, STRIP, false, h);
-                            cin = pk_carry_from_exit(pk, h.exit);
-                        } else cin = pk_carry_from_exit(pk, prev_exit);
-                        int32_t S[STRIP]; int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
-                        if (special) pk_pass2<true, false>(pk, pc, strips[lane], cin, 0, nvs[lane], hasm[lane], S, colmax, nullptr, I_m, iext_m);
-                        else pk_pass2<false, false>(pk, pc, strips[lane], cin, 0, STRIP, false, S, colmax, nullptr, I_m, iext_m);
-                        for (int k = 0; k < nvs[lane]; ++k) { Sc[base + k] = S[k]; Dc[base + k] = strips[lane].D6[k]; }
-                        if (hasm[lane]) {
-                            const int km = nvs[lane];
-                            stash[a] = RowMStash{strips[lane].A[km], strips[lane].D6[km], strips[lane].jp[km], I_m, false};
-                            Dc[base + km] = strips[lane].D6[km];
-                        }
-                        tmax = pk_max(tmax, colmax);
+                };
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint32_t row0 = tic * TILE + lane * STRIP + 1;
+                    const uint32_t base = tile * TILE + lane * STRIP;
+                    const int32_t Sdg0 = row0 == 1 ? pk_from_wide(pk, A.Bprev, r0p.S, r0p.sl, 0) : Sp[base - 1];
+                    for (int k = 0; k < STRIP; ++k) xs[lane][k] = row0 + k <= en.m ? bases[en.seq_off + row0 + k - 1] : 0;
+                    int nv = STRIP; bool hm = false;
+                    if (special) {
+                        const int64_t left = (int64_t)en.m - (int64_t)row0;
+                        nv = left >= STRIP ? STRIP : (left < 0 ? 0 : (int)left);
+                        hm = left >= 0 && left < STRIP;
+                        fill_yc(strips[lane], row0, first);
                     }
-                    tilemax[tile] = tmax;
-                    prev_exit = strips[31].exit;
+                    nvs[lane] = nv; hasm[lane] = hm;
+                    if (A.tb) {
+                        if (special) pk_pass1<true, true>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
+                        else pk_pass1<false, true>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, false, wbase, STRIP, false, strips[lane]);
+                    } else {
+                        if (special) pk_pass1<true, false>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
+                        else pk_pass1<false, false>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, false, wbase, STRIP, false, strips[lane]);
+                    }
                 }
+                int32_t tmax = pk.NEGKEY;
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint32_t row0 = tic * TILE + lane * STRIP + 1;
+                    const uint32_t base = tile * TILE + lane * STRIP;
+                    int32_t cin; uint32_t cin_open = 0;
+                    if (lane > 0) { cin = pk_carry_from_exit(pk, strips[lane - 1].exit); cin_open = strips[lane - 1].exit_open; }
+                    else if (first) { cin = pk_carry_row1(pk, pc, sc, r0); cin_open = 1; }
+                    else if (tile == t_lo) {   // chunk start inside a contig: the halo strip (rows row0-8 .. row0-1)
+                        const uint32_t hb = tile * TILE - STRIP;
+                        uint8_t x[STRIP];
+                        const uint32_t hrow0 = tic * TILE - STRIP + 1;
+                        for (int k = 0; k < STRIP; ++k) x[k] = bases[en.seq_off + hrow0 + k - 1];
+                        PStrip h;
+                        fill_yc(h, hrow0, tic == 1);
+                        pk_pass1<true, true>(pk, pc, Sp + hb, Dp + hb, Sp[hb - 1], x, Jc, false, wbase, STRIP, false, h);
+                        cin = pk_carry_from_exit(pk, h.exit); cin_open = h.exit_open;
+                    } else { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }
+                    int32_t S[STRIP], Iarr[STRIP]; uint8_t tbb[STRIP];
+                    int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
+                    if (A.tb) {
+                        if (special) pk_pass2<true, true>(pk, pc, strips[lane], cin, cin_open, nvs[lane], hasm[lane], S, colmax, tbb, Iarr, I_m, iext_m);
+                        else pk_pass2<false, true>(pk, pc, strips[lane], cin, cin_open, STRIP, false, S, colmax, tbb, Iarr, I_m, iext_m);
+                    } else {
+                        if (special) pk_pass2<true, false>(pk, pc, strips[lane], cin, 0, nvs[lane], hasm[lane], S, colmax, nullptr, nullptr, I_m, iext_m);
+                        else pk_pass2<false, false>(pk, pc, strips[lane], cin, 0, STRIP, false, S, colmax, nullptr, nullptr, I_m, iext_m);
+                    }
+                    for (int k = 0; k < nvs[lane]; ++k) {
+                        Sc[base + k] = S[k]; Dc[base + k] = strips[lane].D6[k];
+                        if (A.tb) {
+                            const uint32_t i = row0 + (uint32_t)k;
+                            if (A.tb_col) A.tb_col[base + k] = tbb[k];
+                            if (A.track || A.lastcol)
+                                pk_cell_records(pk, pc, sc, S[k], Iarr[k], tbb[k], xs[lane][k] == pc.q, en.contig_idx, i, en.m, A.J[a], j, n,
+                                                A.track ? &A.sn[row_index(en, i)] : nullptr, A.lastcol ? &A.last[row_index(en, i)] : nullptr);
+                        }
+                    }
+                    if (hasm[lane]) {
+                        const int km = nvs[lane];
+                        stash[a] = PkRowM{strips[lane].A[km], strips[lane].D6[km], strips[lane].jp[km], I_m, A.tb ? strips[lane].fl[km] : 0u, iext_m};
+                        Dc[base + km] = strips[lane].D6[km];
+                    }
+                    tmax = pk_max(tmax, colmax);
+                }
+                tilemax[tile] = tmax;
+                prev_exit = strips[31].exit; prev_exit_open = strips[31].exit_open;
             }
-            // per contig: tracker / column best over rows < m, finish row m (wide arithmetic), column best
-            for (uint32_t a = 0; a < C; ++a) {
-                const ContigEntry &en = L.ent[a];
-                int32_t kmax = pk.NEGKEY;
-                for (uint32_t t = 0; t < en.ntiles; ++t) kmax = pk_max(kmax, tilemax[en.tile_start + t]);
-                CmPart rows; cm_init(rows);
-                XsPart tr; xs_init(tr);
-                if (en.m >= 2) {
-                    const int32_t smax = pk_rel(pk, kmax);
-                    uint32_t frow = 0;
-                    for (uint32_t t = 0; t < en.ntiles && !frow; ++t) {
-                        if (pk_rel(pk, tilemax[en.tile_start + t]) != smax) continue;
+        }
+        // per contig: tracker / column best over rows < m, finish row m, column best
+        for (uint32_t a = 0; a < C; ++a) {
+            const ContigEntry &en = A.ent[a];
+            int32_t kmax = pk.NEGKEY;
+            for (uint32_t t = 0; t < en.ntiles; ++t) kmax = pk_max(kmax, tilemax[en.tile_start + t]);
+            CmPart rows; cm_init(rows);
+            XsPart tr; xs_init(tr);
+            if (en.m >= 2) {
+                const int32_t smax = pk_rel(pk, kmax);
+                auto first_row = [&](bool full_key) -> uint32_t {
+                    for (uint32_t t = 0; t < en.ntiles; ++t) {
+                        const int32_t tm = tilemax[en.tile_start + t];
+                        if (full_key ? tm != kmax : pk_rel(pk, tm) != smax) continue;
                         for (uint32_t r = 0; r < (uint32_t)TILE; ++r) {
                             const uint32_t i = t * TILE + r + 1;
                             if (i >= en.m) break;
-                            if (pk_rel(pk, Sc[(en.tile_start + t) * TILE + r]) == smax) { frow = i; break; }
+                            const int32_t key = Sc[(en.tile_start + t) * TILE + r];
+                            if (full_key ? key == kmax : pk_rel(pk, key) == smax) return i;
                         }
                     }
-                    if (!frow) throw Error(STITCH_ERR_INTERNAL, "emul packed: column best not found");
-                    const int32_t fkey = Sc[row_linear(en, frow)];
-                    rows.S = B + smax; rows.row = frow; rows.sl = pk_len(pk, fkey); rows.valid = 1;
-                    if (sc.xs != MIN_SCORE) { tr.t = B + smax + sc.xs; tr.len = pk_len(pk, kmax); tr.row = 1; }
+                    throw Error(STITCH_ERR_INTERNAL, "emul packed: column best not found");
+                };
+                const uint32_t frow = first_row(false);
+                const int32_t fkey = Sc[row_linear(en, frow)];
+                rows.S = B + smax; rows.row = frow; rows.sl = pk_len(pk, fkey); rows.valid = 1;
+                if (sc.xs != MIN_SCORE) { tr.t = B + smax + sc.xs; tr.len = pk_len(pk, kmax); tr.row = A.tb ? first_row(true) : 1; }
+            }
+            const PkRowMOut fo = pk_finish_rowm(pk, pc, sc, stash[a], tr, r0, A.J[a], bases[en.seq_off + en.m - 1] == pc.q, en.contig_idx, en.m, j);
+            const RowMOut &ro = fo.ro;
+            Sc[row_linear(en, en.m)] = fo.skey;
+            if (A.tb) {
+                if (A.tb_col) A.tb_col[row_linear(en, en.m)] = (uint8_t)fo.tbbyte;
+                if (A.colrec_col) {
+                    ColRec &cr = A.colrec_col[a];
+                    cr.jscore = A.J[a].score; cr.jlen = A.J[a].len; cr.jidx = A.J[a].idx; cr.jfrom = A.J[a].from; cr.lx = ro.lx;
                 }
-                const RowMStash &sm_ = stash[a];
-                RowM rm{};
-                rm.diag = pk_abs(pk, B, sm_.diag); rm.dgl = pk_len(pk, sm_.diag);
-                rm.D = pk_abs(pk, B, sm_.D6); rm.dl = pk_len(pk, sm_.D6); rm.dext = 0;
-                rm.I = pk_abs(pk, B, sm_.I); rm.il = pk_len(pk, sm_.I); rm.iext = 0;
-                rm.jp.score = pk_abs(pk, B, sm_.jp); rm.jp.len = pk_len(pk, sm_.jp); rm.jp.idx = 0; rm.jp.from = 0;
-                rm.xclip = sc.xp + std::max(sc.yp, sc.o + sc.e * (int32_t)j); rm.xclip_len = r0.sl;
-                rm.yclip = sc.yp + sc.o + sc.e * (int32_t)en.m; rm.yclip_len = 0;
-                rm.is_match = bases[en.seq_off + en.m - 1] == pc.q;
-                const RowMOut ro = finish_rowm(sc, rm, tr, en.contig_idx, en.m);
-                Sc[row_linear(en, en.m)] = pk_from_wide(pk, B, ro.c.S, ro.c.sl, 0);
-                CmPart cmv; cm_init(cmv);
-                cm_add(cmv, r0.S, r0.sl, 0);
-                cmv = cm_merge(cmv, rows);
-                CmPart top; top.S = ro.c.S; top.row = en.m; top.sl = ro.c.sl; top.valid = 1;
-                cmv = cm_merge(cmv, top);
-                cm[a] = cmv.S; cmk[a] = cmv.row; cml[a] = cmv.sl;
-                Sm[a] = ro.c.S; slm[a] = ro.c.sl; tbm[a] = ro.s_tb;
-                SmKey[a] = Sc[row_linear(en, en.m)];
+                const uint32_t p = row_index(en, en.m);
+                if (A.track) sn_update(sc, A.sn[p], ro.c.S, ro.c.sl, ro.c.idx, j, n);
+                if (A.lastcol) {
+                    LastCell lc; lc.S = ro.c.S; lc.I = pk_abs(pk, B, stash[a].I); lc.sl = ro.c.sl; lc.il = pk_len(pk, stash[a].I);
+                    lc.idx = ro.c.idx; lc.from = ro.c.from; lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0;
+                    lc.flags = (uint8_t)((stash[a].iext ? 1 : 0) | ((stash[a].fl & 1u) ? 2 : 0)); lc.pad = 0; lc.pad2 = 0;
+                    A.last[p] = lc;
+                }
             }
-            {
-                int32_t gg = cm[0];
-                for (uint32_t a = 1; a < C; ++a) gg = std::max(gg, cm[a]);
-                F.gcol[j] = gg;
+            CmPart cmv; cm_init(cmv);
+            cm_add(cmv, r0.S, r0.sl, 0);
+            cmv = cm_merge(cmv, rows);
+            CmPart top; top.S = ro.c.S; top.row = en.m; top.sl = ro.c.sl; top.valid = 1;
+            cmv = cm_merge(cmv, top);
+            st.cm[a] = cmv.S; st.cmk[a] = cmv.row; st.cml[a] = cmv.sl;
+            st.Sm[a] = ro.c.S; st.slm[a] = ro.c.sl; st.tbm[a] = ro.s_tb;
+            st.SmKey[a] = fo.skey;
+        }
+    }
+
+    static int32_t max_of(const std::vector<int32_t> &v) { int32_t g = v[0]; for (int32_t x : v) g = std::max(g, x); return g; }
+    static std::vector<uint32_t> owners_of(const ContigEntry *ent, uint32_t C, uint32_t NT) {
+        std::vector<uint32_t> o(NT);
+        for (uint32_t a = 0; a < C; ++a) for (uint32_t t = 0; t < ent[a].ntiles; ++t) o[ent[a].tile_start + t] = a;
+        return o;
+    }
+
+    // Bulk: all n columns, no traceback outputs.  Leaves wide checkpoints, colrec[j] jump records, gcol.
+    void fill_packed_bulk(const Job &job, const Layout &L, uint32_t LB, Fill &F) {
+        const Scoring &sc = al.opts.sc;
+        const uint32_t C = (uint32_t)L.ent.size(), PM = L.PM(), NT = L.n_tiles, n = job.n;
+        const PK pk = pk_make(sc, LB);
+        stats.cells += (uint64_t)L.cells_per_col * n;
+        stats.fills += 1;
+        PkState st;
+        pk_state_init0(pk, L.ent.data(), C, PM, st);
+        const std::vector<uint32_t> owner = owners_of(L.ent.data(), C, NT);
+        F.gcol[0] = 0;
+        std::vector<JumpInfo> J(C);
+        int32_t B = 0;
+        for (uint32_t j = 1; j <= n; ++j) {
+            const int32_t Bprev = B;
+            B = max_of(st.cm);
+            for (uint32_t a = 0; a < C; ++a) {
+                J[a] = select_jump(sc, L.ent.data(), C, a, st.cm.data(), st.cml.data(), st.cmk.data());
+                ColRec &cr = F.colrec[(size_t)j * C + a];
+                cr.jscore = J[a].score; cr.jlen = J[a].len; cr.jidx = J[a].idx; cr.jfrom = J[a].from;
             }
-            // wide checkpoints / hand-over
-            const bool ck = (j % K == 0) && j < n;
-            if (ck || j == j1) {
+            PkCol A{};
+            A.ent = L.ent.data(); A.C = C; A.NT = NT; A.owner = owner.data(); A.read = job.read; A.j = j; A.n = n;
+            A.B = B; A.Bprev = Bprev; A.J = J.data();
+            packed_column(pk, A, st);
+            F.gcol[j] = max_of(st.cm);
+            if ((j % K == 0) && j < n) {
+                const int32_t *Sc = st.S[j & 1].data(), *Dc = st.D[j & 1].data();
                 for (uint32_t a = 0; a < C; ++a) {
                     const ContigEntry &en = L.ent[a];
                     for (uint32_t i = 1; i <= en.m; ++i) {
                         const int32_t s = Sc[row_linear(en, i)], d = Dc[row_linear(en, i)];
-                        const CellState cs{pk_abs(pk, B, s), pk_abs(pk, B, d), pk_len(pk, s), pk_len(pk, d)};
-                        if (ck) F.ck_state[(size_t)(j / K - 1) * PM + row_index(en, i)] = cs;
-                        if (j == j1) F.hand_state[row_index(en, i)] = cs;
+                        F.ck_state[(size_t)(j / K - 1) * PM + row_index(en, i)] = CellState{pk_abs(pk, B, s), pk_abs(pk, B, d), pk_len(pk, s), pk_len(pk, d)};
                     }
-                    const CkSum sum{Sm[a], slm[a], tbm[a], 0};
-                    if (ck) F.ck_sum[(size_t)(j / K - 1) * C + a] = sum;
-                    if (j == j1) F.hand_sum[a] = sum;
+                    F.ck_sum[(size_t)(j / K - 1) * C + a] = CkSum{st.Sm[a], st.slm[a], st.tbm[a], 0};
                 }
             }
         }
     }
 
-    void fill(const Job &job, const Layout &L, uint32_t track_from, Fill &F, bool allow_packed) {
+    // Tail: columns (j0, n] again (j0 = 0 or a checkpointed column) in the traceback variant, with the
+    // y-suffix trackers of every row and the column-n records the fix-up needs.
+    void fill_packed_tail(const Job &job, const Layout &L, uint32_t LB, uint32_t j0, bool tracked, Fill &F) {
+        const Scoring &sc = al.opts.sc;
+        const uint32_t C = (uint32_t)L.ent.size(), PM = L.PM(), NT = L.n_tiles, n = job.n;
+        const PK pk = pk_make(sc, LB);
+        stats.cells += (uint64_t)L.cells_per_col * (n - j0);
+        PkState st;
+        if (j0 == 0) pk_state_init0(pk, L.ent.data(), C, PM, st);
+        else pk_state_from_ck(pk, L.ent.data(), L.ent.data(), C, PM, j0, F.gcol[j0 - 1], F.ck_state.data() + (size_t)(j0 / K - 1) * PM,
+                              F.ck_sum.data() + (size_t)(j0 / K - 1) * C, st);
+        if (tracked)
+            for (uint32_t a = 0; a < C; ++a) {
+                const ContigEntry &en = L.ent[a];
+                for (uint32_t i = 1; i <= en.m; ++i) { Col0 c0 = col0_at(sc, i, en.m); F.sn[row_index(en, i)] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n); }
+            }
+        const std::vector<uint32_t> owner = owners_of(L.ent.data(), C, NT);
+        std::vector<JumpInfo> J(C);
+        for (uint32_t j = j0 + 1; j <= n; ++j) {
+            for (uint32_t a = 0; a < C; ++a) { const ColRec &cr = F.colrec[(size_t)j * C + a]; J[a] = JumpInfo{cr.jscore, cr.jlen, cr.jidx, cr.jfrom}; }
+            PkCol A{};
+            A.ent = L.ent.data(); A.C = C; A.NT = NT; A.owner = owner.data(); A.read = job.read; A.j = j; A.n = n;
+            A.B = F.gcol[j - 1]; A.Bprev = j >= 2 ? F.gcol[j - 2] : 0; A.J = J.data();
+            A.tb = true; A.tb_col = nullptr; A.colrec_col = F.colrec.data() + (size_t)j * C;
+            A.track = tracked; A.sn = F.sn.data(); A.lastcol = j == n; A.last = F.last.data();
+            packed_column(pk, A, st);
+        }
+    }
+
+    void load_unit_packed(const Job &job, const Layout &L, uint32_t LB, const Fill &F, uint32_t a, uint32_t j, std::vector<uint8_t> &bytes,
+                          std::vector<ColRec> &ucr, TbUnit &u) {
+        const Scoring &sc = al.opts.sc;
+        const uint32_t C = (uint32_t)L.ent.size(), PM = L.PM(), n = job.n;
+        const uint32_t b = (j - 1) / K, jb = b * K, je = std::min(jb + K, n);
+        const PK pk = pk_make(sc, LB);
+        ContigEntry en = L.ent[a];
+        const uint32_t pm = en.ntiles * TILE;
+        const ContigEntry en_ck = en;
+        en.tile_start = 0;
+        PkState st;
+        if (b == 0) pk_state_init0(pk, &en, 1, pm, st);
+        else pk_state_from_ck(pk, &en, &en_ck, 1, pm, jb, F.gcol[jb - 1], F.ck_state.data() + (size_t)(b - 1) * PM,
+                              F.ck_sum.data() + (size_t)(b - 1) * C + a, st);
+        bytes.assign((size_t)(je - jb) * pm, 0);
+        ucr.assign(je - jb, ColRec{});
+        stats.cells += (uint64_t)en.m * (je - jb);
+        const std::vector<uint32_t> owner(en.ntiles, 0);
+        for (uint32_t jj = jb + 1; jj <= je; ++jj) {
+            const ColRec &cr = F.colrec[(size_t)jj * C + a];
+            JumpInfo J{cr.jscore, cr.jlen, cr.jidx, cr.jfrom};
+            PkCol A{};
+            A.ent = &en; A.C = 1; A.NT = en.ntiles; A.owner = owner.data(); A.read = job.read; A.j = jj; A.n = n;
+            A.B = F.gcol[jj - 1]; A.Bprev = jj >= 2 ? F.gcol[jj - 2] : 0; A.J = &J;
+            A.tb = true; A.tb_col = bytes.data() + (size_t)(jj - jb - 1) * pm; A.colrec_col = ucr.data() + (jj - jb - 1);
+            packed_column(pk, A, st);
+        }
+        u.bytes = bytes.data(); u.cr = ucr.data(); u.a = a; u.jb = jb; u.je = je; u.pm = pm;
+    }
+
+    // Returns the length bits of the packed path, or 0 when the read ran on the wide path.
+    uint32_t fill(const Job &job, const Layout &L, uint32_t track_from, Fill &F, bool allow_packed) {
         const Scoring &sc = al.opts.sc;
         const uint32_t n = job.n;
         alloc(job, L, F);
         uint32_t m_max = 0;
         for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
         const uint32_t LB = (allow_packed && PACKED) ? pk_plan(sc, n, m_max) : 0;
-        const uint32_t j1 = (LB && n > WINDOW + 1) ? n - WINDOW : 0;
-        if (j1 > 0) { fill_packed(job, L, LB, j1, F); ++stats.launches; if (std::getenv("EMUL_TRACE")) fprintf(stderr, "PACKED n=%u j1=%u LB=%u\n", n, j1, LB); } else if (std::getenv("EMUL_TRACE")) fprintf(stderr, "WIDE n=%u LB=%u\n", n, LB);
-        fill_wide(job, L, j1, std::max(track_from, j1 + 1), F);
+        if (!LB) { fill_wide(job, L, 0, track_from, F); return 0; }
+        fill_packed_bulk(job, L, LB, F);
+        // the tail restarts at the last checkpoint before the first column that can hold a final y-suffix
+        // tracker (dp_core.h: first_candidate_column); column n is always part of it
+        const bool tracked = sc.ys != MIN_SCORE;
+        const uint32_t jc = tracked ? std::min(first_candidate_column(sc, F.gcol.data(), n), n) : n;
+        const uint32_t j0 = ((jc - 1) / K) * K;
+        fill_packed_tail(job, L, LB, j0, tracked, F);
+        F.need_full_track = false;
+        ++stats.launches;
+        return LB;
     }
 
     // Re-fills contig `a` over the block of columns holding column j.
@@ -470,7 +597,7 @@ struct EmulBackend : Backend {
         const bool tracked_mode = sc.ys != MIN_SCORE;   // Sn can only matter when y-suffix clipping is free
         uint32_t track_from = tracked_mode ? (n > WINDOW ? n - WINDOW + 1 : 1) : n + 1;
         Fill F;
-        fill(job, L, track_from, F, true);
+        const uint32_t LB = fill(job, L, track_from, F, true);
         if (F.need_full_track) { ++stats.launches; fill(job, L, 1, F, false); }
         for (uint32_t a = 0; a < C; ++a)
             fixup_contig(sc, L.ent[a], n, F.last.data(), F.sn.data(), tracked_mode, &F.colrec[(size_t)n * C + a].lx);
@@ -489,7 +616,10 @@ struct EmulBackend : Backend {
                 WalkState ws;
                 walk_begin(v, a_end, rc.ops.data(), c, ws, rc.h);
                 uint32_t s;
-                while ((s = walk_run(v, ws, rc.h)) == WALK_NEED_UNIT) load_unit(job, L, F, ws.a, ws.j, unit_bytes, unit_cr, v.unit);
+                while ((s = walk_run(v, ws, rc.h)) == WALK_NEED_UNIT) {
+                    if (LB) load_unit_packed(job, L, LB, F, ws.a, ws.j, unit_bytes, unit_cr, v.unit);
+                    else load_unit(job, L, F, ws.a, ws.j, unit_bytes, unit_cr, v.unit);
+                }
                 if (s != WALK_OVERFLOW) break;
                 c *= 2;
             }
