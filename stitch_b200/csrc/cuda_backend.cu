@@ -37,6 +37,7 @@ using host::Error;
 
 constexpr int FILL_WARPS = 8;
 constexpr int PACK_WARPS = 16;
+constexpr int WALK_WARPS = 16;
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -102,8 +103,14 @@ struct CudaBackend : host::Backend {
     DevBuf<CkSum> d_handsum;
     DevBuf<int32_t> d_pstate, d_wpstate;
     DevBuf<uint32_t> d_tailj0;
+    DevBuf<unsigned long long> d_dbg;
+    bool debug_stats = false;
     DevBuf<ColRec> d_ucr;
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    uint32_t l2_persist = 0;   // STITCH_L2_PERSIST=1: pin the rolling state of the packed kernel in the L2 (measured: no gain)
     uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
+    uint32_t cluster_pref = 1; // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8); measured best on config 2: 1
+    uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
     DevBuf<ColRec> d_colrec;
@@ -132,6 +139,8 @@ struct CudaBackend : host::Backend {
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
         num_sms = prop.multiProcessorCount;
+        l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+        l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
         d_contigs.reserve(al.contigs.blob.size() + 1024);   // strips of the last tile over-read
@@ -140,6 +149,11 @@ struct CudaBackend : host::Backend {
         K = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K));
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
         use_packed = env_u32("STITCH_PACKED", 1);
+        debug_stats = env_u32("STITCH_DEBUG_STATS", 0) != 0;
+        l2_persist = env_u32("STITCH_L2_PERSIST", 0);
+        if (l2_persist && l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
+        cluster_pref = std::min<uint32_t>(8, std::max<uint32_t>(1, env_u32("STITCH_CLUSTER", cluster_pref)));
+        cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
     }
     ~CudaBackend() override {
         cudaSetDevice(device);
@@ -269,8 +283,26 @@ struct CudaBackend : host::Backend {
         d_ops.reserve(ops_n); d_chains.reserve(chains_n); d_jobout.reserve(nj);
         d_state.reserve((uint64_t)grid * 2 * pm_max);
         d_hand.reserve(cell_n); d_handsum.reserve(handsum_n);
-        const uint32_t pgrid = std::min<uint32_t>(n_packed, (uint32_t)num_sms);
-        d_pstate.reserve((uint64_t)pgrid * 2 * ppm_max + 64);
+        // CTAs per read: a cluster of 4 keeps the rolling state of all reads in flight inside the L2 (fewer, faster reads
+        // in flight); small layouts and STITCH_CLUSTER=1 use a single CTA per read
+        uint32_t cluster = cluster_pref;
+        if (ntmax < cluster_min_tiles) cluster = 1;
+        uint32_t pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms / cluster);
+        if (cluster > 1 && n_packed) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)num_sms / cluster * cluster); cfg.blockDim = dim3(PACK_WARPS * 32);
+            cfg.dynamicSmemBytes = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
+            set_smem(fill_packed_kernel<PACK_WARPS>, cfg.dynamicSmemBytes);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, fill_packed_kernel<PACK_WARPS>, &cfg) == cudaSuccess && max_clusters > 0)
+                pteams = std::min<uint32_t>(pteams, (uint32_t)max_clusters);
+            else { cudaGetLastError(); cluster = 1; pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms); }
+        }
+        d_pstate.reserve((uint64_t)pteams * 2 * ppm_max + 64);
         d_tailj0.reserve(nj);
         const uint64_t wps_half = (uint64_t)max_ctiles * TILE;
         d_wpstate.reserve((uint64_t)grid * 2 * wps_half + 64);
@@ -304,28 +336,49 @@ struct CudaBackend : host::Backend {
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
         P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles;
+        if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
         set_smem(fill_wide_kernel<FILL_WARPS>, smem);
         mark(T_PACKED);
         const uint32_t n_wide = nj - n_packed;
         if (n_packed) {
-            // the order list of the packed kernels: jobs on the packed path, largest first
+            // the order list of the packed kernel: jobs on the packed path, largest first
             uint32_t *po = h_order.p + 2 * (size_t)nj;
             uint32_t c = 0;
             for (uint32_t k = 0; k < nj; ++k) if (h_jobs.p[h_order.p[k]].LB) po[c++] = h_order.p[k];
             CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj, po, c * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
             Params Q = P; Q.order = d_order.p + 2 * (size_t)nj; Q.n_jobs = c; Q.counter = d_counter.p + 3;
+            Q.cluster_size = cluster;
             const size_t psmem = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
             set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
-            set_smem(tail_packed_kernel<PACK_WARPS>, psmem);
-            fill_packed_kernel<PACK_WARPS><<<pgrid, PACK_WARPS * 32, psmem, stream>>>(Q);
-            CUDA_CHECK(cudaGetLastError());
-            mark(T_TAIL);
-            Q.counter = d_counter.p + 4;
-            tail_packed_kernel<PACK_WARPS><<<pgrid, PACK_WARPS * 32, psmem, stream>>>(Q);
-            CUDA_CHECK(cudaGetLastError());
-            stats.launches += 2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(PACK_WARPS * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
+            cudaLaunchAttribute at[2];
+            unsigned na = 0;
+            if (cluster > 1) {
+                at[na].id = cudaLaunchAttributeClusterDimension;
+                at[na].val.clusterDim.x = cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+                ++na;
+            }
+            if (l2_persist && l2_persist_max && l2_window_max) {
+                // pin (a fraction of) the rolling column state in the L2: every line of it is read and rewritten once per
+                // column, everything else the kernel touches streams
+                const size_t bytes = (size_t)pteams * 2 * ppm_max * sizeof(int32_t);
+                const size_t win = std::min(bytes, l2_window_max);
+                at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+                at[na].val.accessPolicyWindow.base_ptr = d_pstate.p;
+                at[na].val.accessPolicyWindow.num_bytes = win;
+                at[na].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)l2_persist_max * 0.9 / (double)win);
+                at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                ++na;
+                if (debug_stats) std::fprintf(stderr, "[stitch dbg] L2 persist max %zu MB, window max %zu MB, state %zu MB, hitRatio %.2f\n",
+                                              l2_persist_max >> 20, l2_window_max >> 20, bytes >> 20, at[na - 1].val.accessPolicyWindow.hitRatio);
+            }
+            cfg.attrs = at; cfg.numAttrs = na;
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
+            stats.launches += 1;
         }
         mark(T_WIDE);
         if (n_wide) {
@@ -373,9 +426,14 @@ struct CudaBackend : host::Backend {
         mark(T_WALK);
         {
             Params Wp = P; Wp.counter = d_counter.p + 2;
-            const size_t wsmem = std::max(WideSmem<FILL_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, FILL_WARPS));
-            set_smem(walk_kernel<FILL_WARPS>, wsmem);
-            walk_kernel<FILL_WARPS><<<grid, FILL_WARPS * 32, wsmem, stream>>>(Wp);
+            size_t wsmem = std::max(WideSmem<WALK_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, WALK_WARPS, false));
+            wsmem = (wsmem + 15) / 16 * 16;
+            Wp.walk_stage_smem_off = (uint32_t)wsmem;
+            wsmem += (UnitStage::bytes(K, max_ctiles) + 15) / 16 * 16;
+            const size_t state_b = 2 * wps_half * sizeof(int32_t);
+            if (wsmem + state_b <= 160 * 1024) { Wp.walk_state_smem_off = (uint32_t)wsmem; wsmem += state_b; }
+            set_smem(walk_kernel<WALK_WARPS>, wsmem);
+            walk_kernel<WALK_WARPS><<<std::min<uint32_t>(nj, (uint32_t)num_sms), WALK_WARPS * 32, wsmem, stream>>>(Wp);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
@@ -386,6 +444,12 @@ struct CudaBackend : host::Backend {
         mark(T_END);
         sync("walk");
         collect_marks();
+        if (debug_stats) {
+            unsigned long long h[16];
+            cudaMemcpy(h, d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "[stitch dbg] jobs %u: tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, refill columns %llu, "
+                         "refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6], h[4] * 1e-6, h[5] * 1e-6);
+        }
         stats.tb_bytes += ck_n * sizeof(CellState) + colrec_n * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);
 

@@ -6,7 +6,7 @@
 //                        column-state checkpoints every K columns, the jump record of every
 //                        (contig, column), the best score of every column, and the column the tail
 //                        must restart from.
-//   tail_packed_kernel   the last columns again, from a checkpoint, in the traceback variant: keeps
+//   pk_tail (same kernel) the last columns again, from a checkpoint, in the traceback variant: keeps
 //                        the y-suffix trackers of every row (SCA:432-447) for every column that can
 //                        still hold a final tracker value, and the column-n records the end-of-read
 //                        fix-up edits (SCA:453-555).
@@ -25,21 +25,41 @@
 //   * per column three CTA barriers: jump selection | tiles | per-contig finish (x-suffix tracker,
 //     row m, column best incl. first-row lookup, SCA:407-429, 677-697).
 #pragma once
+#include <cooperative_groups.h>
+#include <cuda_pipeline_primitives.h>
+
 #include "dp_packed.h"
 #include "kernels_wide.cuh"
 
 namespace stitch {
 namespace gpu {
 
+namespace cg = cooperative_groups;
+
+// The CTAs that share one read: a thread-block cluster (size > 1) or a single CTA.  A cluster splits the tiles
+// of every column over its CTAs; the small per-contig tables live in every CTA's shared memory and are kept
+// identical through distributed-shared-memory stores, ordered by two cluster barriers per column.
+struct Team {
+    uint32_t rank, size;
+    __device__ __forceinline__ void sync() const { if (size > 1) cg::this_cluster().sync(); else __syncthreads(); }
+    template <typename T>
+    __device__ __forceinline__ T *peer(T *p, uint32_t r) const { return size > 1 ? cg::this_cluster().map_shared_rank(p, r) : p; }
+};
+
 struct PackSmem {
     int32_t *Jc, *cm, *Sm, *SmKey, *tilemax, *haloS, *haloD;
     uint32_t *cml, *cmk, *slm, *tbm, *haloF;
     PkRowM *stash;
     JumpInfo *Jw;
-    static size_t bytes(uint32_t cmax, uint32_t ntmax, int W) {
-        return sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) + (sizeof(PkRowM) + sizeof(JumpInfo)) * cmax + 64;
+    unsigned char *stage;   // [W][2][STAGE_BYTES]: cp.async double buffer of the next tile (state in global memory only)
+    static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + TILE;   // S keys, D keys, bases of one tile
+    static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, bool staged = true) {
+        return (staged ? (size_t)W * 2 * STAGE_BYTES : 0) + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) +
+               (sizeof(PkRowM) + sizeof(JumpInfo)) * cmax + 64;
     }
-    __device__ void carve(unsigned char *raw, uint32_t cmax, uint32_t ntmax, int W) {
+    __device__ void carve(unsigned char *raw, uint32_t cmax, uint32_t ntmax, int W, bool staged = true) {
+        stage = raw;
+        if (staged) raw += (size_t)W * 2 * STAGE_BYTES;
         Jw = reinterpret_cast<JumpInfo *>(raw);
         stash = reinterpret_cast<PkRowM *>(Jw + cmax);
         Jc = reinterpret_cast<int32_t *>(stash + cmax);
@@ -64,13 +84,22 @@ struct PackCtx {            // uniform per (job, set of contigs)
     int32_t *Sst, *Dst;
     uint32_t n;
     bool yclip_mode;
+    bool state_smem;        // the state arrays live in shared memory (walk kernel re-fills)
+    Team team;
 };
+
+// State loads: through the L2 only when the state is in global memory (it streams, and row m is rewritten by
+// another CTA of the team), plain when it lives in shared memory.
+__device__ __forceinline__ int4 pk_ld_state(const PackCtx &X, const int32_t *p) {
+    return X.state_smem ? *reinterpret_cast<const int4 *>(p) : __ldcg(reinterpret_cast<const int4 *>(p));
+}
 
 struct PkColOut {           // traceback-variant outputs of a column (all optional)
     uint8_t *tb_col;        // packed traceback bytes, linear rows
     ColRec *colrec_col;     // per contig: Lx[j] (+ the jump record)
     SnRec *sn; LastCell *last;
     bool track, lastcol;
+    int32_t track_thr;      // only cells with S >= track_thr can hold a final tracker value (absolute score)
 };
 
 __device__ __forceinline__ void unpack8(const uint2 xb, uint8_t *x) {
@@ -83,7 +112,7 @@ template <bool SPECIAL, bool TB>
 __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, const PkColOut &O, uint32_t j, uint32_t tile,
                                         uint32_t lane, int32_t r0pkey, int32_t cr1key, bool chunk_start, const int32_t *hS,
                                         const int32_t *hD, int32_t &prev_exit, uint32_t &prev_exit_open, int32_t &prev_s7,
-                                        int32_t *outS, int32_t *outD) {
+                                        int32_t *outS, int32_t *outD, const unsigned char *stg) {
     const PK &pk = X.pk;
     const uint32_t a = X.owner ? X.owner[tile] : 0u;
     const ContigEntry en = X.ent[a];
@@ -91,17 +120,26 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     const bool first = tic == 0;
     const uint32_t row0 = tic * TILE + lane * STRIP + 1;
     int32_t Sup[STRIP], Dup[STRIP];
+    uint2 xb;
     {
-        const int4 s0 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + lane * 4);
-        const int4 s1 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + 128 + lane * 4);
-        const int4 d0 = *reinterpret_cast<const int4 *>(X.Dst + tile * TILE + lane * 4);
-        const int4 d1 = *reinterpret_cast<const int4 *>(X.Dst + tile * TILE + 128 + lane * 4);
+        int4 s0, s1, d0, d1;
+        if (stg) {   // this tile was staged in shared memory by cp.async while the previous tile was computed
+            const int4 *q = reinterpret_cast<const int4 *>(stg);
+            s0 = q[lane]; s1 = q[32 + lane]; d0 = q[64 + lane]; d1 = q[96 + lane];
+            xb = reinterpret_cast<const uint2 *>(stg + 2 * TILE * 4)[lane];
+        } else {
+            s0 = pk_ld_state(X, X.Sst + tile * TILE + lane * 4);
+            s1 = pk_ld_state(X, X.Sst + tile * TILE + 128 + lane * 4);
+            d0 = pk_ld_state(X, X.Dst + tile * TILE + lane * 4);
+            d1 = pk_ld_state(X, X.Dst + tile * TILE + 128 + lane * 4);
+            // contig bases are 16-byte aligned per contig and a strip starts at a multiple of 8 (over-reads stay inside the blob's padding)
+            xb = *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
+        }
         Sup[0] = s0.x; Sup[1] = s0.y; Sup[2] = s0.z; Sup[3] = s0.w; Sup[4] = s1.x; Sup[5] = s1.y; Sup[6] = s1.z; Sup[7] = s1.w;
         Dup[0] = d0.x; Dup[1] = d0.y; Dup[2] = d0.z; Dup[3] = d0.w; Dup[4] = d1.x; Dup[5] = d1.y; Dup[6] = d1.z; Dup[7] = d1.w;
     }
     uint8_t x[STRIP];
-    // contig bases are 16-byte aligned per contig and a strip starts at a multiple of 8 (over-reads stay inside the blob's padding)
-    unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1)), x);
+    unpack8(xb, x);
     int32_t Sdg0 = __shfl_up_sync(FULL, Sup[STRIP - 1], 1);
     if (lane == 0) Sdg0 = first ? r0pkey : (chunk_start ? hS[8] : prev_s7);
     const int32_t Jc = S.Jc[a];
@@ -167,13 +205,15 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
             *reinterpret_cast<uint2 *>(O.tb_col + tile * TILE + lane * STRIP) = make_uint2(lo, hi);
         }
         if (O.track || O.lastcol) {
-            const JumpInfo Jw = S.Jw[a];
+            const int32_t thrkey = pk_key(pk, (int64_t)O.track_thr - pc.B, 0, 0);
             STITCH_UNROLL
             for (int k = 0; k < STRIP; ++k) {
-                if (!SPECIAL || k < nv) {
+                const bool trk = O.track && Sn[k] >= thrkey;
+                if ((!SPECIAL || k < nv) && (trk || O.lastcol)) {
+                    const JumpInfo Jw = S.Jw[a];
                     const uint32_t si = state_index(tile, lane, (uint32_t)k);
                     pk_cell_records(pk, pc, X.sc, Sn[k], Iarr[k], tbb[k], x[k] == pc.q, en.contig_idx, row0 + (uint32_t)k, en.m, Jw, j, X.n,
-                                    O.track ? O.sn + si : nullptr, O.lastcol ? O.last + si : nullptr);
+                                    trk ? O.sn + si : nullptr, O.lastcol ? O.last + si : nullptr);
                 }
             }
         }
@@ -186,7 +226,7 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
         }
         if (has_m) {
             PkRowM rm; rm.diag = st.A[nv]; rm.D6 = st.D6[nv]; rm.jp = st.jp[nv]; rm.I = I_m; rm.fl = TB ? st.fl[nv] : 0u; rm.iext = iext_m;
-            S.stash[a] = rm;
+            X.team.peer(S.stash, a % X.team.size)[a] = rm;   // to the CTA that finishes contig a
         }
     }
     STITCH_UNROLL
@@ -197,16 +237,17 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     *reinterpret_cast<int4 *>(X.Dst + tile * TILE + 128 + lane * 4) = make_int4(st.D6[4], st.D6[5], st.D6[6], st.D6[7]);
     STITCH_UNROLL
     for (int d = 16; d >= 1; d >>= 1) colmax = pk_max(colmax, __shfl_xor_sync(FULL, colmax, d));
-    if (lane == 0) S.tilemax[tile] = colmax;
+    if (lane < X.team.size) X.team.peer(S.tilemax, lane)[tile] = colmax;   // every CTA of the team holds the whole tile table
 }
 
 // Halos of the current state into parity slot `slot` (before the first column computed from it).
 template <int W>
 __device__ void pk_init_halos(const PackCtx &X, PackSmem &S, uint32_t slot) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t Weff = X.NT < (uint32_t)W ? X.NT : (uint32_t)W;
-    if (warp >= 1 && warp < Weff && lane < 9) {
-        const uint32_t t_lo = (uint32_t)((uint64_t)X.NT * warp / Weff);
+    const uint32_t GW = X.team.size * W, gw = X.team.rank * W + warp;
+    const uint32_t Weff = X.NT < GW ? X.NT : GW;
+    if (gw >= 1 && gw < Weff && lane < 9) {
+        const uint32_t t_lo = (uint32_t)((uint64_t)X.NT * gw / Weff);
         const uint32_t hl = lane == 0 ? 30u : 31u, hk = lane == 0 ? (uint32_t)STRIP - 1 : lane - 1;
         const uint32_t pi = pk_sidx(t_lo - 1, hl, hk);
         S.haloS[(slot * W + warp) * 9 + lane] = X.Sst[pi];
@@ -224,22 +265,53 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const PK &pk = X.pk;
     const Scoring &sc = X.sc;
     const uint32_t NT = X.NT, C = X.C, par = j & 1u;
-    const uint32_t Weff = NT < (uint32_t)W ? NT : (uint32_t)W;
-    if (warp < Weff) {
-        const uint32_t t_lo = (uint32_t)((uint64_t)NT * warp / Weff), t_hi = (uint32_t)((uint64_t)NT * (warp + 1) / Weff);
+    const Team &team = X.team;
+    const uint32_t GW = team.size * W, gw = team.rank * W + warp;
+    const uint32_t Weff = NT < GW ? NT : GW;
+    if (gw < Weff) {
+        const uint32_t t_lo = (uint32_t)((uint64_t)NT * gw / Weff), t_hi = (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
         int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
         int32_t oS[STRIP], oD[STRIP];
+        // software pipeline: while tile t is computed, cp.async brings tile t+1 (S keys, D keys, bases) into this
+        // warp's shared-memory double buffer; each lane reads back exactly the bytes it copied (no warp sync needed)
+        const bool staged = !X.state_smem;
+        unsigned char *stg0 = S.stage + (size_t)warp * 2 * PackSmem::STAGE_BYTES;
+        auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot) {
+            unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
+            __pipeline_memcpy_async(d + lane * 16, X.Sst + t * TILE + lane * 4, 16);
+            __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * TILE + 128 + lane * 4, 16);
+            __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * TILE + lane * 4, 16);
+            __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * TILE + 128 + lane * 4, 16);
+            __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
+            __pipeline_commit();
+        };
+        ContigEntry en = X.ent[X.owner ? X.owner[t_lo] : 0u];
+        if (staged) prefetch(t_lo, en, 0);
         for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
-            const ContigEntry en = X.ent[X.owner ? X.owner[tile] : 0u];
+            const uint32_t slot = (tile - t_lo) & 1u;
+            ContigEntry en_next = en;
+            if (tile + 1 < t_hi) {
+                en_next = X.ent[X.owner ? X.owner[tile + 1] : 0u];
+                if (staged) prefetch(tile + 1, en_next, slot ^ 1u);
+            }
+            const unsigned char *stg = nullptr;
+            if (staged) {
+                if (tile + 1 < t_hi) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+                stg = stg0 + slot * PackSmem::STAGE_BYTES;
+            }
             const uint32_t tic = tile - en.tile_start;
             if (tic == 0 || tic + 1 == en.ntiles)
-                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD);
+                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg);
             else
-                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD);
+                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg);
+            en = en_next;
         }
-        if (warp + 1 < Weff) {   // publish the halo of the next chunk for the next column
-            int32_t *nS = S.haloS + (par * W + warp + 1) * 9, *nD = S.haloD + (par * W + warp + 1) * 8;
+        if (gw + 1 < Weff) {   // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp)
+            const bool local = warp + 1 < (uint32_t)W;
+            const uint32_t slot = local ? warp + 1 : 0u;
+            int32_t *nS = (local ? S.haloS : team.peer(S.haloS, team.rank + 1)) + (par * W + slot) * 9;
+            int32_t *nD = (local ? S.haloD : team.peer(S.haloD, team.rank + 1)) + (par * W + slot) * 8;
             if (lane == 31) {
                 STITCH_UNROLL
                 for (int k = 0; k < STRIP; ++k) { nS[k + 1] = oS[k]; nD[k] = oD[k]; }
@@ -247,11 +319,11 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             if (lane == 30) nS[0] = oS[STRIP - 1];
         }
     }
-    __syncthreads();
+    team.sync();
 
-    // ---- per contig: tracker + row m + column best ----
+    // ---- per contig: tracker + row m + column best (contig a on CTA a % size) ----
     const Row0 r0 = row0_at(sc, j, X.n);
-    for (uint32_t a = warp; a < C; a += W) {
+    for (uint32_t a = team.rank + team.size * warp; a < C; a += team.size * W) {
         const ContigEntry en = X.ent[a];
         int32_t kmax = pk.NEGKEY;
         for (uint32_t t = lane; t < en.ntiles; t += 32) kmax = pk_max(kmax, S.tilemax[en.tile_start + t]);
@@ -272,8 +344,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 STITCH_UNROLL
                 for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
                 const uint32_t tile = en.tile_start + ft;
-                const int4 s0 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + lane * 4);
-                const int4 s1 = *reinterpret_cast<const int4 *>(X.Sst + tile * TILE + 128 + lane * 4);
+                const int4 s0 = pk_ld_state(X, X.Sst + tile * TILE + lane * 4);
+                const int4 s1 = pk_ld_state(X, X.Sst + tile * TILE + 128 + lane * 4);
                 const int32_t sk[STRIP] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 uint32_t row = 0xffffffffu; int32_t key = 0;
                 STITCH_UNROLL
@@ -312,7 +384,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                     O.colrec_col[a] = cr;
                 }
                 const uint32_t p = state_index(mt, ml, mk);
-                if (O.track) sn_update(sc, O.sn[p], ro.c.S, ro.c.sl, ro.c.idx, j, X.n);
+                if (O.track && ro.c.S >= O.track_thr) sn_update(sc, O.sn[p], ro.c.S, ro.c.sl, ro.c.idx, j, X.n);
                 if (O.lastcol) {
                     LastCell lc; lc.S = ro.c.S; lc.I = pk_abs(pk, pc.B, stash.I); lc.sl = ro.c.sl; lc.il = pk_len(pk, stash.I);
                     lc.idx = ro.c.idx; lc.from = ro.c.from; lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0;
@@ -325,11 +397,14 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             cmv = cm_merge(cmv, rows);
             CmPart top; top.S = ro.c.S; top.row = en.m; top.sl = ro.c.sl; top.valid = 1;
             cmv = cm_merge(cmv, top);
-            S.cm[a] = cmv.S; S.cmk[a] = cmv.row; S.cml[a] = cmv.sl;
-            S.Sm[a] = ro.c.S; S.slm[a] = ro.c.sl; S.tbm[a] = ro.s_tb; S.SmKey[a] = fo.skey;
+            for (uint32_t r = 0; r < team.size; ++r) {   // every CTA of the team keeps the per-contig tables
+                team.peer(S.cm, r)[a] = cmv.S; team.peer(S.cmk, r)[a] = cmv.row; team.peer(S.cml, r)[a] = cmv.sl;
+                team.peer(S.Sm, r)[a] = ro.c.S; team.peer(S.slm, r)[a] = ro.c.sl; team.peer(S.tbm, r)[a] = ro.s_tb;
+                team.peer(S.SmKey, r)[a] = fo.skey;
+            }
         }
     }
-    __syncthreads();
+    team.sync();
 }
 
 // Column 0 (SCA:97-186) of the contigs of X into the packed state (base B_0 = 0) + row-m summaries.
@@ -339,9 +414,9 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
     const uint32_t pm = X.NT * TILE;
-    for (uint32_t p = tid; p < pm; p += T) { X.Sst[p] = pk.NEGKEY; X.Dst[p] = pk.NEGKEY + pk.PD6; }
-    __syncthreads();
-    for (uint32_t tile = warp; tile < X.NT; tile += W) {
+    for (uint32_t p = X.team.rank * T + tid; p < pm; p += X.team.size * T) { X.Sst[p] = pk.NEGKEY; X.Dst[p] = pk.NEGKEY + pk.PD6; }
+    X.team.sync();
+    for (uint32_t tile = X.team.rank * W + warp; tile < X.NT; tile += X.team.size * W) {
         const ContigEntry en = X.ent[X.owner ? X.owner[tile] : 0u];
         const uint32_t tic = tile - en.tile_start;
         STITCH_UNROLL
@@ -360,7 +435,7 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
         S.Sm[a] = cmm.S; S.slm[a] = cmm.sl; S.tbm[a] = cmm.s_tb;
         S.SmKey[a] = pk_from_wide(pk, 0, cmm.S, cmm.sl, 0);
     }
-    __syncthreads();
+    X.team.sync();
 }
 
 // The packed state of column j0 from a wide checkpoint (`ck` in the wide tile-transposed order, first tile of X
@@ -371,7 +446,7 @@ __device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const CellState 
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
     const uint32_t pm = X.NT * TILE;
-    for (uint32_t idx = tid; idx < pm; idx += T) {
+    for (uint32_t idx = X.team.rank * T + tid; idx < pm; idx += X.team.size * T) {
         const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
         const CellState cs = ck[idx];
         const uint32_t pi = pk_sidx(tile, ln, k);
@@ -384,7 +459,7 @@ __device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const CellState 
         S.Sm[a] = cs.Sm; S.slm[a] = cs.slm; S.tbm[a] = cs.tbm;
         S.SmKey[a] = pk_from_wide(pk, Bj0, cs.Sm, cs.slm, 0);
     }
-    __syncthreads();
+    X.team.sync();
 }
 
 // Wide checkpoint of the current packed state (column base B).
@@ -394,17 +469,18 @@ __device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t B, CellState 
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
     const uint32_t pm = X.NT * TILE;
-    for (uint32_t idx = tid; idx < pm; idx += T) {
+    for (uint32_t idx = X.team.rank * T + tid; idx < pm; idx += X.team.size * T) {
         const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
         const uint32_t pi = pk_sidx(tile, ln, k);
         const int32_t s = X.Sst[pi], d = X.Dst[pi];
-        CellState cs; cs.S = pk_abs(pk, B, s); cs.D = pk_abs(pk, B, d); cs.sl = pk_len(pk, s); cs.dl = pk_len(pk, d);
-        dck[idx] = cs;
+        // streaming store: checkpoints are read back once, much later; keep the L2 for the rolling state
+        __stcs(reinterpret_cast<int4 *>(dck + idx), make_int4(pk_abs(pk, B, s), pk_abs(pk, B, d), (int)pk_len(pk, s), (int)pk_len(pk, d)));
     }
-    for (uint32_t a = tid; a < X.C; a += T) {
-        CkSum cs; cs.Sm = S.Sm[a]; cs.slm = S.slm[a]; cs.tbm = S.tbm[a]; cs.pad = 0;
-        dsum[a] = cs;
-    }
+    if (X.team.rank == 0)
+        for (uint32_t a = tid; a < X.C; a += T) {
+            CkSum cs; cs.Sm = S.Sm[a]; cs.slm = S.slm[a]; cs.tbm = S.tbm[a]; cs.pad = 0;
+            dsum[a] = cs;
+        }
 }
 
 struct PkColConst { PCol pc; int32_t r0pkey, cr1key; };
@@ -415,102 +491,6 @@ __device__ __forceinline__ PkColConst pk_col_const(const PK &pk, const Scoring &
     c.r0pkey = pk_from_wide(pk, Bprev, r0p.S, r0p.sl, 0);
     c.cr1key = pk_carry_row1(pk, c.pc, sc, r0);
     return c;
-}
-
-// ---------------------------------------------------------------------------------------------
-// bulk fill
-// ---------------------------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
-    __shared__ uint32_t sJob;
-    __shared__ PkColConst s_cc[2];
-    __shared__ int32_t s_gmax;
-    __shared__ uint32_t s_first;
-    const uint32_t tid = threadIdx.x;
-    constexpr uint32_t T = W * 32;
-    const Scoring sc = P.sc;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) sJob = atomicAdd(P.counter, 1u);
-        __syncthreads();
-        if (sJob >= P.n_jobs) break;
-        const uint32_t job = P.order[sJob];
-        const JobDesc jd = P.jobs[job];
-        const LayoutDesc ld = P.layouts[jd.layout];
-        const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
-        PackCtx X;
-        X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
-        X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
-        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
-        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
-        ColRec *colrec = P.colrec + jd.colrec_off;
-        int32_t *gcol = P.gcol + jd.gcol_off;
-        const uint8_t *read = P.reads + jd.read_off;
-        PkColOut O; O.tb_col = nullptr; O.colrec_col = nullptr; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false;
-
-        pk_state_init0<W>(X, S);
-        pk_init_halos<W>(X, S, 0);
-        if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
-        __syncthreads();
-
-        for (uint32_t j = 1; j <= n; ++j) {
-            const uint32_t par = j & 1u;
-            // ---- base of the column, jump selection (MCA:279-331), per-column constants ----
-            {
-                const int32_t Bprev = s_cc[par ^ 1u].pc.B;
-                if (tid < C || tid == 0) {
-                    int32_t g = S.cm[0];
-                    for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-                    PCol pcl; pcl.B = g; pcl.delta = g - Bprev;
-                    for (uint32_t a = tid; a < C; a += T) {
-                        const JumpInfo J = select_jump(sc, X.ent, C, a, S.cm, S.cml, S.cmk);
-                        ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
-                        cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
-                        colrec[(uint64_t)j * C + a] = cr;
-                        S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
-                    }
-                    if (tid == 0) {
-                        gcol[j - 1] = g;
-                        s_cc[par] = pk_col_const(X.pk, sc, g, Bprev, j, n, read[j - 1]);
-                    }
-                }
-            }
-            __syncthreads();
-            const PkColConst cc = s_cc[par];
-            pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
-            if ((j % K == 0) && j < n)
-                pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
-        }
-        // best score of column n; the column the tail restarts from: the last checkpoint before the first column
-        // that can hold a final y-suffix tracker (dp_core.h: first_candidate_column); column n is always in the tail
-        if (tid == 0) {
-            int32_t g = S.cm[0];
-            for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-            gcol[n] = g;
-            s_gmax = g; s_first = n;
-        }
-        __syncthreads();
-        if (P.tracked_mode) {
-            int32_t g = gcol[n];
-            for (uint32_t jj = tid; jj < n; jj += T) g = gcol[jj] > g ? gcol[jj] : g;
-            atomicMax(&s_gmax, g);
-            __syncthreads();
-            int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
-            if (submax < 0) submax = 0;
-            const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
-            int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
-            gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
-            const int32_t thr = s_gmax - (submax - gmin - submin);
-            uint32_t first = n;
-            for (uint32_t jj = 1 + tid; jj <= n; jj += T) if (gcol[jj] >= thr) { first = jj; break; }
-            atomicMin(&s_first, first);
-            __syncthreads();
-        }
-        if (tid == 0) P.tail_j0[job] = ((s_first - 1) / K) * K;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,62 +513,164 @@ __device__ __forceinline__ void pk_replay_consts(const PackCtx &X, PackSmem &S, 
     if (tid == 0) *s_cc = pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, read[j - 1]);
 }
 
+// The tail of one job on the CTA that ran its bulk pass (s_cc: one shared PkColConst slot).
 template <int W>
-__global__ void __launch_bounds__(W * 32) tail_packed_kernel(const Params P) {
+__device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld, PackCtx &X, PackSmem &S, PkColConst *s_cc, uint32_t j0,
+                        int32_t track_thr) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const Scoring &sc = X.sc;
+    const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
+    ColRec *colrec = P.colrec + jd.colrec_off;
+    const int32_t *gcol = P.gcol + jd.gcol_off;
+    const uint8_t *read = P.reads + jd.read_off;
+    SnRec *sn = P.sn + jd.cell_off;
+    const bool tracked = P.tracked_mode != 0;
+    if (j0 == 0) pk_state_init0<W>(X, S);
+    else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(j0 / K - 1) * PM,
+                             P.ck_sum + jd.cksum_off + (uint64_t)(j0 / K - 1) * C, gcol[j0 - 1]);
+    if (tracked) {   // trackers start from column 0 (SCA:179-183)
+        for (uint32_t tile = X.team.rank * W + warp; tile < X.NT; tile += X.team.size * W) {
+            const ContigEntry en = X.ent[X.owner[tile]];
+            const uint32_t tic = tile - en.tile_start;
+            STITCH_UNROLL
+            for (int k = 0; k < STRIP; ++k) {
+                const uint32_t i = tic * TILE + lane * STRIP + (uint32_t)k + 1;
+                if (i <= en.m) {
+                    const Col0 c0 = col0_at(sc, i, en.m);
+                    sn[state_index(tile, lane, (uint32_t)k)] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n);
+                }
+            }
+        }
+    }
+    pk_init_halos<W>(X, S, j0 & 1u);
+    X.team.sync();   // trackers of every row initialised before any CTA updates them
+    for (uint32_t j = j0 + 1; j <= n; ++j) {
+        pk_replay_consts<W>(X, S, colrec, gcol, read, j, 0, C, s_cc);
+        __syncthreads();
+        const PkColConst cc = *s_cc;
+        PkColOut O; O.tb_col = nullptr; O.colrec_col = colrec + (uint64_t)j * C; O.sn = sn; O.last = P.last + jd.cell_off;
+        O.track = tracked; O.lastcol = j == n; O.track_thr = track_thr;
+        pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bulk fill
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
     __shared__ uint32_t sJob;
-    __shared__ PkColConst s_cc;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __shared__ PkColConst s_cc[2];
+    __shared__ int32_t s_gmax;
+    __shared__ uint32_t s_first;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
     const Scoring sc = P.sc;
 
+    Team team; team.rank = 0; team.size = P.cluster_size;
+    if (team.size > 1) team.rank = cg::this_cluster().block_rank();
+    const uint32_t team_id = blockIdx.x / team.size;
+
     for (;;) {
-        __syncthreads();
-        if (tid == 0) sJob = atomicAdd(P.counter, 1u);
-        __syncthreads();
+        team.sync();
+        if (team.rank == 0 && tid == 0) {
+            const uint32_t jn = atomicAdd(P.counter, 1u);
+            for (uint32_t r = 0; r < team.size; ++r) *team.peer(&sJob, r) = jn;
+        }
+        team.sync();
         if (sJob >= P.n_jobs) break;
         const uint32_t job = P.order[sJob];
         const JobDesc jd = P.jobs[job];
         const LayoutDesc ld = P.layouts[jd.layout];
         const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
-        const uint32_t j0 = P.tail_j0[job];
         PackCtx X;
+        X.team = team;
         X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
-        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
-        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
+        X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
+        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false;
         ColRec *colrec = P.colrec + jd.colrec_off;
-        const int32_t *gcol = P.gcol + jd.gcol_off;
+        int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;
-        SnRec *sn = P.sn + jd.cell_off;
-        const bool tracked = P.tracked_mode != 0;
+        PkColOut O; O.tb_col = nullptr; O.colrec_col = nullptr; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false;
+        O.track_thr = MIN_SCORE;
 
-        if (j0 == 0) pk_state_init0<W>(X, S);
-        else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(j0 / K - 1) * PM,
-                                 P.ck_sum + jd.cksum_off + (uint64_t)(j0 / K - 1) * C, gcol[j0 - 1]);
-        if (tracked) {   // trackers start from column 0 (SCA:179-183)
-            for (uint32_t tile = warp; tile < X.NT; tile += W) {
-                const ContigEntry en = X.ent[X.owner[tile]];
-                const uint32_t tic = tile - en.tile_start;
-                STITCH_UNROLL
-                for (int k = 0; k < STRIP; ++k) {
-                    const uint32_t i = tic * TILE + lane * STRIP + (uint32_t)k + 1;
-                    if (i <= en.m) {
-                        const Col0 c0 = col0_at(sc, i, en.m);
-                        sn[state_index(tile, lane, (uint32_t)k)] = sn_init(sc, c0.S, c0.sl, en.contig_idx, n);
+        const long long t_bulk0 = clock64();
+        pk_state_init0<W>(X, S);
+        pk_init_halos<W>(X, S, 0);
+        if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
+        __syncthreads();
+
+        for (uint32_t j = 1; j <= n; ++j) {
+            const uint32_t par = j & 1u;
+            // ---- base of the column, jump selection (MCA:279-331), per-column constants ----
+            {
+                const int32_t Bprev = s_cc[par ^ 1u].pc.B;
+                if (tid < C || tid == 0) {
+                    int32_t g = S.cm[0];
+                    for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
+                    PCol pcl; pcl.B = g; pcl.delta = g - Bprev;
+                    for (uint32_t a = tid; a < C; a += T) {
+                        const JumpInfo J = select_jump(sc, X.ent, C, a, S.cm, S.cml, S.cmk);
+                        if (team.rank == 0) {
+                            ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
+                            cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
+                            colrec[(uint64_t)j * C + a] = cr;
+                        }
+                        S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
+                    }
+                    if (tid == 0) {
+                        if (team.rank == 0) gcol[j - 1] = g;
+                        s_cc[par] = pk_col_const(X.pk, sc, g, Bprev, j, n, read[j - 1]);
                     }
                 }
             }
-        }
-        pk_init_halos<W>(X, S, j0 & 1u);
-        __syncthreads();
-        for (uint32_t j = j0 + 1; j <= n; ++j) {
-            pk_replay_consts<W>(X, S, colrec, gcol, read, j, 0, C, &s_cc);
             __syncthreads();
-            const PkColConst cc = s_cc;
-            PkColOut O; O.tb_col = nullptr; O.colrec_col = colrec + (uint64_t)j * C; O.sn = sn; O.last = P.last + jd.cell_off;
-            O.track = tracked; O.lastcol = j == n;
-            pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+            const PkColConst cc = s_cc[par];
+            pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+            if ((j % K == 0) && j < n)
+                pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
+        }
+        // best score of column n; the column the tail restarts from: the last checkpoint before the first column
+        // that can hold a final y-suffix tracker (dp_core.h: first_candidate_column); column n is always in the tail
+        if (tid == 0) {
+            int32_t g = S.cm[0];
+            for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
+            if (team.rank == 0) gcol[n] = g;
+            s_gmax = g; s_first = n;
+        }
+        team.sync();   // gcol / colrec of the whole read (written by rank 0) visible to the team
+        int32_t track_thr = MIN_SCORE;
+        if (P.tracked_mode) {
+            int32_t g = gcol[n];
+            for (uint32_t jj = tid; jj < n; jj += T) g = gcol[jj] > g ? gcol[jj] : g;
+            atomicMax(&s_gmax, g);
+            __syncthreads();
+            int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
+            if (submax < 0) submax = 0;
+            const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+            int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+            gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+            const int32_t thr = s_gmax - (submax - gmin - submin);
+            track_thr = thr;
+            uint32_t first = n;
+            for (uint32_t jj = 1 + tid; jj <= n; jj += T) if (gcol[jj] >= thr) { first = jj; break; }
+            atomicMin(&s_first, first);
+            __syncthreads();
+        }
+        // ---- tail: the last columns again, traceback variant with trackers (same CTA: no launch boundary, and a
+        // CTA with a short tail moves on to the next read while others are still in theirs) ----
+        const uint32_t j0 = ((s_first - 1) / K) * K;
+        if (tid == 0 && team.rank == 0) P.tail_j0[job] = j0;
+        __syncthreads();
+        const long long t_tail0 = clock64();
+        pk_tail<W>(P, jd, ld, X, S, &s_cc[0], j0, track_thr);
+        if (P.dbg && tid == 0 && team.rank == 0) {
+            atomicAdd(P.dbg + 0, (unsigned long long)(n - j0));
+            atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_tail0));
+            atomicAdd(P.dbg + 2, (unsigned long long)(t_tail0 - t_bulk0));
         }
     }
 }
@@ -596,33 +678,71 @@ __global__ void __launch_bounds__(W * 32) tail_packed_kernel(const Params P) {
 // ---------------------------------------------------------------------------------------------
 // walk: packed re-fill of one unit (contig `a`, the block of K columns holding column j)
 // ---------------------------------------------------------------------------------------------
+// Per-unit staging in shared memory: the jump records, column bases and read bases of the unit's columns and
+// the contig's bases, so that a re-filled column touches global memory only for its traceback bytes.
+struct UnitStage {
+    JumpInfo *J;        // [K]
+    int32_t *B;         // [K + 1]: B[t] = base of column jb + t  (B[0] = base of the checkpointed column jb)
+    uint8_t *q;         // [K]
+    uint8_t *bases;     // contig bases (+ 16 bytes of padding for the strip over-read)
+    static __host__ __device__ size_t r16(size_t v) { return (v + 15) / 16 * 16; }
+    static size_t bytes(uint32_t K, uint32_t max_ctiles) {
+        return r16(sizeof(JumpInfo) * K) + r16(sizeof(int32_t) * (K + 1)) + r16(K) + r16((size_t)max_ctiles * TILE + 16);
+    }
+    __device__ void carve(unsigned char *raw, uint32_t K) {   // raw is 16-byte aligned; every part stays 16-byte aligned
+        J = reinterpret_cast<JumpInfo *>(raw);
+        B = reinterpret_cast<int32_t *>(raw + r16(sizeof(JumpInfo) * K));
+        q = reinterpret_cast<uint8_t *>(B) + r16(sizeof(int32_t) * (K + 1));
+        bases = q + r16(K);
+    }
+};
+
 template <int W>
-__device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc &ld, PackSmem &S, ContigEntry *s_en, PkColConst *s_cc,
-                               uint32_t a, uint32_t j, int32_t *pstate, uint64_t pstate_half, uint8_t *bytes, ColRec *ucr, TbUnit *unit_out) {
+__device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc &ld, PackSmem &S, UnitStage &U, ContigEntry *s_en,
+                               PkColConst *s_cc, uint32_t a, uint32_t j, int32_t *pstate, uint64_t pstate_half, bool state_smem,
+                               uint8_t *bytes, ColRec *ucr, TbUnit *unit_out) {
     const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
     const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
     const uint32_t b = (j - 1) / K, jb = b * K, je = (jb + K < n) ? jb + K : n;
     const ContigEntry gen = P.ents[ld.ent_off + a];
     const uint32_t pm = gen.ntiles * TILE, gbase = gen.tile_start * TILE;
-    if (tid == 0) { *s_en = gen; s_en->tile_start = 0; }
-    __syncthreads();
-    PackCtx X;
-    X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = P.contig_bases;
-    X.Sst = pstate; X.Dst = pstate + pstate_half; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     const int32_t *gcol = P.gcol + jd.gcol_off;
     const ColRec *colrec = P.colrec + jd.colrec_off;
     const uint8_t *read = P.reads + jd.read_off;
+    if (tid == 0) { *s_en = gen; s_en->tile_start = 0; s_en->seq_off = 0; }
+    for (uint32_t t = tid; t < je - jb; t += T) {
+        const ColRec cr = colrec[(uint64_t)(jb + 1 + t) * C + a];
+        JumpInfo J; J.score = cr.jscore; J.len = cr.jlen; J.idx = cr.jidx; J.from = cr.jfrom;
+        U.J[t] = J;
+        U.q[t] = read[jb + t];
+    }
+    for (uint32_t t = tid; t <= je - jb; t += T) U.B[t] = (jb + t >= 1) ? gcol[jb + t - 1] : 0;
+    for (uint32_t t = tid; t < pm + 16; t += T) U.bases[t] = t < gen.m ? P.contig_bases[gen.seq_off + t] : (uint8_t)0;
+    __syncthreads();
+    PackCtx X;
+    X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
+    X.Sst = pstate; X.Dst = pstate + pstate_half; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
+    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(b - 1) * PM + gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
-                             gcol[jb - 1]);
+                             U.B[0]);
     pk_init_halos<W>(X, S, jb & 1u);
     __syncthreads();
     for (uint32_t jj = jb + 1; jj <= je; ++jj) {
-        pk_replay_consts<W>(X, S, colrec, gcol, read, jj, a, C, s_cc);
+        const uint32_t t = jj - jb - 1;
+        if (tid == 0) {
+            const int32_t B = U.B[t + 1], Bprev = U.B[t];   // B[t+1] = G(jj-1) = base of column jj
+            const JumpInfo J = U.J[t];
+            PCol pcl; pcl.B = B; pcl.delta = B - Bprev;
+            S.Jw[0] = J;
+            S.Jc[0] = pk_jc(X.pk, pcl, J.score, J.len);
+            *s_cc = pk_col_const(X.pk, X.sc, B, Bprev, jj, n, U.q[t]);
+        }
         __syncthreads();
         const PkColConst cc = *s_cc;
-        PkColOut O; O.tb_col = bytes + (uint64_t)(jj - jb - 1) * pm; O.colrec_col = ucr + (jj - jb - 1); O.sn = nullptr; O.last = nullptr;
-        O.track = false; O.lastcol = false;
+        PkColOut O; O.tb_col = bytes + (uint64_t)t * pm; O.colrec_col = ucr + t; O.sn = nullptr; O.last = nullptr;
+        O.track = false; O.lastcol = false; O.track_thr = MIN_SCORE;
         pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, jj, O);
     }
     if (tid == 0) { unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; }

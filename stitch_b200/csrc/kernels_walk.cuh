@@ -13,8 +13,9 @@ template <int W>
 __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WideSmem<W> S; S.carve(smem_raw, 1);
-    PackSmem PS; PS.carve(smem_raw, 1, P.max_ctiles, W);   // same bytes: a job uses one of the two
+    PackSmem PS; PS.carve(smem_raw, 1, P.max_ctiles, W, false);   // same bytes: a job uses one of the two
     __shared__ PkColConst s_cc;
+    UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
     __shared__ uint32_t sJob, sCmd, sUa, sUj;
     __shared__ ContigEntry s_en;
     __shared__ TbUnit s_unit;
@@ -24,7 +25,9 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
     CellState *st1 = st0 + P.state_half;
     uint8_t *ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
     ColRec *ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
-    int32_t *wps = P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
+    // packed state of the unit's contig: in shared memory when it fits (a contig is a few tiles), else global
+    int32_t *wps = P.walk_state_smem_off ? reinterpret_cast<int32_t *>(smem_raw + P.walk_state_smem_off)
+                                         : P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
 
     for (;;) {
         __syncthreads();
@@ -34,6 +37,7 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
         const uint32_t job = P.order[sJob];
         const JobDesc jd = P.jobs[job];
         const LayoutDesc ld = P.layouts[jd.layout];
+        const long long t_job0 = clock64();
 
         // thread-0 state
         ReadView v; WalkState ws; ChainHdr h;
@@ -87,11 +91,22 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
             }
             __syncthreads();
             if (sCmd == WCMD_DONE) break;
-            if (jd.LB) pk_refill_unit<W>(P, jd, ld, PS, &s_en, &s_cc, sUa, sUj, wps, P.wpstate_half, ubytes, ucr, &s_unit);
+            const long long t_r0 = clock64();
+            if (jd.LB) pk_refill_unit<W>(P, jd, ld, PS, US, &s_en, &s_cc, sUa, sUj, wps, P.wpstate_half, P.walk_state_smem_off != 0, ubytes, ucr, &s_unit);
             else refill_unit<W>(P, jd, ld, S, &s_en, sUa, sUj, st0, st1, ubytes, ucr, &s_unit);
-            if (tid == 0) v.unit = s_unit;
+            if (tid == 0) {
+                v.unit = s_unit;
+                if (P.dbg) {
+                    atomicAdd(P.dbg + 3, 1ull);
+                    atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - t_r0));
+                    atomicAdd(P.dbg + 6, (unsigned long long)(s_unit.je - s_unit.jb));
+                }
+            }
         }
-        if (tid == 0) { JobOut o; o.n_chains = n_chains; o.status = status; P.job_out[job] = o; }
+        if (tid == 0) {
+            JobOut o; o.n_chains = n_chains; o.status = status; P.job_out[job] = o;
+            if (P.dbg) atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - t_job0));
+        }
     }
 }
 

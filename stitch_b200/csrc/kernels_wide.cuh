@@ -70,11 +70,15 @@ struct Params {
     int32_t *pstate;         // packed kernel, per CTA: S keys then D keys
     uint64_t pstate_stride, pstate_half;
     uint32_t ntmax;          // largest tile count among the packed jobs
+    uint32_t cluster_size;   // packed kernel: CTAs per read (thread-block cluster), 1 = no cluster
     uint32_t *tail_j0;       // per job: the checkpointed column the packed tail restarts from
     int32_t *wpstate;        // walk kernel, per CTA: packed state of one contig (S keys then D keys)
     uint64_t wpstate_stride, wpstate_half;
     ColRec *unit_cr;         // walk kernel, per CTA: K per-column records of the loaded unit
     uint32_t max_ctiles;     // most tiles of any single contig (walk kernel shared memory)
+    unsigned long long *dbg; // optional counters (STITCH_DEBUG_STATS): see cuda_backend.cu
+    uint32_t walk_stage_smem_off;   // walk kernel: byte offset of the per-unit staging area in dynamic shared memory
+    uint32_t walk_state_smem_off;   // walk kernel: byte offset of the packed unit state in dynamic shared memory (0: global)
     int32_t *gcol;
     OutOp *ops;
     ChainHdr *chains;

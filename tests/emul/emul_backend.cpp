@@ -232,6 +232,7 @@ struct EmulBackend : Backend {
         const uint8_t *read; uint32_t j, n; int32_t B, Bprev; const JumpInfo *J;
         bool tb; uint8_t *tb_col; ColRec *colrec_col;       // traceback variant: packed bytes, Lx[j] per contig
         bool track; SnRec *sn; bool lastcol; LastCell *last;
+        int32_t track_thr;                                  // only cells with S >= track_thr can hold a final tracker value
     };
 
     void pk_state_init0(const PK &pk, const ContigEntry *ent, uint32_t C, uint32_t pm, PkState &st) {
@@ -351,9 +352,10 @@ struct EmulBackend : Backend {
                         if (A.tb) {
                             const uint32_t i = row0 + (uint32_t)k;
                             if (A.tb_col) A.tb_col[base + k] = tbb[k];
-                            if (A.track || A.lastcol)
+                            const bool trk = A.track && pk_abs(pk, B, S[k]) >= A.track_thr;
+                            if (trk || A.lastcol)
                                 pk_cell_records(pk, pc, sc, S[k], Iarr[k], tbb[k], xs[lane][k] == pc.q, en.contig_idx, i, en.m, A.J[a], j, n,
-                                                A.track ? &A.sn[row_index(en, i)] : nullptr, A.lastcol ? &A.last[row_index(en, i)] : nullptr);
+                                                trk ? &A.sn[row_index(en, i)] : nullptr, A.lastcol ? &A.last[row_index(en, i)] : nullptr);
                         }
                     }
                     if (hasm[lane]) {
@@ -404,7 +406,7 @@ struct EmulBackend : Backend {
                     cr.jscore = A.J[a].score; cr.jlen = A.J[a].len; cr.jidx = A.J[a].idx; cr.jfrom = A.J[a].from; cr.lx = ro.lx;
                 }
                 const uint32_t p = row_index(en, en.m);
-                if (A.track) sn_update(sc, A.sn[p], ro.c.S, ro.c.sl, ro.c.idx, j, n);
+                if (A.track && ro.c.S >= A.track_thr) sn_update(sc, A.sn[p], ro.c.S, ro.c.sl, ro.c.idx, j, n);
                 if (A.lastcol) {
                     LastCell lc; lc.S = ro.c.S; lc.I = pk_abs(pk, B, stash[a].I); lc.sl = ro.c.sl; lc.il = pk_len(pk, stash[a].I);
                     lc.idx = ro.c.idx; lc.from = ro.c.from; lc.s_tb = (uint8_t)ro.s_tb; lc.i_tb = 0;
@@ -488,13 +490,20 @@ struct EmulBackend : Backend {
             }
         const std::vector<uint32_t> owner = owners_of(L.ent.data(), C, NT);
         std::vector<JumpInfo> J(C);
+        // every row ends with a tracker value >= max_j G(j) - W' (dp_core.h: first_candidate_column): cells below can be skipped
+        int32_t thr = MIN_SCORE;
+        if (tracked) {
+            int32_t submax = std::max(std::max(sc.match, sc.mismatch), 0), submin = std::min(sc.match, sc.mismatch);
+            int32_t gmin = std::min(sc.g_same, std::min(sc.g_opp, sc.g_inter));
+            thr = max_of(F.gcol) - (submax - gmin - submin);
+        }
         for (uint32_t j = j0 + 1; j <= n; ++j) {
             for (uint32_t a = 0; a < C; ++a) { const ColRec &cr = F.colrec[(size_t)j * C + a]; J[a] = JumpInfo{cr.jscore, cr.jlen, cr.jidx, cr.jfrom}; }
             PkCol A{};
             A.ent = L.ent.data(); A.C = C; A.NT = NT; A.owner = owner.data(); A.read = job.read; A.j = j; A.n = n;
             A.B = F.gcol[j - 1]; A.Bprev = j >= 2 ? F.gcol[j - 2] : 0; A.J = J.data();
             A.tb = true; A.tb_col = nullptr; A.colrec_col = F.colrec.data() + (size_t)j * C;
-            A.track = tracked; A.sn = F.sn.data(); A.lastcol = j == n; A.last = F.last.data();
+            A.track = tracked; A.sn = F.sn.data(); A.lastcol = j == n; A.last = F.last.data(); A.track_thr = thr;
             packed_column(pk, A, st);
         }
     }

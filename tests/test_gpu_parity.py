@@ -17,19 +17,28 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # Small checkpoint spacing / tracking window so that tiny fuzz reads still span several checkpoint
 # blocks, re-filled units and window re-runs (the library reads these when a context is created).
 TUNING = {"STITCH_CK_EVERY": "7", "STITCH_TRACK_WINDOW": "6"}
+ALL_TUNING_KEYS = ("STITCH_CK_EVERY", "STITCH_TRACK_WINDOW", "STITCH_CLUSTER", "STITCH_CLUSTER_MIN_TILES", "STITCH_PACKED")
+
+
+def cluster_tuning(seed, base=None):
+    """Thread-block clusters of 1 / 2 / 4 CTAs per read, also for layouts of a few tiles."""
+    t = dict(base or {})
+    t["STITCH_CLUSTER"] = str((1, 2, 4)[seed % 3])
+    t["STITCH_CLUSTER_MIN_TILES"] = "1"
+    return t
 
 
 def gpu_aligners(kw, named, max_inflight=0, tuning=None):
     import stitch_b200
     targets = [stitch_b200.TargetSeq(n, s) for n, s in named]
-    for k in TUNING:
+    for k in ALL_TUNING_KEYS:
         os.environ.pop(k, None)
     if tuning:
         os.environ.update(tuning)
     try:
         al = stitch_b200.Builder(**kw).build_aligners(targets, device=0)
     finally:
-        for k in TUNING:
+        for k in ALL_TUNING_KEYS:
             os.environ.pop(k, None)
     if max_inflight:
         al.set_max_inflight(max_inflight)
@@ -182,7 +191,7 @@ def test_fuzz_packed_small(oracle, block):
         alphabet = [b"ACGT", b"AC", b"A", b"ACGTN"][seed % 4]
         contigs, reads = gen.fuzz_case(seed + 7000, max_contigs=5, max_len=90, max_read=70, alphabet=alphabet)
         kw = gen.fuzz_opts_packed(seed, 8)
-        got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 3 != 0), tuning=TUNING)
+        got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 3 != 0), tuning=cluster_tuning(seed, TUNING))
         compare(got, exp, f"seed {seed} {kw}")
 
 
@@ -202,5 +211,5 @@ def test_fuzz_packed_multi_tile(oracle, block):
         reads = [r if r else b"A" for r in reads]
         kw = gen.fuzz_opts_packed(seed + 100 * block, 8)
         got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 2 == 0),
-                            tuning={"STITCH_CK_EVERY": "50", "STITCH_TRACK_WINDOW": "8"})
+                            tuning=cluster_tuning(seed + block, {"STITCH_CK_EVERY": "50", "STITCH_TRACK_WINDOW": "8"}))
         compare(got, exp, f"seed {seed} {kw}")
