@@ -38,6 +38,7 @@ using host::Error;
 constexpr int FILL_WARPS = 8;
 constexpr int PACK_WARPS = 16;
 constexpr int WALK_WARPS = 16;
+constexpr int FUSED_WARPS = 8;
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -109,6 +110,7 @@ struct CudaBackend : host::Backend {
     size_t l2_persist_max = 0, l2_window_max = 0;
     uint32_t l2_persist = 0;   // STITCH_L2_PERSIST=1: pin the rolling state of the packed kernel in the L2 (measured: no gain)
     uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
+    uint32_t use_fused = 0;    // STITCH_FUSED=1: one persistent kernel per read (fill, tail, fix-up, walk; per-CTA arenas); measured slower
     uint32_t cluster_pref = 1; // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8); measured best on config 2: 1
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     DevBuf<CkSum> d_cksum;
@@ -149,6 +151,7 @@ struct CudaBackend : host::Backend {
         K = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K));
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
         use_packed = env_u32("STITCH_PACKED", 1);
+        use_fused = env_u32("STITCH_FUSED", 0);
         debug_stats = env_u32("STITCH_DEBUG_STATS", 0) != 0;
         l2_persist = env_u32("STITCH_L2_PERSIST", 0);
         if (l2_persist && l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
@@ -189,12 +192,30 @@ struct CudaBackend : host::Backend {
     }
 
     uint32_t blocks_of(uint32_t n) const { return (n + K - 1) / K; }
-    // device bytes one job holds from its fill until its walk is done
-    uint64_t job_bytes(const host::Job &j) const {
+    uint32_t plan_LB(const host::Job &j) const {   // length bits of the packed path, 0 = wide path
+        if (!use_packed) return 0;
+        const host::Layout &L = al.layouts.layouts[j.layout];
+        uint32_t m_max = 0;
+        for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
+        const uint32_t LB = pk_plan(al.opts.sc, j.n, m_max);
+        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) > 180 * 1024) return 0;   // tile table must fit shared memory
+        return LB;
+    }
+    bool fused_path() const { return use_fused && cluster_pref == 1; }
+    // records a read holds from its fill until its walk is done (CellState/ColRec/... counts)
+    struct Need { uint64_t colrec, cell, ck, cksum, gcol; };
+    Need need_of(const host::Job &j) const {
         const host::Layout &L = al.layouts.layouts[j.layout];
         const uint64_t C = L.ent.size(), PM = L.PM(), nb = blocks_of(j.n);
-        return (nb - 1) * (PM * sizeof(CellState) + C * sizeof(CkSum)) + (uint64_t)(j.n + 1) * (C * sizeof(ColRec) + 4) +
-               PM * (sizeof(LastCell) + sizeof(SnRec) + sizeof(CellState)) + (uint64_t)(2 * j.n + 4 * C + 64) * sizeof(OutOp) + 4096;
+        return Need{(uint64_t)(j.n + 1) * C, PM, (nb - 1) * PM, (nb - 1) * C, (uint64_t)j.n + 1};
+    }
+    static uint64_t need_bytes(const Need &n) {
+        return n.colrec * sizeof(ColRec) + n.cell * (sizeof(LastCell) + sizeof(SnRec) + sizeof(CellState)) + n.ck * sizeof(CellState) +
+               n.cksum * sizeof(CkSum) + n.gcol * 4;
+    }
+    uint64_t out_bytes(const host::Job &j) const {
+        const uint64_t C = al.layouts.layouts[j.layout].ent.size();
+        return (uint64_t)(2 * j.n + 4 * C + 64) * sizeof(OutOp) + 4096;
     }
 
     void run(const std::vector<host::Job> &jobs, std::vector<host::JobResult> &out) override {
@@ -205,23 +226,28 @@ struct CudaBackend : host::Backend {
         upload_layouts();
         size_t free_b = 0, total_b = 0;
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        // memory the per-job arenas may take: what is free now plus what our own arenas already hold
+        // memory our arenas may take: what is free now plus what they already hold
         const uint64_t held = d_ck.cap * sizeof(CellState) + d_colrec.cap * sizeof(ColRec) + d_last.cap * sizeof(LastCell) +
-                              d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp);
-        const uint64_t budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.60);
+                              d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_hand.cap * sizeof(CellState);
+        mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.70);
+        const bool fused = fused_path();
         size_t begin = 0;
         while (begin < jobs.size()) {
+            // a chunk: per-read records of the reads that are not on the fused path + the outputs of all; the fused
+            // path's working memory is per CTA and is budgeted in run_chunk
             size_t end = begin; uint64_t used = 0;
             while (end < jobs.size()) {
-                const uint64_t b = job_bytes(jobs[end]);
-                if (end > begin && (used + b > budget || (max_inflight && end - begin >= max_inflight))) break;
-                if (b > budget) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
+                const bool arena = fused && plan_LB(jobs[end]) != 0;
+                const uint64_t b = out_bytes(jobs[end]) + (arena ? 0 : need_bytes(need_of(jobs[end])));
+                if (end > begin && (used + b > mem_budget / 2 || (max_inflight && end - begin >= max_inflight))) break;
+                if (b > mem_budget) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
                 used += b; ++end;
             }
             run_chunk(jobs, begin, end, out);
             begin = end;
         }
     }
+    uint64_t mem_budget = 0;
 
     template <typename KernelT>
     void set_smem(KernelT kernel, size_t smem) {
@@ -231,83 +257,103 @@ struct CudaBackend : host::Backend {
     void run_chunk(const std::vector<host::Job> &jobs, size_t begin, size_t end, std::vector<host::JobResult> &out) {
         const uint32_t nj = (uint32_t)(end - begin);
         const auto &Ls = al.layouts.layouts;
-        h_jobs.reserve(nj); h_order.reserve(3 * (size_t)nj);
+        h_jobs.reserve(nj); h_order.reserve(4 * (size_t)nj + 16);
         const bool tracked = al.opts.sc.ys != MIN_SCORE;
-        uint64_t reads_b = 0, colrec_n = 0, cell_n = 0, ck_n = 0, cksum_n = 0, gcol_n = 0, ops_n = 0, chains_n = 0, pm_max = 0,
-                 unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0;
+        const bool fused = fused_path();
+        uint64_t reads_b = 0, ops_n = 0, chains_n = 0, pm_max = 0, unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0, per_job_bytes = 0;
+        Need tot{0, 0, 0, 0, 0}, arena{0, 0, 0, 0, 0};
         uint32_t n_packed = 0, ntmax = 1, max_ctiles = 1;
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
             const host::Layout &L = Ls[j.layout];
             const uint32_t C = (uint32_t)L.ent.size();
-            const uint64_t nb = blocks_of(j.n);
             JobDesc d{};
             d.read_off = device_reads ? (uint64_t)(uintptr_t)j.read : reads_b;
-            d.colrec_off = colrec_n; d.cell_off = cell_n; d.ck_off = ck_n; d.cksum_off = cksum_n; d.gcol_off = gcol_n; d.ops_off = ops_n;
+            d.colrec_off = tot.colrec; d.cell_off = tot.cell; d.ck_off = tot.ck; d.cksum_off = tot.cksum; d.gcol_off = tot.gcol; d.ops_off = ops_n;
             d.n = j.n; d.layout = j.layout; d.walk = j.walk; d.from_contig = j.from_contig;
             d.max_chains = j.walk == host::WALK_ALL ? C : 1;
             const uint32_t per_chain = j.n / 2 + 4 * C + 64;
             d.ops_cap = per_chain * (j.walk == host::WALK_ALL ? std::min<uint32_t>(C, 8) : 1) * ops_scale;
             d.chain_first = (uint32_t)chains_n;
             d.track_from = tracked ? (j.n > WINDOW ? j.n - WINDOW + 1 : 1) : j.n + 1;
-            d.hand_off = cell_n; d.handsum_off = handsum_n;
-            {
-                uint32_t m_max = 0;
-                for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
-                d.LB = use_packed ? pk_plan(al.opts.sc, j.n, m_max) : 0;
-                if (d.LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) > 200 * 1024) d.LB = 0;   // tile table must fit shared memory
-                d.j0 = 0;
-                if (d.LB) { stats.packed_cells += L.cells_per_col * j.n; ++n_packed; ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM()); }
-                max_ctiles = std::max(max_ctiles, m_max / (uint32_t)TILE + 1);
-            }
-            handsum_n += C;
-            h_jobs.p[k] = d;
-            reads_b += round_up(j.n, 16);
-            colrec_n += (uint64_t)(j.n + 1) * C; cell_n += L.PM(); ck_n += (nb - 1) * L.PM(); cksum_n += (nb - 1) * C;
-            gcol_n += j.n + 1; ops_n += d.ops_cap; chains_n += d.max_chains;
-            pm_max = std::max<uint64_t>(pm_max, L.PM());
+            d.hand_off = tot.cell; d.handsum_off = handsum_n;
+            d.LB = plan_LB(j); d.j0 = 0;
+            const Need nd = need_of(j);
             uint32_t mct = 0;
             for (const auto &e : L.ent) mct = std::max(mct, e.ntiles);
+            max_ctiles = std::max(max_ctiles, mct);
+            if (d.LB) {
+                stats.packed_cells += L.cells_per_col * j.n; ++n_packed;
+                ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM());
+            }
+            if (d.LB && fused) {   // records live in the CTA's arena
+                arena.colrec = std::max(arena.colrec, nd.colrec); arena.cell = std::max(arena.cell, nd.cell); arena.ck = std::max(arena.ck, nd.ck);
+                arena.cksum = std::max(arena.cksum, nd.cksum); arena.gcol = std::max(arena.gcol, nd.gcol);
+            } else {
+                tot.colrec += nd.colrec; tot.cell += nd.cell; tot.ck += nd.ck; tot.cksum += nd.cksum; tot.gcol += nd.gcol;
+                handsum_n += C; per_job_bytes += need_bytes(nd);
+                pm_max = std::max<uint64_t>(pm_max, L.PM());
+            }
+            h_jobs.p[k] = d;
+            reads_b += round_up(j.n, 16);
+            ops_n += d.ops_cap; chains_n += d.max_chains;
             unit_max = std::max<uint64_t>(unit_max, (uint64_t)mct * TILE * std::min<uint32_t>(K, j.n));
             cells += L.cells_per_col * j.n;
         }
+        const uint32_t n_wide = nj - n_packed;
         std::iota(h_order.p, h_order.p + nj, 0u);
         std::stable_sort(h_order.p, h_order.p + nj, [&](uint32_t x, uint32_t y) {
             const host::Job &a = jobs[begin + x], &b = jobs[begin + y];
             return Ls[a.layout].cells_per_col * a.n > Ls[b.layout].cells_per_col * b.n;
         });
-        const int ctas_per_sm = 2;
-        const uint32_t grid = std::min<uint32_t>(nj, (uint32_t)(num_sms * ctas_per_sm));
-        d_jobs.reserve(nj); d_order.reserve(3 * (size_t)nj); d_colrec.reserve(colrec_n); d_last.reserve(cell_n);
-        d_sn.reserve(cell_n); d_ck.reserve(ck_n); d_cksum.reserve(cksum_n); d_gcol.reserve(gcol_n);
-        d_ops.reserve(ops_n); d_chains.reserve(chains_n); d_jobout.reserve(nj);
-        d_state.reserve((uint64_t)grid * 2 * pm_max);
-        d_hand.reserve(cell_n); d_handsum.reserve(handsum_n);
-        // CTAs per read: a cluster of 4 keeps the rolling state of all reads in flight inside the L2 (fewer, faster reads
-        // in flight); small layouts and STITCH_CLUSTER=1 use a single CTA per read
+        // order lists: [0, nj) all jobs; then the packed jobs; then the wide jobs; then re-runs
+        uint32_t *po = h_order.p + nj, *wo = po + n_packed, *ro = wo + n_wide;
+        { uint32_t a = 0, b = 0; for (uint32_t k = 0; k < nj; ++k) { if (h_jobs.p[h_order.p[k]].LB) po[a++] = h_order.p[k]; else wo[b++] = h_order.p[k]; } }
+
+        // grids.  Fused path: two 8-warp CTAs per SM, each with its own arena; clustered path: one team per read.
+        const uint32_t wgrid = std::min<uint32_t>(std::max<uint32_t>(fused ? n_wide : nj, 1), (uint32_t)num_sms);   // walk / wide kernels
         uint32_t cluster = cluster_pref;
         if (ntmax < cluster_min_tiles) cluster = 1;
-        uint32_t pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms / cluster);
-        if (cluster > 1 && n_packed) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)num_sms / cluster * cluster); cfg.blockDim = dim3(PACK_WARPS * 32);
-            cfg.dynamicSmemBytes = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
-            set_smem(fill_packed_kernel<PACK_WARPS>, cfg.dynamicSmemBytes);
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int max_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, fill_packed_kernel<PACK_WARPS>, &cfg) == cudaSuccess && max_clusters > 0)
-                pteams = std::min<uint32_t>(pteams, (uint32_t)max_clusters);
-            else { cudaGetLastError(); cluster = 1; pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms); }
+        uint32_t fgrid = 0, pteams = 0;
+        const size_t fsmem_tables = (PackSmem::bytes(cmax, ntmax, FUSED_WARPS) + 15) / 16 * 16;
+        const size_t fsmem = fsmem_tables + UnitStage::bytes(K, max_ctiles);
+        if (n_packed && fused) {
+            fgrid = std::min<uint32_t>(n_packed, (uint32_t)num_sms * (fsmem <= 110 * 1024 ? 2 : 1));
+            const uint64_t per_cta = need_bytes(arena) + 2 * ppm_max * 4 + unit_max + 2 * (uint64_t)max_ctiles * TILE * 4 + K * sizeof(ColRec);
+            const uint64_t avail = mem_budget > per_job_bytes + ops_n * sizeof(OutOp) ? mem_budget - per_job_bytes - ops_n * sizeof(OutOp) : 0;
+            if (per_cta > avail) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
+            fgrid = (uint32_t)std::min<uint64_t>(fgrid, avail / per_cta);
+        } else if (n_packed) {
+            pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms / cluster);
+            if (cluster > 1) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)num_sms / cluster * cluster); cfg.blockDim = dim3(PACK_WARPS * 32);
+                cfg.dynamicSmemBytes = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
+                set_smem(fill_packed_kernel<PACK_WARPS>, cfg.dynamicSmemBytes);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int max_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&max_clusters, fill_packed_kernel<PACK_WARPS>, &cfg) == cudaSuccess && max_clusters > 0)
+                    pteams = std::min<uint32_t>(pteams, (uint32_t)max_clusters);
+                else { cudaGetLastError(); cluster = 1; pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms); }
+            }
         }
-        d_pstate.reserve((uint64_t)pteams * 2 * ppm_max + 64);
+        const uint32_t bufgrid = std::max(wgrid, fgrid);   // CTAs that own walk buffers
+        d_jobs.reserve(nj); d_order.reserve(4 * (size_t)nj + 16);
+        d_colrec.reserve(tot.colrec + (uint64_t)fgrid * arena.colrec); d_last.reserve(tot.cell + (uint64_t)fgrid * arena.cell);
+        d_sn.reserve(tot.cell + (uint64_t)fgrid * arena.cell); d_ck.reserve(tot.ck + (uint64_t)fgrid * arena.ck);
+        d_cksum.reserve(tot.cksum + (uint64_t)fgrid * arena.cksum); d_gcol.reserve(tot.gcol + (uint64_t)fgrid * arena.gcol);
+        d_ops.reserve(ops_n); d_chains.reserve(chains_n); d_jobout.reserve(nj);
+        d_state.reserve((uint64_t)wgrid * 2 * pm_max + 64);
+        d_hand.reserve(tot.cell + 64); d_handsum.reserve(handsum_n + 64);
+        d_pstate.reserve((uint64_t)std::max(fgrid, pteams) * 2 * ppm_max + 64);
         d_tailj0.reserve(nj);
         const uint64_t wps_half = (uint64_t)max_ctiles * TILE;
-        d_wpstate.reserve((uint64_t)grid * 2 * wps_half + 64);
-        d_ucr.reserve((uint64_t)grid * K + 64);
-        d_unit.reserve((uint64_t)grid * round_up(unit_max, 256));
+        d_wpstate.reserve((uint64_t)bufgrid * 2 * wps_half + 64);
+        d_ucr.reserve((uint64_t)bufgrid * K + 64);
+        d_unit.reserve((uint64_t)bufgrid * round_up(unit_max, 256));
         if (!device_reads) { d_reads.reserve(reads_b); h_reads.reserve(reads_b); }
         h_ops.reserve(ops_n); h_chains.reserve(chains_n); h_jobout.reserve(nj);
 
@@ -320,8 +366,8 @@ struct CudaBackend : host::Backend {
             stats.h2d += reads_b;
         }
         CUDA_CHECK(cudaMemcpyAsync(d_jobs.p, h_jobs.p, nj * sizeof(JobDesc), cudaMemcpyHostToDevice, stream));
-        CUDA_CHECK(cudaMemcpyAsync(d_order.p, h_order.p, nj * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        stats.h2d += nj * (sizeof(JobDesc) + sizeof(uint32_t));
+        CUDA_CHECK(cudaMemcpyAsync(d_order.p, h_order.p, 2 * (size_t)nj * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        stats.h2d += nj * (sizeof(JobDesc) + 2 * sizeof(uint32_t));
         CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 8 * sizeof(uint32_t), stream));
 
         Params P{};
@@ -335,20 +381,25 @@ struct CudaBackend : host::Backend {
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
-        P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles;
+        P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1;
+        P.arena.colrec_base = tot.colrec; P.arena.colrec_stride = arena.colrec; P.arena.cell_base = tot.cell; P.arena.cell_stride = arena.cell;
+        P.arena.ck_base = tot.ck; P.arena.ck_stride = arena.ck; P.arena.cksum_base = tot.cksum; P.arena.cksum_stride = arena.cksum;
+        P.arena.gcol_base = tot.gcol; P.arena.gcol_stride = arena.gcol;
         if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
         set_smem(fill_wide_kernel<FILL_WARPS>, smem);
         mark(T_PACKED);
-        const uint32_t n_wide = nj - n_packed;
-        if (n_packed) {
-            // the order list of the packed kernel: jobs on the packed path, largest first
-            uint32_t *po = h_order.p + 2 * (size_t)nj;
-            uint32_t c = 0;
-            for (uint32_t k = 0; k < nj; ++k) if (h_jobs.p[h_order.p[k]].LB) po[c++] = h_order.p[k];
-            CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj, po, c * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-            Params Q = P; Q.order = d_order.p + 2 * (size_t)nj; Q.n_jobs = c; Q.counter = d_counter.p + 3;
+        if (n_packed && fused) {
+            // the whole pipeline of the packed reads in one persistent kernel (fill, tail, fix-up, walk)
+            Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
+            Q.walk_stage_smem_off = (uint32_t)fsmem_tables;
+            set_smem(align_packed_kernel<FUSED_WARPS>, fsmem);
+            align_packed_kernel<FUSED_WARPS><<<fgrid, FUSED_WARPS * 32, fsmem, stream>>>(Q);
+            CUDA_CHECK(cudaGetLastError());
+            stats.launches += 1;
+        } else if (n_packed) {
+            Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster;
             const size_t psmem = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
             set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
@@ -362,8 +413,7 @@ struct CudaBackend : host::Backend {
                 ++na;
             }
             if (l2_persist && l2_persist_max && l2_window_max) {
-                // pin (a fraction of) the rolling column state in the L2: every line of it is read and rewritten once per
-                // column, everything else the kernel touches streams
+                // pin (a fraction of) the rolling column state in the L2 (measured: no gain on B200)
                 const size_t bytes = (size_t)pteams * 2 * ppm_max * sizeof(int32_t);
                 const size_t win = std::min(bytes, l2_window_max);
                 at[na].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -373,8 +423,6 @@ struct CudaBackend : host::Backend {
                 at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 ++na;
-                if (debug_stats) std::fprintf(stderr, "[stitch dbg] L2 persist max %zu MB, window max %zu MB, state %zu MB, hitRatio %.2f\n",
-                                              l2_persist_max >> 20, l2_window_max >> 20, bytes >> 20, at[na - 1].val.accessPolicyWindow.hitRatio);
             }
             cfg.attrs = at; cfg.numAttrs = na;
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
@@ -382,20 +430,23 @@ struct CudaBackend : host::Backend {
         }
         mark(T_WIDE);
         if (n_wide) {
-            // jobs outside the packed regime run on the wide kernel (order list: the rest, largest first)
-            uint32_t *wo = h_order.p + 2 * (size_t)nj + n_packed;
-            uint32_t c = 0;
-            for (uint32_t k = 0; k < nj; ++k) if (!h_jobs.p[h_order.p[k]].LB) wo[c++] = h_order.p[k];
-            CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj + n_packed, wo, c * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-            Params Q = P; Q.order = d_order.p + 2 * (size_t)nj + n_packed; Q.n_jobs = c;
-            fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(c, grid), FILL_WARPS * 32, smem, stream>>>(Q);
+            // jobs outside the packed regime run on the wide kernel
+            Params Q = P; Q.order = d_order.p + nj + n_packed; Q.n_jobs = n_wide;
+            fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_wide, 2 * (uint32_t)num_sms), FILL_WARPS * 32, smem, stream>>>(Q);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
+        // fix-up and walk kernels: the wide reads, plus the packed ones when they did not run fused
+        const uint32_t n_post = fused ? n_wide : nj;
+        const uint32_t *post_order = fused ? d_order.p + nj + n_packed : d_order.p;
         mark(T_FIXUP);
-        fixup_kernel<<<nj, 64, 0, stream>>>(P);
-        CUDA_CHECK(cudaGetLastError());
-        stats.launches += 1; stats.fills += nj; stats.cells += cells;
+        if (n_post) {
+            Params Q = P; Q.order = post_order; Q.n_jobs = n_post;
+            fixup_kernel<<<n_post, 64, 0, stream>>>(Q);
+            CUDA_CHECK(cudaGetLastError());
+            stats.launches += 1;
+        }
+        stats.fills += nj; stats.cells += cells;
         if (tracked && n_wide) {
             // wide-path reads whose tracking window was too narrow are filled again from an earlier checkpoint
             CUDA_CHECK(cudaMemcpyAsync(h_jobout.p, d_jobout.p, nj * sizeof(JobOut), cudaMemcpyDeviceToHost, stream));
@@ -404,19 +455,21 @@ struct CudaBackend : host::Backend {
             collect_marks();
             uint32_t n_redo = 0;
             h_redo.reserve(nj); d_redo.reserve(nj);
-            for (uint32_t k = 0; k < nj; ++k) if (h_jobout.p[k].status == JOB_NEED_FULL_TRACK) {
-                h_order.p[nj + n_redo++] = k;
+            for (uint32_t t = 0; t < n_wide; ++t) {
+                const uint32_t k = wo[t];
+                if (h_jobout.p[k].status != JOB_NEED_FULL_TRACK) continue;
+                ro[n_redo++] = k;
                 const uint32_t first = h_jobout.p[k].n_chains;   // first column that may hold a final y-suffix tracker
                 h_redo.p[k] = first > 0 ? ((first - 1) / K) * K : 0;
                 stats.cells += Ls[jobs[begin + k].layout].cells_per_col * (jobs[begin + k].n - h_redo.p[k]);
             }
             mark(T_REDO);
             if (n_redo) {
-                CUDA_CHECK(cudaMemcpyAsync(d_order.p + nj, h_order.p + nj, n_redo * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                CUDA_CHECK(cudaMemcpyAsync(d_order.p + 2 * (size_t)nj, ro, n_redo * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
                 CUDA_CHECK(cudaMemcpyAsync(d_redo.p, h_redo.p, nj * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-                Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_redo; Q.force_full = 1; Q.counter = d_counter.p + 1;
+                Params Q = P; Q.order = d_order.p + 2 * (size_t)nj; Q.n_jobs = n_redo; Q.force_full = 1; Q.counter = d_counter.p + 1;
                 Q.redo_j0 = d_redo.p;
-                fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_redo, grid), FILL_WARPS * 32, smem, stream>>>(Q);
+                fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_redo, 2 * (uint32_t)num_sms), FILL_WARPS * 32, smem, stream>>>(Q);
                 CUDA_CHECK(cudaGetLastError());
                 fixup_kernel<<<n_redo, 64, 0, stream>>>(Q);
                 CUDA_CHECK(cudaGetLastError());
@@ -424,8 +477,8 @@ struct CudaBackend : host::Backend {
             }
         }
         mark(T_WALK);
-        {
-            Params Wp = P; Wp.counter = d_counter.p + 2;
+        if (n_post) {
+            Params Wp = P; Wp.order = post_order; Wp.n_jobs = n_post; Wp.counter = d_counter.p + 2;
             size_t wsmem = std::max(WideSmem<WALK_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, WALK_WARPS, false));
             wsmem = (wsmem + 15) / 16 * 16;
             Wp.walk_stage_smem_off = (uint32_t)wsmem;
@@ -433,7 +486,7 @@ struct CudaBackend : host::Backend {
             const size_t state_b = 2 * wps_half * sizeof(int32_t);
             if (wsmem + state_b <= 160 * 1024) { Wp.walk_state_smem_off = (uint32_t)wsmem; wsmem += state_b; }
             set_smem(walk_kernel<WALK_WARPS>, wsmem);
-            walk_kernel<WALK_WARPS><<<std::min<uint32_t>(nj, (uint32_t)num_sms), WALK_WARPS * 32, wsmem, stream>>>(Wp);
+            walk_kernel<WALK_WARPS><<<wgrid, WALK_WARPS * 32, wsmem, stream>>>(Wp);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
@@ -447,10 +500,11 @@ struct CudaBackend : host::Backend {
         if (debug_stats) {
             unsigned long long h[16];
             cudaMemcpy(h, d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
-            std::fprintf(stderr, "[stitch dbg] jobs %u: tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, refill columns %llu, "
-                         "refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6], h[4] * 1e-6, h[5] * 1e-6);
+            std::fprintf(stderr, "[stitch dbg] jobs %u (fused grid %u): tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, "
+                         "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, fgrid, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
+                         h[4] * 1e-6, h[5] * 1e-6);
         }
-        stats.tb_bytes += ck_n * sizeof(CellState) + colrec_n * sizeof(ColRec);
+        stats.tb_bytes += (tot.ck + (uint64_t)fgrid * arena.ck) * sizeof(CellState) + (tot.colrec + (uint64_t)fgrid * arena.colrec) * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);
 
         bool overflow = false;

@@ -85,6 +85,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     uint32_t n;
     bool yclip_mode;
     bool state_smem;        // the state arrays live in shared memory (walk kernel re-fills)
+    bool staged;            // cp.async double-buffering of tiles (state and bases both in global memory, stage buffers carved)
     Team team;
 };
 
@@ -275,7 +276,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         int32_t oS[STRIP], oD[STRIP];
         // software pipeline: while tile t is computed, cp.async brings tile t+1 (S keys, D keys, bases) into this
         // warp's shared-memory double buffer; each lane reads back exactly the bytes it copied (no warp sync needed)
-        const bool staged = !X.state_smem;
+        const bool staged = X.staged;
         unsigned char *stg0 = S.stage + (size_t)warp * 2 * PackSmem::STAGE_BYTES;
         auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot) {
             unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
@@ -554,6 +555,74 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
     }
 }
 
+// Base of column j, jump selection for every contig (MCA:279-331), per-column constants (the CTA must synchronise
+// before using them).  s_cc[(j-1)&1].pc.B holds the base of column j-1.
+template <int W>
+__device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, ColRec *colrec, int32_t *gcol, const uint8_t *read,
+                                                 uint32_t j, PkColConst *s_cc, bool writer) {
+    const uint32_t tid = threadIdx.x, par = j & 1u, C = X.C;
+    constexpr uint32_t T = W * 32;
+    const int32_t Bprev = s_cc[par ^ 1u].pc.B;
+    if (tid < C || tid == 0) {
+        int32_t g = S.cm[0];
+        for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
+        PCol pcl; pcl.B = g; pcl.delta = g - Bprev;
+        for (uint32_t a = tid; a < C; a += T) {
+            const JumpInfo J = select_jump(X.sc, X.ent, C, a, S.cm, S.cml, S.cmk);
+            if (writer) {
+                ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
+                cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
+                colrec[(uint64_t)j * C + a] = cr;
+            }
+            S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
+        }
+        if (tid == 0) {
+            if (writer) gcol[j - 1] = g;
+            s_cc[par] = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, read[j - 1]);
+        }
+    }
+}
+
+// After the bulk pass: best score of column n, and the column the tail restarts from: the last checkpoint before
+// the first column that can hold a final y-suffix tracker (dp_core.h: first_candidate_column); column n is always
+// part of the tail.  Also the score below which a cell cannot hold a final tracker value.
+template <int W>
+__device__ uint32_t pk_tail_start(const Params &P, PackSmem &S, const Scoring &sc, int32_t *gcol, uint32_t n, uint32_t C, uint32_t K,
+                                  int32_t *s_gmax, uint32_t *s_first, int32_t &track_thr, bool writer) {
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    __syncthreads();
+    if (tid == 0) {
+        int32_t g = S.cm[0];
+        for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
+        if (writer) gcol[n] = g;
+        *s_gmax = g; *s_first = n;
+    }
+    __syncthreads();
+    track_thr = MIN_SCORE;
+    if (P.tracked_mode) {
+        int32_t g = *s_gmax;
+        for (uint32_t jj = tid; jj < n; jj += T) g = gcol[jj] > g ? gcol[jj] : g;
+        atomicMax(s_gmax, g);
+        __syncthreads();
+        int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
+        if (submax < 0) submax = 0;
+        const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+        int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+        gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+        const int32_t gmax = *s_gmax;
+        const int32_t thr = gmax - (submax - gmin - submin);
+        track_thr = thr;
+        uint32_t first = n;
+        for (uint32_t jj = 1 + tid; jj < n; jj += T) if (gcol[jj] >= thr) { first = jj; break; }
+        atomicMin(s_first, first);
+        __syncthreads();
+    }
+    const uint32_t j0 = ((*s_first - 1) / K) * K;
+    __syncthreads();
+    return j0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // bulk fill
 // ---------------------------------------------------------------------------------------------
@@ -590,7 +659,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
-        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false;
+        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;
@@ -605,64 +674,19 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
 
         for (uint32_t j = 1; j <= n; ++j) {
             const uint32_t par = j & 1u;
-            // ---- base of the column, jump selection (MCA:279-331), per-column constants ----
-            {
-                const int32_t Bprev = s_cc[par ^ 1u].pc.B;
-                if (tid < C || tid == 0) {
-                    int32_t g = S.cm[0];
-                    for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-                    PCol pcl; pcl.B = g; pcl.delta = g - Bprev;
-                    for (uint32_t a = tid; a < C; a += T) {
-                        const JumpInfo J = select_jump(sc, X.ent, C, a, S.cm, S.cml, S.cmk);
-                        if (team.rank == 0) {
-                            ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
-                            cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
-                            colrec[(uint64_t)j * C + a] = cr;
-                        }
-                        S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
-                    }
-                    if (tid == 0) {
-                        if (team.rank == 0) gcol[j - 1] = g;
-                        s_cc[par] = pk_col_const(X.pk, sc, g, Bprev, j, n, read[j - 1]);
-                    }
-                }
-            }
+            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0);
             __syncthreads();
             const PkColConst cc = s_cc[par];
             pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
             if ((j % K == 0) && j < n)
                 pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
         }
-        // best score of column n; the column the tail restarts from: the last checkpoint before the first column
-        // that can hold a final y-suffix tracker (dp_core.h: first_candidate_column); column n is always in the tail
-        if (tid == 0) {
-            int32_t g = S.cm[0];
-            for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-            if (team.rank == 0) gcol[n] = g;
-            s_gmax = g; s_first = n;
-        }
-        team.sync();   // gcol / colrec of the whole read (written by rank 0) visible to the team
         int32_t track_thr = MIN_SCORE;
-        if (P.tracked_mode) {
-            int32_t g = gcol[n];
-            for (uint32_t jj = tid; jj < n; jj += T) g = gcol[jj] > g ? gcol[jj] : g;
-            atomicMax(&s_gmax, g);
-            __syncthreads();
-            int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
-            if (submax < 0) submax = 0;
-            const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
-            int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
-            gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
-            const int32_t thr = s_gmax - (submax - gmin - submin);
-            track_thr = thr;
-            uint32_t first = n;
-            for (uint32_t jj = 1 + tid; jj <= n; jj += T) if (gcol[jj] >= thr) { first = jj; break; }
-            atomicMin(&s_first, first);
-            __syncthreads();
+        if (team.size > 1) {   // gcol / colrec of the whole read (written by rank 0) must be visible to the team
+            if (tid == 0 && team.rank == 0) { int32_t g = S.cm[0]; for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g; gcol[n] = g; }
+            team.sync();
         }
-        // ---- tail: the last columns again, traceback variant with trackers (same CTA: no launch boundary, and a
-        // CTA with a short tail moves on to the next read while others are still in theirs) ----
-        const uint32_t j0 = ((s_first - 1) / K) * K;
+        const uint32_t j0 = pk_tail_start<W>(P, S, sc, gcol, n, C, K, &s_gmax, &s_first, track_thr, team.rank == 0);
         if (tid == 0 && team.rank == 0) P.tail_j0[job] = j0;
         __syncthreads();
         const long long t_tail0 = clock64();
@@ -723,7 +747,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     PackCtx X;
     X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
     X.Sst = pstate; X.Dst = pstate + pstate_half; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
-    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem;
+    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(b - 1) * PM + gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);

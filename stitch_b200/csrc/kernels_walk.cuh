@@ -1,7 +1,15 @@
-// kernels_walk.cuh — end-contig selection + pointer walk (traceback/mod.rs:129-373 of the reference), one CTA
-// per read: thread 0 walks; whenever the walk needs packed traceback bytes that are not loaded the whole CTA
-// re-fills that unit (one contig over one block of K columns) from the column-state checkpoint before it,
-// with the packed-key columns (kernels_packed.cuh) or, for scorings outside their regime, the wide ones.
+// kernels_walk.cuh — end-contig selection + pointer walk (traceback/mod.rs:129-373 of the reference) and the
+// fused per-read kernel of the packed path.
+//
+//   walk_job             thread 0 walks; whenever the walk needs packed traceback bytes that are not loaded the whole
+//                        CTA re-fills that unit (one contig over one block of K columns) from the column-state
+//                        checkpoint before it, with the packed-key columns (kernels_packed.cuh) or, for scorings
+//                        outside their regime, the wide ones.
+//   walk_kernel          walk_job for the reads of the wide path (their fill ran in fill_wide_kernel).
+//   align_packed_kernel  the whole per-read pipeline of the packed path in ONE persistent kernel: a CTA pulls a
+//                        read, runs its bulk fill, tail, end-of-read fix-up and walk, then pulls the next read.
+//                        Two CTAs share an SM, so the latency-bound phases of one read (walk, fix-up) overlap the
+//                        bandwidth-bound fill of another; all working memory is per CTA, not per read.
 #pragma once
 #include "kernels_packed.cuh"
 #include "kernels_wide.cuh"
@@ -9,26 +17,115 @@
 namespace stitch {
 namespace gpu {
 
+struct WalkShared {
+    uint32_t cmd, ua, uj;
+    ContigEntry en;
+    TbUnit unit;
+    PkColConst cc;
+    uint8_t seen[MAX_STRANDS];
+};
+
+struct WalkBufs {           // per CTA
+    CellState *st0, *st1;   // wide re-fill state
+    int32_t *wps; bool wps_smem;   // packed re-fill state
+    uint8_t *ubytes; ColRec *ucr;
+};
+
+// `jd` carries the offsets of the read's records (per read for the wide path, per CTA arena for the fused kernel).
+template <int W, bool PACKED_ONLY>
+__device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDesc &jd, const LayoutDesc &ld, WideSmem<W> *WS, PackSmem &PS,
+                         UnitStage &US, WalkShared &sh, const WalkBufs &B) {
+    const uint32_t tid = threadIdx.x;
+    const long long t_job0 = clock64();
+    // thread-0 state
+    ReadView v; WalkState ws; ChainHdr h;
+    uint32_t used = 0, n_chains = 0, status = WALK_OK, n_seen = 0, a_cur = 0;
+    bool walking = false, finished = false;
+    OutOp *ops = P.ops + jd.ops_off;
+    ChainHdr *hdr = P.chains + jd.chain_first;
+    if (tid == 0) {
+        v.sc = P.sc; v.ent = P.ents + ld.ent_off; v.C = ld.C; v.n = jd.n;
+        v.colrec = P.colrec + jd.colrec_off; v.last = P.last + jd.cell_off; v.sn = P.sn + jd.cell_off;
+        v.contig_bases = P.contig_bases; v.read = P.reads + jd.read_off; v.pos_of = P.posof + ld.posof_off;
+        v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
+        if (jd.walk == host::WALK_ALL) for (uint32_t a = 0; a < ld.C; ++a) sh.seen[a] = 0;
+    }
+    for (;;) {
+        if (tid == 0) {
+            sh.cmd = WCMD_DONE;
+            while (!finished) {
+                if (!walking) {   // choose the next chain to walk
+                    int a_end = -1;
+                    if (jd.walk == host::WALK_BEST) { if (n_chains == 0 && used == 0) a_end = (int)pick_end(v, nullptr); }
+                    else if (jd.walk == host::WALK_FROM) {
+                        if (n_chains == 0 && used == 0) a_end = jd.from_contig < MAX_STRANDS ? v.pos_of[jd.from_contig] : -1;
+                    } else if (n_seen < ld.C) a_end = (int)pick_end(v, sh.seen);
+                    if (a_end < 0) { finished = true; break; }
+                    a_cur = (uint32_t)a_end;
+                    walk_begin(v, a_cur, ops + used, jd.ops_cap - used, ws, h);
+                    walking = true;
+                }
+                const uint32_t s = walk_run(v, ws, h);
+                if (s == WALK_NEED_UNIT) { sh.cmd = WCMD_UNIT; sh.ua = ws.a; sh.uj = ws.j; break; }
+                walking = false;
+                auto mark = [&](uint32_t idx) {
+                    const int p = idx < MAX_STRANDS ? v.pos_of[idx] : -1;
+                    if (p >= 0 && !sh.seen[p]) { sh.seen[p] = 1; ++n_seen; }
+                };
+                if (jd.walk == host::WALK_ALL) {
+                    if (s == WALK_NONE) { mark(v.ent[a_cur].contig_idx); continue; }
+                    if (s != WALK_OK) { status = s; finished = true; break; }
+                    mark(h.start_contig_idx); mark(h.end_contig_idx);
+                    for (uint32_t k = 0; k < h.n_ops; ++k) if (ops[used + k].kind == OP_XJUMP) mark(ops[used + k].a);
+                    if (n_chains >= jd.max_chains) { status = WALK_OVERFLOW; finished = true; break; }
+                    hdr[n_chains++] = h;
+                    used += h.n_ops;
+                } else {
+                    if (s == WALK_OK) { hdr[0] = h; n_chains = 1; }
+                    else if (s != WALK_NONE) status = s;
+                    finished = true;
+                }
+            }
+        }
+        __syncthreads();
+        if (sh.cmd == WCMD_DONE) break;
+        const long long t_r0 = clock64();
+        if (PACKED_ONLY || jd.LB)
+            pk_refill_unit<W>(P, jd, ld, PS, US, &sh.en, &sh.cc, sh.ua, sh.uj, B.wps, P.wpstate_half, B.wps_smem, B.ubytes, B.ucr, &sh.unit);
+        else if (!PACKED_ONLY)
+            refill_unit<W>(P, jd, ld, *WS, &sh.en, sh.ua, sh.uj, B.st0, B.st1, B.ubytes, B.ucr, &sh.unit);
+        if (tid == 0) {
+            v.unit = sh.unit;
+            if (P.dbg) {
+                atomicAdd(P.dbg + 3, 1ull);
+                atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - t_r0));
+                atomicAdd(P.dbg + 6, (unsigned long long)(sh.unit.je - sh.unit.jb));
+            }
+        }
+    }
+    if (tid == 0) {
+        JobOut o; o.n_chains = n_chains; o.status = status; P.job_out[job] = o;
+        if (P.dbg) atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - t_job0));
+    }
+    __syncthreads();
+}
+
 template <int W>
 __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WideSmem<W> S; S.carve(smem_raw, 1);
     PackSmem PS; PS.carve(smem_raw, 1, P.max_ctiles, W, false);   // same bytes: a job uses one of the two
-    __shared__ PkColConst s_cc;
     UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
-    __shared__ uint32_t sJob, sCmd, sUa, sUj;
-    __shared__ ContigEntry s_en;
-    __shared__ TbUnit s_unit;
-    __shared__ uint8_t s_seen[MAX_STRANDS];
+    __shared__ uint32_t sJob;
+    __shared__ WalkShared sh;
     const uint32_t tid = threadIdx.x;
-    CellState *st0 = P.state + (uint64_t)blockIdx.x * P.state_stride;
-    CellState *st1 = st0 + P.state_half;
-    uint8_t *ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
-    ColRec *ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
+    WalkBufs B;
+    B.st0 = P.state + (uint64_t)blockIdx.x * P.state_stride; B.st1 = B.st0 + P.state_half;
+    B.ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
+    B.ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
     // packed state of the unit's contig: in shared memory when it fits (a contig is a few tiles), else global
-    int32_t *wps = P.walk_state_smem_off ? reinterpret_cast<int32_t *>(smem_raw + P.walk_state_smem_off)
-                                         : P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
-
+    B.wps_smem = P.walk_state_smem_off != 0;
+    B.wps = B.wps_smem ? reinterpret_cast<int32_t *>(smem_raw + P.walk_state_smem_off) : P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
     for (;;) {
         __syncthreads();
         if (tid == 0) sJob = atomicAdd(P.counter, 1u);
@@ -37,75 +134,116 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
         const uint32_t job = P.order[sJob];
         const JobDesc jd = P.jobs[job];
         const LayoutDesc ld = P.layouts[jd.layout];
-        const long long t_job0 = clock64();
+        walk_job<W, false>(P, job, jd, ld, &S, PS, US, sh, B);   // (this kernel does nothing else: no copies needed)
+    }
+}
 
-        // thread-0 state
-        ReadView v; WalkState ws; ChainHdr h;
-        uint32_t used = 0, n_chains = 0, status = WALK_OK, n_seen = 0, a_cur = 0;
-        bool walking = false, finished = false;
-        OutOp *ops = P.ops + jd.ops_off;
-        ChainHdr *hdr = P.chains + jd.chain_first;
-        if (tid == 0) {
-            v.sc = P.sc; v.ent = P.ents + ld.ent_off; v.C = ld.C; v.n = jd.n;
-            v.colrec = P.colrec + jd.colrec_off; v.last = P.last + jd.cell_off; v.sn = P.sn + jd.cell_off;
-            v.contig_bases = P.contig_bases; v.read = P.reads + jd.read_off; v.pos_of = P.posof + ld.posof_off;
-            v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
-            if (jd.walk == host::WALK_ALL) for (uint32_t a = 0; a < ld.C; ++a) s_seen[a] = 0;
+// Everything after the bulk pass of one read of the fused kernel: tail, end-of-read fix-up, walk.
+template <int W>
+__device__ __noinline__ void finish_job(const Params &P, uint32_t job, const JobDesc &jd, const LayoutDesc &ld, PackCtx &X, PackSmem &S,
+                                        UnitStage &US, WalkShared &sh, const WalkBufs &B, PkColConst *s_cc, int32_t *s_gmax, uint32_t *s_first,
+                                        long long t_bulk0) {
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    const Scoring &sc = X.sc;
+    const uint32_t C = ld.C, n = jd.n, K = P.K;
+    ColRec *colrec = P.colrec + jd.colrec_off;
+    int32_t *gcol = P.gcol + jd.gcol_off;
+    int32_t track_thr = MIN_SCORE;
+    const uint32_t j0 = pk_tail_start<W>(P, S, sc, gcol, n, C, K, s_gmax, s_first, track_thr, true);
+    // ---- tail: the last columns again, traceback variant with trackers ----
+    const long long t_tail0 = clock64();
+    pk_tail<W>(P, jd, ld, X, S, s_cc, j0, track_thr);
+    if (P.dbg && tid == 0) {
+        atomicAdd(P.dbg + 0, (unsigned long long)(n - j0));
+        atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_tail0));
+        atomicAdd(P.dbg + 2, (unsigned long long)(t_tail0 - t_bulk0));
+    }
+    // ---- end-of-read fix-up (SCA:453-555), one thread per contig-strand ----
+    __syncthreads();
+    for (uint32_t a = tid; a < C; a += T)
+        fixup_contig(sc, X.ent[a], n, P.last + jd.cell_off, P.sn + jd.cell_off, P.tracked_mode != 0, &colrec[(uint64_t)n * C + a].lx);
+    __syncthreads();
+    // ---- walk ----
+    walk_job<W, true>(P, job, jd, ld, nullptr, S, US, sh, B);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused per-read kernel of the packed path
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
+    UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
+    __shared__ uint32_t sJob;
+    __shared__ PkColConst s_cc[2];
+    __shared__ int32_t s_gmax;
+    __shared__ uint32_t s_first;
+    __shared__ WalkShared sh;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    const Scoring sc = P.sc;
+    Team team; team.rank = 0; team.size = 1;
+    WalkBufs B;
+    B.st0 = nullptr; B.st1 = nullptr;
+    B.ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
+    B.ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
+    B.wps_smem = false;
+    B.wps = P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sJob = atomicAdd(P.counter, 1u);
+        __syncthreads();
+        if (sJob >= P.n_jobs) break;
+        const uint32_t job = P.order[sJob];
+        JobDesc jd = P.jobs[job];
+        // all records of the read live in this CTA's arena
+        jd.colrec_off = P.arena.colrec_base + (uint64_t)blockIdx.x * P.arena.colrec_stride;
+        jd.cell_off = P.arena.cell_base + (uint64_t)blockIdx.x * P.arena.cell_stride;
+        jd.ck_off = P.arena.ck_base + (uint64_t)blockIdx.x * P.arena.ck_stride;
+        jd.cksum_off = P.arena.cksum_base + (uint64_t)blockIdx.x * P.arena.cksum_stride;
+        jd.gcol_off = P.arena.gcol_base + (uint64_t)blockIdx.x * P.arena.gcol_stride;
+        const LayoutDesc ld = P.layouts[jd.layout];
+        const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
+        PackCtx X;
+        X.team = team;
+        X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
+        X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
+        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
+        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
+        ColRec *colrec = P.colrec + jd.colrec_off;
+        int32_t *gcol = P.gcol + jd.gcol_off;
+        const uint8_t *read = P.reads + jd.read_off;
+        PkColOut O; O.tb_col = nullptr; O.colrec_col = nullptr; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false;
+        O.track_thr = MIN_SCORE;
+
+        // ---- bulk: all n columns ----
+        const long long t_bulk0 = clock64();
+        pk_state_init0<W>(X, S);
+        pk_init_halos<W>(X, S, 0);
+        for (uint32_t a = tid; a < C; a += T) {   // column-0 record: Lx[0]
+            int32_t t; uint32_t lx; col0_tracker(sc, X.ent[a].m, t, lx);
+            ColRec cr; cr.jscore = 0; cr.jlen = 0; cr.jidx = 0; cr.jfrom = 0; cr.lx = lx; cr.pad0 = cr.pad1 = cr.pad2 = 0;
+            colrec[a] = cr;
         }
-        for (;;) {
-            if (tid == 0) {
-                sCmd = WCMD_DONE;
-                while (!finished) {
-                    if (!walking) {   // choose the next chain to walk
-                        int a_end = -1;
-                        if (jd.walk == host::WALK_BEST) { if (n_chains == 0 && used == 0) a_end = (int)pick_end(v, nullptr); }
-                        else if (jd.walk == host::WALK_FROM) {
-                            if (n_chains == 0 && used == 0) a_end = jd.from_contig < MAX_STRANDS ? v.pos_of[jd.from_contig] : -1;
-                        } else if (n_seen < ld.C) a_end = (int)pick_end(v, s_seen);
-                        if (a_end < 0) { finished = true; break; }
-                        a_cur = (uint32_t)a_end;
-                        walk_begin(v, a_cur, ops + used, jd.ops_cap - used, ws, h);
-                        walking = true;
-                    }
-                    const uint32_t s = walk_run(v, ws, h);
-                    if (s == WALK_NEED_UNIT) { sCmd = WCMD_UNIT; sUa = ws.a; sUj = ws.j; break; }
-                    walking = false;
-                    auto mark = [&](uint32_t idx) {
-                        const int p = idx < MAX_STRANDS ? v.pos_of[idx] : -1;
-                        if (p >= 0 && !s_seen[p]) { s_seen[p] = 1; ++n_seen; }
-                    };
-                    if (jd.walk == host::WALK_ALL) {
-                        if (s == WALK_NONE) { mark(v.ent[a_cur].contig_idx); continue; }
-                        if (s != WALK_OK) { status = s; finished = true; break; }
-                        mark(h.start_contig_idx); mark(h.end_contig_idx);
-                        for (uint32_t k = 0; k < h.n_ops; ++k) if (ops[used + k].kind == OP_XJUMP) mark(ops[used + k].a);
-                        if (n_chains >= jd.max_chains) { status = WALK_OVERFLOW; finished = true; break; }
-                        hdr[n_chains++] = h;
-                        used += h.n_ops;
-                    } else {
-                        if (s == WALK_OK) { hdr[0] = h; n_chains = 1; }
-                        else if (s != WALK_NONE) status = s;
-                        finished = true;
-                    }
-                }
-            }
+        if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
+        __syncthreads();
+        for (uint32_t j = 1; j <= n; ++j) {
+            const uint32_t par = j & 1u;
+            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, true);
             __syncthreads();
-            if (sCmd == WCMD_DONE) break;
-            const long long t_r0 = clock64();
-            if (jd.LB) pk_refill_unit<W>(P, jd, ld, PS, US, &s_en, &s_cc, sUa, sUj, wps, P.wpstate_half, P.walk_state_smem_off != 0, ubytes, ucr, &s_unit);
-            else refill_unit<W>(P, jd, ld, S, &s_en, sUa, sUj, st0, st1, ubytes, ucr, &s_unit);
-            if (tid == 0) {
-                v.unit = s_unit;
-                if (P.dbg) {
-                    atomicAdd(P.dbg + 3, 1ull);
-                    atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - t_r0));
-                    atomicAdd(P.dbg + 6, (unsigned long long)(s_unit.je - s_unit.jb));
-                }
-            }
+            const PkColConst cc = s_cc[par];
+            pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+            if ((j % K == 0) && j < n)
+                pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
         }
-        if (tid == 0) {
-            JobOut o; o.n_chains = n_chains; o.status = status; P.job_out[job] = o;
-            if (P.dbg) atomicAdd(P.dbg + 5, (unsigned long long)(clock64() - t_job0));
+        // ---- tail, fix-up, walk: a real call on copies, so that the bulk loop above keeps its pointer tables in
+        // registers and its register allocation to itself ----
+        {
+            PackCtx X2 = X; PackSmem S2 = S; UnitStage US2 = US; WalkBufs B2 = B; JobDesc jd2 = jd; LayoutDesc ld2 = ld;
+            finish_job<W>(P, job, jd2, ld2, X2, S2, US2, sh, B2, &s_cc[0], &s_gmax, &s_first, t_bulk0);
         }
     }
 }

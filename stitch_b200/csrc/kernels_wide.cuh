@@ -44,8 +44,12 @@ struct LayoutDesc { uint32_t ent_off, C, n_tiles, owner_off, posof_off, PM, max_
 enum : uint32_t { JOB_OK = 0, JOB_NEED_FULL_TRACK = 100 };
 struct JobOut { uint32_t n_chains, status; };
 
+// Per-CTA working memory of the fused kernel: record offsets = base + blockIdx.x * stride (in records).
+struct Arena { uint64_t colrec_base, colrec_stride, cell_base, cell_stride, ck_base, ck_stride, cksum_base, cksum_stride, gcol_base, gcol_stride; };
+
 struct Params {
     Scoring sc;
+    Arena arena;
     const JobDesc *jobs;
     const uint32_t *order;
     uint32_t n_jobs, cmax;
