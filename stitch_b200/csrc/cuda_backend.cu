@@ -102,7 +102,7 @@ struct CudaBackend : host::Backend {
     DevBuf<uint32_t> d_order;
     DevBuf<CellState> d_state, d_ck, d_hand;
     DevBuf<CkSum> d_handsum;
-    DevBuf<int32_t> d_pstate, d_wpstate;
+    DevBuf<int32_t> d_pstate, d_wpstate, d_pck;
     DevBuf<uint32_t> d_tailj0;
     DevBuf<unsigned long long> d_dbg;
     bool debug_stats = false;
@@ -203,14 +203,15 @@ struct CudaBackend : host::Backend {
     }
     bool fused_path() const { return use_fused && cluster_pref == 1; }
     // records a read holds from its fill until its walk is done (CellState/ColRec/... counts)
-    struct Need { uint64_t colrec, cell, ck, cksum, gcol; };
-    Need need_of(const host::Job &j) const {
+    // ck: wide checkpoints (CellState records); pck: packed checkpoints (raw keys, 2 per cell)
+    struct Need { uint64_t colrec, cell, ck, cksum, gcol, pck; };
+    Need need_of(const host::Job &j, bool packed) const {
         const host::Layout &L = al.layouts.layouts[j.layout];
         const uint64_t C = L.ent.size(), PM = L.PM(), nb = blocks_of(j.n);
-        return Need{(uint64_t)(j.n + 1) * C, PM, (nb - 1) * PM, (nb - 1) * C, (uint64_t)j.n + 1};
+        return Need{(uint64_t)(j.n + 1) * C, PM, packed ? 0 : (nb - 1) * PM, (nb - 1) * C, (uint64_t)j.n + 1, packed ? (nb - 1) * 2 * PM : 0};
     }
     static uint64_t need_bytes(const Need &n) {
-        return n.colrec * sizeof(ColRec) + n.cell * (sizeof(LastCell) + sizeof(SnRec) + sizeof(CellState)) + n.ck * sizeof(CellState) +
+        return n.colrec * sizeof(ColRec) + n.cell * (sizeof(LastCell) + sizeof(SnRec)) + n.ck * sizeof(CellState) + n.pck * 4 +
                n.cksum * sizeof(CkSum) + n.gcol * 4;
     }
     uint64_t out_bytes(const host::Job &j) const {
@@ -228,20 +229,28 @@ struct CudaBackend : host::Backend {
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         // memory our arenas may take: what is free now plus what they already hold
         const uint64_t held = d_ck.cap * sizeof(CellState) + d_colrec.cap * sizeof(ColRec) + d_last.cap * sizeof(LastCell) +
-                              d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_hand.cap * sizeof(CellState);
+                              d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_pck.cap * 4;
         mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.70);
         const bool fused = fused_path();
+        // chunks: per-read records of the reads that are not on the fused path + the outputs of all (the fused path's
+        // working memory is per CTA and is budgeted in run_chunk); equal-sized chunks so that no chunk is a sliver
+        std::vector<uint64_t> bytes(jobs.size());
+        uint64_t total = 0;
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            const bool packed = plan_LB(jobs[k]) != 0;
+            bytes[k] = out_bytes(jobs[k]) + ((fused && packed) ? 0 : need_bytes(need_of(jobs[k], packed)));
+            if (bytes[k] > mem_budget) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
+            total += bytes[k];
+        }
+        const uint64_t cap = fused ? mem_budget / 2 : mem_budget;
+        const uint64_t n_chunks = (total + cap - 1) / cap;
+        const uint64_t target = total / n_chunks + 1;
         size_t begin = 0;
         while (begin < jobs.size()) {
-            // a chunk: per-read records of the reads that are not on the fused path + the outputs of all; the fused
-            // path's working memory is per CTA and is budgeted in run_chunk
             size_t end = begin; uint64_t used = 0;
             while (end < jobs.size()) {
-                const bool arena = fused && plan_LB(jobs[end]) != 0;
-                const uint64_t b = out_bytes(jobs[end]) + (arena ? 0 : need_bytes(need_of(jobs[end])));
-                if (end > begin && (used + b > mem_budget / 2 || (max_inflight && end - begin >= max_inflight))) break;
-                if (b > mem_budget) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
-                used += b; ++end;
+                if (end > begin && (used + bytes[end] > cap || used >= target || (max_inflight && end - begin >= max_inflight))) break;
+                used += bytes[end]; ++end;
             }
             run_chunk(jobs, begin, end, out);
             begin = end;
@@ -261,7 +270,7 @@ struct CudaBackend : host::Backend {
         const bool tracked = al.opts.sc.ys != MIN_SCORE;
         const bool fused = fused_path();
         uint64_t reads_b = 0, ops_n = 0, chains_n = 0, pm_max = 0, unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0, per_job_bytes = 0;
-        Need tot{0, 0, 0, 0, 0}, arena{0, 0, 0, 0, 0};
+        Need tot{0, 0, 0, 0, 0, 0}, arena{0, 0, 0, 0, 0, 0};
         uint32_t n_packed = 0, ntmax = 1, max_ctiles = 1;
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
@@ -269,7 +278,7 @@ struct CudaBackend : host::Backend {
             const uint32_t C = (uint32_t)L.ent.size();
             JobDesc d{};
             d.read_off = device_reads ? (uint64_t)(uintptr_t)j.read : reads_b;
-            d.colrec_off = tot.colrec; d.cell_off = tot.cell; d.ck_off = tot.ck; d.cksum_off = tot.cksum; d.gcol_off = tot.gcol; d.ops_off = ops_n;
+            d.colrec_off = tot.colrec; d.cell_off = tot.cell; d.cksum_off = tot.cksum; d.gcol_off = tot.gcol; d.ops_off = ops_n;
             d.n = j.n; d.layout = j.layout; d.walk = j.walk; d.from_contig = j.from_contig;
             d.max_chains = j.walk == host::WALK_ALL ? C : 1;
             const uint32_t per_chain = j.n / 2 + 4 * C + 64;
@@ -278,7 +287,8 @@ struct CudaBackend : host::Backend {
             d.track_from = tracked ? (j.n > WINDOW ? j.n - WINDOW + 1 : 1) : j.n + 1;
             d.hand_off = tot.cell; d.handsum_off = handsum_n;
             d.LB = plan_LB(j); d.j0 = 0;
-            const Need nd = need_of(j);
+            d.ck_off = d.LB ? tot.pck : tot.ck;
+            const Need nd = need_of(j, d.LB != 0);
             uint32_t mct = 0;
             for (const auto &e : L.ent) mct = std::max(mct, e.ntiles);
             max_ctiles = std::max(max_ctiles, mct);
@@ -287,10 +297,10 @@ struct CudaBackend : host::Backend {
                 ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM());
             }
             if (d.LB && fused) {   // records live in the CTA's arena
-                arena.colrec = std::max(arena.colrec, nd.colrec); arena.cell = std::max(arena.cell, nd.cell); arena.ck = std::max(arena.ck, nd.ck);
+                arena.colrec = std::max(arena.colrec, nd.colrec); arena.cell = std::max(arena.cell, nd.cell); arena.pck = std::max(arena.pck, nd.pck);
                 arena.cksum = std::max(arena.cksum, nd.cksum); arena.gcol = std::max(arena.gcol, nd.gcol);
             } else {
-                tot.colrec += nd.colrec; tot.cell += nd.cell; tot.ck += nd.ck; tot.cksum += nd.cksum; tot.gcol += nd.gcol;
+                tot.colrec += nd.colrec; tot.cell += nd.cell; tot.ck += nd.ck; tot.pck += nd.pck; tot.cksum += nd.cksum; tot.gcol += nd.gcol;
                 handsum_n += C; per_job_bytes += need_bytes(nd);
                 pm_max = std::max<uint64_t>(pm_max, L.PM());
             }
@@ -343,11 +353,11 @@ struct CudaBackend : host::Backend {
         const uint32_t bufgrid = std::max(wgrid, fgrid);   // CTAs that own walk buffers
         d_jobs.reserve(nj); d_order.reserve(4 * (size_t)nj + 16);
         d_colrec.reserve(tot.colrec + (uint64_t)fgrid * arena.colrec); d_last.reserve(tot.cell + (uint64_t)fgrid * arena.cell);
-        d_sn.reserve(tot.cell + (uint64_t)fgrid * arena.cell); d_ck.reserve(tot.ck + (uint64_t)fgrid * arena.ck);
+        d_sn.reserve(tot.cell + (uint64_t)fgrid * arena.cell); d_ck.reserve(tot.ck + 64); d_pck.reserve(tot.pck + (uint64_t)fgrid * arena.pck + 64);
         d_cksum.reserve(tot.cksum + (uint64_t)fgrid * arena.cksum); d_gcol.reserve(tot.gcol + (uint64_t)fgrid * arena.gcol);
         d_ops.reserve(ops_n); d_chains.reserve(chains_n); d_jobout.reserve(nj);
         d_state.reserve((uint64_t)wgrid * 2 * pm_max + 64);
-        d_hand.reserve(tot.cell + 64); d_handsum.reserve(handsum_n + 64);
+        d_hand.reserve(64); d_handsum.reserve(handsum_n + 64);   // (hand-over buffers of the retired packed -> wide tail)
         d_pstate.reserve((uint64_t)std::max(fgrid, pteams) * 2 * ppm_max + 64);
         d_tailj0.reserve(nj);
         const uint64_t wps_half = (uint64_t)max_ctiles * TILE;
@@ -376,14 +386,14 @@ struct CudaBackend : host::Backend {
         P.contig_bases = d_contigs.p; P.reads = device_reads ? device_reads : d_reads.p;
         P.state = d_state.p; P.state_stride = 2 * pm_max; P.state_half = pm_max;
         P.unit_bytes = d_unit.p; P.unit_stride = round_up(unit_max, 256);
-        P.colrec = d_colrec.p; P.last = d_last.p; P.sn = d_sn.p; P.ck_state = d_ck.p; P.ck_sum = d_cksum.p; P.gcol = d_gcol.p;
+        P.colrec = d_colrec.p; P.last = d_last.p; P.sn = d_sn.p; P.ck_state = d_ck.p; P.pck = d_pck.p; P.ck_sum = d_cksum.p; P.gcol = d_gcol.p;
         P.ops = d_ops.p; P.chains = d_chains.p; P.job_out = d_jobout.p; P.counter = d_counter.p;
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
         P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1;
         P.arena.colrec_base = tot.colrec; P.arena.colrec_stride = arena.colrec; P.arena.cell_base = tot.cell; P.arena.cell_stride = arena.cell;
-        P.arena.ck_base = tot.ck; P.arena.ck_stride = arena.ck; P.arena.cksum_base = tot.cksum; P.arena.cksum_stride = arena.cksum;
+        P.arena.ck_base = tot.pck; P.arena.ck_stride = arena.pck; P.arena.cksum_base = tot.cksum; P.arena.cksum_stride = arena.cksum;
         P.arena.gcol_base = tot.gcol; P.arena.gcol_stride = arena.gcol;
         if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
 
@@ -504,7 +514,7 @@ struct CudaBackend : host::Backend {
                          "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, fgrid, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
                          h[4] * 1e-6, h[5] * 1e-6);
         }
-        stats.tb_bytes += (tot.ck + (uint64_t)fgrid * arena.ck) * sizeof(CellState) + (tot.colrec + (uint64_t)fgrid * arena.colrec) * sizeof(ColRec);
+        stats.tb_bytes += tot.ck * sizeof(CellState) + (tot.pck + (uint64_t)fgrid * arena.pck) * 4 + (tot.colrec + (uint64_t)fgrid * arena.colrec) * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);
 
         bool overflow = false;

@@ -72,8 +72,11 @@ struct PackSmem {
     }
 };
 
+// State layout: per tile 2 KB contiguous, [256 S keys][256 D keys], each as [k / 4][lane][k % 4] so that a lane's 8 keys
+// are two 16-byte words and a warp access is 512 contiguous bytes.  Dst = Sst + TILE.
+constexpr uint32_t ST = 2 * TILE;
 __device__ __forceinline__ uint32_t pk_sidx(uint32_t tile, uint32_t lane, uint32_t k) {
-    return tile * TILE + (k >> 2) * 128u + lane * 4u + (k & 3u);
+    return tile * ST + (k >> 2) * 128u + lane * 4u + (k & 3u);
 }
 
 struct PackCtx {            // uniform per (job, set of contigs)
@@ -129,10 +132,10 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
             s0 = q[lane]; s1 = q[32 + lane]; d0 = q[64 + lane]; d1 = q[96 + lane];
             xb = reinterpret_cast<const uint2 *>(stg + 2 * TILE * 4)[lane];
         } else {
-            s0 = pk_ld_state(X, X.Sst + tile * TILE + lane * 4);
-            s1 = pk_ld_state(X, X.Sst + tile * TILE + 128 + lane * 4);
-            d0 = pk_ld_state(X, X.Dst + tile * TILE + lane * 4);
-            d1 = pk_ld_state(X, X.Dst + tile * TILE + 128 + lane * 4);
+            s0 = pk_ld_state(X, X.Sst + tile * ST + lane * 4);
+            s1 = pk_ld_state(X, X.Sst + tile * ST + 128 + lane * 4);
+            d0 = pk_ld_state(X, X.Dst + tile * ST + lane * 4);
+            d1 = pk_ld_state(X, X.Dst + tile * ST + 128 + lane * 4);
             // contig bases are 16-byte aligned per contig and a strip starts at a multiple of 8 (over-reads stay inside the blob's padding)
             xb = *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
         }
@@ -232,10 +235,10 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     }
     STITCH_UNROLL
     for (int k = 0; k < STRIP; ++k) { outS[k] = Sn[k]; outD[k] = st.D6[k]; }
-    *reinterpret_cast<int4 *>(X.Sst + tile * TILE + lane * 4) = make_int4(Sn[0], Sn[1], Sn[2], Sn[3]);
-    *reinterpret_cast<int4 *>(X.Sst + tile * TILE + 128 + lane * 4) = make_int4(Sn[4], Sn[5], Sn[6], Sn[7]);
-    *reinterpret_cast<int4 *>(X.Dst + tile * TILE + lane * 4) = make_int4(st.D6[0], st.D6[1], st.D6[2], st.D6[3]);
-    *reinterpret_cast<int4 *>(X.Dst + tile * TILE + 128 + lane * 4) = make_int4(st.D6[4], st.D6[5], st.D6[6], st.D6[7]);
+    *reinterpret_cast<int4 *>(X.Sst + tile * ST + lane * 4) = make_int4(Sn[0], Sn[1], Sn[2], Sn[3]);
+    *reinterpret_cast<int4 *>(X.Sst + tile * ST + 128 + lane * 4) = make_int4(Sn[4], Sn[5], Sn[6], Sn[7]);
+    *reinterpret_cast<int4 *>(X.Dst + tile * ST + lane * 4) = make_int4(st.D6[0], st.D6[1], st.D6[2], st.D6[3]);
+    *reinterpret_cast<int4 *>(X.Dst + tile * ST + 128 + lane * 4) = make_int4(st.D6[4], st.D6[5], st.D6[6], st.D6[7]);
     STITCH_UNROLL
     for (int d = 16; d >= 1; d >>= 1) colmax = pk_max(colmax, __shfl_xor_sync(FULL, colmax, d));
     if (lane < X.team.size) X.team.peer(S.tilemax, lane)[tile] = colmax;   // every CTA of the team holds the whole tile table
@@ -280,10 +283,10 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         unsigned char *stg0 = S.stage + (size_t)warp * 2 * PackSmem::STAGE_BYTES;
         auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot) {
             unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
-            __pipeline_memcpy_async(d + lane * 16, X.Sst + t * TILE + lane * 4, 16);
-            __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * TILE + 128 + lane * 4, 16);
-            __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * TILE + lane * 4, 16);
-            __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * TILE + 128 + lane * 4, 16);
+            __pipeline_memcpy_async(d + lane * 16, X.Sst + t * ST + lane * 4, 16);
+            __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * ST + 128 + lane * 4, 16);
+            __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * ST + lane * 4, 16);
+            __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * ST + 128 + lane * 4, 16);
             __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
             __pipeline_commit();
         };
@@ -345,8 +348,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 STITCH_UNROLL
                 for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
                 const uint32_t tile = en.tile_start + ft;
-                const int4 s0 = pk_ld_state(X, X.Sst + tile * TILE + lane * 4);
-                const int4 s1 = pk_ld_state(X, X.Sst + tile * TILE + 128 + lane * 4);
+                const int4 s0 = pk_ld_state(X, X.Sst + tile * ST + lane * 4);
+                const int4 s1 = pk_ld_state(X, X.Sst + tile * ST + 128 + lane * 4);
                 const int32_t sk[STRIP] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 uint32_t row = 0xffffffffu; int32_t key = 0;
                 STITCH_UNROLL
@@ -415,7 +418,7 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
     const uint32_t pm = X.NT * TILE;
-    for (uint32_t p = X.team.rank * T + tid; p < pm; p += X.team.size * T) { X.Sst[p] = pk.NEGKEY; X.Dst[p] = pk.NEGKEY + pk.PD6; }
+    for (uint32_t p = X.team.rank * T + tid; p < 2 * pm; p += X.team.size * T) X.Sst[p] = (p % ST) < (uint32_t)TILE ? pk.NEGKEY : pk.NEGKEY + pk.PD6;
     X.team.sync();
     for (uint32_t tile = X.team.rank * W + warp; tile < X.NT; tile += X.team.size * W) {
         const ContigEntry en = X.ent[X.owner ? X.owner[tile] : 0u];
@@ -439,21 +442,17 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
     X.team.sync();
 }
 
-// The packed state of column j0 from a wide checkpoint (`ck` in the wide tile-transposed order, first tile of X
-// at ck[0]); Bj0 = base of column j0.
+// The packed state of column j0 from a checkpoint: a raw copy of the state arrays (keys relative to the base of
+// column j0, which the caller passes for the row-m key); `ck` points at the first tile of X.
 template <int W>
-__device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const CellState *ck, const CkSum *sums, int32_t Bj0) {
+__device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const int32_t *ck, const CkSum *sums, int32_t Bj0) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
-    const uint32_t pm = X.NT * TILE;
-    for (uint32_t idx = X.team.rank * T + tid; idx < pm; idx += X.team.size * T) {
-        const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
-        const CellState cs = ck[idx];
-        const uint32_t pi = pk_sidx(tile, ln, k);
-        X.Sst[pi] = pk_from_wide(pk, Bj0, cs.S, cs.sl, 0);
-        X.Dst[pi] = pk_from_wide(pk, Bj0, cs.D, cs.dl, PP_D);
-    }
+    const uint32_t words = X.NT * ST / 4;
+    const int4 *src = reinterpret_cast<const int4 *>(ck);
+    int4 *dst = reinterpret_cast<int4 *>(X.Sst);
+    for (uint32_t idx = X.team.rank * T + tid; idx < words; idx += X.team.size * T) dst[idx] = __ldcs(src + idx);
     for (uint32_t a = tid; a < X.C; a += T) {
         const CkSum cs = sums[a];
         S.cm[a] = 0; S.cml[a] = 0; S.cmk[a] = 0;
@@ -463,20 +462,16 @@ __device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const CellState 
     X.team.sync();
 }
 
-// Wide checkpoint of the current packed state (column base B).
+// Checkpoint of the current packed state: a raw copy (8 bytes per cell).
 template <int W>
-__device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t B, CellState *dck, CkSum *dsum) {
+__device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t *dck, CkSum *dsum) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
-    const PK &pk = X.pk;
-    const uint32_t pm = X.NT * TILE;
-    for (uint32_t idx = X.team.rank * T + tid; idx < pm; idx += X.team.size * T) {
-        const uint32_t tile = idx / TILE, w = idx % TILE, k = w / 32, ln = w % 32;
-        const uint32_t pi = pk_sidx(tile, ln, k);
-        const int32_t s = X.Sst[pi], d = X.Dst[pi];
-        // streaming store: checkpoints are read back once, much later; keep the L2 for the rolling state
-        __stcs(reinterpret_cast<int4 *>(dck + idx), make_int4(pk_abs(pk, B, s), pk_abs(pk, B, d), (int)pk_len(pk, s), (int)pk_len(pk, d)));
-    }
+    const uint32_t words = X.NT * ST / 4;
+    const int4 *src = reinterpret_cast<const int4 *>(X.Sst);
+    int4 *dst = reinterpret_cast<int4 *>(dck);
+    // streaming store: checkpoints are read back once, much later; keep the L2 for the rolling state
+    for (uint32_t idx = X.team.rank * T + tid; idx < words; idx += X.team.size * T) __stcs(dst + idx, pk_ld_state(X, reinterpret_cast<const int32_t *>(src + idx)));
     if (X.team.rank == 0)
         for (uint32_t a = tid; a < X.C; a += T) {
             CkSum cs; cs.Sm = S.Sm[a]; cs.slm = S.slm[a]; cs.tbm = S.tbm[a]; cs.pad = 0;
@@ -527,7 +522,7 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
     SnRec *sn = P.sn + jd.cell_off;
     const bool tracked = P.tracked_mode != 0;
     if (j0 == 0) pk_state_init0<W>(X, S);
-    else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(j0 / K - 1) * PM,
+    else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j0 / K - 1) * 2 * PM,
                              P.ck_sum + jd.cksum_off + (uint64_t)(j0 / K - 1) * C, gcol[j0 - 1]);
     if (tracked) {   // trackers start from column 0 (SCA:179-183)
         for (uint32_t tile = X.team.rank * W + warp; tile < X.NT; tile += X.team.size * W) {
@@ -658,7 +653,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         X.team = team;
         X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
-        X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
+        X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.Dst = X.Sst + TILE;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
@@ -679,7 +674,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
             const PkColConst cc = s_cc[par];
             pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
             if ((j % K == 0) && j < n)
-                pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
+                pk_write_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j / K - 1) * 2 * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
         }
         int32_t track_thr = MIN_SCORE;
         if (team.size > 1) {   // gcol / colrec of the whole read (written by rank 0) must be visible to the team
@@ -746,10 +741,10 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     __syncthreads();
     PackCtx X;
     X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
-    X.Sst = pstate; X.Dst = pstate + pstate_half; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
+    X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
     if (b == 0) pk_state_init0<W>(X, S);
-    else pk_state_from_ck<W>(X, S, P.ck_state + jd.ck_off + (uint64_t)(b - 1) * PM + gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
+    else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);
     pk_init_halos<W>(X, S, jb & 1u);
     __syncthreads();

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P)
         X.team = team;
         X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
-        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + P.pstate_half;
+        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + TILE;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P)
             const PkColConst cc = s_cc[par];
             pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
             if ((j % K == 0) && j < n)
-                pk_write_ck<W>(X, S, cc.pc.B, P.ck_state + jd.ck_off + (uint64_t)(j / K - 1) * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
+                pk_write_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j / K - 1) * 2 * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
         }
         // ---- tail, fix-up, walk: a real call on copies, so that the bulk loop above keeps its pointer tables in
         // registers and its register allocation to itself ----

@@ -67,7 +67,8 @@ struct Params {
     ColRec *colrec;
     LastCell *last;
     SnRec *sn;
-    CellState *ck_state;
+    CellState *ck_state;     // checkpoints of the wide path
+    int32_t *pck;            // checkpoints of the packed path: raw copies of the packed state (2 * PM keys each)
     CkSum *ck_sum;
     CellState *hand_state;
     CkSum *hand_sum;
