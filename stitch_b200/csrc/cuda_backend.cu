@@ -103,13 +103,14 @@ struct CudaBackend : host::Backend {
     DevBuf<CellState> d_state, d_ck, d_hand;
     DevBuf<CkSum> d_handsum;
     DevBuf<int32_t> d_pstate, d_wpstate, d_pck;
-    DevBuf<uint32_t> d_tailj0;
+    DevBuf<uint32_t> d_tailj0, d_done;
     DevBuf<unsigned long long> d_dbg;
     bool debug_stats = false;
     DevBuf<ColRec> d_ucr;
     size_t l2_persist_max = 0, l2_window_max = 0;
     uint32_t l2_persist = 0;   // STITCH_L2_PERSIST=1: pin the rolling state of the packed kernel in the L2 (measured: no gain)
     uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
+    uint32_t walk_in_kernel = 1;   // STITCH_WALK_IN_KERNEL=0: separate fix-up / walk kernels after the packed fill
     uint32_t use_fused = 0;    // STITCH_FUSED=1: one persistent kernel per read (fill, tail, fix-up, walk; per-CTA arenas); measured slower
     uint32_t cluster_pref = 1; // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8); measured best on config 2: 1
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
@@ -152,6 +153,7 @@ struct CudaBackend : host::Backend {
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
         use_packed = env_u32("STITCH_PACKED", 1);
         use_fused = env_u32("STITCH_FUSED", 0);
+        walk_in_kernel = env_u32("STITCH_WALK_IN_KERNEL", 1);
         debug_stats = env_u32("STITCH_DEBUG_STATS", 0) != 0;
         l2_persist = env_u32("STITCH_L2_PERSIST", 0);
         if (l2_persist && l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
@@ -321,7 +323,7 @@ struct CudaBackend : host::Backend {
         { uint32_t a = 0, b = 0; for (uint32_t k = 0; k < nj; ++k) { if (h_jobs.p[h_order.p[k]].LB) po[a++] = h_order.p[k]; else wo[b++] = h_order.p[k]; } }
 
         // grids.  Fused path: two 8-warp CTAs per SM, each with its own arena; clustered path: one team per read.
-        const uint32_t wgrid = std::min<uint32_t>(std::max<uint32_t>(fused ? n_wide : nj, 1), (uint32_t)num_sms);   // walk / wide kernels
+        const uint32_t wgrid = std::min<uint32_t>(nj, (uint32_t)num_sms);   // walk / wide kernels
         uint32_t cluster = cluster_pref;
         if (ntmax < cluster_min_tiles) cluster = 1;
         uint32_t fgrid = 0, pteams = 0;
@@ -350,7 +352,8 @@ struct CudaBackend : host::Backend {
                 else { cudaGetLastError(); cluster = 1; pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms); }
             }
         }
-        const uint32_t bufgrid = std::max(wgrid, fgrid);   // CTAs that own walk buffers
+        const bool packed_walks_in_kernel = !fused && walk_in_kernel && cluster == 1 && n_packed > 0;
+        const uint32_t bufgrid = std::max(std::max(wgrid, fgrid), packed_walks_in_kernel ? pteams : 0u);   // CTAs that own walk buffers
         d_jobs.reserve(nj); d_order.reserve(4 * (size_t)nj + 16);
         d_colrec.reserve(tot.colrec + (uint64_t)fgrid * arena.colrec); d_last.reserve(tot.cell + (uint64_t)fgrid * arena.cell);
         d_sn.reserve(tot.cell + (uint64_t)fgrid * arena.cell); d_ck.reserve(tot.ck + 64); d_pck.reserve(tot.pck + (uint64_t)fgrid * arena.pck + 64);
@@ -411,7 +414,14 @@ struct CudaBackend : host::Backend {
         } else if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster;
-            const size_t psmem = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
+            size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS) + 15) / 16 * 16;
+            if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads
+                d_done.reserve(nj);
+                CUDA_CHECK(cudaMemsetAsync(d_done.p, 0, nj * sizeof(uint32_t), stream));
+                Q.done = d_done.p;
+                Q.walk_stage_smem_off = (uint32_t)psmem;
+                psmem += UnitStage::bytes(K, max_ctiles);
+            }
             set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(PACK_WARPS * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
@@ -446,9 +456,10 @@ struct CudaBackend : host::Backend {
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
-        // fix-up and walk kernels: the wide reads, plus the packed ones when they did not run fused
-        const uint32_t n_post = fused ? n_wide : nj;
-        const uint32_t *post_order = fused ? d_order.p + nj + n_packed : d_order.p;
+        // fix-up and walk kernels: the wide reads, plus the packed ones when their kernel did not do it itself
+        const bool packed_done = fused || packed_walks_in_kernel;
+        const uint32_t n_post = packed_done ? n_wide : nj;
+        const uint32_t *post_order = packed_done ? d_order.p + nj + n_packed : d_order.p;
         mark(T_FIXUP);
         if (n_post) {
             Params Q = P; Q.order = post_order; Q.n_jobs = n_post;

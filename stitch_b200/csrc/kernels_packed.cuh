@@ -618,6 +618,8 @@ __device__ uint32_t pk_tail_start(const Params &P, PackSmem &S, const Scoring &s
     return j0;
 }
 
+template <int W> __device__ void pk_walk_phase(const Params P, unsigned char *smem_raw);   // kernels_walk.cuh
+
 // ---------------------------------------------------------------------------------------------
 // bulk fill
 // ---------------------------------------------------------------------------------------------
@@ -691,7 +693,15 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
             atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_tail0));
             atomicAdd(P.dbg + 2, (unsigned long long)(t_tail0 - t_bulk0));
         }
+        if (P.done) {   // publish: every record of this read is written
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicExch(P.done + job, 1u); }
+        }
     }
+    // ---- second phase of the persistent kernel (single-CTA teams): CTAs that find the fill queue empty walk the
+    // reads in the order they were filled, so the end-of-read fix-ups and walks fill the SMs that the last fills
+    // leave idle.  A CTA only waits for reads that other, running CTAs of this launch are still filling. ----
+    if (P.done) pk_walk_phase<W>(P, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -168,6 +168,44 @@ __device__ __noinline__ void finish_job(const Params &P, uint32_t job, const Job
     walk_job<W, true>(P, job, jd, ld, nullptr, S, US, sh, B);
 }
 
+// Walk phase of fill_packed_kernel (see there).  Shared memory: the tables of PackSmem as carved by the kernel, the
+// per-unit staging area after them, and the re-fill state of one contig in the (now idle) cp.async stage buffers.
+template <int W>
+__device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_raw) {   // by value: the caller's P stays in the constant bank
+    PackSmem PS; PS.carve(smem_raw, P.cmax, P.ntmax, W);
+    UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
+    __shared__ uint32_t sJob;
+    __shared__ WalkShared sh;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = W * 32;
+    WalkBufs B;
+    B.st0 = nullptr; B.st1 = nullptr;
+    B.ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
+    B.ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
+    B.wps_smem = 2ull * P.wpstate_half * sizeof(int32_t) <= (uint64_t)W * 2 * PackSmem::STAGE_BYTES;
+    B.wps = B.wps_smem ? reinterpret_cast<int32_t *>(PS.stage) : P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sJob = atomicAdd(P.counter + 1, 1u);
+        __syncthreads();
+        if (sJob >= P.n_jobs) break;
+        const uint32_t job = P.order[sJob];
+        if (tid == 0) {
+            while (*reinterpret_cast<volatile uint32_t *>(P.done + job) == 0u) __nanosleep(2000);
+            __threadfence();
+        }
+        __syncthreads();
+        const JobDesc jd = P.jobs[job];
+        const LayoutDesc ld = P.layouts[jd.layout];
+        // end-of-read fix-up (SCA:453-555), one thread per contig-strand
+        for (uint32_t a = tid; a < ld.C; a += T)
+            fixup_contig(P.sc, P.ents[ld.ent_off + a], jd.n, P.last + jd.cell_off, P.sn + jd.cell_off, P.tracked_mode != 0,
+                         &P.colrec[jd.colrec_off + (uint64_t)jd.n * ld.C + a].lx);
+        __syncthreads();
+        walk_job<W, true>(P, job, jd, ld, nullptr, PS, US, sh, B);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused per-read kernel of the packed path
 // ---------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ struct Params {
     ColRec *unit_cr;         // walk kernel, per CTA: K per-column records of the loaded unit
     uint32_t max_ctiles;     // most tiles of any single contig (walk kernel shared memory)
     unsigned long long *dbg; // optional counters (STITCH_DEBUG_STATS): see cuda_backend.cu
+    uint32_t *done;          // packed kernel with the in-kernel walk phase: per job, 1 once its fill and tail are complete
     uint32_t walk_stage_smem_off;   // walk kernel: byte offset of the per-unit staging area in dynamic shared memory
     uint32_t walk_state_smem_off;   // walk kernel: byte offset of the packed unit state in dynamic shared memory (0: global)
     int32_t *gcol;
