@@ -104,12 +104,13 @@ typedef struct stitch_stats {
     double total_ms;              /* CUDA-event time, first H2D to last D2H of the batch       */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t traceback_bytes;     /* bytes of checkpoints + jump records written to HBM        */
-    double packed_fill_ms;        /* of fill_ms: the packed-key fill kernel                    */
+    double packed_fill_ms;        /* of fill_ms: the packed-key kernel (bulk fill + tail + in-kernel fix-up/walk phase) */
     double wide_fill_ms;          /* of fill_ms: the wide kernel (last columns / fallback)     */
     double redo_fill_ms;          /* of fill_ms: re-runs of reads whose tracking window was too narrow */
     uint64_t packed_cells;        /* cell updates done by the packed-key kernel                */
     uint64_t redo_fills;          /* number of such re-runs                                    */
-    double tail_fill_ms;          /* of fill_ms: the packed tail (last columns again, with trackers)  */
+    double tail_fill_ms;          /* of fill_ms: the packed tail when it ran as its own launch (0: same launch as the fill) */
+    uint64_t packed_launches;     /* launches of the packed-key kernel (one per chunk of reads)        */
 } stitch_stats;
 
 typedef struct stitch_ctx stitch_ctx;

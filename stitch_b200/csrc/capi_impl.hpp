@@ -91,7 +91,7 @@ int STITCH_API(get_stats)(const stitch_ctx *ctx, stitch_stats *out) {
     out->cells = s.cells; out->fills = s.fills; out->kernel_launches = s.launches;
     out->fill_ms = s.fill_ms; out->traceback_ms = s.tb_ms; out->total_ms = s.total_ms;
     out->h2d_bytes = s.h2d; out->d2h_bytes = s.d2h; out->traceback_bytes = s.tb_bytes;
-    out->packed_fill_ms = s.packed_ms; out->wide_fill_ms = s.wide_ms; out->redo_fill_ms = s.redo_ms; out->tail_fill_ms = s.tail_ms;
+    out->packed_fill_ms = s.packed_ms; out->wide_fill_ms = s.wide_ms; out->redo_fill_ms = s.redo_ms; out->tail_fill_ms = s.tail_ms; out->packed_launches = s.packed_launches;
     out->packed_cells = s.packed_cells; out->redo_fills = s.refills;
     return STITCH_OK;
 }

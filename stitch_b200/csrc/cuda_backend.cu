@@ -232,7 +232,7 @@ struct CudaBackend : host::Backend {
         // memory our arenas may take: what is free now plus what they already hold
         const uint64_t held = d_ck.cap * sizeof(CellState) + d_colrec.cap * sizeof(ColRec) + d_last.cap * sizeof(LastCell) +
                               d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_pck.cap * 4;
-        mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.70);
+        mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.85);
         const bool fused = fused_path();
         // chunks: per-read records of the reads that are not on the fused path + the outputs of all (the fused path's
         // working memory is per CTA and is budgeted in run_chunk); equal-sized chunks so that no chunk is a sliver
@@ -410,7 +410,7 @@ struct CudaBackend : host::Backend {
             set_smem(align_packed_kernel<FUSED_WARPS>, fsmem);
             align_packed_kernel<FUSED_WARPS><<<fgrid, FUSED_WARPS * 32, fsmem, stream>>>(Q);
             CUDA_CHECK(cudaGetLastError());
-            stats.launches += 1;
+            stats.launches += 1; stats.packed_launches += 1;
         } else if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster;
@@ -446,7 +446,7 @@ struct CudaBackend : host::Backend {
             }
             cfg.attrs = at; cfg.numAttrs = na;
             CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
-            stats.launches += 1;
+            stats.launches += 1; stats.packed_launches += 1;
         }
         mark(T_WIDE);
         if (n_wide) {
