@@ -89,7 +89,8 @@ struct CudaBackend : host::Backend {
     uint32_t max_inflight = 0;
     size_t uploaded_layouts = 0;
     uint32_t cmax = 1;
-    uint32_t K = 256;        // checkpoint spacing (columns); STITCH_CK_EVERY overrides (tests)
+    uint32_t K = 256;        // checkpoint spacing (columns) of the current batch
+    uint32_t K_base = 256;   // its default; STITCH_CK_EVERY overrides (tests)
     uint32_t WINDOW = 64;    // columns at the end of the read with y-suffix tracking; STITCH_TRACK_WINDOW
     const uint8_t *device_reads = nullptr;   // set for run_device()
 
@@ -149,7 +150,8 @@ struct CudaBackend : host::Backend {
         d_contigs.reserve(al.contigs.blob.size() + 1024);   // strips of the last tile over-read
         CUDA_CHECK(cudaMemcpy(d_contigs.p, al.contigs.blob.data(), al.contigs.blob.size(), cudaMemcpyHostToDevice));
         d_counter.reserve(8);
-        K = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K));
+        K_base = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K_base));
+        K = K_base;
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
         use_packed = env_u32("STITCH_PACKED", 1);
         use_fused = env_u32("STITCH_FUSED", 0);
@@ -200,7 +202,9 @@ struct CudaBackend : host::Backend {
         uint32_t m_max = 0;
         for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
         const uint32_t LB = pk_plan(al.opts.sc, j.n, m_max);
-        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) > 180 * 1024) return 0;   // tile table must fit shared memory
+        // shared memory of the packed kernels: tile table + cp.async stage buffers + the walk phase's staging of one
+        // contig's bases; otherwise the read takes the (slow, exact) wide path
+        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 200 * 1024) return 0;
         return LB;
     }
     bool fused_path() const { return use_fused && cluster_pref == 1; }
@@ -233,6 +237,15 @@ struct CudaBackend : host::Backend {
         const uint64_t held = d_ck.cap * sizeof(CellState) + d_colrec.cap * sizeof(ColRec) + d_last.cap * sizeof(LastCell) +
                               d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_pck.cap * 4;
         mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.85);
+        // checkpoint spacing: K_base columns, widened so that no read holds more than ~512 MB of checkpoints
+        // (long reads against large references: config 4 is 100 kb x 2 M rows)
+        K = K_base;
+        for (const auto &j : jobs) {
+            const uint64_t per_ck = (uint64_t)al.layouts.layouts[j.layout].PM() * 8;
+            const uint64_t max_cks = std::max<uint64_t>(1, (512ull << 20) / std::max<uint64_t>(per_ck, 1));
+            const uint64_t need_K = ((uint64_t)j.n + max_cks) / (max_cks + 1);
+            if (need_K > K) K = (uint32_t)((need_K + K_base - 1) / K_base * K_base);
+        }
         const bool fused = fused_path();
         // chunks: per-read records of the reads that are not on the fused path + the outputs of all (the fused path's
         // working memory is per CTA and is budgeted in run_chunk); equal-sized chunks so that no chunk is a sliver

@@ -216,3 +216,58 @@ def test_fuzz_packed_multi_tile(oracle, block):
         got, exp = run_both(oracle, kw, contigs, reads, raw=(seed % 2 == 0),
                             tuning=cluster_tuning(seed + block, {"STITCH_CK_EVERY": "50", "STITCH_TRACK_WINDOW": "8"}))
         compare(got, exp, f"seed {seed} {kw}")
+
+
+def test_config3_config4_shapes_downscaled(oracle):
+    """BASELINE config 3 (many contigs: the reference's limit of 256 contig-strands) and config 4 (reads several
+    times longer than the contigs, many segments) down-scaled so the oracle finishes in seconds."""
+    rng = random.Random(20243)
+    contigs = [gen.rand_seq(rng, rng.randint(50, 100)) for _ in range(128)]      # 256 contig-strands
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(100, 250), rng.randint(3, 8), strands=True) for _ in range(4)]
+    got, exp = run_both(oracle, dict(double_strand=True), contigs, reads, raw=False, tuning={"STITCH_CK_EVERY": "32"})
+    compare(got, exp, "config3 slice")
+    rng = random.Random(20244)
+    contigs = [gen.rand_seq(rng, 400) for _ in range(25)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(2000, 3000), rng.randint(10, 30), strands=True) for _ in range(3)]
+    got, exp = run_both(oracle, dict(double_strand=True), contigs, reads, raw=False)
+    compare(got, exp, "config4")
+    got, exp = run_both(oracle, dict(double_strand=True, suboptimal=True), contigs, reads[:1], raw=False)
+    compare(got, exp, "config4 suboptimal")
+
+
+def _exact_read(rng, contigs, nseg, seglen):
+    segs = []
+    for _ in range(nseg):
+        c = rng.randrange(len(contigs))
+        s = rng.randrange(0, len(contigs[c]) - seglen)
+        piece = contigs[c][s:s + seglen]
+        segs.append(gen.revcomp(piece) if rng.random() < 0.5 else piece)
+    return b"".join(segs)
+
+
+def test_config3_config4_full_size_properties():
+    """Full-size shapes of configs 3 and 4 (no oracle): reads that are exact concatenations of contig substrings must
+    score sum(len) + jumps * jump_score with one jump per junction, span the whole read, and validate.  Exercises 19
+    length bits, 256 contig-strands / 2 M rows (7.8 k tiles), and the widened checkpoint spacing."""
+    rng = random.Random(6)
+    contigs = [gen.rand_seq(rng, rng.randint(5000, 10000)) for _ in range(128)]   # config 3 slice: 256 contig-strands
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    read = _exact_read(rng, contigs, 5, 2400)
+    al = gpu_aligners(dict(double_strand=True), named)
+    a = al.align_batch([read])[0][0]
+    assert (a.score, a.length, a.ystart, a.yend) == (12000 - 4 * 10, 12000, 0, 12000)
+    a.validate()
+    assert sum(1 for k, _, _ in a.ops if k == 6) == 4
+    al.close()
+    rng = random.Random(7)
+    contigs = [gen.rand_seq(rng, 20000) for _ in range(50)]                        # config 4: 1 Mb panel, both strands
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    read = _exact_read(rng, contigs, 12, 5000)                                     # 60 kb, 12 segments
+    al = gpu_aligners(dict(double_strand=True), named)
+    a = al.align_batch([read])[0][0]
+    assert (a.score, a.length, a.ystart, a.yend) == (60000 - 11 * 10, 60000, 0, 60000)
+    a.validate()
+    assert sum(1 for k, _, _ in a.ops if k == 6) == 11
+    st = al.stats()
+    assert st.packed_cells == st.cells == 60000 * 2 * 50 * 20000
+    al.close()
