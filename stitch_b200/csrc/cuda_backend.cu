@@ -115,6 +115,7 @@ struct CudaBackend : host::Backend {
     uint32_t use_fused = 0;    // STITCH_FUSED=1: one persistent kernel per read (fill, tail, fix-up, walk; per-CTA arenas); measured slower
     uint32_t cluster_pref = 1; // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8); measured best on config 2: 1
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
+    uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
     DevBuf<ColRec> d_colrec;
@@ -159,8 +160,9 @@ struct CudaBackend : host::Backend {
         debug_stats = env_u32("STITCH_DEBUG_STATS", 0) != 0;
         l2_persist = env_u32("STITCH_L2_PERSIST", 0);
         if (l2_persist && l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
-        cluster_pref = std::min<uint32_t>(8, std::max<uint32_t>(1, env_u32("STITCH_CLUSTER", cluster_pref)));
+        cluster_pref = std::min<uint32_t>(16, std::max<uint32_t>(1, env_u32("STITCH_CLUSTER", cluster_pref)));
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
+        cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
     }
     ~CudaBackend() override {
         cudaSetDevice(device);
@@ -204,7 +206,7 @@ struct CudaBackend : host::Backend {
         const uint32_t LB = pk_plan(al.opts.sc, j.n, m_max);
         // shared memory of the packed kernels: tile table + cp.async stage buffers + the walk phase's staging of one
         // contig's bases; otherwise the read takes the (slow, exact) wide path
-        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 200 * 1024) return 0;
+        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 200 * 1024) return 0;
         return LB;
     }
     bool fused_path() const { return use_fused && cluster_pref == 1; }
@@ -340,7 +342,8 @@ struct CudaBackend : host::Backend {
         uint32_t cluster = cluster_pref;
         if (ntmax < cluster_min_tiles) cluster = 1;
         uint32_t fgrid = 0, pteams = 0;
-        const size_t fsmem_tables = (PackSmem::bytes(cmax, ntmax, FUSED_WARPS) + 15) / 16 * 16;
+        size_t cstate_bytes = 0, pstage = PackSmem::default_stage(PACK_WARPS);
+        const size_t fsmem_tables = (PackSmem::bytes(cmax, ntmax, FUSED_WARPS, PackSmem::default_stage(FUSED_WARPS)) + 15) / 16 * 16;
         const size_t fsmem = fsmem_tables + UnitStage::bytes(K, max_ctiles);
         if (n_packed && fused) {
             fgrid = std::min<uint32_t>(n_packed, (uint32_t)num_sms * (fsmem <= 110 * 1024 ? 2 : 1));
@@ -353,8 +356,14 @@ struct CudaBackend : host::Backend {
             if (cluster > 1) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)num_sms / cluster * cluster); cfg.blockDim = dim3(PACK_WARPS * 32);
-                cfg.dynamicSmemBytes = PackSmem::bytes(cmax, ntmax, PACK_WARPS);
+                // rolling state in the cluster's shared memory when every CTA's slice of the largest read fits
+                // (a CTA owns the chunks of its 16 warps: up to 16 tiles even when the read has fewer than 16 x cluster tiles)
+                const size_t slice = std::max<size_t>(std::min<size_t>(ntmax, PACK_WARPS), (size_t)ntmax / cluster + 2) * ST * sizeof(int32_t);
+                if (cluster_smem && PackSmem::bytes(cmax, ntmax, PACK_WARPS, slice) <= 220 * 1024) cstate_bytes = slice;
+                pstage = cstate_bytes ? cstate_bytes : PackSmem::default_stage(PACK_WARPS);
+                cfg.dynamicSmemBytes = PackSmem::bytes(cmax, ntmax, PACK_WARPS, pstage);
                 set_smem(fill_packed_kernel<PACK_WARPS>, cfg.dynamicSmemBytes);
+                if (cluster > 8) CUDA_CHECK(cudaFuncSetAttribute(fill_packed_kernel<PACK_WARPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -362,7 +371,8 @@ struct CudaBackend : host::Backend {
                 int max_clusters = 0;
                 if (cudaOccupancyMaxActiveClusters(&max_clusters, fill_packed_kernel<PACK_WARPS>, &cfg) == cudaSuccess && max_clusters > 0)
                     pteams = std::min<uint32_t>(pteams, (uint32_t)max_clusters);
-                else { cudaGetLastError(); cluster = 1; pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms); }
+                else { cudaGetLastError(); cluster = 1; cstate_bytes = 0; pstage = PackSmem::default_stage(PACK_WARPS); pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms); }
+                if (debug_stats) std::fprintf(stderr, "[stitch dbg] cluster %u: max active clusters %d, state in smem %zu B/CTA\n", cluster, max_clusters, cstate_bytes);
             }
         }
         const bool packed_walks_in_kernel = !fused && walk_in_kernel && cluster == 1 && n_packed > 0;
@@ -419,15 +429,15 @@ struct CudaBackend : host::Backend {
         if (n_packed && fused) {
             // the whole pipeline of the packed reads in one persistent kernel (fill, tail, fix-up, walk)
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
-            Q.walk_stage_smem_off = (uint32_t)fsmem_tables;
+            Q.walk_stage_smem_off = (uint32_t)fsmem_tables; Q.stage_bytes = (uint32_t)PackSmem::default_stage(FUSED_WARPS);
             set_smem(align_packed_kernel<FUSED_WARPS>, fsmem);
             align_packed_kernel<FUSED_WARPS><<<fgrid, FUSED_WARPS * 32, fsmem, stream>>>(Q);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1; stats.packed_launches += 1;
         } else if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
-            Q.cluster_size = cluster;
-            size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS) + 15) / 16 * 16;
+            Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes;
+            size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS, pstage) + 15) / 16 * 16;
             if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads
                 d_done.reserve(nj);
                 CUDA_CHECK(cudaMemsetAsync(d_done.p, 0, nj * sizeof(uint32_t), stream));
@@ -513,7 +523,7 @@ struct CudaBackend : host::Backend {
         mark(T_WALK);
         if (n_post) {
             Params Wp = P; Wp.order = post_order; Wp.n_jobs = n_post; Wp.counter = d_counter.p + 2;
-            size_t wsmem = std::max(WideSmem<WALK_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, WALK_WARPS, false));
+            size_t wsmem = std::max(WideSmem<WALK_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, WALK_WARPS, 0));
             wsmem = (wsmem + 15) / 16 * 16;
             Wp.walk_stage_smem_off = (uint32_t)wsmem;
             wsmem += (UnitStage::bytes(K, max_ctiles) + 15) / 16 * 16;

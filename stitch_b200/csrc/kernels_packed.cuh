@@ -53,13 +53,15 @@ struct PackSmem {
     JumpInfo *Jw;
     unsigned char *stage;   // [W][2][STAGE_BYTES]: cp.async double buffer of the next tile (state in global memory only)
     static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + TILE;   // S keys, D keys, bases of one tile
-    static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, bool staged = true) {
-        return (staged ? (size_t)W * 2 * STAGE_BYTES : 0) + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) +
-               (sizeof(PkRowM) + sizeof(JumpInfo)) * cmax + 64;
+    // `stage_bytes`: the front area = cp.async double buffers (default_stage), or the cluster's slice of the rolling
+    // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
+    static size_t default_stage(int W) { return (size_t)W * 2 * STAGE_BYTES; }
+    static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
+        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) + (sizeof(PkRowM) + sizeof(JumpInfo)) * cmax + 64;
     }
-    __device__ void carve(unsigned char *raw, uint32_t cmax, uint32_t ntmax, int W, bool staged = true) {
+    __device__ void carve(unsigned char *raw, uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
         stage = raw;
-        if (staged) raw += (size_t)W * 2 * STAGE_BYTES;
+        raw += stage_bytes;
         Jw = reinterpret_cast<JumpInfo *>(raw);
         stash = reinterpret_cast<PkRowM *>(Jw + cmax);
         Jc = reinterpret_cast<int32_t *>(stash + cmax);
@@ -90,7 +92,32 @@ struct PackCtx {            // uniform per (job, set of contigs)
     bool state_smem;        // the state arrays live in shared memory (walk kernel re-fills)
     bool staged;            // cp.async double-buffering of tiles (state and bases both in global memory, stage buffers carved)
     Team team;
+    // Tiles [own_lo, own_hi) are this CTA's (all tiles for a single-CTA team).  Sst/Dst address them as
+    // Sst + tile * ST.  With cluster_smem the state of a tile lives in the shared memory of the CTA that owns it
+    // (cstate = this CTA's block, same offset in every CTA of the cluster) and Sst = cstate - own_lo * ST.
+    uint32_t own_lo, own_hi, warps;
+    bool cluster_smem;
+    int32_t *cstate;
+    const uint32_t *cta_lo;   // shared memory: first tile of every CTA of the team, [size + 1]
 };
+
+// First tile of the chunk of global warp `gw` (chunks are contiguous and cover [0, NT)).
+__device__ __forceinline__ uint32_t pk_chunk_lo(uint32_t NT, uint32_t Weff, uint32_t gw) {
+    return gw >= Weff ? NT : (uint32_t)((uint64_t)NT * gw / Weff);
+}
+__device__ __forceinline__ void pk_set_ownership(PackCtx &X, uint32_t W) {
+    const uint32_t GW = X.team.size * W, Weff = X.NT < GW ? X.NT : GW;
+    X.warps = W;
+    X.own_lo = pk_chunk_lo(X.NT, Weff, X.team.rank * W);
+    X.own_hi = pk_chunk_lo(X.NT, Weff, (X.team.rank + 1) * W);
+}
+// The 512-key block of any tile of the read (possibly in another CTA's shared memory).
+__device__ __forceinline__ int32_t *pk_tile_ptr(const PackCtx &X, uint32_t tile) {
+    if (!X.cluster_smem) return X.Sst + tile * ST;
+    uint32_t r = 0;
+    while (r + 1 < X.team.size && X.cta_lo[r + 1] <= tile) ++r;
+    return X.team.peer(X.cstate, r) + (tile - X.cta_lo[r]) * ST;
+}
 
 // State loads: through the L2 only when the state is in global memory (it streams, and row m is rewritten by
 // another CTA of the team), plain when it lives in shared memory.
@@ -253,9 +280,9 @@ __device__ void pk_init_halos(const PackCtx &X, PackSmem &S, uint32_t slot) {
     if (gw >= 1 && gw < Weff && lane < 9) {
         const uint32_t t_lo = (uint32_t)((uint64_t)X.NT * gw / Weff);
         const uint32_t hl = lane == 0 ? 30u : 31u, hk = lane == 0 ? (uint32_t)STRIP - 1 : lane - 1;
-        const uint32_t pi = pk_sidx(t_lo - 1, hl, hk);
-        S.haloS[(slot * W + warp) * 9 + lane] = X.Sst[pi];
-        if (lane >= 1) S.haloD[(slot * W + warp) * 8 + lane - 1] = X.Dst[pi];
+        const int32_t *tp = pk_tile_ptr(X, t_lo - 1) + (hk >> 2) * 128u + hl * 4u + (hk & 3u);
+        S.haloS[(slot * W + warp) * 9 + lane] = tp[0];
+        if (lane >= 1) S.haloD[(slot * W + warp) * 8 + lane - 1] = tp[TILE];
     }
 }
 
@@ -348,8 +375,9 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 STITCH_UNROLL
                 for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
                 const uint32_t tile = en.tile_start + ft;
-                const int4 s0 = pk_ld_state(X, X.Sst + tile * ST + lane * 4);
-                const int4 s1 = pk_ld_state(X, X.Sst + tile * ST + 128 + lane * 4);
+                const int32_t *tp = pk_tile_ptr(X, tile);
+                const int4 s0 = pk_ld_state(X, tp + lane * 4);
+                const int4 s1 = pk_ld_state(X, tp + 128 + lane * 4);
                 const int32_t sk[STRIP] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 uint32_t row = 0xffffffffu; int32_t key = 0;
                 STITCH_UNROLL
@@ -379,7 +407,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             const RowMOut &ro = fo.ro;
             const uint32_t r = en.m - 1;
             const uint32_t mt = en.tile_start + r / TILE, ml = (r % TILE) / STRIP, mk = r % STRIP;
-            X.Sst[pk_sidx(mt, ml, mk)] = fo.skey;
+            pk_tile_ptr(X, mt)[(mk >> 2) * 128u + ml * 4u + (mk & 3u)] = fo.skey;
             if (TB) {
                 if (O.tb_col) O.tb_col[mt * TILE + ml * STRIP + mk] = (uint8_t)fo.tbbyte;
                 if (O.colrec_col) {
@@ -417,10 +445,9 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
-    const uint32_t pm = X.NT * TILE;
-    for (uint32_t p = X.team.rank * T + tid; p < 2 * pm; p += X.team.size * T) X.Sst[p] = (p % ST) < (uint32_t)TILE ? pk.NEGKEY : pk.NEGKEY + pk.PD6;
-    X.team.sync();
-    for (uint32_t tile = X.team.rank * W + warp; tile < X.NT; tile += X.team.size * W) {
+    for (uint32_t p = X.own_lo * ST + tid; p < X.own_hi * ST; p += T) X.Sst[p] = (p % ST) < (uint32_t)TILE ? pk.NEGKEY : pk.NEGKEY + pk.PD6;
+    __syncthreads();
+    for (uint32_t tile = X.own_lo + warp; tile < X.own_hi; tile += W) {
         const ContigEntry en = X.ent[X.owner ? X.owner[tile] : 0u];
         const uint32_t tic = tile - en.tile_start;
         STITCH_UNROLL
@@ -449,10 +476,9 @@ __device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const int32_t *c
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const PK &pk = X.pk;
-    const uint32_t words = X.NT * ST / 4;
     const int4 *src = reinterpret_cast<const int4 *>(ck);
     int4 *dst = reinterpret_cast<int4 *>(X.Sst);
-    for (uint32_t idx = X.team.rank * T + tid; idx < words; idx += X.team.size * T) dst[idx] = __ldcs(src + idx);
+    for (uint32_t idx = X.own_lo * (ST / 4) + tid; idx < X.own_hi * (ST / 4); idx += T) dst[idx] = __ldcs(src + idx);
     for (uint32_t a = tid; a < X.C; a += T) {
         const CkSum cs = sums[a];
         S.cm[a] = 0; S.cml[a] = 0; S.cmk[a] = 0;
@@ -467,11 +493,11 @@ template <int W>
 __device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t *dck, CkSum *dsum) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
-    const uint32_t words = X.NT * ST / 4;
     const int4 *src = reinterpret_cast<const int4 *>(X.Sst);
     int4 *dst = reinterpret_cast<int4 *>(dck);
     // streaming store: checkpoints are read back once, much later; keep the L2 for the rolling state
-    for (uint32_t idx = X.team.rank * T + tid; idx < words; idx += X.team.size * T) __stcs(dst + idx, pk_ld_state(X, reinterpret_cast<const int32_t *>(src + idx)));
+    for (uint32_t idx = X.own_lo * (ST / 4) + tid; idx < X.own_hi * (ST / 4); idx += T)
+        __stcs(dst + idx, pk_ld_state(X, reinterpret_cast<const int32_t *>(src + idx)));
     if (X.team.rank == 0)
         for (uint32_t a = tid; a < X.C; a += T) {
             CkSum cs; cs.Sm = S.Sm[a]; cs.slm = S.slm[a]; cs.tbm = S.tbm[a]; cs.pad = 0;
@@ -626,11 +652,12 @@ template <int W> __device__ void pk_walk_phase(const Params P, unsigned char *sm
 template <int W>
 __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
+    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
     __shared__ uint32_t sJob;
     __shared__ PkColConst s_cc[2];
     __shared__ int32_t s_gmax;
     __shared__ uint32_t s_first;
+    __shared__ uint32_t s_cta_lo[17];
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const Scoring sc = P.sc;
@@ -655,8 +682,21 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         X.team = team;
         X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
-        X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.Dst = X.Sst + TILE;
-        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
+        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
+        pk_set_ownership(X, W);
+        if (tid <= team.size) {
+            const uint32_t GW = team.size * W, Weff = X.NT < GW ? X.NT : GW;
+            s_cta_lo[tid] = pk_chunk_lo(X.NT, Weff, tid * W);
+        }
+        X.cta_lo = s_cta_lo;
+        X.cluster_smem = P.cluster_state_smem != 0;
+        X.cstate = reinterpret_cast<int32_t *>(S.stage);
+        if (X.cluster_smem) {   // the rolling state lives in the cluster's shared memory: no HBM traffic per column
+            X.Sst = X.cstate - (size_t)X.own_lo * ST; X.state_smem = true; X.staged = false;
+        } else {
+            X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.state_smem = false; X.staged = true;
+        }
+        X.Dst = X.Sst + TILE;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;
@@ -753,6 +793,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
+    pk_set_ownership(X, W); X.cluster_smem = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);

@@ -114,7 +114,7 @@ template <int W>
 __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WideSmem<W> S; S.carve(smem_raw, 1);
-    PackSmem PS; PS.carve(smem_raw, 1, P.max_ctiles, W, false);   // same bytes: a job uses one of the two
+    PackSmem PS; PS.carve(smem_raw, 1, P.max_ctiles, W, 0);   // same bytes: a job uses one of the two
     UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
     __shared__ uint32_t sJob;
     __shared__ WalkShared sh;
@@ -172,7 +172,7 @@ __device__ __noinline__ void finish_job(const Params &P, uint32_t job, const Job
 // per-unit staging area after them, and the re-fill state of one contig in the (now idle) cp.async stage buffers.
 template <int W>
 __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_raw) {   // by value: the caller's P stays in the constant bank
-    PackSmem PS; PS.carve(smem_raw, P.cmax, P.ntmax, W);
+    PackSmem PS; PS.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
     UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
     __shared__ uint32_t sJob;
     __shared__ WalkShared sh;
@@ -182,7 +182,7 @@ __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_r
     B.st0 = nullptr; B.st1 = nullptr;
     B.ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
     B.ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
-    B.wps_smem = 2ull * P.wpstate_half * sizeof(int32_t) <= (uint64_t)W * 2 * PackSmem::STAGE_BYTES;
+    B.wps_smem = 2ull * P.wpstate_half * sizeof(int32_t) <= (uint64_t)P.stage_bytes;
     B.wps = B.wps_smem ? reinterpret_cast<int32_t *>(PS.stage) : P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
     for (;;) {
         __syncthreads();
@@ -212,7 +212,7 @@ __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_r
 template <int W>
 __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W);
+    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
     UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
     __shared__ uint32_t sJob;
     __shared__ PkColConst s_cc[2];
@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P)
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + TILE;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
+        pk_set_ownership(X, W); X.cluster_smem = false; X.cstate = nullptr; X.cta_lo = nullptr;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;

@@ -18,14 +18,15 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # blocks, re-filled units and window re-runs (the library reads these when a context is created).
 TUNING = {"STITCH_CK_EVERY": "7", "STITCH_TRACK_WINDOW": "6"}
 ALL_TUNING_KEYS = ("STITCH_CK_EVERY", "STITCH_TRACK_WINDOW", "STITCH_CLUSTER", "STITCH_CLUSTER_MIN_TILES", "STITCH_PACKED",
-                   "STITCH_FUSED")
+                   "STITCH_FUSED", "STITCH_CLUSTER_SMEM")
 
 
 def cluster_tuning(seed, base=None):
     """Thread-block clusters of 1 / 2 / 4 CTAs per read, also for layouts of a few tiles."""
     t = dict(base or {})
-    t["STITCH_CLUSTER"] = str((1, 2, 4)[seed % 3])      # > 1: the clustered fill kernel + separate fix-up / walk kernels
+    t["STITCH_CLUSTER"] = str((1, 2, 4, 16, 8)[seed % 5])   # > 1: the clustered fill kernel + separate fix-up / walk kernels
     t["STITCH_CLUSTER_MIN_TILES"] = "1"
+    t["STITCH_CLUSTER_SMEM"] = str(seed % 2)              # rolling state in the cluster's shared memory / in global memory
     if seed % 6 == 3:
         t["STITCH_FUSED"] = "1"                           # one CTA per read: the fused per-read kernel (per-CTA arenas)
     return t
