@@ -143,10 +143,9 @@ template <bool SPECIAL, bool TB>
 __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, const PkColOut &O, uint32_t j, uint32_t tile,
                                         uint32_t lane, int32_t r0pkey, int32_t cr1key, bool chunk_start, const int32_t *hS,
                                         const int32_t *hD, int32_t &prev_exit, uint32_t &prev_exit_open, int32_t &prev_s7,
-                                        int32_t *outS, int32_t *outD, const unsigned char *stg) {
+                                        int32_t *outS, int32_t *outD, const unsigned char *stg, uint32_t a, const ContigEntry &en,
+                                        int32_t Jc) {
     const PK &pk = X.pk;
-    const uint32_t a = X.owner ? X.owner[tile] : 0u;
-    const ContigEntry en = X.ent[a];
     const uint32_t tic = tile - en.tile_start;
     const bool first = tic == 0;
     const uint32_t row0 = tic * TILE + lane * STRIP + 1;
@@ -173,7 +172,6 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     unpack8(xb, x);
     int32_t Sdg0 = __shfl_up_sync(FULL, Sup[STRIP - 1], 1);
     if (lane == 0) Sdg0 = first ? r0pkey : (chunk_start ? hS[8] : prev_s7);
-    const int32_t Jc = S.Jc[a];
     PStrip st;
     int nv = STRIP; bool has_m = false;
     if (SPECIAL) {
@@ -317,13 +315,18 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
             __pipeline_commit();
         };
-        ContigEntry en = X.ent[X.owner ? X.owner[t_lo] : 0u];
+        // contig of the current tile and of the next one (reloaded only when the chunk crosses into the next contig)
+        uint32_t a = X.owner ? X.owner[t_lo] : 0u;
+        ContigEntry en = X.ent[a];
+        int32_t Jc = S.Jc[a];
         if (staged) prefetch(t_lo, en, 0);
         for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
             const uint32_t slot = (tile - t_lo) & 1u;
+            uint32_t a_next = a;
             ContigEntry en_next = en;
+            int32_t Jc_next = Jc;
             if (tile + 1 < t_hi) {
-                en_next = X.ent[X.owner ? X.owner[tile + 1] : 0u];
+                if (tile + 1 >= en.tile_start + en.ntiles) { a_next = X.owner[tile + 1]; en_next = X.ent[a_next]; Jc_next = S.Jc[a_next]; }
                 if (staged) prefetch(tile + 1, en_next, slot ^ 1u);
             }
             const unsigned char *stg = nullptr;
@@ -333,10 +336,10 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             }
             const uint32_t tic = tile - en.tile_start;
             if (tic == 0 || tic + 1 == en.ntiles)
-                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg);
+                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg, a, en, Jc);
             else
-                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg);
-            en = en_next;
+                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg, a, en, Jc);
+            a = a_next; en = en_next; Jc = Jc_next;
         }
         if (gw + 1 < Weff) {   // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp)
             const bool local = warp + 1 < (uint32_t)W;
