@@ -113,7 +113,10 @@ struct CudaBackend : host::Backend {
     uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
     uint32_t walk_in_kernel = 1;   // STITCH_WALK_IN_KERNEL=0: separate fix-up / walk kernels after the packed fill
     uint32_t use_fused = 0;    // STITCH_FUSED=1: one persistent kernel per read (fill, tail, fix-up, walk; per-CTA arenas); measured slower
-    uint32_t cluster_pref = 1; // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8); measured best on config 2: 1
+    // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8, 16); 0 = automatic: one CTA per read when there are
+    // enough reads to fill the GPU (measured best on config 2), a cluster per read when there are only a few (the origin
+    // re-alignment fills, small batches), with the rolling state in the cluster's shared memory when it fits
+    uint32_t cluster_pref = 0;
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
     DevBuf<CkSum> d_cksum;
@@ -160,7 +163,7 @@ struct CudaBackend : host::Backend {
         debug_stats = env_u32("STITCH_DEBUG_STATS", 0) != 0;
         l2_persist = env_u32("STITCH_L2_PERSIST", 0);
         if (l2_persist && l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
-        cluster_pref = std::min<uint32_t>(16, std::max<uint32_t>(1, env_u32("STITCH_CLUSTER", cluster_pref)));
+        cluster_pref = std::min<uint32_t>(16, env_u32("STITCH_CLUSTER", cluster_pref));
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
     }
@@ -209,7 +212,7 @@ struct CudaBackend : host::Backend {
         if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 200 * 1024) return 0;
         return LB;
     }
-    bool fused_path() const { return use_fused && cluster_pref == 1; }
+    bool fused_path() const { return use_fused && cluster_pref <= 1; }
     // records a read holds from its fill until its walk is done (CellState/ColRec/... counts)
     // ck: wide checkpoints (CellState records); pck: packed checkpoints (raw keys, 2 per cell)
     struct Need { uint64_t colrec, cell, ck, cksum, gcol, pck; };
@@ -340,6 +343,10 @@ struct CudaBackend : host::Backend {
         // grids.  Fused path: two 8-warp CTAs per SM, each with its own arena; clustered path: one team per read.
         const uint32_t wgrid = std::min<uint32_t>(nj, (uint32_t)num_sms);   // walk / wide kernels
         uint32_t cluster = cluster_pref;
+        if (cluster == 0) {   // automatic: the largest cluster that still gives every read its own team in one wave
+            cluster = 1;
+            if (!fused) while (cluster < 16 && (uint64_t)n_packed * cluster * 2 <= (uint64_t)num_sms * 3 / 4) cluster *= 2;
+        }
         if (ntmax < cluster_min_tiles) cluster = 1;
         uint32_t fgrid = 0, pteams = 0;
         size_t cstate_bytes = 0, pstage = PackSmem::default_stage(PACK_WARPS);
