@@ -148,6 +148,23 @@ const stitch_chain *stitch_results_chains(const stitch_results *r, uint64_t *n_c
 const stitch_op *stitch_results_ops(const stitch_results *r, uint64_t *n_ops);
 void stitch_free_results(stitch_results *r);
 
+/* Options of the SAM record layer: Options.{soft_clip,use_eq_and_x,pick_primary,filter_secondary,filter_secondary_pct},
+ * LIB/align/aligners/mod.rs:106-115 (defaults: false, false, query-length, false, 10.0). */
+typedef struct stitch_sam_opts {
+    uint8_t soft_clip, use_eq_and_x, pick_primary /* 0 query-length, 1 score */, filter_secondary;
+    float filter_secondary_pct;
+} stitch_sam_opts;
+
+/* SamRecordFormatter::format (LIB/align/aligners/mod.rs:622-972) with SubAlignmentBuilder::build
+ * (LIB/align/sub_alignment.rs:170-241) for read `read` of `res`: one SAM text line per record (flags, RNAME, POS,
+ * MAPQ, CIGAR with soft/hard clips, SEQ/QUAL orientation, the custom tags qs qe ts te as xs si sc cl ci cn, AS, NM,
+ * SA), lines separated by '\n'.  `read_header` is the FASTQ header (name = first word), `quals` may be NULL; they
+ * are passed through as given.  `*out_text` is malloc'ed: release it with stitch_free_text.  sopts == NULL: defaults. */
+int stitch_format_sam(stitch_ctx *ctx, const stitch_results *res, uint32_t read, const char *read_header,
+                      const uint8_t *bases, const uint8_t *quals, uint32_t n_bases, int has_pre_align_score,
+                      int32_t pre_align_score, const stitch_sam_opts *sopts, char **out_text);
+void stitch_free_text(char *text);
+
 int stitch_get_stats(const stitch_ctx *ctx, stitch_stats *out);
 /* Upper bound on reads in flight; 0 = choose from free HBM. */
 int stitch_set_max_inflight(stitch_ctx *ctx, uint32_t max_reads);

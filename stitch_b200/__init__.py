@@ -129,6 +129,31 @@ class Aligners:
         finally:
             self._lib.stitch_free_results(res)
 
+    def align_batch_sam(self, reads: Sequence[bytes], headers: Sequence[str], quals=None, sam_opts=None, subsets=None):
+        """Aligners::align followed by SamRecordFormatter::format (aligners/mod.rs:622-972) for each read:
+        -> (chains per read, SAM text lines per read)."""
+        from . import _lib
+        buf, offs = pack_reads(reads)
+        res = C.c_void_p()
+        words, stride = None, 0
+        if subsets is not None:
+            n_strands = len(self.target_seqs) * (2 if self.opts.double_strand else 1)
+            stride = (n_strands + 31) // 32
+            words = (C.c_uint32 * (stride * len(reads)))()
+            for r, sub in enumerate(subsets):
+                for c in (sub or ()):
+                    words[r * stride + c // 32] |= 1 << (c % 32)
+        rc = self._lib.stitch_align_batch(self._h, buf, offs, len(reads), words, stride, C.byref(res))
+        if rc != 0:
+            raise StitchError(f"stitch_align_batch failed ({rc}): {self.last_error()}")
+        try:
+            chains = _lib.read_results(self._lib, _lib.PRODUCT_RESULTS, res)
+            sam = [_lib.format_sam(self._lib, "stitch_", self._h, res, r, headers[r], bytes(reads[r]).upper(),
+                                   None if quals is None else quals[r], None, sam_opts) for r in range(len(reads))]
+            return chains, sam
+        finally:
+            self._lib.stitch_free_results(res)
+
     def align_batch(self, reads: Sequence[bytes], subsets=None) -> List[List[Alignment]]:
         """Aligners::align for each read (chains per read; empty list = unmapped)."""
         return self._run(self._lib.stitch_align_batch, reads, subsets)

@@ -50,6 +50,11 @@ class StitchStats(C.Structure):
     ]
 
 
+class StitchSamOpts(C.Structure):
+    _fields_ = [("soft_clip", C.c_uint8), ("use_eq_and_x", C.c_uint8), ("pick_primary", C.c_uint8), ("filter_secondary", C.c_uint8),
+                ("filter_secondary_pct", C.c_float)]
+
+
 def make_opts(mode=MODE_LOCAL, match_score=1, mismatch_score=-4, gap_open=-6, gap_extend=-2,
               default_jump_score=-10, jump_score_same_contig_and_strand=None,
               jump_score_same_contig_opposite_strand=None, jump_score_inter_contig=None,

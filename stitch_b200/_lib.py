@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "stitch_create", "stitch_align_batch", "stitch_custom_batch", "stitch_custom_batch_device",
     "stitch_results_n_reads", "stitch_results_read", "stitch_results_chains", "stitch_results_ops",
     "stitch_free_results", "stitch_get_stats", "stitch_set_max_inflight", "stitch_destroy",
-    "stitch_last_error", "stitch_abi_version", "stitch_measure_int32_peak",
+    "stitch_last_error", "stitch_abi_version", "stitch_measure_int32_peak", "stitch_format_sam", "stitch_free_text",
 ]
 
 _lib = None
@@ -39,6 +39,43 @@ def declare_results_api(lib, prefix_map):
     free = getattr(lib, prefix_map["free"])
     free.restype = None
     free.argtypes = [C.c_void_p]
+
+
+def declare_sam_api(lib, prefix):
+    f = getattr(lib, prefix + "format_sam")
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int32,
+                  C.c_void_p, C.POINTER(C.c_void_p)]
+    g = getattr(lib, prefix + "free_text")
+    g.restype = None
+    g.argtypes = [C.c_void_p]
+
+
+def format_sam(lib, prefix, ctx, results_handle, read, header, bases, quals=None, pre_align_score=None, sam_opts=None):
+    """SAM text lines of one read of a results handle (stitch_format_sam)."""
+    from ._abi import StitchSamOpts
+    bases = bytes(bases)
+    bbuf = (C.c_uint8 * max(1, len(bases))).from_buffer_copy(bases if bases else b"\0")
+    qbuf = None
+    if quals is not None:
+        quals = bytes(quals)
+        qbuf = (C.c_uint8 * max(1, len(quals))).from_buffer_copy(quals if quals else b"\0")
+    so = None
+    if sam_opts:
+        so = StitchSamOpts(soft_clip=int(bool(sam_opts.get("soft_clip", False))), use_eq_and_x=int(bool(sam_opts.get("use_eq_and_x", False))),
+                           pick_primary=int(sam_opts.get("pick_primary", 0)), filter_secondary=int(bool(sam_opts.get("filter_secondary", False))),
+                           filter_secondary_pct=float(sam_opts.get("filter_secondary_pct", 10.0)))
+    out = C.c_void_p()
+    hdr = header.encode() if isinstance(header, str) else bytes(header)
+    rc = getattr(lib, prefix + "format_sam")(ctx, results_handle, read, hdr, bbuf, qbuf, len(bases), int(pre_align_score is not None),
+                                             int(pre_align_score or 0), C.byref(so) if so else None, C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"format_sam failed ({rc}): {getattr(lib, prefix + 'last_error')(ctx).decode()}")
+    try:
+        text = C.string_at(out).decode()
+        return text.split("\n") if text else []   # (every record can be filtered out by filter_secondary)
+    finally:
+        getattr(lib, prefix + "free_text")(out)
 
 
 def read_results(lib, prefix_map, handle):
@@ -87,6 +124,7 @@ def load():
     lib.stitch_custom_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32,
                                                C.POINTER(C.c_void_p)]
     declare_results_api(lib, PRODUCT_RESULTS)
+    declare_sam_api(lib, "stitch_")
     lib.stitch_get_stats.restype = C.c_int
     lib.stitch_get_stats.argtypes = [C.c_void_p, C.POINTER(StitchStats)]
     lib.stitch_set_max_inflight.restype = C.c_int

@@ -10,6 +10,7 @@
 #include <string>
 
 #include "host_common.hpp"
+#include "host_sam.hpp"
 
 namespace stitch { namespace host { Backend *stitch_make_backend(Aligner &al, int device); } }
 
@@ -84,6 +85,30 @@ const stitch_op *STITCH_API(results_ops)(const stitch_results *r, uint64_t *n) {
     *n = r->res.ops.size(); return r->res.ops.data();
 }
 void STITCH_API(free_results)(stitch_results *r) { delete r; }
+
+int STITCH_API(format_sam)(stitch_ctx *ctx, const stitch_results *res, uint32_t read, const char *read_header, const uint8_t *bases,
+                           const uint8_t *quals, uint32_t n_bases, int has_pre_align_score, int32_t pre_align_score,
+                           const stitch_sam_opts *sopts, char **out_text) {
+    if (!ctx) return STITCH_ERR_INVALID;
+    STITCH_GUARD_BEGIN
+    if (!res || !read_header || (!bases && n_bases) || !out_text) throw stitch::host::Error(STITCH_ERR_INVALID, "null argument");
+    if (read >= res->res.first.size()) throw stitch::host::Error(STITCH_ERR_INVALID, "read index out of range");
+    stitch::host::SamOpts o;
+    if (sopts) {
+        o.soft_clip = sopts->soft_clip != 0; o.use_eq_and_x = sopts->use_eq_and_x != 0; o.filter_secondary = sopts->filter_secondary != 0;
+        o.pick_primary = sopts->pick_primary; o.filter_secondary_pct = sopts->filter_secondary_pct;
+    }
+    const std::string text = stitch::host::format_sam(ctx->al.contigs, ctx->al.opts.sc, o, read_header, bases, quals, n_bases,
+                                                      res->res.chains.data() + res->res.first[read], res->res.count[read],
+                                                      res->res.ops.data(), has_pre_align_score != 0, pre_align_score);
+    char *buf = static_cast<char *>(std::malloc(text.size() + 1));
+    if (!buf) throw std::bad_alloc();
+    std::memcpy(buf, text.c_str(), text.size() + 1);
+    *out_text = buf;
+    return STITCH_OK;
+    STITCH_GUARD_END(ctx)
+}
+void STITCH_API(free_text)(char *t) { std::free(t); }
 
 int STITCH_API(get_stats)(const stitch_ctx *ctx, stitch_stats *out) {
     if (!ctx || !out) return STITCH_ERR_INVALID;

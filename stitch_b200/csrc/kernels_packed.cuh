@@ -143,8 +143,7 @@ template <bool SPECIAL, bool TB>
 __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, const PkColOut &O, uint32_t j, uint32_t tile,
                                         uint32_t lane, int32_t r0pkey, int32_t cr1key, bool chunk_start, const int32_t *hS,
                                         const int32_t *hD, int32_t &prev_exit, uint32_t &prev_exit_open, int32_t &prev_s7,
-                                        int32_t *outS, int32_t *outD, const unsigned char *stg, uint32_t a, const ContigEntry &en,
-                                        int32_t Jc) {
+                                        const unsigned char *stg, uint32_t a, const ContigEntry &en, int32_t Jc) {
     const PK &pk = X.pk;
     const uint32_t tic = tile - en.tile_start;
     const bool first = tic == 0;
@@ -258,8 +257,6 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
             X.team.peer(S.stash, a % X.team.size)[a] = rm;   // to the CTA that finishes contig a
         }
     }
-    STITCH_UNROLL
-    for (int k = 0; k < STRIP; ++k) { outS[k] = Sn[k]; outD[k] = st.D6[k]; }
     *reinterpret_cast<int4 *>(X.Sst + tile * ST + lane * 4) = make_int4(Sn[0], Sn[1], Sn[2], Sn[3]);
     *reinterpret_cast<int4 *>(X.Sst + tile * ST + 128 + lane * 4) = make_int4(Sn[4], Sn[5], Sn[6], Sn[7]);
     *reinterpret_cast<int4 *>(X.Dst + tile * ST + lane * 4) = make_int4(st.D6[0], st.D6[1], st.D6[2], st.D6[3]);
@@ -301,7 +298,6 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         const uint32_t t_lo = (uint32_t)((uint64_t)NT * gw / Weff), t_hi = (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
         int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
-        int32_t oS[STRIP], oD[STRIP];
         // software pipeline: while tile t is computed, cp.async brings tile t+1 (S keys, D keys, bases) into this
         // warp's shared-memory double buffer; each lane reads back exactly the bytes it copied (no warp sync needed)
         const bool staged = X.staged;
@@ -336,9 +332,9 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             }
             const uint32_t tic = tile - en.tile_start;
             if (tic == 0 || tic + 1 == en.ntiles)
-                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg, a, en, Jc);
+                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc);
             else
-                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, oS, oD, stg, a, en, Jc);
+                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc);
             a = a_next; en = en_next; Jc = Jc_next;
         }
         if (gw + 1 < Weff) {   // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp)
@@ -346,11 +342,15 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             const uint32_t slot = local ? warp + 1 : 0u;
             int32_t *nS = (local ? S.haloS : team.peer(S.haloS, team.rank + 1)) + (par * W + slot) * 9;
             int32_t *nD = (local ? S.haloD : team.peer(S.haloD, team.rank + 1)) + (par * W + slot) * 8;
+            // (read back from the state this warp has just written: keeps 16 registers out of the tile loop)
+            const int32_t *tp = X.Sst + (t_hi - 1) * ST;
             if (lane == 31) {
-                STITCH_UNROLL
-                for (int k = 0; k < STRIP; ++k) { nS[k + 1] = oS[k]; nD[k] = oD[k]; }
+                const int4 s0 = *reinterpret_cast<const int4 *>(tp + 31 * 4), s1 = *reinterpret_cast<const int4 *>(tp + 128 + 31 * 4);
+                const int4 d0 = *reinterpret_cast<const int4 *>(tp + TILE + 31 * 4), d1 = *reinterpret_cast<const int4 *>(tp + TILE + 128 + 31 * 4);
+                nS[1] = s0.x; nS[2] = s0.y; nS[3] = s0.z; nS[4] = s0.w; nS[5] = s1.x; nS[6] = s1.y; nS[7] = s1.z; nS[8] = s1.w;
+                nD[0] = d0.x; nD[1] = d0.y; nD[2] = d0.z; nD[3] = d0.w; nD[4] = d1.x; nD[5] = d1.y; nD[6] = d1.z; nD[7] = d1.w;
             }
-            if (lane == 30) nS[0] = oS[STRIP - 1];
+            if (lane == 30) nS[0] = tp[128 + 30 * 4 + 3];
         }
     }
     team.sync();
@@ -647,7 +647,7 @@ __device__ uint32_t pk_tail_start(const Params &P, PackSmem &S, const Scoring &s
     return j0;
 }
 
-template <int W> __device__ void pk_walk_phase(const Params P, unsigned char *smem_raw);   // kernels_walk.cuh
+template <int W> __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_raw);   // kernels_walk.cuh
 
 // ---------------------------------------------------------------------------------------------
 // bulk fill
@@ -662,7 +662,6 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
     __shared__ uint32_t s_first;
     __shared__ uint32_t s_cta_lo[17];
     const uint32_t tid = threadIdx.x;
-    constexpr uint32_t T = W * 32;
     const Scoring sc = P.sc;
 
     Team team; team.rank = 0; team.size = P.cluster_size;

@@ -34,6 +34,7 @@ def lib(strip=8):
         f.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_uint32,
                       C.POINTER(C.c_void_p)]
     _lib.declare_results_api(e, EMUL_RESULTS)
+    _lib.declare_sam_api(e, "emul_")
     e.emul_destroy.restype = None
     e.emul_destroy.argtypes = [C.c_void_p]
     e.emul_last_error.restype = C.c_char_p
@@ -73,6 +74,21 @@ class EmulAligners:
             raise EmulError(f"batch failed ({rc}): {self.e.emul_last_error(self._h).decode()}")
         try:
             return _lib.read_results(self.e, EMUL_RESULTS, res)
+        finally:
+            self.e.emul_free_results(res)
+
+    def batch_sam(self, reads, headers, quals=None, sam_opts=None):
+        """align_batch + the product's SAM record layer (host code shared with the CUDA library)."""
+        buf, offs = _abi.pack_reads(reads)
+        res = C.c_void_p()
+        rc = self.e.emul_align_batch(self._h, buf, offs, len(reads), None, 0, C.byref(res))
+        if rc != 0:
+            raise EmulError(f"batch failed ({rc}): {self.e.emul_last_error(self._h).decode()}")
+        try:
+            chains = _lib.read_results(self.e, EMUL_RESULTS, res)
+            sam = [_lib.format_sam(self.e, "emul_", self._h, res, r, headers[r], bytes(reads[r]).upper(),
+                                   None if quals is None else quals[r], None, sam_opts) for r in range(len(reads))]
+            return chains, sam
         finally:
             self.e.emul_free_results(res)
 

@@ -272,3 +272,31 @@ def test_config3_config4_full_size_properties():
     st = al.stats()
     assert st.packed_cells == st.cells == 60000 * 2 * 50 * 20000
     al.close()
+
+
+def test_sam_records_on_gpu(oracle):
+    """Aligners::align + SamRecordFormatter::format through the C ABI on the GPU (stitch_format_sam) against the
+    restated reference (oracle/ aligner + oracle/sam_oracle.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sam_oracle
+    import stitch_b200
+    rng = random.Random(31)
+    contigs = [gen.rand_seq(rng, rng.randint(300, 700)) for _ in range(5)]
+    reads = [gen.chimeric_read(rng, contigs, 500, rng.randint(2, 5), strands=True, wrap=True) for _ in range(6)]
+    named = [(f"ctg{k}", s) for k, s in enumerate(contigs)]
+    headers = [f"r{k} extra" for k in range(len(reads))]
+    quals = [bytes(rng.randrange(33, 74) for _ in r) for r in reads]
+    for kw, so in ((dict(double_strand=True, circular=True), dict()),
+                   (dict(double_strand=True, suboptimal=True, suboptimal_pct=0.0), dict(soft_clip=True, use_eq_and_x=True, pick_primary=1)),
+                   (dict(double_strand=True, suboptimal=True, suboptimal_pct=0.0), dict(filter_secondary=True, filter_secondary_pct=50.0))):
+        o = make_opts(**kw)
+        exp_chains, _ = oracle.OracleAligners(o, named).batch(reads, raw=False)
+        al = stitch_b200.Builder(**kw).build_aligners([stitch_b200.TargetSeq(n, s) for n, s in named], device=0)
+        chains, sam = al.align_batch_sam(reads, headers, quals, so)
+        al.close()
+        compare(chains, exp_chains, f"sam {kw}")
+        for r in range(len(reads)):
+            exp = sam_oracle.format_sam(headers[r], reads[r].upper(), quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
+                                        (o.match_score, o.mismatch_score, o.gap_open, o.gap_extend), **so)
+            assert sam[r] == exp, f"read {r} {kw} {so}"
