@@ -225,7 +225,8 @@ def main():
 
     def timed(fn, steps):
         agg = {"cells": 0, "fill_ms": 0.0, "tb_ms": 0.0, "launches": 0, "h2d": 0, "d2h": 0, "fills": 0, "tb_bytes": 0,
-               "packed_ms": 0.0, "wide_ms": 0.0, "redo_ms": 0.0, "packed_cells": 0, "redo_fills": 0, "tail_ms": 0.0, "packed_launches": 0}
+               "packed_ms": 0.0, "wide_ms": 0.0, "redo_ms": 0.0, "packed_cells": 0, "redo_fills": 0, "tail_ms": 0.0, "packed_launches": 0,
+               "tile_columns": 0, "quiet_tile_columns": 0}
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -234,6 +235,7 @@ def main():
             agg["launches"] += s.kernel_launches; agg["h2d"] += s.h2d_bytes; agg["d2h"] += s.d2h_bytes
             agg["fills"] += s.fills; agg["tb_bytes"] += s.traceback_bytes
             agg["packed_ms"] += s.packed_fill_ms; agg["wide_ms"] += s.wide_fill_ms; agg["redo_ms"] += s.redo_fill_ms
+            agg["tile_columns"] += s.tile_columns; agg["quiet_tile_columns"] += s.quiet_tile_columns
             agg["packed_cells"] += s.packed_cells; agg["redo_fills"] += s.redo_fills; agg["tail_ms"] += s.tail_fill_ms; agg["packed_launches"] += s.packed_launches
         barrier()
         dt = time.perf_counter() - t0
@@ -285,6 +287,11 @@ def main():
                     "h2d_bytes_per_step": agg_e["h2d"] / args.steps, "d2h_bytes_per_step": agg_e["d2h"] / args.steps,
                     "fills_per_step": agg_e["fills"] / args.steps, "ms_per_step": dt_e / args.steps * 1e3},
             "gpu_launches": agg["launches_all"],
+            "quiet_tiles": {"tile_columns": agg["tile_columns"], "skipped": agg["quiet_tile_columns"],
+                            "frac_skipped": agg["quiet_tile_columns"] / agg["tile_columns"] if agg["tile_columns"] else 0.0,
+                            "note": "bulk pass of fill_packed_kernel on this rank: (256-row tile, column) pairs proven to be in the closed form "
+                                    "jump + substitution score and therefore neither loaded, computed nor stored (dp_packed.h, PkQuiet); "
+                                    "GCUPS counts every cell of every fill, as the metric defines it"},
             "phases_ms_per_step": {"packed_fill": agg["packed_ms"] / args.steps, "packed_tail": agg["tail_ms"] / args.steps, "wide_fill": agg["wide_ms"] / args.steps,
                                    "window_reruns": agg["redo_ms"] / args.steps, "fixup_walk": agg["tb_ms"] / args.steps,
                                    "window_rerun_reads": agg["redo_fills"] / args.steps,

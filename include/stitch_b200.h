@@ -111,6 +111,8 @@ typedef struct stitch_stats {
     uint64_t redo_fills;          /* number of such re-runs                                    */
     double tail_fill_ms;          /* of fill_ms: the packed tail when it ran as its own launch (0: same launch as the fill) */
     uint64_t packed_launches;     /* launches of the packed-key kernel (one per chunk of reads)        */
+    uint64_t tile_columns;        /* packed bulk pass: (256-row tile, column) pairs of the batch               */
+    uint64_t quiet_tile_columns;  /* of those: skipped because the tile was provably quiet (dp_packed.h)       */
 } stitch_stats;
 
 typedef struct stitch_ctx stitch_ctx;

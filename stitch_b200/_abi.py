@@ -47,6 +47,7 @@ class StitchStats(C.Structure):
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("traceback_bytes", C.c_uint64),
         ("packed_fill_ms", C.c_double), ("wide_fill_ms", C.c_double), ("redo_fill_ms", C.c_double),
         ("packed_cells", C.c_uint64), ("redo_fills", C.c_uint64), ("tail_fill_ms", C.c_double), ("packed_launches", C.c_uint64),
+        ("tile_columns", C.c_uint64), ("quiet_tile_columns", C.c_uint64),
     ]
 
 

@@ -118,6 +118,7 @@ int STITCH_API(get_stats)(const stitch_ctx *ctx, stitch_stats *out) {
     out->h2d_bytes = s.h2d; out->d2h_bytes = s.d2h; out->traceback_bytes = s.tb_bytes;
     out->packed_fill_ms = s.packed_ms; out->wide_fill_ms = s.wide_ms; out->redo_fill_ms = s.redo_ms; out->tail_fill_ms = s.tail_ms; out->packed_launches = s.packed_launches;
     out->packed_cells = s.packed_cells; out->redo_fills = s.refills;
+    out->tile_columns = s.tile_columns; out->quiet_tile_columns = s.quiet_tile_columns;
     return STITCH_OK;
 }
 

@@ -105,7 +105,7 @@ struct CudaBackend : host::Backend {
     DevBuf<CkSum> d_handsum;
     DevBuf<int32_t> d_pstate, d_wpstate, d_pck;
     DevBuf<uint32_t> d_tailj0, d_done;
-    DevBuf<unsigned long long> d_dbg;
+    DevBuf<unsigned long long> d_dbg, d_qstats;
     bool debug_stats = false;
     DevBuf<ColRec> d_ucr;
     size_t l2_persist_max = 0, l2_window_max = 0;
@@ -119,6 +119,7 @@ struct CudaBackend : host::Backend {
     uint32_t cluster_pref = 0;
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
+    uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
     DevBuf<ColRec> d_colrec;
@@ -166,6 +167,7 @@ struct CudaBackend : host::Backend {
         cluster_pref = std::min<uint32_t>(16, env_u32("STITCH_CLUSTER", cluster_pref));
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
+        quiet_tiles = env_u32("STITCH_QUIET", 1);
     }
     ~CudaBackend() override {
         cudaSetDevice(device);
@@ -421,6 +423,7 @@ struct CudaBackend : host::Backend {
         P.unit_bytes = d_unit.p; P.unit_stride = round_up(unit_max, 256);
         P.colrec = d_colrec.p; P.last = d_last.p; P.sn = d_sn.p; P.ck_state = d_ck.p; P.pck = d_pck.p; P.ck_sum = d_cksum.p; P.gcol = d_gcol.p;
         P.ops = d_ops.p; P.chains = d_chains.p; P.job_out = d_jobout.p; P.counter = d_counter.p;
+        d_qstats.reserve(2); CUDA_CHECK(cudaMemsetAsync(d_qstats.p, 0, 2 * sizeof(unsigned long long), stream)); P.qstats = d_qstats.p;
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
@@ -444,6 +447,7 @@ struct CudaBackend : host::Backend {
         } else if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes;
+            Q.quiet = quiet_tiles;
             size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS, pstage) + 15) / 16 * 16;
             if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads
                 d_done.reserve(nj);
@@ -548,12 +552,19 @@ struct CudaBackend : host::Backend {
         mark(T_END);
         sync("walk");
         collect_marks();
+        {
+            unsigned long long hq[2];
+            CUDA_CHECK(cudaMemcpy(hq, d_qstats.p, sizeof(hq), cudaMemcpyDeviceToHost));
+            stats.tile_columns += hq[0]; stats.quiet_tile_columns += hq[1];
+        }
         if (debug_stats) {
             unsigned long long h[16];
             cudaMemcpy(h, d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
             std::fprintf(stderr, "[stitch dbg] jobs %u (fused grid %u): tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, "
                          "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, fgrid, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
                          h[4] * 1e-6, h[5] * 1e-6);
+            std::fprintf(stderr, "[stitch dbg] bulk columns, Mcycles summed over reads: select %.1f, tile phase %.1f (mean warp busy %.1f), per-contig finish %.1f\n",
+                         h[7] * 1e-6, h[8] * 1e-6, h[10] * 1e-6, h[9] * 1e-6);
         }
         stats.tb_bytes += tot.ck * sizeof(CellState) + (tot.pck + (uint64_t)fgrid * arena.pck) * 4 + (tot.colrec + (uint64_t)fgrid * arena.colrec) * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);

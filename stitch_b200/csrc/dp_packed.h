@@ -302,6 +302,94 @@ SHD PkRowMOut pk_finish_rowm(const PK &p, const PCol &c, const Scoring &sc, cons
     return o;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Quiet tiles.  Away from the alignment paths every cell of a column takes the jump move
+// (MCA:279-331 makes it available everywhere), so its S is J(c) + sub(x_i, y_j): one of TWO keys
+// per (contig, column), decided by a byte compare.  A warp tile all of whose cells are in that
+// closed form is "quiet"; while a handful of per-(contig, column) integer compares (pk_quiet_next)
+// prove that a quiet tile stays quiet, the bulk fill neither loads, computes nor stores it.  The
+// state of a quiet tile is re-materialised from the closed form when it is needed again (a column
+// that fails the test, a checkpoint column, a neighbour that is not quiet).
+//
+//   S(r, j) = bk_j[sub(r, j)]
+//   D(r, j) = clean6(max_k t_j[k][sub(r, j-1-k)], NEGKEY)   (k = 0 .. PKQ_L-1)   or any DEAD value
+//     t[0] = open from S(r, j-1), t[k] = k-fold extension of the open from S(r, j-1-k); older deletion
+//     runs are required to be dead.  On equal scores the dense fill keeps the OLDEST run (an extension
+//     wins the tie against an open, SCA:329-338), so t[k] carries priority k while the max is taken.
+//     A D value v (relative to B_j) is DEAD - can never win or tie again, now or after any number
+//     of extensions - when v <= o + gmin + submin - 1: the best cell of column j-1 can itself be
+//     extended by deletions, so G(j-1+k) >= G(j-1) + o + e k, and every cell of column j+k has the
+//     jump candidate >= G(j-1+k) + gmin + submin (SCA:329-338, 373-382).  Dead values may differ
+//     between the closed form and the dense fill; nothing observable does.
+//
+// sub index: 0 = the bases are equal (match score), 1 = not.
+constexpr int PKQ_L = 3;
+struct PkQuiet {            // per (contig, column)
+    int32_t bk[2];          // clean S key of a quiet cell
+    int32_t t[PKQ_L][2];    // raw D candidates (as pass 1 forms them, before clean6; priority field = k)
+    int32_t stay;           // tiles quiet at column j-1 (with a quiet predecessor tile) are quiet at column j
+    int32_t why;            // which of C1..C5 failed (bit k-1), bit 5 = not allowed (diagnostics)
+};
+SHD int32_t pk_deadrel(const Scoring &sc) {
+    int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
+    int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
+    gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
+    return sc.o + gmin + submin - 1;
+}
+SHD int32_t pk_clean6(const PK &p, int32_t v) { return (pk_max(v, p.NEGKEY) & p.NPM) | p.PD6; }
+SHD PkQuiet pk_quiet_init(const PK &p) {
+    PkQuiet q;
+    q.bk[0] = q.bk[1] = p.NEGKEY; q.stay = 0; q.why = 0;
+    for (int k = 0; k < PKQ_L; ++k) q.t[k][0] = q.t[k][1] = p.NEGKEY;
+    return q;
+}
+// Closed form of column j from the one of column j-1.  `Jc` = pk_jc of the contig for column j.
+// `allow` = this column may be skipped at all (not a checkpoint column, read base is one of ACGT, ...).
+SHD PkQuiet pk_quiet_next(const PK &p, const Scoring &sc, const PCol &c, int32_t Jc, const PkQuiet &prev, bool allow) {
+    PkQuiet q;
+    const int32_t jM = Jc + c.cM, jX = Jc + c.cX;
+    q.bk[0] = jM & p.NPM; q.bk[1] = jX & p.NPM;
+    int32_t dcap = p.NEGKEY;
+    STITCH_UNROLL
+    for (int s = 0; s < 2; ++s) {
+        q.t[0][s] = (int32_t)((uint32_t)prev.bk[s] + (uint32_t)c.cOE);
+        STITCH_UNROLL
+        for (int k = 1; k < PKQ_L; ++k)   // stored D (PP_D) + cE has priority 1; make it k
+            q.t[k][s] = (int32_t)((uint32_t)pk_clean6(p, prev.t[k - 1][s]) + (uint32_t)c.cE + (uint32_t)((k - 1) * p.P1));
+        STITCH_UNROLL
+        for (int k = 0; k < PKQ_L; ++k) dcap = pk_max(dcap, q.t[k][s]);
+    }
+    const int32_t jlo = pk_max(jM, jX) == jM ? jX : jM;                 // the weaker of the two jump candidates
+    const int32_t pbk = pk_max(prev.bk[0], prev.bk[1]);
+    // C1 the diagonal from a quiet cell does not beat the jump (equal keys are the same cell value)
+    const bool c1 = (int32_t)((uint32_t)pbk + (uint32_t)c.cM) <= (jM | p.PB8) && (int32_t)((uint32_t)pbk + (uint32_t)c.cX) <= (jX | p.PB8);
+    // C2 no D of a quiet cell reaches the jump's score (D wins ties)
+    const bool c2 = (dcap >> p.SH) < (jlo >> p.SH);
+    // C3 x-prefix clip loses (lower priority than the jump: a plain key compare)
+    const bool c3 = c.XC < jlo;
+    // C4 no insertion chain out of a quiet cell of this column reaches the jump's score
+    const bool c4 = (((int32_t)((uint32_t)pk_max(q.bk[0], q.bk[1]) + (uint32_t)c.cOEi)) >> p.SH) < (jlo >> p.SH);
+    // C5 the deletion runs the closed form drops (extensions of the oldest term of column j-1) are dead
+    const int32_t dropped = (int32_t)((uint32_t)pk_clean6(p, pk_max(prev.t[PKQ_L - 1][0], prev.t[PKQ_L - 1][1])) + (uint32_t)c.cE);
+    const bool c5 = (dropped >> p.SH) <= pk_deadrel(sc);
+    const bool ok = c1 && c2 && c3 && c4 && c5;
+    q.why = (c1 ? 0 : 1) | (c2 ? 0 : 2) | (c3 ? 0 : 4) | (c4 ? 0 : 8) | (c5 ? 0 : 16) | (allow ? 0 : 32);
+    q.stay = (ok && allow) ? 1 : 0;
+    return q;
+}
+// The closed form of one cell of column j.  s[k] = sub index of the cell's contig base against y_{j-k}, k = 0 .. PKQ_L.
+SHD int32_t pk_quiet_S(const PkQuiet &q, int s0) { return q.bk[s0]; }
+SHD int32_t pk_quiet_D(const PK &p, const PkQuiet &q, const int *s) {
+    int32_t d = q.t[0][s[1]];
+    STITCH_UNROLL
+    for (int k = 1; k < PKQ_L; ++k) d = pk_max(d, q.t[k][s[k + 1]]);
+    return pk_clean6(p, d);
+}
+// Is a densely computed cell of column j in the closed form?
+SHD bool pk_quiet_cell(const PK &p, const PkQuiet &q, int32_t deadrel, int32_t Skey, int32_t D6, const int *s) {
+    return Skey == q.bk[s[0]] && (D6 == pk_quiet_D(p, q, s) || (D6 >> p.SH) <= deadrel);
+}
+
 // Carry into a lane from the previous lane's exit (PP_INC -> PP_ICARRY).
 SHD int32_t pk_carry_from_exit(const PK &p, int32_t exit_key) { return exit_key + p.P1; }
 

@@ -187,7 +187,7 @@ struct JobResult { std::vector<RawChain> chains; };
 struct BackendStats {
     uint64_t cells = 0, fills = 0, launches = 0, h2d = 0, d2h = 0, tb_bytes = 0, refills = 0;
     double fill_ms = 0, tb_ms = 0, total_ms = 0, packed_ms = 0, wide_ms = 0, redo_ms = 0, tail_ms = 0;
-    uint64_t packed_cells = 0, packed_launches = 0;
+    uint64_t packed_cells = 0, packed_launches = 0, tile_columns = 0, quiet_tile_columns = 0;
     void reset() { *this = BackendStats(); }
 };
 

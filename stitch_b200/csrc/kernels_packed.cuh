@@ -51,15 +51,22 @@ struct PackSmem {
     uint32_t *cml, *cmk, *slm, *tbm, *haloF;
     PkRowM *stash;
     JumpInfo *Jw;
+    PkQuiet *Q;             // [2][cmax]: closed form of a quiet tile per contig, by column parity (dp_packed.h)
+    uint8_t *tq, *tmask;    // per tile: quiet flag of the latest column / base classes present (bit 0..3 = A C G T, 4 = other)
+    uint8_t *tmode;         // per tile: what the tile does in the current column (0 skip, 1 materialise, 2 load)
+    uint32_t cmax;
     unsigned char *stage;   // [W][2][STAGE_BYTES]: cp.async double buffer of the next tile (state in global memory only)
     static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + TILE;   // S keys, D keys, bases of one tile
     // `stage_bytes`: the front area = cp.async double buffers (default_stage), or the cluster's slice of the rolling
     // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
     static size_t default_stage(int W) { return (size_t)W * 2 * STAGE_BYTES; }
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
-        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) + (sizeof(PkRowM) + sizeof(JumpInfo)) * cmax + 64;
+        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) + (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet)) * cmax +
+               3 * (size_t)ntmax + 64;
     }
-    __device__ void carve(unsigned char *raw, uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
+    __device__ void carve(unsigned char *raw, uint32_t cmax_, uint32_t ntmax, int W, size_t stage_bytes) {
+        const uint32_t cmax = cmax_;
+        this->cmax = cmax_;
         stage = raw;
         raw += stage_bytes;
         Jw = reinterpret_cast<JumpInfo *>(raw);
@@ -71,6 +78,10 @@ struct PackSmem {
         haloS = tilemax + ntmax;                             // [2][W][9]
         haloD = haloS + 2 * W * 9;                           // [2][W][8]
         haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W] (unused)
+        Q = reinterpret_cast<PkQuiet *>(haloF + 2 * W);
+        tq = reinterpret_cast<uint8_t *>(Q + 2 * cmax);
+        tmask = tq + ntmax;
+        tmode = tmask + ntmax;
     }
 };
 
@@ -97,6 +108,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     // (cstate = this CTA's block, same offset in every CTA of the cluster) and Sst = cstate - own_lo * ST.
     uint32_t own_lo, own_hi, warps;
     bool cluster_smem;
+    bool quiet;             // the bulk pass may skip quiet tiles (single-CTA teams with the state in global memory)
     int32_t *cstate;
     const uint32_t *cta_lo;   // shared memory: first tile of every CTA of the team, [size + 1]
 };
@@ -139,18 +151,46 @@ __device__ __forceinline__ void unpack8(const uint2 xb, uint8_t *x) {
 }
 
 // One tile of one column.  `prev_*` carry what the next tile of the same chunk needs.
-template <bool SPECIAL, bool TB>
-__device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, const PkColOut &O, uint32_t j, uint32_t tile,
+// Quiet tiles (QUIET, bulk pass only; dp_packed.h): `qz.mat` = the tile's own state of column j-1 is the closed form
+// (its memory may be stale): materialise it instead of loading; `qz.prev_skipped` = the previous tile of this chunk
+// was skipped in this column (its last row and its chain exit come from the closed form).  Returns whether every
+// ordinary cell of the tile is in the closed form of column j.
+struct PkColStat { uint32_t skipped; unsigned long long t_tiles, t_finish, t_busy, t_select; };   // per job, shared memory
+struct PkQuietArgs {
+    bool mat, prev_skipped;
+    const PkQuiet *Qp, *Qn;     // closed forms of column j-1 / j of this tile's contig (shared memory)
+    const uint8_t *yq;          // yq[k] = read base y_{j-k}, 0 when there is none
+    int32_t deadrel;
+};
+__device__ __forceinline__ int32_t pk_quiet_D_dev(const PK &pk, const PkQuiet &q, uint8_t xb, const uint8_t *yq) {
+    int32_t d = xb == yq[1] ? q.t[0][0] : q.t[0][1];
+    STITCH_UNROLL
+    for (int k = 1; k < PKQ_L; ++k) d = pk_max(d, xb == yq[k + 1] ? q.t[k][0] : q.t[k][1]);
+    return pk_clean6(pk, d);
+}
+
+template <bool SPECIAL, bool TB, bool QUIET>
+__device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSmem &S, const PkColOut &O, uint32_t j, uint32_t tile,
                                         uint32_t lane, int32_t r0pkey, int32_t cr1key, bool chunk_start, const int32_t *hS,
                                         const int32_t *hD, int32_t &prev_exit, uint32_t &prev_exit_open, int32_t &prev_s7,
-                                        const unsigned char *stg, uint32_t a, const ContigEntry &en, int32_t Jc) {
+                                        const unsigned char *stg, uint32_t a, const ContigEntry &en, int32_t Jc, const PkQuietArgs &qz) {
     const PK &pk = X.pk;
     const uint32_t tic = tile - en.tile_start;
     const bool first = tic == 0;
     const uint32_t row0 = tic * TILE + lane * STRIP + 1;
     int32_t Sup[STRIP], Dup[STRIP];
     uint2 xb;
-    {
+    if (QUIET && qz.mat) {
+        xb = *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
+        uint8_t xm[STRIP];
+        unpack8(xb, xm);
+        const PkQuiet qp = *qz.Qp;
+        STITCH_UNROLL
+        for (int k = 0; k < STRIP; ++k) {
+            Sup[k] = xm[k] == qz.yq[1] ? qp.bk[0] : qp.bk[1];
+            Dup[k] = pk_quiet_D_dev(pk, qp, xm[k], qz.yq + 1);
+        }
+    } else {
         int4 s0, s1, d0, d1;
         if (stg) {   // this tile was staged in shared memory by cp.async while the previous tile was computed
             const int4 *q = reinterpret_cast<const int4 *>(stg);
@@ -170,7 +210,12 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     uint8_t x[STRIP];
     unpack8(xb, x);
     int32_t Sdg0 = __shfl_up_sync(FULL, Sup[STRIP - 1], 1);
-    if (lane == 0) Sdg0 = first ? r0pkey : (chunk_start ? hS[8] : prev_s7);
+    if (lane == 0) {
+        if (first) Sdg0 = r0pkey;
+        else if (chunk_start) Sdg0 = hS[8];
+        else if (QUIET && qz.prev_skipped) Sdg0 = X.bases[en.seq_off + row0 - 2] == qz.yq[1] ? qz.Qp->bk[0] : qz.Qp->bk[1];   // last row of a quiet tile
+        else Sdg0 = prev_s7;
+    }
     PStrip st;
     int nv = STRIP; bool has_m = false;
     if (SPECIAL) {
@@ -210,7 +255,10 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
         }
         pk_pass1<true, TB>(pk, pc, hs, hd, hS[0], hx, Jc, false, 0, STRIP, false, h);
         if (lane == 0) { cin = pk_carry_from_exit(pk, h.exit); if (TB) cin_open = h.exit_open; }
-    } else if (lane == 0) { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }
+    } else if (lane == 0) {
+        if (QUIET && qz.prev_skipped) { cin = pk.NEGKEY + pk.PI5; cin_open = 0; }   // the chain out of a quiet tile is dead (C4)
+        else { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }
+    }
 
     int32_t Sn[STRIP], Iarr[STRIP]; uint8_t tbb[STRIP];
     int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
@@ -264,6 +312,19 @@ __device__ __forceinline__ void pk_tile(const PackCtx &X, const PCol &pc, PackSm
     STITCH_UNROLL
     for (int d = 16; d >= 1; d >>= 1) colmax = pk_max(colmax, __shfl_xor_sync(FULL, colmax, d));
     if (lane < X.team.size) X.team.peer(S.tilemax, lane)[tile] = colmax;   // every CTA of the team holds the whole tile table
+    if (QUIET) {   // is the tile in the closed form of column j?  (S first: the cheap test, and the one that usually fails)
+        const PkQuiet qn = *qz.Qn;
+        bool ok = true;
+        STITCH_UNROLL
+        for (int k = 0; k < STRIP; ++k)
+            if (!SPECIAL || k < nv) ok = ok && Sn[k] == (x[k] == pc.q ? qn.bk[0] : qn.bk[1]);
+        if (!__all_sync(FULL, ok)) return false;
+        STITCH_UNROLL
+        for (int k = 0; k < STRIP; ++k)
+            if (!SPECIAL || k < nv) ok = ok && (st.D6[k] == pk_quiet_D_dev(pk, qn, x[k], qz.yq) || (st.D6[k] >> pk.SH) <= qz.deadrel);
+        return __all_sync(FULL, ok);
+    }
+    return false;
 }
 
 // Halos of the current state into parity slot `slot` (before the first column computed from it).
@@ -284,9 +345,11 @@ __device__ void pk_init_halos(const PackCtx &X, PackSmem &S, uint32_t slot) {
 // Phases T and F of one column.  On entry S.Jc (and S.Jw for the traceback variant), S.Sm/slm/tbm/SmKey of
 // column j-1 and the halos of parity (j-1)&1 are set and the CTA is synchronised; on exit S.cm/cml/cmk,
 // S.Sm/slm/tbm/SmKey describe column j and the CTA is synchronised.
-template <int W, bool TB>
+__device__ __forceinline__ uint32_t pk_base_bit(uint8_t b) { return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 16u; }
+
+template <int W, bool TB, bool QUIET = false>
 __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t r0pkey, int32_t cr1key, uint32_t j,
-                          const PkColOut &O) {
+                          const PkColOut &O, const uint8_t *yq = nullptr, PkColStat *cs = nullptr) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const PK &pk = X.pk;
     const Scoring &sc = X.sc;
@@ -294,6 +357,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const Team &team = X.team;
     const uint32_t GW = team.size * W, gw = team.rank * W + warp;
     const uint32_t Weff = NT < GW ? NT : GW;
+    const PkQuiet *Qp = S.Q + (par ^ 1u) * S.cmax, *Qn = S.Q + par * S.cmax;
+    const long long c0 = cs ? clock64() : 0;
     if (gw < Weff) {
         const uint32_t t_lo = (uint32_t)((uint64_t)NT * gw / Weff), t_hi = (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
@@ -311,32 +376,91 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
             __pipeline_commit();
         };
-        // contig of the current tile and of the next one (reloaded only when the chunk crosses into the next contig)
+        PkQuietArgs qz; qz.mat = false; qz.prev_skipped = false; qz.Qp = Qp; qz.Qn = Qn; qz.yq = yq; qz.deadrel = QUIET ? pk_deadrel(sc) : 0;
+        // quiet tiles: the plan of this warp's chunk for this column, from the flags of column j-1 (a warp owns the flags
+        // of its chunk), one tile per lane: 0 = skip, 1 = compute from the materialised closed form, 2 = load + compute.
+        // The first and last tile of a chunk and of a contig are always computed (halos, row 1, row m).  A skipped tile
+        // only contributes its best key (the better of the closed form's two keys among the bases it holds).
+        if (QUIET) {
+            const uint32_t mb = pk_base_bit(pc.q);
+            for (uint32_t t = t_lo + lane; t < t_hi; t += 32) {
+                uint32_t mode = 2;
+                if (S.tq[t]) {
+                    const uint32_t a_t = X.owner[t];
+                    const uint32_t tic = t - X.ent[a_t].tile_start;
+                    const PkQuiet &qn = Qn[a_t];
+                    mode = (tic != 0 && tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi && S.tq[t - 1] && qn.stay) ? 0u : 1u;
+                    if (mode == 0) {
+                        const uint32_t tm = S.tmask[t];
+                        S.tilemax[t] = (tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1];
+                    }
+                }
+                S.tmode[t] = (uint8_t)mode;
+            }
+            __syncwarp();
+        }
+        // contig of the current tile (reloaded only when the chunk crosses into the next contig)
         uint32_t a = X.owner ? X.owner[t_lo] : 0u;
         ContigEntry en = X.ent[a];
         int32_t Jc = S.Jc[a];
-        if (staged) prefetch(t_lo, en, 0);
-        for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
-            const uint32_t slot = (tile - t_lo) & 1u;
-            uint32_t a_next = a;
-            ContigEntry en_next = en;
-            int32_t Jc_next = Jc;
-            if (tile + 1 < t_hi) {
-                if (tile + 1 >= en.tile_start + en.ntiles) { a_next = X.owner[tile + 1]; en_next = X.ent[a_next]; Jc_next = S.Jc[a_next]; }
-                if (staged) prefetch(tile + 1, en_next, slot ^ 1u);
+        uint32_t nskipped = 0;
+        uint32_t pf_tile = 0xffffffffu, pf_slot = 1;   // the latest prefetch: tile and stage slot
+        bool last_skipped = false;                      // tile base-1 was skipped
+        for (uint32_t base = t_lo; base < t_hi; base += 32) {
+            const uint32_t nb = t_hi - base, validm = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            uint32_t skipm = 0, loadm = validm, loadm_next = base + 32 < t_hi ? 1u : 0u;
+            if (QUIET) {
+                const uint32_t m0 = base + lane < t_hi ? S.tmode[base + lane] : 3u;
+                const uint32_t m1 = base + 32 + lane < t_hi ? S.tmode[base + 32 + lane] : 3u;
+                skipm = __ballot_sync(FULL, m0 == 0u); loadm = __ballot_sync(FULL, m0 == 2u); loadm_next = __ballot_sync(FULL, m1 == 2u);
+                nskipped += __popc(skipm);
             }
-            const unsigned char *stg = nullptr;
-            if (staged) {
-                if (tile + 1 < t_hi) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-                stg = stg0 + slot * PackSmem::STAGE_BYTES;
+            uint32_t dm = ~skipm & validm;
+            while (dm) {
+                const uint32_t b = __ffs(dm) - 1u;
+                dm &= dm - 1u;
+                const uint32_t tile = base + b;
+                const bool is_load = (loadm >> b) & 1u;
+                qz.prev_skipped = QUIET && (b ? ((skipm >> (b - 1u)) & 1u) != 0 : last_skipped);
+                if (tile >= en.tile_start + en.ntiles) { a = X.owner[tile]; en = X.ent[a]; Jc = S.Jc[a]; }
+                // software pipeline: the tile to load sits (or arrives) in a stage slot; the next tile that will be loaded
+                // is prefetched into the other slot while this one is computed
+                uint32_t cur_slot = 0;
+                if (staged && is_load) {
+                    if (pf_tile != tile) { pf_slot ^= 1u; prefetch(tile, en, pf_slot); pf_tile = tile; }
+                    cur_slot = pf_slot;
+                }
+                bool issued = false;
+                if (staged) {
+                    const uint32_t rest = b == 31u ? 0u : (loadm & ~((2u << b) - 1u));
+                    uint32_t nl = 0xffffffffu;
+                    if (rest) nl = base + __ffs(rest) - 1u;
+                    else if (loadm_next) nl = base + 32u + __ffs(loadm_next) - 1u;
+                    if (nl != 0xffffffffu && nl != pf_tile) {
+                        pf_slot ^= 1u;
+                        if (nl < en.tile_start + en.ntiles) prefetch(nl, en, pf_slot);
+                        else { const ContigEntry e2 = X.ent[X.owner[nl]]; prefetch(nl, e2, pf_slot); }
+                        pf_tile = nl; issued = true;
+                    }
+                }
+                const unsigned char *stg = nullptr;
+                if (staged && is_load) {
+                    if (issued) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+                    stg = stg0 + cur_slot * PackSmem::STAGE_BYTES;
+                }
+                qz.mat = QUIET && !is_load;
+                qz.Qp = Qp + a; qz.Qn = Qn + a;
+                const uint32_t tic = tile - en.tile_start;
+                bool qnow;
+                if (tic == 0 || tic + 1 == en.ntiles)
+                    qnow = pk_tile<true, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
+                else
+                    qnow = pk_tile<false, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
+                if (QUIET && lane == 0) S.tq[tile] = (qnow && tic + 1 != en.ntiles) ? 1 : 0;
             }
-            const uint32_t tic = tile - en.tile_start;
-            if (tic == 0 || tic + 1 == en.ntiles)
-                pk_tile<true, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc);
-            else
-                pk_tile<false, TB>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc);
-            a = a_next; en = en_next; Jc = Jc_next;
+            last_skipped = (skipm >> 31) != 0;
         }
+        if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
         if (gw + 1 < Weff) {   // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp)
             const bool local = warp + 1 < (uint32_t)W;
             const uint32_t slot = local ? warp + 1 : 0u;
@@ -355,6 +479,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     }
     team.sync();
 
+    const long long c1 = cs ? clock64() : 0;
     // ---- per contig: tracker + row m + column best (contig a on CTA a % size) ----
     const Row0 r0 = row0_at(sc, j, X.n);
     for (uint32_t a = team.rank + team.size * warp; a < C; a += team.size * W) {
@@ -378,10 +503,19 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 STITCH_UNROLL
                 for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
                 const uint32_t tile = en.tile_start + ft;
-                const int32_t *tp = pk_tile_ptr(X, tile);
-                const int4 s0 = pk_ld_state(X, tp + lane * 4);
-                const int4 s1 = pk_ld_state(X, tp + 128 + lane * 4);
-                const int32_t sk[STRIP] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                int32_t sk[STRIP];
+                if (QUIET && S.tq[tile]) {   // a quiet tile (its memory may be stale): the closed form of column j
+                    uint8_t xq[STRIP];
+                    unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + ft * TILE + lane * STRIP), xq);
+                    const PkQuiet &qn = Qn[a];
+                    STITCH_UNROLL
+                    for (int k = 0; k < STRIP; ++k) sk[k] = xq[k] == pc.q ? qn.bk[0] : qn.bk[1];
+                } else {
+                    const int32_t *tp = pk_tile_ptr(X, tile);
+                    const int4 s0 = pk_ld_state(X, tp + lane * 4);
+                    const int4 s1 = pk_ld_state(X, tp + 128 + lane * 4);
+                    sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
+                }
                 uint32_t row = 0xffffffffu; int32_t key = 0;
                 STITCH_UNROLL
                 for (int k = STRIP - 1; k >= 0; --k) {
@@ -440,6 +574,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         }
     }
     team.sync();
+    if (cs && tid == 0) { cs->t_tiles += (unsigned long long)(c1 - c0); cs->t_finish += (unsigned long long)(clock64() - c1); }
 }
 
 // Column 0 (SCA:97-186) of the contigs of X into the packed state (base B_0 = 0) + row-m summaries.
@@ -508,7 +643,7 @@ __device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t *dck, CkSum *
         }
 }
 
-struct PkColConst { PCol pc; int32_t r0pkey, cr1key; };
+struct PkColConst { PCol pc; int32_t r0pkey, cr1key; uint8_t yq[PKQ_L + 2]; };   // yq[k] = y_{j-k} (bulk pass), 0 = none
 __device__ __forceinline__ PkColConst pk_col_const(const PK &pk, const Scoring &sc, int32_t B, int32_t Bprev, uint32_t j, uint32_t n, uint8_t q) {
     PkColConst c;
     c.pc = pk_col(pk, sc, B, Bprev, j, n, q);
@@ -583,7 +718,7 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
 // before using them).  s_cc[(j-1)&1].pc.B holds the base of column j-1.
 template <int W>
 __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, ColRec *colrec, int32_t *gcol, const uint8_t *read,
-                                                 uint32_t j, PkColConst *s_cc, bool writer) {
+                                                 uint32_t j, PkColConst *s_cc, bool writer, uint32_t K) {
     const uint32_t tid = threadIdx.x, par = j & 1u, C = X.C;
     constexpr uint32_t T = W * 32;
     const int32_t Bprev = s_cc[par ^ 1u].pc.B;
@@ -598,11 +733,19 @@ __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, 
                 cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
                 colrec[(uint64_t)j * C + a] = cr;
             }
-            S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
+            const int32_t Jc = pk_jc(X.pk, pcl, J.score, J.len);
+            S.Jc[a] = Jc;
+            if (X.quiet) {   // closed form of a quiet tile of this contig in column j, and whether quiet tiles stay quiet
+                const uint8_t q = read[j - 1];
+                const bool allow = !((j % K == 0) && j < X.n) && pk_base_bit(q) != 16u;
+                S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, pk_col(X.pk, X.sc, g, Bprev, j, X.n, q), Jc, S.Q[(par ^ 1u) * S.cmax + a], allow);
+            }
         }
         if (tid == 0) {
             if (writer) gcol[j - 1] = g;
             s_cc[par] = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, read[j - 1]);
+            STITCH_UNROLL
+            for (int k = 0; k < PKQ_L + 2; ++k) s_cc[par].yq[k] = j >= 1u + (uint32_t)k ? read[j - 1 - (uint32_t)k] : (uint8_t)0;
         }
     }
 }
@@ -661,6 +804,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
     __shared__ int32_t s_gmax;
     __shared__ uint32_t s_first;
     __shared__ uint32_t s_cta_lo[17];
+    __shared__ PkColStat s_cs;
     const uint32_t tid = threadIdx.x;
     const Scoring sc = P.sc;
 
@@ -709,16 +853,44 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         pk_state_init0<W>(X, S);
         pk_init_halos<W>(X, S, 0);
         if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
+        X.quiet = P.quiet != 0 && team.size == 1 && !X.cluster_smem;
+        if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = 0; }
+        if (X.quiet) {   // quiet tiles: no tile is quiet yet; base classes of every tile
+            for (uint32_t a = tid; a < C; a += W * 32) S.Q[a] = pk_quiet_init(X.pk);
+            const uint32_t lane = tid & 31u;
+            for (uint32_t t = tid >> 5; t < X.NT; t += W) {
+                const ContigEntry e = X.ent[X.owner[t]];
+                const uint32_t r0 = (t - e.tile_start) * TILE + lane * STRIP;
+                uint8_t xq[STRIP];
+                unpack8(*reinterpret_cast<const uint2 *>(X.bases + e.seq_off + r0), xq);
+                uint32_t bits = 0;
+                STITCH_UNROLL
+                for (int k = 0; k < STRIP; ++k) if (r0 + (uint32_t)k < e.m) bits |= pk_base_bit(xq[k]);
+                bits = __reduce_or_sync(FULL, bits);
+                if (lane == 0) { S.tmask[t] = (uint8_t)bits; S.tq[t] = 0; }
+            }
+        }
         __syncthreads();
 
         for (uint32_t j = 1; j <= n; ++j) {
             const uint32_t par = j & 1u;
-            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0);
+            const long long cs0 = clock64();
+            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0, K);
             __syncthreads();
+            if (tid == 0) s_cs.t_select += (unsigned long long)(clock64() - cs0);
             const PkColConst cc = s_cc[par];
-            pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+            if (X.quiet) pk_column<W, false, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O, cc.yq, &s_cs);
+            else pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
             if ((j % K == 0) && j < n)
                 pk_write_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j / K - 1) * 2 * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
+        }
+        if (tid == 0 && team.rank == 0 && P.qstats) {
+            atomicAdd(P.qstats + 0, (unsigned long long)X.NT * n);
+            if (s_cs.skipped) atomicAdd(P.qstats + 1, (unsigned long long)s_cs.skipped);
+            if (P.dbg) {
+                atomicAdd(P.dbg + 7, s_cs.t_select); atomicAdd(P.dbg + 8, s_cs.t_tiles); atomicAdd(P.dbg + 9, s_cs.t_finish);
+                atomicAdd(P.dbg + 10, s_cs.t_busy / W);
+            }
         }
         int32_t track_thr = MIN_SCORE;
         if (team.size > 1) {   // gcol / colrec of the whole read (written by rank 0) must be visible to the team
@@ -795,7 +967,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
-    pk_set_ownership(X, W); X.cluster_smem = false; X.cstate = nullptr; X.cta_lo = nullptr;
+    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P)
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + TILE;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
-        pk_set_ownership(X, W); X.cluster_smem = false; X.cstate = nullptr; X.cta_lo = nullptr;
+        pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.cstate = nullptr; X.cta_lo = nullptr;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P)
         __syncthreads();
         for (uint32_t j = 1; j <= n; ++j) {
             const uint32_t par = j & 1u;
-            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, true);
+            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, true, P.K);
             __syncthreads();
             const PkColConst cc = s_cc[par];
             pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);

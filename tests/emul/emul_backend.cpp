@@ -8,8 +8,13 @@
 #include "../../stitch_b200/csrc/capi_impl.hpp"
 #include "../../stitch_b200/csrc/dp_packed.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
+
+// process-wide counters of the quiet-tile path (tests assert that tiles were actually skipped)
+static unsigned long long g_quiet_tiles = 0, g_quiet_skipped = 0, g_quiet_mat = 0;
+extern "C" void emul_quiet_counters(unsigned long long *out) { out[0] = g_quiet_tiles; out[1] = g_quiet_skipped; out[2] = g_quiet_mat; }
 
 namespace stitch {
 namespace host {
@@ -133,11 +138,29 @@ static void emul_column(const ColumnArgs &A) {
 struct EmulBackend : Backend {
     Aligner &al;
     uint32_t dump_seq = 0;
-    uint32_t K, WINDOW, PACKED;
+    uint32_t K, WINDOW, PACKED, QUIET;
     explicit EmulBackend(Aligner &a) : al(a) {
         K = std::max<uint32_t>(1, env_u32("EMUL_K", 7));          // checkpoint spacing (columns)
         WINDOW = std::max<uint32_t>(1, env_u32("EMUL_WINDOW", 6));  // columns at the end of the read filled by the wide path
         PACKED = env_u32("EMUL_PACKED", 1);                         // 0: wide path only
+        QUIET = env_u32("EMUL_QUIET", 1);                           // 0: the bulk pass never skips quiet tiles
+    }
+    ~EmulBackend() {
+        g_quiet_tiles += q_tiles; g_quiet_skipped += q_skipped; g_quiet_mat += q_mat;
+        if (std::getenv("EMUL_QUIET_STATS") && q_tiles) {
+            std::fprintf(stderr, "   why:");
+            for (int k = 0; k < 64; ++k) if (q_why[k]) std::fprintf(stderr, " %d:%llu", k, (unsigned long long)q_why[k]);
+            std::fprintf(stderr, "\n   first failing cell of a tile: S %llu D-only %llu; failing cells S %llu D-only %llu", (unsigned long long)q_failS, (unsigned long long)q_failD, (unsigned long long)q_failcells[0], (unsigned long long)q_failcells[1]);
+            std::fprintf(stderr, "\n   dense interior tiles by #non-boring S cells: 0:%llu 1-2:%llu 3-8:%llu 9-32:%llu 33-100:%llu >100:%llu", (unsigned long long)q_hist[0], (unsigned long long)q_hist[1], (unsigned long long)q_hist[2], (unsigned long long)q_hist[3], (unsigned long long)q_hist[4], (unsigned long long)q_hist[5]);
+            std::fprintf(stderr, "\n   delta:");
+            for (int k = 0; k < 64; ++k) if (q_delta[k]) std::fprintf(stderr, " %d:%llu", k - 32, (unsigned long long)q_delta[k]);
+            std::fprintf(stderr, "\n");
+        }
+        if (std::getenv("EMUL_QUIET_STATS") && q_tiles)
+            std::fprintf(stderr, "[emul quiet] tile-columns %llu skipped %llu (%.1f%%) materialised %llu\n", (unsigned long long)q_tiles,
+                         (unsigned long long)q_skipped, 100.0 * (double)q_skipped / (double)q_tiles, (unsigned long long)q_mat),
+            std::fprintf(stderr, "   dense because: special %.1f%% boundary %.1f%% !stay %.1f%% !self %.1f%% !left %.1f%%\n", 100.0 * q_special / q_tiles,
+                         100.0 * q_boundary / q_tiles, 100.0 * q_nostay / q_tiles, 100.0 * q_noself / q_tiles, 100.0 * q_noleft / q_tiles);
     }
 
     struct Fill {
@@ -226,8 +249,23 @@ struct EmulBackend : Backend {
     struct PkState {           // rolling packed state of a set of contigs (tile_start relative to these arrays)
         std::vector<int32_t> S[2], D[2];
         std::vector<int32_t> cm, Sm, SmKey; std::vector<uint32_t> cml, cmk, slm, tbm;
+        // quiet tiles (bulk pass only): flag per tile (state of the latest column is in the closed form), base
+        // classes present in the tile (bit 0..3 = A C G T, bit 4 = anything else), closed form of the latest column
+        bool quiet_on = false;
+        std::vector<uint8_t> quiet, tmask; std::vector<PkQuiet> Q;
     };
+    static uint32_t base_bit(uint8_t b) { return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 16u; }
+    static const int32_t POISON = 0x7f7f7f7f;   // what a skipped tile leaves in the state arrays (nobody may read it)
+    uint64_t q_hist[6] = {0}; uint64_t q_failS = 0, q_failD = 0, q_failcells[2] = {0, 0}; uint64_t q_why[64] = {0}, q_delta[64] = {0}; uint64_t q_tiles = 0, q_skipped = 0, q_mat = 0, q_special = 0, q_boundary = 0, q_nostay = 0, q_noself = 0, q_noleft = 0;
+    void pk_quiet_setup(const PK &pk, const ContigEntry *ent, uint32_t C, uint32_t NT, PkState &st) {
+        const uint8_t *bases = al.contigs.blob.data();
+        st.quiet_on = QUIET != 0;
+        st.quiet.assign(NT, 0); st.tmask.assign(NT, 0); st.Q.assign(C, pk_quiet_init(pk));
+        for (uint32_t a = 0; a < C; ++a)
+            for (uint32_t i = 1; i <= ent[a].m; ++i) st.tmask[ent[a].tile_start + (i - 1) / TILE] |= (uint8_t)base_bit(bases[ent[a].seq_off + i - 1]);
+    }
     struct PkCol {
+        bool allow_skip = false;                            // bulk: this column may skip quiet tiles (not a checkpoint column)
         const ContigEntry *ent; uint32_t C, NT; const uint32_t *owner;
         const uint8_t *read; uint32_t j, n; int32_t B, Bprev; const JumpInfo *J;
         bool tb; uint8_t *tb_col; ColRec *colrec_col;       // traceback variant: packed bytes, Lx[j] per contig
@@ -277,9 +315,25 @@ struct EmulBackend : Backend {
         std::vector<PkRowM> stash(C);
         const uint32_t Weff = std::min<uint32_t>((uint32_t)W, NT);
         const bool ycmode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
+        // quiet tiles: closed form of this column per contig; sub index of a contig base against y_j, y_{j-1}, y_{j-2}, y_{j-3}
+        const bool quiet_on = st.quiet_on && !A.tb;
+        const int32_t deadrel = pk_deadrel(sc);
+        // sv(xb, back, s): s[k] = sub index of contig base xb against y_{j-back-k}, k = 0 .. PKQ_L
+        auto sidx = [&](uint8_t xb, int back) -> int { return ((int)j - back >= 1 && xb == A.read[j - 1 - (uint32_t)back]) ? 0 : 1; };
+        auto sv = [&](uint8_t xb, int back, int *s) { for (int k = 0; k <= PKQ_L; ++k) s[k] = sidx(xb, back + k); };
+        std::vector<PkQuiet> Qn(C);
+        if (quiet_on) {
+            const bool allow = A.allow_skip && base_bit(pc.q) != 16u;
+            for (uint32_t a = 0; a < C; ++a) {
+                Qn[a] = pk_quiet_next(pk, sc, pc, pk_jc(pk, pc, A.J[a].score, A.J[a].len), st.Q[a], allow);
+                ++q_why[Qn[a].why & 63]; ++q_delta[(uint32_t)(pc.delta + 32) & 63];
+            }
+        }
+        std::vector<int32_t> Smat(TILE), Dmat(TILE);
         for (uint32_t w = 0; w < Weff; ++w) {
             const uint32_t t_lo = (uint32_t)((uint64_t)NT * w / Weff), t_hi = (uint32_t)((uint64_t)NT * (w + 1) / Weff);
             int32_t prev_exit = 0; uint32_t prev_exit_open = 0;
+            bool prev_skipped = false; uint8_t qold_left = 0;
             for (uint32_t tile = t_lo; tile < t_hi; ++tile) {
                 const uint32_t a = A.owner[tile];
                 const ContigEntry &en = A.ent[a];
@@ -287,6 +341,35 @@ struct EmulBackend : Backend {
                 const bool first = tic == 0, lastt = tic + 1 == en.ntiles;
                 const bool special = first || lastt;
                 const int32_t Jc = pk_jc(pk, pc, A.J[a].score, A.J[a].len);
+                // ---- quiet tiles: skip / materialise decisions from the flags of column j-1 ----
+                const uint8_t qold = quiet_on ? st.quiet[tile] : 0;
+                const uint8_t qleft = (tile > t_lo && !first) ? qold_left : 0;   // tile-1 of the same contig and chunk was quiet at j-1
+                qold_left = qold;
+                if (quiet_on) {
+                    ++q_tiles;
+                    if (special) ++q_special; else if (tile == t_lo || tile + 1 == t_hi) ++q_boundary; else if (!Qn[a].stay) ++q_nostay;
+                    else if (!qold) ++q_noself; else if (!qleft) ++q_noleft;
+                }
+                if (quiet_on && !special && tile != t_lo && tile + 1 != t_hi && qold && qleft && Qn[a].stay) {
+                    const uint32_t mb = base_bit(pc.q);
+                    const bool hm = (st.tmask[tile] & mb) != 0, hx = (st.tmask[tile] & ~mb) != 0;
+                    tilemax[tile] = hm ? (hx ? pk_max(Qn[a].bk[0], Qn[a].bk[1]) : Qn[a].bk[0]) : Qn[a].bk[1];
+                    for (uint32_t r = 0; r < (uint32_t)TILE; ++r) { Sc[tile * TILE + r] = POISON; Dc[tile * TILE + r] = POISON; }
+                    prev_skipped = true; ++q_skipped;
+                    continue;   // stays quiet
+                }
+                const int32_t *SpT = Sp, *DpT = Dp;   // state of column j-1 as this tile reads it (own rows: base .. base+TILE)
+                if (qold) {   // the tile's own state of column j-1 is the closed form (memory may be stale): materialise
+                    ++q_mat;
+                    const PkQuiet &Qp = st.Q[a];
+                    for (uint32_t r = 0; r < (uint32_t)TILE; ++r) {
+                        const uint8_t xb = bases[en.seq_off + tic * TILE + r];
+                        int sx[PKQ_L + 1]; sv(xb, 1, sx);
+                        Smat[r] = pk_quiet_S(Qp, sx[0]);
+                        Dmat[r] = pk_quiet_D(pk, Qp, sx);
+                    }
+                    SpT = Smat.data() - (size_t)tile * TILE; DpT = Dmat.data() - (size_t)tile * TILE;
+                }
                 const bool wrap0 = first && en.circular && st.tbm[a] != TB_XCLIP_SUFFIX;
                 const int32_t wbase = pk_wbase(pk, st.SmKey[a]);
                 PStrip strips[32];
@@ -303,7 +386,11 @@ struct EmulBackend : Backend {
                 for (uint32_t lane = 0; lane < 32; ++lane) {
                     const uint32_t row0 = tic * TILE + lane * STRIP + 1;
                     const uint32_t base = tile * TILE + lane * STRIP;
-                    const int32_t Sdg0 = row0 == 1 ? pk_from_wide(pk, A.Bprev, r0p.S, r0p.sl, 0) : Sp[base - 1];
+                    int32_t Sdg0;
+                    if (row0 == 1) Sdg0 = pk_from_wide(pk, A.Bprev, r0p.S, r0p.sl, 0);
+                    else if (lane > 0) Sdg0 = SpT[base - 1];
+                    else if (qleft) Sdg0 = pk_quiet_S(st.Q[a], sidx(bases[en.seq_off + row0 - 2], 1));   // last row of a quiet tile
+                    else Sdg0 = Sp[base - 1];
                     for (int k = 0; k < STRIP; ++k) xs[lane][k] = row0 + k <= en.m ? bases[en.seq_off + row0 + k - 1] : 0;
                     int nv = STRIP; bool hm = false;
                     if (special) {
@@ -314,14 +401,15 @@ struct EmulBackend : Backend {
                     }
                     nvs[lane] = nv; hasm[lane] = hm;
                     if (A.tb) {
-                        if (special) pk_pass1<true, true>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
-                        else pk_pass1<false, true>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, false, wbase, STRIP, false, strips[lane]);
+                        if (special) pk_pass1<true, true>(pk, pc, SpT + base, DpT + base, Sdg0, xs[lane], Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
+                        else pk_pass1<false, true>(pk, pc, SpT + base, DpT + base, Sdg0, xs[lane], Jc, false, wbase, STRIP, false, strips[lane]);
                     } else {
-                        if (special) pk_pass1<true, false>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
-                        else pk_pass1<false, false>(pk, pc, Sp + base, Dp + base, Sdg0, xs[lane], Jc, false, wbase, STRIP, false, strips[lane]);
+                        if (special) pk_pass1<true, false>(pk, pc, SpT + base, DpT + base, Sdg0, xs[lane], Jc, wrap0 && lane == 0, wbase, nv, hm, strips[lane]);
+                        else pk_pass1<false, false>(pk, pc, SpT + base, DpT + base, Sdg0, xs[lane], Jc, false, wbase, STRIP, false, strips[lane]);
                     }
                 }
                 int32_t tmax = pk.NEGKEY;
+                bool tile_quiet = quiet_on && !lastt; uint32_t nfailS = 0;
                 for (uint32_t lane = 0; lane < 32; ++lane) {
                     const uint32_t row0 = tic * TILE + lane * STRIP + 1;
                     const uint32_t base = tile * TILE + lane * STRIP;
@@ -337,7 +425,8 @@ struct EmulBackend : Backend {
                         fill_yc(h, hrow0, tic == 1);
                         pk_pass1<true, true>(pk, pc, Sp + hb, Dp + hb, Sp[hb - 1], x, Jc, false, wbase, STRIP, false, h);
                         cin = pk_carry_from_exit(pk, h.exit); cin_open = h.exit_open;
-                    } else { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }
+                    } else if (prev_skipped) { cin = pk.NEGKEY + pk.PI5; cin_open = 0; }   // chain out of a quiet tile: dead (C4)
+                    else { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }
                     int32_t S[STRIP], Iarr[STRIP]; uint8_t tbb[STRIP];
                     int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
                     if (A.tb) {
@@ -349,6 +438,12 @@ struct EmulBackend : Backend {
                     }
                     for (int k = 0; k < nvs[lane]; ++k) {
                         Sc[base + k] = S[k]; Dc[base + k] = strips[lane].D6[k];
+                        if (quiet_on && !lastt) {
+                            int sx[PKQ_L + 1]; sv(xs[lane][k], 0, sx);
+                            const bool okc = pk_quiet_cell(pk, Qn[a], deadrel, S[k], strips[lane].D6[k], sx);
+                            if (!okc) { const bool sOK = S[k] == Qn[a].bk[sx[0]]; ++q_failcells[sOK ? 1 : 0]; if (!sOK) ++nfailS; if (tile_quiet) { if (sOK) ++q_failD; else ++q_failS; } }
+                            tile_quiet = tile_quiet && okc;
+                        }
                         if (A.tb) {
                             const uint32_t i = row0 + (uint32_t)k;
                             if (A.tb_col) A.tb_col[base + k] = tbb[k];
@@ -367,8 +462,12 @@ struct EmulBackend : Backend {
                 }
                 tilemax[tile] = tmax;
                 prev_exit = strips[31].exit; prev_exit_open = strips[31].exit_open;
+                prev_skipped = false;
+                if (quiet_on) st.quiet[tile] = tile_quiet ? 1 : 0;
+                if (quiet_on && !special) ++q_hist[nfailS == 0 ? 0 : nfailS <= 2 ? 1 : nfailS <= 8 ? 2 : nfailS <= 32 ? 3 : nfailS <= 100 ? 4 : 5];
             }
         }
+        if (quiet_on) st.Q = Qn;
         // per contig: tracker / column best over rows < m, finish row m, column best
         for (uint32_t a = 0; a < C; ++a) {
             const ContigEntry &en = A.ent[a];
@@ -376,6 +475,12 @@ struct EmulBackend : Backend {
             for (uint32_t t = 0; t < en.ntiles; ++t) kmax = pk_max(kmax, tilemax[en.tile_start + t]);
             CmPart rows; cm_init(rows);
             XsPart tr; xs_init(tr);
+            // S key of an ordinary row of column j: the closed form in a quiet tile (its memory may be stale)
+            auto cell_key = [&](uint32_t a_, const ContigEntry &en_, uint32_t i) -> int32_t {
+                const uint32_t tile = en_.tile_start + (i - 1) / TILE;
+                if (quiet_on && st.quiet[tile]) return pk_quiet_S(Qn[a_], sidx(bases[en_.seq_off + i - 1], 0));
+                return Sc[row_linear(en_, i)];
+            };
             if (en.m >= 2) {
                 const int32_t smax = pk_rel(pk, kmax);
                 auto first_row = [&](bool full_key) -> uint32_t {
@@ -385,14 +490,14 @@ struct EmulBackend : Backend {
                         for (uint32_t r = 0; r < (uint32_t)TILE; ++r) {
                             const uint32_t i = t * TILE + r + 1;
                             if (i >= en.m) break;
-                            const int32_t key = Sc[(en.tile_start + t) * TILE + r];
+                            const int32_t key = cell_key(a, en, i);
                             if (full_key ? key == kmax : pk_rel(pk, key) == smax) return i;
                         }
                     }
                     throw Error(STITCH_ERR_INTERNAL, "emul packed: column best not found");
                 };
                 const uint32_t frow = first_row(false);
-                const int32_t fkey = Sc[row_linear(en, frow)];
+                const int32_t fkey = cell_key(a, en, frow);
                 rows.S = B + smax; rows.row = frow; rows.sl = pk_len(pk, fkey); rows.valid = 1;
                 if (sc.xs != MIN_SCORE) { tr.t = B + smax + sc.xs; tr.len = pk_len(pk, kmax); tr.row = A.tb ? first_row(true) : 1; }
             }
@@ -441,6 +546,7 @@ struct EmulBackend : Backend {
         stats.fills += 1;
         PkState st;
         pk_state_init0(pk, L.ent.data(), C, PM, st);
+        pk_quiet_setup(pk, L.ent.data(), C, NT, st);
         const std::vector<uint32_t> owner = owners_of(L.ent.data(), C, NT);
         F.gcol[0] = 0;
         std::vector<JumpInfo> J(C);
@@ -456,6 +562,7 @@ struct EmulBackend : Backend {
             PkCol A{};
             A.ent = L.ent.data(); A.C = C; A.NT = NT; A.owner = owner.data(); A.read = job.read; A.j = j; A.n = n;
             A.B = B; A.Bprev = Bprev; A.J = J.data();
+            A.allow_skip = !((j % K == 0) && j < n);   // a checkpoint column is computed (and stored) by every tile
             packed_column(pk, A, st);
             F.gcol[j] = max_of(st.cm);
             if ((j % K == 0) && j < n) {

@@ -18,7 +18,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # blocks, re-filled units and window re-runs (the library reads these when a context is created).
 TUNING = {"STITCH_CK_EVERY": "7", "STITCH_TRACK_WINDOW": "6"}
 ALL_TUNING_KEYS = ("STITCH_CK_EVERY", "STITCH_TRACK_WINDOW", "STITCH_CLUSTER", "STITCH_CLUSTER_MIN_TILES", "STITCH_PACKED",
-                   "STITCH_FUSED", "STITCH_CLUSTER_SMEM")
+                   "STITCH_FUSED", "STITCH_CLUSTER_SMEM", "STITCH_QUIET")
 
 
 def cluster_tuning(seed, base=None):
@@ -300,3 +300,31 @@ def test_sam_records_on_gpu(oracle):
             exp = sam_oracle.format_sam(headers[r], reads[r].upper(), quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
                                         (o.match_score, o.mismatch_score, o.gap_open, o.gap_extend), **so)
             assert sam[r] == exp, f"read {r} {kw} {so}"
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_quiet_tiles_on_gpu(oracle, case):
+    """Quiet tiles (dp_packed.h): with the default checkpoint spacing the bulk pass skips the warp tiles that are
+    provably in the closed form "jump + substitution score" and re-materialises them when needed.  Same chains
+    as the oracle, a good share of the tile-columns skipped, and the same chains again with STITCH_QUIET=0."""
+    rng = random.Random(4400 + case)
+    kw = [dict(double_strand=True, circular=True), dict(mode=1, double_strand=True), dict(mode=3, circular=True),
+          dict(mode=2, double_strand=True, match_score=2, mismatch_score=-3, gap_open=-4, gap_extend=-2,
+               jump_score_same_contig_and_strand=-8, jump_score_same_contig_opposite_strand=-9, jump_score_inter_contig=-11)][case]
+    contigs = [gen.rand_seq(rng, rng.randint(2300, 3500)) for _ in range(4)] + [gen.rand_seq(rng, 700)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(700, 1100), rng.randint(2, 4), strands=bool(kw.get("double_strand")),
+                               wrap=bool(kw.get("circular"))) for _ in range(5)]
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    exp, _ = oracle.OracleAligners(make_opts(**kw), named).batch(reads, raw=False)
+    al = gpu_aligners(kw, named, tuning={"STITCH_CLUSTER": "1"})   # (few reads would otherwise get a cluster per read: no quiet tiles there)
+    got = al.align_batch(reads)
+    st = al.stats()
+    al.close()
+    compare(got, exp, f"quiet case {case}")
+    assert st.tile_columns > 0 and st.quiet_tile_columns > 0.1 * st.tile_columns, (st.tile_columns, st.quiet_tile_columns)
+    al = gpu_aligners(kw, named, tuning={"STITCH_QUIET": "0", "STITCH_CLUSTER": "1"})
+    got0 = al.align_batch(reads)
+    st0 = al.stats()
+    al.close()
+    compare(got0, exp, f"quiet off case {case}")
+    assert st0.quiet_tile_columns == 0
