@@ -120,6 +120,7 @@ struct CudaBackend : host::Backend {
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
     uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
+    uint32_t pack_warps = 16;    // STITCH_PACK_WARPS=8: 8-warp CTAs, two per SM (one read each), when no cluster is used
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
     DevBuf<ColRec> d_colrec;
@@ -168,6 +169,7 @@ struct CudaBackend : host::Backend {
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
         quiet_tiles = env_u32("STITCH_QUIET", 1);
+        pack_warps = env_u32("STITCH_PACK_WARPS", pack_warps) == 8 ? 8 : 16;
     }
     ~CudaBackend() override {
         cudaSetDevice(device);
@@ -211,7 +213,7 @@ struct CudaBackend : host::Backend {
         const uint32_t LB = pk_plan(al.opts.sc, j.n, m_max);
         // shared memory of the packed kernels: tile table + cp.async stage buffers + the walk phase's staging of one
         // contig's bases; otherwise the read takes the (slow, exact) wide path
-        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 200 * 1024) return 0;
+        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 216 * 1024) return 0;
         return LB;
     }
     bool fused_path() const { return use_fused && cluster_pref <= 1; }
@@ -385,6 +387,14 @@ struct CudaBackend : host::Backend {
             }
         }
         const bool packed_walks_in_kernel = !fused && walk_in_kernel && cluster == 1 && n_packed > 0;
+        // 8-warp CTAs, two per SM: while one read is in the serial phases of a column (jump selection, per-contig finish,
+        // barriers) the other one's tiles keep the SM busy
+        bool half_ctas = false;
+        if (!fused && n_packed && cluster == 1 && pack_warps == 8) {
+            const size_t st8 = PackSmem::default_stage(8);
+            const size_t sm8 = (PackSmem::bytes(cmax, ntmax, 8, st8) + 15) / 16 * 16 + (packed_walks_in_kernel ? UnitStage::bytes(K, max_ctiles) : 0);
+            if (2 * (sm8 + 1024) <= 227 * 1024) { half_ctas = true; pstage = st8; pteams = std::min<uint32_t>(n_packed, 2u * (uint32_t)num_sms); }
+        }
         const uint32_t bufgrid = std::max(std::max(wgrid, fgrid), packed_walks_in_kernel ? pteams : 0u);   // CTAs that own walk buffers
         d_jobs.reserve(nj); d_order.reserve(4 * (size_t)nj + 16);
         d_colrec.reserve(tot.colrec + (uint64_t)fgrid * arena.colrec); d_last.reserve(tot.cell + (uint64_t)fgrid * arena.cell);
@@ -448,7 +458,8 @@ struct CudaBackend : host::Backend {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes;
             Q.quiet = quiet_tiles;
-            size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS, pstage) + 15) / 16 * 16;
+            const int pw = half_ctas ? 8 : PACK_WARPS;
+            size_t psmem = (PackSmem::bytes(cmax, ntmax, pw, pstage) + 15) / 16 * 16;
             if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads
                 d_done.reserve(nj);
                 CUDA_CHECK(cudaMemsetAsync(d_done.p, 0, nj * sizeof(uint32_t), stream));
@@ -456,9 +467,9 @@ struct CudaBackend : host::Backend {
                 Q.walk_stage_smem_off = (uint32_t)psmem;
                 psmem += UnitStage::bytes(K, max_ctiles);
             }
-            set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
+            if (half_ctas) set_smem(fill_packed_kernel<8>, psmem); else set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(PACK_WARPS * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
+            cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(pw * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
             cudaLaunchAttribute at[2];
             unsigned na = 0;
             if (cluster > 1) {
@@ -479,7 +490,8 @@ struct CudaBackend : host::Backend {
                 ++na;
             }
             cfg.attrs = at; cfg.numAttrs = na;
-            CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
+            if (half_ctas) CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<8>, Q));
+            else CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
             stats.launches += 1; stats.packed_launches += 1;
         }
         mark(T_WIDE);
@@ -563,8 +575,8 @@ struct CudaBackend : host::Backend {
             std::fprintf(stderr, "[stitch dbg] jobs %u (fused grid %u): tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, "
                          "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, fgrid, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
                          h[4] * 1e-6, h[5] * 1e-6);
-            std::fprintf(stderr, "[stitch dbg] bulk columns, Mcycles summed over reads: select %.1f, tile phase %.1f (mean warp busy %.1f), per-contig finish %.1f\n",
-                         h[7] * 1e-6, h[8] * 1e-6, h[10] * 1e-6, h[9] * 1e-6);
+            std::fprintf(stderr, "[stitch dbg] bulk columns, Mcycles summed over reads: select %.1f, tile phase %.1f (mean warp busy %.1f), per-contig finish %.1f (warp 0: tile maxima reduced at %.1f, look-ups done at %.1f, row m done at %.1f)\n",
+                         h[7] * 1e-6, h[8] * 1e-6, h[10] * 1e-6, h[9] * 1e-6, h[13] * 1e-6, h[11] * 1e-6, h[12] * 1e-6);
         }
         stats.tb_bytes += tot.ck * sizeof(CellState) + (tot.pck + (uint64_t)fgrid * arena.pck) * 4 + (tot.colrec + (uint64_t)fgrid * arena.colrec) * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);

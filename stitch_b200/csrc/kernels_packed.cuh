@@ -52,8 +52,12 @@ struct PackSmem {
     PkRowM *stash;
     JumpInfo *Jw;
     PkQuiet *Q;             // [2][cmax]: closed form of a quiet tile per contig, by column parity (dp_packed.h)
-    uint8_t *tq, *tmask;    // per tile: quiet flag of the latest column / base classes present (bit 0..3 = A C G T, 4 = other)
-    uint8_t *tmode;         // per tile: what the tile does in the current column (0 skip, 1 materialise, 2 load)
+    // per tile, one byte: bits 0..4 base classes present (A C G T other), bit 5 quiet flag of the latest column,
+    // bits 6..7 what the tile does in the current column (0 skip, 1 materialise, 2 load); owned by the tile's warp
+    uint8_t *tb;
+    static constexpr uint32_t TB_MASK = 31u, TB_Q = 32u;
+    ContigEntry *ent_s;     // [cmax]: the layout's contig table (bulk pass: no global loads in the per-column serial phases)
+    uint16_t *owner_s;      // [ntmax]: contig position of every tile
     uint32_t cmax;
     unsigned char *stage;   // [W][2][STAGE_BYTES]: cp.async double buffer of the next tile (state in global memory only)
     static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + TILE;   // S keys, D keys, bases of one tile
@@ -61,8 +65,8 @@ struct PackSmem {
     // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
     static size_t default_stage(int W) { return (size_t)W * 2 * STAGE_BYTES; }
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
-        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) + (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet)) * cmax +
-               3 * (size_t)ntmax + 64;
+        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) +
+               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 3 * (size_t)ntmax + 64;
     }
     __device__ void carve(unsigned char *raw, uint32_t cmax_, uint32_t ntmax, int W, size_t stage_bytes) {
         const uint32_t cmax = cmax_;
@@ -79,9 +83,9 @@ struct PackSmem {
         haloD = haloS + 2 * W * 9;                           // [2][W][8]
         haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W] (unused)
         Q = reinterpret_cast<PkQuiet *>(haloF + 2 * W);
-        tq = reinterpret_cast<uint8_t *>(Q + 2 * cmax);
-        tmask = tq + ntmax;
-        tmode = tmask + ntmax;
+        ent_s = reinterpret_cast<ContigEntry *>(Q + 2 * cmax);
+        owner_s = reinterpret_cast<uint16_t *>(ent_s + cmax);
+        tb = reinterpret_cast<uint8_t *>(owner_s + ntmax);
     }
 };
 
@@ -155,7 +159,7 @@ __device__ __forceinline__ void unpack8(const uint2 xb, uint8_t *x) {
 // (its memory may be stale): materialise it instead of loading; `qz.prev_skipped` = the previous tile of this chunk
 // was skipped in this column (its last row and its chain exit come from the closed form).  Returns whether every
 // ordinary cell of the tile is in the closed form of column j.
-struct PkColStat { uint32_t skipped; unsigned long long t_tiles, t_finish, t_busy, t_select; };   // per job, shared memory
+struct PkColStat { uint32_t skipped; unsigned long long t_tiles, t_finish, t_busy, t_select, t_f1, t_f2, t_fa; };   // per job, shared memory
 struct PkQuietArgs {
     bool mat, prev_skipped;
     const PkQuiet *Qp, *Qn;     // closed forms of column j-1 / j of this tile's contig (shared memory)
@@ -385,17 +389,18 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             const uint32_t mb = pk_base_bit(pc.q);
             for (uint32_t t = t_lo + lane; t < t_hi; t += 32) {
                 uint32_t mode = 2;
-                if (S.tq[t]) {
+                const uint32_t tbv = S.tb[t];
+                if (tbv & PackSmem::TB_Q) {
                     const uint32_t a_t = X.owner[t];
                     const uint32_t tic = t - X.ent[a_t].tile_start;
                     const PkQuiet &qn = Qn[a_t];
-                    mode = (tic != 0 && tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi && S.tq[t - 1] && qn.stay) ? 0u : 1u;
+                    mode = (tic != 0 && tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi && (S.tb[t - 1] & PackSmem::TB_Q) && qn.stay) ? 0u : 1u;
                     if (mode == 0) {
-                        const uint32_t tm = S.tmask[t];
+                        const uint32_t tm = tbv & PackSmem::TB_MASK;
                         S.tilemax[t] = (tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1];
                     }
                 }
-                S.tmode[t] = (uint8_t)mode;
+                S.tb[t] = (uint8_t)((tbv & 63u) | (mode << 6));
             }
             __syncwarp();
         }
@@ -410,8 +415,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             const uint32_t nb = t_hi - base, validm = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
             uint32_t skipm = 0, loadm = validm, loadm_next = base + 32 < t_hi ? 1u : 0u;
             if (QUIET) {
-                const uint32_t m0 = base + lane < t_hi ? S.tmode[base + lane] : 3u;
-                const uint32_t m1 = base + 32 + lane < t_hi ? S.tmode[base + 32 + lane] : 3u;
+                const uint32_t m0 = base + lane < t_hi ? (uint32_t)S.tb[base + lane] >> 6 : 3u;
+                const uint32_t m1 = base + 32 + lane < t_hi ? (uint32_t)S.tb[base + 32 + lane] >> 6 : 3u;
                 skipm = __ballot_sync(FULL, m0 == 0u); loadm = __ballot_sync(FULL, m0 == 2u); loadm_next = __ballot_sync(FULL, m1 == 2u);
                 nskipped += __popc(skipm);
             }
@@ -456,7 +461,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                     qnow = pk_tile<true, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
                 else
                     qnow = pk_tile<false, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-                if (QUIET && lane == 0) S.tq[tile] = (qnow && tic + 1 != en.ntiles) ? 1 : 0;
+                if (QUIET && lane == 0) S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && tic + 1 != en.ntiles) ? PackSmem::TB_Q : 0u));
             }
             last_skipped = (skipm >> 31) != 0;
         }
@@ -482,55 +487,69 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const long long c1 = cs ? clock64() : 0;
     // ---- per contig: tracker + row m + column best (contig a on CTA a % size) ----
     const Row0 r0 = row0_at(sc, j, X.n);
-    for (uint32_t a = team.rank + team.size * warp; a < C; a += team.size * W) {
+    // Four contigs per warp at a time, one per group of 8 lanes (the groups' memory latencies overlap and the four
+    // serial row-m finishes run side by side on the groups' first lanes).
+    const uint32_t grp = lane >> 3, gl = lane & 7u;
+    for (uint32_t slot = warp * 4u + grp; __any_sync(FULL, team.rank + team.size * slot < C); slot += (uint32_t)W * 4u) {
+        const bool act = team.rank + team.size * slot < C;
+        const uint32_t a = act ? team.rank + team.size * slot : 0u;   // idle groups shadow contig 0 (no writes)
         const ContigEntry en = X.ent[a];
         int32_t kmax = pk.NEGKEY;
-        for (uint32_t t = lane; t < en.ntiles; t += 32) kmax = pk_max(kmax, S.tilemax[en.tile_start + t]);
+        for (uint32_t t = gl; t < en.ntiles; t += 8) kmax = pk_max(kmax, S.tilemax[en.tile_start + t]);
         STITCH_UNROLL
-        for (int d = 16; d >= 1; d >>= 1) kmax = pk_max(kmax, __shfl_xor_sync(FULL, kmax, d));
+        for (int d = 4; d >= 1; d >>= 1) kmax = pk_max(kmax, __shfl_xor_sync(FULL, kmax, d));
         const int32_t smax = pk_rel(pk, kmax);
+        if (cs && tid == 0) cs->t_fa += (unsigned long long)(clock64() - c1);
         // first row (< m) whose S has the best score (column best, SCA:680-687) / equals the best key (tracker, SCA:411-416)
         uint32_t frow = 0, trow = 0; int32_t fkey = 0;
-        if (en.m >= 2) {
-            STITCH_UNROLL
-            for (int pass = 0; pass < (TB ? 2 : 1); ++pass) {
-                const bool full = pass == 1;
-                uint32_t ft = 0xffffffffu;
-                for (uint32_t t = lane; t < en.ntiles; t += 32) {
-                    const int32_t tm = S.tilemax[en.tile_start + t];
-                    if (full ? tm == kmax : pk_rel(pk, tm) == smax) { ft = t; break; }
-                }
-                STITCH_UNROLL
-                for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
-                const uint32_t tile = en.tile_start + ft;
-                int32_t sk[STRIP];
-                if (QUIET && S.tq[tile]) {   // a quiet tile (its memory may be stale): the closed form of column j
-                    uint8_t xq[STRIP];
-                    unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + ft * TILE + lane * STRIP), xq);
-                    const PkQuiet &qn = Qn[a];
-                    STITCH_UNROLL
-                    for (int k = 0; k < STRIP; ++k) sk[k] = xq[k] == pc.q ? qn.bk[0] : qn.bk[1];
-                } else {
-                    const int32_t *tp = pk_tile_ptr(X, tile);
-                    const int4 s0 = pk_ld_state(X, tp + lane * 4);
-                    const int4 s1 = pk_ld_state(X, tp + 128 + lane * 4);
-                    sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
-                }
-                uint32_t row = 0xffffffffu; int32_t key = 0;
-                STITCH_UNROLL
-                for (int k = STRIP - 1; k >= 0; --k) {
-                    const uint32_t i = ft * TILE + lane * STRIP + (uint32_t)k + 1;
-                    if (i < en.m && (full ? sk[k] == kmax : pk_rel(pk, sk[k]) == smax)) { row = i; key = sk[k]; }
-                }
-                uint32_t best = row;
-                STITCH_UNROLL
-                for (int d = 16; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, best, d); best = o < best ? o : best; }
-                const uint32_t src = __ffs(__ballot_sync(FULL, row == best)) - 1;
-                key = __shfl_sync(FULL, key, src);
-                if (full) trow = best; else { frow = best; fkey = key; }
+        STITCH_UNROLL
+        for (int pass = 0; pass < (TB ? 2 : 1); ++pass) {
+            const bool full = pass == 1;
+            uint32_t ft = 0xffffffffu;
+            for (uint32_t t = gl; t < en.ntiles; t += 8) {
+                const int32_t tm = S.tilemax[en.tile_start + t];
+                if (full ? tm == kmax : pk_rel(pk, tm) == smax) { ft = t; break; }
             }
+            STITCH_UNROLL
+            for (int d = 4; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, ft, d); ft = o < ft ? o : ft; }
+            uint32_t row = 0xffffffffu; int32_t key = 0;
+            if (en.m >= 2 && ft != 0xffffffffu) {
+                const uint32_t tile = en.tile_start + ft;
+                const bool quiet_tile = QUIET && (S.tb[tile] & PackSmem::TB_Q);   // (its memory may be stale): the closed form of column j
+                const int32_t *tp = quiet_tile ? nullptr : pk_tile_ptr(X, tile);
+                // the group's lane g scans strips 4g .. 4g+3 of the tile (32 consecutive rows), last strip first so that the
+                // first matching row is what remains
+                STITCH_UNROLL
+                for (int u = 3; u >= 0; --u) {
+                    const uint32_t sl_ = gl * 4u + (uint32_t)u;
+                    int32_t sk[STRIP];
+                    if (quiet_tile) {
+                        uint8_t xq[STRIP];
+                        unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + ft * TILE + sl_ * STRIP), xq);
+                        const PkQuiet &qn = Qn[a];
+                        STITCH_UNROLL
+                        for (int k = 0; k < STRIP; ++k) sk[k] = xq[k] == pc.q ? qn.bk[0] : qn.bk[1];
+                    } else {
+                        const int4 s0 = pk_ld_state(X, tp + sl_ * 4);
+                        const int4 s1 = pk_ld_state(X, tp + 128 + sl_ * 4);
+                        sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
+                    }
+                    STITCH_UNROLL
+                    for (int k = STRIP - 1; k >= 0; --k) {
+                        const uint32_t i = ft * TILE + sl_ * STRIP + (uint32_t)k + 1;
+                        if (i < en.m && (full ? sk[k] == kmax : pk_rel(pk, sk[k]) == smax)) { row = i; key = sk[k]; }
+                    }
+                }
+            }
+            uint32_t best = row;
+            STITCH_UNROLL
+            for (int d = 4; d >= 1; d >>= 1) { const uint32_t o = __shfl_xor_sync(FULL, best, d); best = o < best ? o : best; }
+            const uint32_t hit = (__ballot_sync(FULL, row == best) >> (grp * 8u)) & 0xffu;   // never empty: the best lane itself
+            key = __shfl_sync(FULL, key, grp * 8u + (uint32_t)__ffs(hit) - 1u);
+            if (en.m >= 2) { if (full) trow = best; else { frow = best; fkey = key; } }
         }
-        if (lane == 0) {
+        if (cs && tid == 0) cs->t_f1 += (unsigned long long)(clock64() - c1);
+        if (gl == 0 && act) {
             CmPart rows; cm_init(rows);
             XsPart tr; xs_init(tr);
             if (en.m >= 2) {
@@ -573,6 +592,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             }
         }
     }
+    if (cs && tid == 0) cs->t_f2 += (unsigned long long)(clock64() - c1);
     team.sync();
     if (cs && tid == 0) { cs->t_tiles += (unsigned long long)(c1 - c0); cs->t_finish += (unsigned long long)(clock64() - c1); }
 }
@@ -796,7 +816,7 @@ template <int W> __device__ __noinline__ void pk_walk_phase(const Params P, unsi
 // bulk fill
 // ---------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
+__global__ void __launch_bounds__(W * 32, W <= 8 ? 2 : 1) fill_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
     __shared__ uint32_t sJob;
@@ -826,7 +846,11 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
         PackCtx X;
         X.team = team;
-        X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
+        X.pk = pk_make(sc, jd.LB); X.sc = sc;
+        // the layout's contig and tile-owner tables are staged in shared memory (every CTA of a team holds its own copy)
+        for (uint32_t a = tid; a < C; a += W * 32) S.ent_s[a] = P.ents[ld.ent_off + a];
+        for (uint32_t t = tid; t < ld.n_tiles; t += W * 32) S.owner_s[t] = P.owners[ld.owner_off + t];
+        X.ent = S.ent_s; X.owner = S.owner_s;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
         pk_set_ownership(X, W);
@@ -854,7 +878,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
         pk_init_halos<W>(X, S, 0);
         if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
         X.quiet = P.quiet != 0 && team.size == 1 && !X.cluster_smem;
-        if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = 0; }
+        if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
         if (X.quiet) {   // quiet tiles: no tile is quiet yet; base classes of every tile
             for (uint32_t a = tid; a < C; a += W * 32) S.Q[a] = pk_quiet_init(X.pk);
             const uint32_t lane = tid & 31u;
@@ -867,7 +891,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
                 STITCH_UNROLL
                 for (int k = 0; k < STRIP; ++k) if (r0 + (uint32_t)k < e.m) bits |= pk_base_bit(xq[k]);
                 bits = __reduce_or_sync(FULL, bits);
-                if (lane == 0) { S.tmask[t] = (uint8_t)bits; S.tq[t] = 0; }
+                if (lane == 0) S.tb[t] = (uint8_t)bits;
             }
         }
         __syncthreads();
@@ -877,8 +901,8 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
             const long long cs0 = clock64();
             pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0, K);
             __syncthreads();
-            if (tid == 0) s_cs.t_select += (unsigned long long)(clock64() - cs0);
             const PkColConst cc = s_cc[par];
+            if (tid == 0) s_cs.t_select += (unsigned long long)(clock64() - cs0);
             if (X.quiet) pk_column<W, false, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O, cc.yq, &s_cs);
             else pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
             if ((j % K == 0) && j < n)
@@ -889,7 +913,7 @@ __global__ void __launch_bounds__(W * 32) fill_packed_kernel(const Params P) {
             if (s_cs.skipped) atomicAdd(P.qstats + 1, (unsigned long long)s_cs.skipped);
             if (P.dbg) {
                 atomicAdd(P.dbg + 7, s_cs.t_select); atomicAdd(P.dbg + 8, s_cs.t_tiles); atomicAdd(P.dbg + 9, s_cs.t_finish);
-                atomicAdd(P.dbg + 10, s_cs.t_busy / W);
+                atomicAdd(P.dbg + 10, s_cs.t_busy / W); atomicAdd(P.dbg + 11, s_cs.t_f1); atomicAdd(P.dbg + 12, s_cs.t_f2); atomicAdd(P.dbg + 13, s_cs.t_fa);
             }
         }
         int32_t track_thr = MIN_SCORE;

@@ -152,6 +152,8 @@ struct EmulBackend : Backend {
             for (int k = 0; k < 64; ++k) if (q_why[k]) std::fprintf(stderr, " %d:%llu", k, (unsigned long long)q_why[k]);
             std::fprintf(stderr, "\n   first failing cell of a tile: S %llu D-only %llu; failing cells S %llu D-only %llu", (unsigned long long)q_failS, (unsigned long long)q_failD, (unsigned long long)q_failcells[0], (unsigned long long)q_failcells[1]);
             std::fprintf(stderr, "\n   dense interior tiles by #non-boring S cells: 0:%llu 1-2:%llu 3-8:%llu 9-32:%llu 33-100:%llu >100:%llu", (unsigned long long)q_hist[0], (unsigned long long)q_hist[1], (unsigned long long)q_hist[2], (unsigned long long)q_hist[3], (unsigned long long)q_hist[4], (unsigned long long)q_hist[5]);
+            std::fprintf(stderr, "\n   age (columns since the contig's last !stay) at which a dense tile turns quiet:");
+            for (int k = 0; k < 12; ++k) std::fprintf(stderr, " %d:%llu", k, (unsigned long long)q_agehist[k]);
             std::fprintf(stderr, "\n   delta:");
             for (int k = 0; k < 64; ++k) if (q_delta[k]) std::fprintf(stderr, " %d:%llu", k - 32, (unsigned long long)q_delta[k]);
             std::fprintf(stderr, "\n");
@@ -256,7 +258,7 @@ struct EmulBackend : Backend {
     };
     static uint32_t base_bit(uint8_t b) { return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 16u; }
     static const int32_t POISON = 0x7f7f7f7f;   // what a skipped tile leaves in the state arrays (nobody may read it)
-    uint64_t q_hist[6] = {0}; uint64_t q_failS = 0, q_failD = 0, q_failcells[2] = {0, 0}; uint64_t q_why[64] = {0}, q_delta[64] = {0}; uint64_t q_tiles = 0, q_skipped = 0, q_mat = 0, q_special = 0, q_boundary = 0, q_nostay = 0, q_noself = 0, q_noleft = 0;
+    uint64_t q_hist[6] = {0}; uint64_t q_agehist[12] = {0}; std::vector<uint32_t> q_age; uint64_t q_failS = 0, q_failD = 0, q_failcells[2] = {0, 0}; uint64_t q_why[64] = {0}, q_delta[64] = {0}; uint64_t q_tiles = 0, q_skipped = 0, q_mat = 0, q_special = 0, q_boundary = 0, q_nostay = 0, q_noself = 0, q_noleft = 0;
     void pk_quiet_setup(const PK &pk, const ContigEntry *ent, uint32_t C, uint32_t NT, PkState &st) {
         const uint8_t *bases = al.contigs.blob.data();
         st.quiet_on = QUIET != 0;
@@ -327,6 +329,8 @@ struct EmulBackend : Backend {
             for (uint32_t a = 0; a < C; ++a) {
                 Qn[a] = pk_quiet_next(pk, sc, pc, pk_jc(pk, pc, A.J[a].score, A.J[a].len), st.Q[a], allow);
                 ++q_why[Qn[a].why & 63]; ++q_delta[(uint32_t)(pc.delta + 32) & 63];
+                if (q_age.size() < C) q_age.assign(C, 0);
+                if (!Qn[a].stay) q_age[a] = 0; else if (q_age[a] < 11) ++q_age[a];
             }
         }
         std::vector<int32_t> Smat(TILE), Dmat(TILE);
@@ -463,6 +467,7 @@ struct EmulBackend : Backend {
                 tilemax[tile] = tmax;
                 prev_exit = strips[31].exit; prev_exit_open = strips[31].exit_open;
                 prev_skipped = false;
+                if (quiet_on && tile_quiet && !qold) ++q_agehist[q_age[a]];
                 if (quiet_on) st.quiet[tile] = tile_quiet ? 1 : 0;
                 if (quiet_on && !special) ++q_hist[nfailS == 0 ? 0 : nfailS <= 2 ? 1 : nfailS <= 8 ? 2 : nfailS <= 32 ? 3 : nfailS <= 100 ? 4 : 5];
             }

@@ -309,7 +309,7 @@ def test_quiet_tiles_on_gpu(oracle, case):
     as the oracle, a good share of the tile-columns skipped, and the same chains again with STITCH_QUIET=0."""
     rng = random.Random(4400 + case)
     kw = [dict(double_strand=True, circular=True), dict(mode=1, double_strand=True), dict(mode=3, circular=True),
-          dict(mode=2, double_strand=True, match_score=2, mismatch_score=-3, gap_open=-4, gap_extend=-2,
+          dict(mode=2, double_strand=True, match_score=2, mismatch_score=-3, gap_open=-4, gap_extend=-3,
                jump_score_same_contig_and_strand=-8, jump_score_same_contig_opposite_strand=-9, jump_score_inter_contig=-11)][case]
     contigs = [gen.rand_seq(rng, rng.randint(2300, 3500)) for _ in range(4)] + [gen.rand_seq(rng, 700)]
     reads = [gen.chimeric_read(rng, contigs, rng.randint(700, 1100), rng.randint(2, 4), strands=bool(kw.get("double_strand")),
