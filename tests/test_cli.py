@@ -1,0 +1,156 @@
+"""CPU tier: the `stitch align` front-end (stitch_b200/csrc/stitch_align_cli.cpp) - option parsing, FASTA/FASTQ(.gz)
+readers, the align-identical-runs-once rule, output order, SAM text and BAM/BGZF encoding.  The binary binds the
+C ABI at run time; here it is pointed at the CPU emulator of the kernels (tests/emul, TEST INFRASTRUCTURE), so the
+records must equal what the emulator's own batch_sam returns (which test_sam_layer.py checks against the
+restated reference), and the BAM stream must decode to the same records."""
+import gzip
+import os
+import random
+import struct
+import subprocess
+import zlib
+
+import pytest
+
+import gen
+from stitch_b200._abi import make_opts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "stitch_b200", "stitch-b200")
+SRC = os.path.join(ROOT, "stitch_b200", "csrc", "stitch_align_cli.cpp")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    import emul_lib
+    emul_lib.build()
+    if not os.path.exists(CLI) or os.path.getmtime(CLI) < os.path.getmtime(SRC):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", CLI, SRC, "-ldl", "-lz"])
+    env = dict(os.environ, STITCH_B200_LIB=os.path.join(ROOT, "tests", "emul", "libemul_s8.so"), STITCH_B200_PREFIX="emul_")
+
+    def run(args):
+        p = subprocess.run([CLI, "align"] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr.decode()
+        return p.stdout
+    return run
+
+
+def bgzf_decompress(data):
+    out, p = bytearray(), 0
+    while p < len(data):
+        assert data[p:p + 4] == b"\x1f\x8b\x08\x04"
+        xlen = struct.unpack_from("<H", data, p + 10)[0]
+        assert data[p + 12:p + 16] == b"BC\x02\x00"
+        bsize = struct.unpack_from("<H", data, p + 16)[0] + 1
+        cdata = data[p + 12 + xlen:p + bsize - 8]
+        crc, isize = struct.unpack_from("<II", data, p + bsize - 8)
+        block = zlib.decompress(cdata, -15) if cdata else b""
+        assert len(block) == isize and zlib.crc32(block) == crc
+        out += block
+        p += bsize
+    return bytes(out), data[-28:]
+
+
+def bam_to_sam(raw):
+    """Minimal BAM decoder -> (header text, reference names, SAM lines)."""
+    assert raw[:4] == b"BAM\x01"
+    l_text = struct.unpack_from("<I", raw, 4)[0]
+    text = raw[8:8 + l_text].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<I", raw, p)[0]; p += 4
+    refs = []
+    for _ in range(n_ref):
+        l = struct.unpack_from("<I", raw, p)[0]; p += 4
+        refs.append((raw[p:p + l - 1].decode(), struct.unpack_from("<I", raw, p + l)[0])); p += l + 4
+    lines = []
+    while p < len(raw):
+        bs = struct.unpack_from("<I", raw, p)[0]; p += 4
+        rec = raw[p:p + bs]; p += bs
+        rid, pos, l_name, mapq, _bin, n_cig, flag, l_seq, nrid, npos, tlen = struct.unpack_from("<iiBBHHHIiii", rec, 0)
+        q = 32
+        name = rec[q:q + l_name - 1].decode(); q += l_name
+        cig = ""
+        for _ in range(n_cig):
+            v = struct.unpack_from("<I", rec, q)[0]; q += 4
+            cig += f"{v >> 4}{'MIDNSHP=X'[v & 15]}"
+        seq = "".join("=ACMGRSVTWYHKDBN"[(rec[q + k // 2] >> (4 if k % 2 == 0 else 0)) & 15] for k in range(l_seq)); q += (l_seq + 1) // 2
+        qual = rec[q:q + l_seq]; q += l_seq
+        qual = "*" if l_seq == 0 or qual[0] == 0xff else "".join(chr(c + 33) for c in qual)
+        tags = []
+        while q < len(rec):
+            tag, ty = rec[q:q + 2].decode(), chr(rec[q + 2]); q += 3
+            if ty in "cCsSiI":
+                fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I"}[ty]
+                tags.append(f"{tag}:i:{struct.unpack_from(fmt, rec, q)[0]}"); q += struct.calcsize(fmt)
+            elif ty == "Z":
+                e = rec.index(0, q); tags.append(f"{tag}:Z:{rec[q:e].decode()}"); q = e + 1
+            elif ty == "A":
+                tags.append(f"{tag}:A:{chr(rec[q])}"); q += 1
+            else:
+                raise AssertionError(ty)
+        rn = lambda i, same: "*" if i < 0 else ("=" if same and i == rid else refs[i][0])
+        lines.append("\t".join([name, str(flag), rn(rid, False), str(pos + 1), str(mapq), cig or "*", rn(nrid, True), str(npos + 1), str(tlen),
+                                seq or "*", qual] + tags))
+    return text, refs, lines
+
+
+def test_cli_sam_and_bam(cli, tmp_path):
+    import emul_lib
+    rng = random.Random(31)
+    contigs = [gen.rand_seq(rng, rng.randint(150, 400)) for _ in range(3)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(60, 200), rng.randint(1, 3), strands=True, wrap=True) for _ in range(9)]
+    reads.insert(3, reads[2]); reads.insert(4, reads[2].lower())          # a run of identical sequences: aligned once
+    reads.append(gen.rand_seq(rng, 40))                                    # unrelated to the contigs: a short local hit somewhere
+    heads = [f"read{k} extra words {k}" for k in range(len(reads))]
+    quals = ["".join(chr(33 + rng.randint(2, 40)) for _ in r) for r in reads]
+    ref = tmp_path / "ref.fa"
+    with open(ref, "w") as f:
+        for k, c in enumerate(contigs):
+            s = c.decode()
+            s = s.lower() if k == 1 else s
+            f.write(f">ctg{k} some description\n" + "\n".join(s[i:i + 70] for i in range(0, len(s), 70)) + "\n")
+    fq = tmp_path / "reads.fq.gz"
+    with gzip.open(fq, "wt") as f:
+        for h, r, q in zip(heads, reads, quals):
+            f.write(f"@{h}\n{r.decode()}\n+\n{q}\n")
+    fa = tmp_path / "reads.fa"
+    with open(fa, "w") as f:
+        for h, r in zip(heads, reads):
+            f.write(f">{h}\n{r.decode()}\n")
+    for extra, kw, sam_opts in (
+            ([], {}, None),
+            (["-d", "-C", "--circular-slop", "5", "-S", "-X"], dict(double_strand=True, circular=True, circular_slop=5), dict(soft_clip=True, use_eq_and_x=True)),
+            (["-m", "query-local", "-d", "--suboptimal", "--suboptimal-pct=50", "-P", "score", "--filter-secondary", "--filter-secondary-pct", "40",
+              "-A", "2", "-B", "-3", "-O", "-4", "-E", "-3", "-J", "-9", "--jump-score-inter-contig", "-11"],
+             dict(mode=1, double_strand=True, suboptimal=True, suboptimal_pct=50.0, match_score=2, mismatch_score=-3, gap_open=-4, gap_extend=-3,
+                  default_jump_score=-9, jump_score_inter_contig=-11), dict(pick_primary=1, filter_secondary=True, filter_secondary_pct=40.0))):
+        named = [(f"ctg{k}", c) for k, c in enumerate(contigs)]
+        e = emul_lib.EmulAligners(make_opts(**kw), named, strip=8)
+        _, exp = e.batch_sam([r.upper() for r in reads], heads, quals=[q.encode() for q in quals], sam_opts=sam_opts)
+        e.close()
+        exp_lines = [l for per_read in exp for l in per_read]
+        # SAM text, reads from gzip FASTQ, batches of 4 records (runs of identical sequences stay together)
+        out = cli(["-f", str(fq), "-r", str(ref), "--sam", "--batch", "4"] + extra).decode().splitlines()
+        hdr = [l for l in out if l.startswith("@")]
+        assert hdr[0].startswith("@HD") and [l.split("\t")[1] for l in hdr if l.startswith("@SQ")] == ["SN:ctg0", "SN:ctg1", "SN:ctg2"]
+        assert hdr[-1].startswith("@PG\tID:stitch")
+        assert [l for l in out if not l.startswith("@")] == exp_lines
+        # BAM on stdout (the reference's output), decoded back
+        raw, tail = bgzf_decompress(cli(["-f", str(fq), "-r", str(ref), "-c", "1"] + extra))
+        assert tail == bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+        text, refs, lines = bam_to_sam(raw)
+        assert refs == [(f"ctg{k}", len(c)) for k, c in enumerate(contigs)] and text.startswith("@HD")
+        assert lines == exp_lines
+        # FASTA reads: no qualities
+        e = emul_lib.EmulAligners(make_opts(**kw), named, strip=8)
+        _, exp = e.batch_sam([r.upper() for r in reads], heads, quals=None, sam_opts=sam_opts)
+        e.close()
+        out = cli(["-a", str(fa), "-r", str(ref), "--sam"] + extra).decode().splitlines()
+        assert [l for l in out if not l.startswith("@")] == [l for per_read in exp for l in per_read]
+
+
+def test_cli_rejects_what_it_cannot_do(cli, tmp_path):
+    p = subprocess.run([CLI, "align", "-r", "x.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode != 0 and b"exactly one of --reads-fastq or --reads-fasta" in p.stderr
+    p = subprocess.run([CLI, "align", "-f", "a.fq", "-r", "x.fa", "-p"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode != 0 and b"--pre-align is not supported" in p.stderr
