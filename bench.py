@@ -29,9 +29,11 @@ sys.path.insert(0, ROOT)
 ALG_OPS_PER_CELL = 32            # INT32 ops per cell update
 ALG_BYTES_PER_CELL = 0.5         # the traceback stream, <= 0.5 B per cell update
 # what the fill kernel really moves (ncu profiles/): the rolling column state, one S key and one D key
-# per cell, read and written once per column, plus checkpoints and jump records
+# per cell, read and written once per column by every tile that is not skipped as quiet, plus checkpoints and jump records
 STATE_BYTES_PER_CELL = 16.0
-DRAM_BYTES_PER_CELL_NCU = 17.2   # dram__bytes_read+write / cell updates of fill_packed_kernel (profiles/r01_ncu_fill_packed.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum per cell update of fill_packed_kernel with quiet tiles (1.32 TB + 1.84 TB for the
+# 4.73e11 cell updates of 148 config-2 reads; profiles/r01_ncu_fill_packed_quiet_details.txt).  Without quiet tiles: 17.2 B.
+DRAM_BYTES_PER_CELL_NCU = 6.67
 
 
 def read_peaks():
@@ -269,6 +271,7 @@ def main():
         fill_gcups = agg["packed_cells"] / fill_s / 1e9 if fill_s > 0 else 0.0
         launches_fill = max(1, agg["packed_launches"])   # fill_packed_kernel launches in the timed region (one per chunk of reads)
         ach = agg["packed_cells"] * ALG_BYTES_PER_CELL / fill_s / 1e9 if fill_s > 0 else 0.0
+        skipped_frac = agg["quiet_tile_columns"] / agg["tile_columns"] if agg["tile_columns"] else 0.0
         gops = C.c_double(0)
         lib.stitch_measure_int32_peak(local_rank, C.byref(gops))
         line = {
@@ -278,8 +281,8 @@ def main():
             "config": {"workload": workload, "reads_per_gpu_per_step": len(reads), "read_len": len(reads[0]),
                        "contig_strands": len(named) * (2 if kw.get("double_strand") else 1),
                        "cells_per_step": agg["cells_all"] / args.steps,
-                       "l2": "inputs larger than L2: every column streams the whole rolling state of the reads in flight (148 x 2.6 MB) "
-                             "and a step touches > 100 GB of checkpoints; no flush needed",
+                       "l2": "inputs larger than L2: the rolling state of the reads in flight (148 x 2.6 MB) is streamed by every computed "
+                             "tile-column and a step touches > 100 GB of checkpoints; no flush needed",
                        "parallelism": f"reads sharded over {world} GPU(s), no collective"},
             "reads_per_s": len(reads) * world * args.steps / dt,
             "clocks": clocks,
@@ -302,12 +305,15 @@ def main():
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": ALG_BYTES_PER_CELL,
                          "avg_launch_ms": agg["packed_ms"] / launches_fill if launches_fill else None, "kernel_gcups": fill_gcups,
-                         "state_stream_gbs": fill_gcups * STATE_BYTES_PER_CELL,
-                         "state_stream_frac_of_peak": fill_gcups * STATE_BYTES_PER_CELL / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None,
+                         "state_stream_gbs": fill_gcups * STATE_BYTES_PER_CELL * (1.0 - skipped_frac),
+                         "state_stream_frac_of_peak": fill_gcups * STATE_BYTES_PER_CELL * (1.0 - skipped_frac) / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None,
                          "note": "achieved = 0.5 B x cell updates / CUDA-event time of fill_packed_kernel (one launch per step; its time "
-                                 "includes the tail columns and the in-kernel fix-up/walk phase). The kernel is bound by streaming the rolling "
-                                 "column state through HBM (16 B per cell update, ncu: 17.2 B, 76 % of the measured HBM peak), which is 34x the "
-                                 "algorithmic bytes: the state of a read (2.6 MB) does not fit one SM; see DESIGN.md section 4 for the plan"},
+                                 "includes the tail columns and the in-kernel fix-up/walk phase). traffic = 6.67 B per cell update (ncu, this "
+                                 "kernel) x cell updates per launch: the rolling column state (16 B per cell update of a computed tile) is "
+                                 "streamed through HBM because a read's state (2.6 MB) does not fit one SM; quiet tiles (about 60 % of the "
+                                 "tile-columns on this workload) are neither loaded nor stored. With them the kernel is no longer HBM-bound "
+                                 "(ncu: DRAM 23 % of peak, issue slots 39 %, top stalls: CTA barriers, fixed-latency dependencies, long "
+                                 "scoreboard): see int_roofline and DESIGN.md section 4"},
             "int_roofline": {"bound": "int32", "achieved": fill_gcups * ALG_OPS_PER_CELL, "peak": gops.value,
                              "unit": "Gop/s", "frac": fill_gcups * ALG_OPS_PER_CELL / gops.value if gops.value else None,
                              "ops_per_cell": ALG_OPS_PER_CELL,

@@ -328,3 +328,39 @@ def test_quiet_tiles_on_gpu(oracle, case):
     al.close()
     compare(got0, exp, f"quiet off case {case}")
     assert st0.quiet_tile_columns == 0
+
+
+def test_cli_on_gpu(oracle, tmp_path):
+    """`stitch-b200 align` (stitch_b200/csrc/stitch_align_cli.cpp) end to end on the device: FASTQ + FASTA in, SAM text
+    out, against the restated reference (oracle/ aligner + oracle/sam_oracle.py); records in input order."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import sam_oracle
+    cli = os.path.join(root, "stitch_b200", "stitch-b200")
+    if not os.path.exists(cli):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", cli, os.path.join(root, "stitch_b200", "csrc", "stitch_align_cli.cpp"), "-ldl", "-lz"])
+    rng = random.Random(77)
+    contigs = [gen.rand_seq(rng, rng.randint(400, 900)) for _ in range(4)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(200, 600), rng.randint(1, 4), strands=True, wrap=True) for _ in range(10)]
+    reads.insert(5, reads[4])
+    named = [(f"ctg{k}", s) for k, s in enumerate(contigs)]
+    heads = [f"r{k} x" for k in range(len(reads))]
+    quals = [bytes(rng.randrange(35, 74) for _ in r) for r in reads]
+    ref, fq = tmp_path / "ref.fa", tmp_path / "reads.fq"
+    ref.write_text("".join(f">{n}\n{s.decode()}\n" for n, s in named))
+    fq.write_text("".join(f"@{h}\n{r.decode()}\n+\n{q.decode()}\n" for h, r, q in zip(heads, reads, quals)))
+    kw = dict(double_strand=True, circular=True)
+    o = make_opts(**kw)
+    exp_chains, _ = oracle.OracleAligners(o, named).batch(reads, raw=False)
+    exp = []
+    for r in range(len(reads)):
+        exp += sam_oracle.format_sam(heads[r], reads[r].upper(), quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
+                                     (o.match_score, o.mismatch_score, o.gap_open, o.gap_extend))
+    env = {k: v for k, v in os.environ.items() if k not in ("STITCH_B200_LIB", "STITCH_B200_PREFIX")}
+    p = subprocess.run([cli, "align", "-f", str(fq), "-r", str(ref), "-d", "-C", "--sam", "--batch", "3"], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
+    got = [l for l in p.stdout.decode().splitlines() if not l.startswith("@")]
+    assert got == exp
