@@ -119,7 +119,8 @@ struct CudaBackend : host::Backend {
     uint32_t cluster_pref = 0;
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
-    uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
+    uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column; 1: quiet tiles with static
+                                 // warp chunks (default); 2: quiet tiles, the runs of computed tiles dealt to the warps from a queue (slower)
     uint32_t pack_warps = 16;    // STITCH_PACK_WARPS=8: 8-warp CTAs, two per SM (one read each), when no cluster is used
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
@@ -168,7 +169,7 @@ struct CudaBackend : host::Backend {
         cluster_pref = std::min<uint32_t>(16, env_u32("STITCH_CLUSTER", cluster_pref));
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
-        quiet_tiles = env_u32("STITCH_QUIET", 1);
+        quiet_tiles = env_u32("STITCH_QUIET", quiet_tiles);
         pack_warps = env_u32("STITCH_PACK_WARPS", pack_warps) == 8 ? 8 : 16;
     }
     ~CudaBackend() override {

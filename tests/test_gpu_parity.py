@@ -316,12 +316,18 @@ def test_quiet_tiles_on_gpu(oracle, case):
                                wrap=bool(kw.get("circular"))) for _ in range(5)]
     named = [(f"c{k}", s) for k, s in enumerate(contigs)]
     exp, _ = oracle.OracleAligners(make_opts(**kw), named).batch(reads, raw=False)
-    al = gpu_aligners(kw, named, tuning={"STITCH_CLUSTER": "1"})   # (few reads would otherwise get a cluster per read: no quiet tiles there)
-    got = al.align_batch(reads)
-    st = al.stats()
-    al.close()
-    compare(got, exp, f"quiet case {case}")
-    assert st.tile_columns > 0 and st.quiet_tile_columns > 0.1 * st.tile_columns, (st.tile_columns, st.quiet_tile_columns)
+    # (few reads would otherwise get a cluster per read: no quiet tiles there)
+    for quiet in ("2", "1"):   # 2: runs of computed tiles dealt to the warps from a queue, 1: static warp chunks (default)
+        al = gpu_aligners(kw, named, tuning={"STITCH_CLUSTER": "1", "STITCH_QUIET": quiet})
+        got = al.align_batch(reads)
+        st = al.stats()
+        al.close()
+        compare(got, exp, f"quiet {quiet} case {case}")
+        assert st.tile_columns > 0 and st.quiet_tile_columns > 0.1 * st.tile_columns, (st.tile_columns, st.quiet_tile_columns)
+        if quiet == "2":
+            skipped = st.quiet_tile_columns
+        else:
+            assert st.quiet_tile_columns == skipped   # which tiles are skipped does not depend on the scheduling
     al = gpu_aligners(kw, named, tuning={"STITCH_QUIET": "0", "STITCH_CLUSTER": "1"})
     got0 = al.align_batch(reads)
     st0 = al.stats()
