@@ -190,7 +190,7 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
     int32_t Sup[STRIP], Dup[STRIP];
     uint2 xb;
     if (QUIET && qz.mat) {
-        xb = *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
+        xb = stg ? reinterpret_cast<const uint2 *>(stg + 2 * TILE * 4)[lane] : *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
         uint8_t xm[STRIP];
         unpack8(xb, xm);
         const PkQuiet qp = *qz.Qp;
@@ -532,12 +532,15 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         // warp's shared-memory double buffer; each lane reads back exactly the bytes it copied (no warp sync needed)
         const bool staged = X.staged;
         unsigned char *stg0 = S.stage + (size_t)warp * 2 * PackSmem::STAGE_BYTES;
-        auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot) {
+        // (`full` = the tile's state is loaded; a materialised tile only needs its bases)
+        auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot, bool full) {
             unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
-            __pipeline_memcpy_async(d + lane * 16, X.Sst + t * ST + lane * 4, 16);
-            __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * ST + 128 + lane * 4, 16);
-            __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * ST + lane * 4, 16);
-            __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * ST + 128 + lane * 4, 16);
+            if (full) {
+                __pipeline_memcpy_async(d + lane * 16, X.Sst + t * ST + lane * 4, 16);
+                __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * ST + 128 + lane * 4, 16);
+                __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * ST + lane * 4, 16);
+                __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * ST + 128 + lane * 4, 16);
+            }
             __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
             __pipeline_commit();
         };
@@ -574,14 +577,17 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         bool last_skipped = false;                      // tile base-1 was skipped
         for (uint32_t base = t_lo; base < t_hi; base += 32) {
             const uint32_t nb = t_hi - base, validm = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-            uint32_t skipm = 0, loadm = validm, loadm_next = base + 32 < t_hi ? 1u : 0u;
+            // loadm: tiles whose state is loaded; compm / compm_next: tiles that are computed (each gets a stage slot: state + bases,
+            // or the bases alone when its state is materialised)
+            uint32_t skipm = 0, loadm = validm, compm = validm, compm_next = base + 32 < t_hi ? 1u : 0u, loadm_next = compm_next;
             if (QUIET) {
-                const uint32_t m0 = base + lane < t_hi ? (uint32_t)S.tb[base + lane] >> 6 : 3u;
-                const uint32_t m1 = base + 32 + lane < t_hi ? (uint32_t)S.tb[base + 32 + lane] >> 6 : 3u;
-                skipm = __ballot_sync(FULL, m0 == 0u); loadm = __ballot_sync(FULL, m0 == 2u); loadm_next = __ballot_sync(FULL, m1 == 2u);
+                const uint32_t m0 = base + lane < t_hi ? (uint32_t)S.tb[base + lane] >> 6 : 0u;
+                const uint32_t m1 = base + 32 + lane < t_hi ? (uint32_t)S.tb[base + 32 + lane] >> 6 : 0u;
+                skipm = __ballot_sync(FULL, m0 == 0u) & validm; loadm = __ballot_sync(FULL, m0 == 2u);
+                compm = ~skipm & validm; compm_next = __ballot_sync(FULL, m1 != 0u); loadm_next = __ballot_sync(FULL, m1 == 2u);
                 nskipped += __popc(skipm);
             }
-            uint32_t dm = ~skipm & validm;
+            uint32_t dm = compm;
             while (dm) {
                 const uint32_t b = __ffs(dm) - 1u;
                 dm &= dm - 1u;
@@ -592,25 +598,25 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 // software pipeline: the tile to load sits (or arrives) in a stage slot; the next tile that will be loaded
                 // is prefetched into the other slot while this one is computed
                 uint32_t cur_slot = 0;
-                if (staged && is_load) {
-                    if (pf_tile != tile) { pf_slot ^= 1u; prefetch(tile, en, pf_slot); pf_tile = tile; }
+                if (staged) {
+                    if (pf_tile != tile) { pf_slot ^= 1u; prefetch(tile, en, pf_slot, is_load); pf_tile = tile; }
                     cur_slot = pf_slot;
                 }
                 bool issued = false;
                 if (staged) {
-                    const uint32_t rest = b == 31u ? 0u : (loadm & ~((2u << b) - 1u));
-                    uint32_t nl = 0xffffffffu;
-                    if (rest) nl = base + __ffs(rest) - 1u;
-                    else if (loadm_next) nl = base + 32u + __ffs(loadm_next) - 1u;
+                    const uint32_t rest = b == 31u ? 0u : (compm & ~((2u << b) - 1u));
+                    uint32_t nl = 0xffffffffu; bool nfull = true;
+                    if (rest) { const uint32_t nb_ = (uint32_t)__ffs((int)rest) - 1u; nl = base + nb_; nfull = (loadm >> nb_) & 1u; }
+                    else if (compm_next) { const uint32_t nb_ = (uint32_t)__ffs((int)compm_next) - 1u; nl = base + 32u + nb_; nfull = (loadm_next >> nb_) & 1u; }
                     if (nl != 0xffffffffu && nl != pf_tile) {
                         pf_slot ^= 1u;
-                        if (nl < en.tile_start + en.ntiles) prefetch(nl, en, pf_slot);
-                        else { const ContigEntry e2 = X.ent[X.owner[nl]]; prefetch(nl, e2, pf_slot); }
+                        if (nl < en.tile_start + en.ntiles) prefetch(nl, en, pf_slot, nfull);
+                        else { const ContigEntry e2 = X.ent[X.owner[nl]]; prefetch(nl, e2, pf_slot, nfull); }
                         pf_tile = nl; issued = true;
                     }
                 }
                 const unsigned char *stg = nullptr;
-                if (staged && is_load) {
+                if (staged) {
                     if (issued) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
                     stg = stg0 + cur_slot * PackSmem::STAGE_BYTES;
                 }
