@@ -328,7 +328,16 @@ struct PkQuiet {            // per (contig, column)
     int32_t bk[2];          // clean S key of a quiet cell
     int32_t t[PKQ_L][2];    // raw D candidates (as pass 1 forms them, before clean6; priority field = k)
     int32_t stay;           // tiles quiet at column j-1 (with a quiet predecessor tile) are quiet at column j
+    int32_t stay_first;     // ... and so is the FIRST tile of the contig (row 1: diagonal / chain from row 0, wrap, y-clip)
     int32_t why;            // which of C1..C5 failed (bit k-1), bit 5 = not allowed (diagnostics)
+};
+// What row 1 of a contig sees in column j beyond an ordinary row (SCA:188-239, 258-289, 391-399), as pk_tile forms it.
+struct PkFirstIn {
+    int32_t r0pkey;         // S(0, j-1): the diagonal source of row 1
+    int32_t cr1key;         // insertion chain arriving at row 1 from row 0 (PP_ICARRY)
+    int32_t wbase;          // circular wrap source pk_wbase(S(m, j-1)); only read when `wrap`
+    int32_t yc1;            // y-prefix clip candidate of row 1 (PP_YC) or NEGKEY
+    bool wrap;              // the contig is circular and the S code of (m, j-1) is not XCLIP_SUFFIX
 };
 SHD int32_t pk_deadrel(const Scoring &sc) {
     int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
@@ -339,13 +348,14 @@ SHD int32_t pk_deadrel(const Scoring &sc) {
 SHD int32_t pk_clean6(const PK &p, int32_t v) { return (pk_max(v, p.NEGKEY) & p.NPM) | p.PD6; }
 SHD PkQuiet pk_quiet_init(const PK &p) {
     PkQuiet q;
-    q.bk[0] = q.bk[1] = p.NEGKEY; q.stay = 0; q.why = 0;
+    q.bk[0] = q.bk[1] = p.NEGKEY; q.stay = 0; q.stay_first = 0; q.why = 0;
     for (int k = 0; k < PKQ_L; ++k) q.t[k][0] = q.t[k][1] = p.NEGKEY;
     return q;
 }
 // Closed form of column j from the one of column j-1.  `Jc` = pk_jc of the contig for column j.
 // `allow` = this column may be skipped at all (not a checkpoint column, read base is one of ACGT, ...).
-SHD PkQuiet pk_quiet_next(const PK &p, const Scoring &sc, const PCol &c, int32_t Jc, const PkQuiet &prev, bool allow) {
+SHD PkQuiet pk_quiet_next(const PK &p, const Scoring &sc, const PCol &c, int32_t Jc, const PkQuiet &prev, bool allow,
+                          const PkFirstIn *fi = nullptr) {
     PkQuiet q;
     const int32_t jM = Jc + c.cM, jX = Jc + c.cX;
     q.bk[0] = jM & p.NPM; q.bk[1] = jX & p.NPM;
@@ -375,6 +385,16 @@ SHD PkQuiet pk_quiet_next(const PK &p, const Scoring &sc, const PCol &c, int32_t
     const bool ok = c1 && c2 && c3 && c4 && c5;
     q.why = (c1 ? 0 : 1) | (c2 ? 0 : 2) | (c3 ? 0 : 4) | (c4 ? 0 : 8) | (c5 ? 0 : 16) | (allow ? 0 : 32);
     q.stay = (ok && allow) ? 1 : 0;
+    q.stay_first = 0;
+    if (fi && q.stay) {
+        // C6 the diagonal from row 0 does not beat the jump in row 1; C7 the chain from row 0 stays below the jump's score;
+        // C8 the circular wrap (a second jump candidate of row 1) does not beat the jump; C9 the y-prefix clip loses
+        const bool c6 = (int32_t)((uint32_t)fi->r0pkey + (uint32_t)c.cM) <= (jM | p.PB8) && (int32_t)((uint32_t)fi->r0pkey + (uint32_t)c.cX) <= (jX | p.PB8);
+        const bool c7 = (fi->cr1key >> p.SH) < (jlo >> p.SH);
+        const bool c8 = !fi->wrap || fi->wbase <= Jc;
+        const bool c9 = fi->yc1 < jlo;
+        q.stay_first = (c6 && c7 && c8 && c9) ? 1 : 0;
+    }
     return q;
 }
 // The closed form of one cell of column j.  s[k] = sub index of the cell's contig base against y_{j-k}, k = 0 .. PKQ_L.

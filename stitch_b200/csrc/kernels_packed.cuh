@@ -118,6 +118,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     bool cluster_smem;
     bool quiet;             // the bulk pass may skip quiet tiles (single-CTA teams with the state in global memory)
     bool dynamic;           // ... and deals the runs of computed tiles of a column to the warps from a queue
+    bool quiet_first, quiet_edge;   // the first tile of a contig / the first and last tile of a warp chunk may be skipped too
     int32_t *cstate;
     const uint32_t *cta_lo;   // shared memory: first tile of every CTA of the team, [size + 1]
 };
@@ -382,7 +383,9 @@ __device__ __forceinline__ void pk_tiles_dynamic(const PackCtx &X, PackSmem &S, 
                 const uint32_t a_t = X.owner[t];
                 const uint32_t tic = t - X.ent[a_t].tile_start;
                 const PkQuiet &qn = Qn[a_t];
-                mode = (tic != 0 && tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi && (S.tb[t - 1] & PackSmem::TB_Q) && qn.stay) ? 0u : 1u;
+                // (the first tile of a contig has no upper neighbour but four more conditions: stay_first)
+                mode = (tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi &&
+                        (tic == 0 ? qn.stay_first != 0 : ((S.tb[t - 1] & PackSmem::TB_Q) && qn.stay))) ? 0u : 1u;
                 if (mode == 0) {
                     const uint32_t tm = tbv & PackSmem::TB_MASK;
                     S.tilemax[t] = (tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1];
@@ -549,6 +552,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         // of its chunk), one tile per lane: 0 = skip, 1 = compute from the materialised closed form, 2 = load + compute.
         // The first and last tile of a chunk and of a contig are always computed (halos, row 1, row m).  A skipped tile
         // only contributes its best key (the better of the closed form's two keys among the bases it holds).
+        const bool edge = QUIET && X.quiet_edge;
+        const uint32_t lq0 = (edge && gw > 0) ? S.haloF[(par ^ 1u) * W + warp] : 0u;   // last tile of the previous chunk was quiet at column j-1
         if (QUIET) {
             const uint32_t mb = pk_base_bit(pc.q);
             for (uint32_t t = t_lo + lane; t < t_hi; t += 32) {
@@ -558,7 +563,11 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                     const uint32_t a_t = X.owner[t];
                     const uint32_t tic = t - X.ent[a_t].tile_start;
                     const PkQuiet &qn = Qn[a_t];
-                    mode = (tic != 0 && tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi && (S.tb[t - 1] & PackSmem::TB_Q) && qn.stay) ? 0u : 1u;
+                    // (the first tile of a contig has no upper neighbour but four more conditions: stay_first; the first tile
+                    // of a chunk reads the flag its neighbour chunk's owner published with the halo)
+                    const bool left_ok = t != t_lo ? (S.tb[t - 1] & PackSmem::TB_Q) != 0 : lq0 != 0u;
+                    mode = (tic + 1 != X.ent[a_t].ntiles && (edge || (t != t_lo && t + 1 != t_hi)) &&
+                            (tic == 0 ? qn.stay_first != 0 : (left_ok && qn.stay))) ? 0u : 1u;
                     if (mode == 0) {
                         const uint32_t tm = tbv & PackSmem::TB_MASK;
                         S.tilemax[t] = (tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1];
@@ -567,6 +576,19 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 S.tb[t] = (uint8_t)((tbv & 63u) | (mode << 6));
             }
             __syncwarp();
+            if (lq0 && ((uint32_t)S.tb[t_lo] >> 6) != 0u) {
+                // the chunk's first tile is computed and its upper neighbour (another warp's tile) is quiet, its memory possibly
+                // stale: the 17-key halo of column j-1 comes from the closed form instead of the published copy
+                const uint32_t a0 = X.owner[t_lo];
+                const uint32_t tic0 = t_lo - X.ent[a0].tile_start;
+                if (tic0 != 0 && lane < 9) {
+                    const uint8_t xb = X.bases[X.ent[a0].seq_off + tic0 * TILE - STRIP + lane - 1];   // rows hrow0-1 .. hrow0+7
+                    const PkQuiet qp = Qp[a0];
+                    S.haloS[((par ^ 1u) * W + warp) * 9 + lane] = xb == yq[1] ? qp.bk[0] : qp.bk[1];
+                    if (lane >= 1) S.haloD[((par ^ 1u) * W + warp) * 8 + lane - 1] = pk_quiet_D_dev(pk, qp, xb, yq + 1);
+                }
+                __syncwarp();
+            }
         }
         // contig of the current tile (reloaded only when the chunk crosses into the next contig)
         uint32_t a = X.owner ? X.owner[t_lo] : 0u;
@@ -633,7 +655,10 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             last_skipped = (skipm >> 31) != 0;
         }
         if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
-        if (gw + 1 < Weff) {   // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp)
+        if (QUIET && gw + 1 < Weff && lane == 0) S.haloF[par * W + warp + 1] = (S.tb[t_hi - 1] & PackSmem::TB_Q) ? 1u : 0u;
+        if (gw + 1 < Weff && (!QUIET || ((uint32_t)S.tb[t_hi - 1] >> 6) != 0u)) {
+            // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp); a skipped
+            // last tile publishes only its flag (above): its memory is stale and the consumer uses the closed form
             const bool local = warp + 1 < (uint32_t)W;
             const uint32_t slot = local ? warp + 1 : 0u;
             int32_t *nS = (local ? S.haloS : team.peer(S.haloS, team.rank + 1)) + (par * W + slot) * 9;
@@ -926,7 +951,12 @@ __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, 
             if (X.quiet) {   // closed form of a quiet tile of this contig in column j, and whether quiet tiles stay quiet
                 const uint8_t q = read[j - 1];
                 const bool allow = !((j % K == 0) && j < X.n) && pk_base_bit(q) != 16u;
-                S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, pk_col(X.pk, X.sc, g, Bprev, j, X.n, q), Jc, S.Q[(par ^ 1u) * S.cmax + a], allow);
+                const PkColConst ccl = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, q);
+                PkFirstIn fi;   // what row 1 of this contig sees beyond an ordinary row
+                fi.r0pkey = ccl.r0pkey; fi.cr1key = ccl.cr1key; fi.wbase = pk_wbase(X.pk, S.SmKey[a]);
+                fi.wrap = X.ent[a].circular && S.tbm[a] != TB_XCLIP_SUFFIX;
+                fi.yc1 = X.yclip_mode ? pk_key(X.pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e - g, PP_YC, col0_slen(X.sc, 1, X.ent[a].m)) : X.pk.NEGKEY;
+                S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, ccl.pc, Jc, S.Q[(par ^ 1u) * S.cmax + a], allow, X.quiet_first ? &fi : nullptr);
             }
         }
         if (tid == 0) {
@@ -1047,6 +1077,8 @@ __global__ void __launch_bounds__(W * 32, W <= 8 ? 2 : 1) fill_packed_kernel(con
         if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
         X.quiet = P.quiet != 0 && team.size == 1 && !X.cluster_smem;
         X.dynamic = X.quiet && P.quiet >= 2 && X.NT < (1u << 30);
+        X.quiet_first = X.quiet && P.quiet_first != 0; X.quiet_edge = X.quiet && !X.dynamic && P.quiet_edge != 0;
+        if (tid < 2 * W) S.haloF[tid] = 0;
         if (tid == 0) { S.q[0] = 0; S.q[1] = 0; }
         if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
         if (X.quiet) {   // quiet tiles: no tile is quiet yet; base classes of every tile
@@ -1161,7 +1193,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
-    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.cstate = nullptr; X.cta_lo = nullptr;
+    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);

@@ -138,12 +138,13 @@ static void emul_column(const ColumnArgs &A) {
 struct EmulBackend : Backend {
     Aligner &al;
     uint32_t dump_seq = 0;
-    uint32_t K, WINDOW, PACKED, QUIET;
+    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE;
     explicit EmulBackend(Aligner &a) : al(a) {
         K = std::max<uint32_t>(1, env_u32("EMUL_K", 7));          // checkpoint spacing (columns)
         WINDOW = std::max<uint32_t>(1, env_u32("EMUL_WINDOW", 6));  // columns at the end of the read filled by the wide path
         PACKED = env_u32("EMUL_PACKED", 1);                         // 0: wide path only
         QUIET = env_u32("EMUL_QUIET", 1);                           // 0: the bulk pass never skips quiet tiles
+        QUIET_EDGE = env_u32("EMUL_QUIET_EDGE", 1);                 // 0: the first and last tile of a warp chunk are always computed
     }
     ~EmulBackend() {
         g_quiet_tiles += q_tiles; g_quiet_skipped += q_skipped; g_quiet_mat += q_mat;
@@ -327,13 +328,21 @@ struct EmulBackend : Backend {
         if (quiet_on) {
             const bool allow = A.allow_skip && base_bit(pc.q) != 16u;
             for (uint32_t a = 0; a < C; ++a) {
-                Qn[a] = pk_quiet_next(pk, sc, pc, pk_jc(pk, pc, A.J[a].score, A.J[a].len), st.Q[a], allow);
+                PkFirstIn fi;
+                fi.r0pkey = pk_from_wide(pk, A.Bprev, r0p.S, r0p.sl, 0);
+                fi.cr1key = pk_carry_row1(pk, pc, sc, r0);
+                fi.wbase = pk_wbase(pk, st.SmKey[a]);
+                fi.wrap = A.ent[a].circular && st.tbm[a] != TB_XCLIP_SUFFIX;
+                fi.yc1 = ycmode ? pk_key(pk, (int64_t)sc.yp + sc.o + (int64_t)sc.e - B, PP_YC, col0_slen(sc, 1, A.ent[a].m)) : pk.NEGKEY;
+                Qn[a] = pk_quiet_next(pk, sc, pc, pk_jc(pk, pc, A.J[a].score, A.J[a].len), st.Q[a], allow, &fi);
                 ++q_why[Qn[a].why & 63]; ++q_delta[(uint32_t)(pc.delta + 32) & 63];
                 if (q_age.size() < C) q_age.assign(C, 0);
                 if (!Qn[a].stay) q_age[a] = 0; else if (q_age[a] < 11) ++q_age[a];
             }
         }
         std::vector<int32_t> Smat(TILE), Dmat(TILE);
+        const std::vector<uint8_t> quiet_old = st.quiet;   // flags of column j-1 (what a chunk reads of its left neighbour chunk)
+        const bool edge_on = quiet_on && QUIET_EDGE != 0;
         for (uint32_t w = 0; w < Weff; ++w) {
             const uint32_t t_lo = (uint32_t)((uint64_t)NT * w / Weff), t_hi = (uint32_t)((uint64_t)NT * (w + 1) / Weff);
             int32_t prev_exit = 0; uint32_t prev_exit_open = 0;
@@ -347,14 +356,15 @@ struct EmulBackend : Backend {
                 const int32_t Jc = pk_jc(pk, pc, A.J[a].score, A.J[a].len);
                 // ---- quiet tiles: skip / materialise decisions from the flags of column j-1 ----
                 const uint8_t qold = quiet_on ? st.quiet[tile] : 0;
-                const uint8_t qleft = (tile > t_lo && !first) ? qold_left : 0;   // tile-1 of the same contig and chunk was quiet at j-1
+                // tile-1 of the same contig was quiet at j-1 (across a chunk boundary: the flag its owner published)
+                const uint8_t qleft = first ? 0 : (tile > t_lo ? qold_left : (edge_on ? quiet_old[tile - 1] : 0));
                 qold_left = qold;
                 if (quiet_on) {
                     ++q_tiles;
-                    if (special) ++q_special; else if (tile == t_lo || tile + 1 == t_hi) ++q_boundary; else if (!Qn[a].stay) ++q_nostay;
+                    if (lastt || (first && !Qn[a].stay_first && Qn[a].stay)) ++q_special; else if (!edge_on && (tile == t_lo || tile + 1 == t_hi)) ++q_boundary; else if (!Qn[a].stay) ++q_nostay;
                     else if (!qold) ++q_noself; else if (!qleft) ++q_noleft;
                 }
-                if (quiet_on && !special && tile != t_lo && tile + 1 != t_hi && qold && qleft && Qn[a].stay) {
+                if (quiet_on && !lastt && (edge_on || (tile != t_lo && tile + 1 != t_hi)) && qold && (first ? Qn[a].stay_first != 0 : (qleft && Qn[a].stay))) {
                     const uint32_t mb = base_bit(pc.q);
                     const bool hm = (st.tmask[tile] & mb) != 0, hx = (st.tmask[tile] & ~mb) != 0;
                     tilemax[tile] = hm ? (hx ? pk_max(Qn[a].bk[0], Qn[a].bk[1]) : Qn[a].bk[0]) : Qn[a].bk[1];
@@ -427,7 +437,19 @@ struct EmulBackend : Backend {
                         for (int k = 0; k < STRIP; ++k) x[k] = bases[en.seq_off + hrow0 + k - 1];
                         PStrip h;
                         fill_yc(h, hrow0, tic == 1);
-                        pk_pass1<true, true>(pk, pc, Sp + hb, Dp + hb, Sp[hb - 1], x, Jc, false, wbase, STRIP, false, h);
+                        int32_t hs[STRIP + 1], hd[STRIP];   // S of the row before the halo rows and of the halo rows, D of the halo rows (column j-1)
+                        for (int k = 0; k <= STRIP; ++k) {
+                            const uint32_t row = hrow0 - 1 + (uint32_t)k;   // 1-based
+                            if (qleft) {   // the neighbour chunk's last tile is quiet (its memory may be stale): closed form
+                                int sx[PKQ_L + 1]; sv(bases[en.seq_off + row - 1], 1, sx);
+                                hs[k] = pk_quiet_S(st.Q[a], sx[0]);
+                                if (k >= 1) hd[k - 1] = pk_quiet_D(pk, st.Q[a], sx);
+                            } else {
+                                hs[k] = Sp[hb - 1 + (uint32_t)k];
+                                if (k >= 1) hd[k - 1] = Dp[hb - 1 + (uint32_t)k];
+                            }
+                        }
+                        pk_pass1<true, true>(pk, pc, hs + 1, hd, hs[0], x, Jc, false, wbase, STRIP, false, h);
                         cin = pk_carry_from_exit(pk, h.exit); cin_open = h.exit_open;
                     } else if (prev_skipped) { cin = pk.NEGKEY + pk.PI5; cin_open = 0; }   // chain out of a quiet tile: dead (C4)
                     else { cin = pk_carry_from_exit(pk, prev_exit); cin_open = prev_exit_open; }

