@@ -410,6 +410,26 @@ SHD bool pk_quiet_cell(const PK &p, const PkQuiet &q, int32_t deadrel, int32_t S
     return Skey == q.bk[s[0]] && (D6 == pk_quiet_D(p, q, s) || (D6 >> p.SH) <= deadrel);
 }
 
+// Row m of a contig whose LAST tile is skipped as quiet in column j: the candidates pk_tile would have stashed for
+// pk_finish_rowm.  Row m itself is never in the closed form (it accumulates the x-suffix tracker, SCA:407-429), so its
+// own S / D keys of column j-1 are kept per contig (SmKey / DmKey); the row above it is a quiet cell; the insertion chain
+// arriving from quiet rows is dead (C4), which leaves the outcome of finish_rowm unchanged (a candidate below the jump's
+// score loses to the jump or to whatever beats the jump).  Returns the stash; `*dm_new` = D key of (m, j) to keep.
+SHD PkRowM pk_quiet_rowm(const PK &p, const PCol &c, const PkQuiet &qprev, int32_t Jc, int32_t SmKey_prev, int32_t DmKey_prev,
+                         int s_above_prev /* sub index of row m-1 against y_{j-1} */, bool m_match /* x_m == y_j */, int32_t *dm_new) {
+    const int32_t cc = m_match ? c.cM : c.cX;
+    const int32_t ext = pk_addmax(DmKey_prev, c.cE, p.NEGKEY);
+    const int32_t Dp = pk_addmax(SmKey_prev, c.cOE, ext);
+    PkRowM rm;
+    rm.D6 = (Dp & p.NPM) | p.PD6;
+    rm.diag = (int32_t)((uint32_t)qprev.bk[s_above_prev] + (uint32_t)cc);
+    rm.jp = Jc + cc;
+    rm.I = p.NEGKEY + p.PI4;
+    rm.fl = 0; rm.iext = 0;
+    *dm_new = rm.D6;
+    return rm;
+}
+
 // Carry into a lane from the previous lane's exit (PP_INC -> PP_ICARRY).
 SHD int32_t pk_carry_from_exit(const PK &p, int32_t exit_key) { return exit_key + p.P1; }
 

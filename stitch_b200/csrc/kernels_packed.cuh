@@ -47,7 +47,7 @@ struct Team {
 };
 
 struct PackSmem {
-    int32_t *Jc, *cm, *Sm, *SmKey, *tilemax, *haloS, *haloD;
+    int32_t *Jc, *cm, *Sm, *SmKey, *DmKey, *tilemax, *haloS, *haloD;   // DmKey: D key of row m of every contig (latest column)
     uint32_t *cml, *cmk, *slm, *tbm, *haloF;
     PkRowM *stash;
     JumpInfo *Jw;
@@ -66,7 +66,7 @@ struct PackSmem {
     // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
     static size_t default_stage(int W) { return (size_t)W * 2 * STAGE_BYTES; }
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
-        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 8 + ntmax + 2 * W * 18) +
+        return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 9 + ntmax + 2 * W * 18) +
                (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 3 * (size_t)ntmax +
                4 * ((size_t)ntmax / 2 + W + 8) + 64;
     }
@@ -80,7 +80,8 @@ struct PackSmem {
         Jc = reinterpret_cast<int32_t *>(stash + cmax);
         cm = Jc + cmax; Sm = cm + cmax; SmKey = Sm + cmax;
         cml = reinterpret_cast<uint32_t *>(SmKey + cmax); cmk = cml + cmax; slm = cmk + cmax; tbm = slm + cmax;
-        tilemax = reinterpret_cast<int32_t *>(tbm + cmax);
+        DmKey = reinterpret_cast<int32_t *>(tbm + cmax);
+        tilemax = DmKey + cmax;
         haloS = tilemax + ntmax;                             // [2][W][9]
         haloD = haloS + 2 * W * 9;                           // [2][W][8]
         haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W] (unused)
@@ -118,7 +119,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     bool cluster_smem;
     bool quiet;             // the bulk pass may skip quiet tiles (single-CTA teams with the state in global memory)
     bool dynamic;           // ... and deals the runs of computed tiles of a column to the warps from a queue
-    bool quiet_first, quiet_edge;   // the first tile of a contig / the first and last tile of a warp chunk may be skipped too
+    bool quiet_first, quiet_edge, quiet_last;   // the first / last tile of a contig, the first and last tile of a warp chunk may be skipped too
     int32_t *cstate;
     const uint32_t *cta_lo;   // shared memory: first tile of every CTA of the team, [size + 1]
 };
@@ -199,6 +200,8 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
         for (int k = 0; k < STRIP; ++k) {
             Sup[k] = xm[k] == qz.yq[1] ? qp.bk[0] : qp.bk[1];
             Dup[k] = pk_quiet_D_dev(pk, qp, xm[k], qz.yq + 1);
+            // row m is never in the closed form: its keys of column j-1 are kept per contig
+            if (SPECIAL && row0 + (uint32_t)k == en.m) { Sup[k] = S.SmKey[a]; Dup[k] = S.DmKey[a]; }
         }
     } else {
         int4 s0, s1, d0, d1;
@@ -313,6 +316,7 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
         if (has_m) {
             PkRowM rm; rm.diag = st.A[nv]; rm.D6 = st.D6[nv]; rm.jp = st.jp[nv]; rm.I = I_m; rm.fl = TB ? st.fl[nv] : 0u; rm.iext = iext_m;
             X.team.peer(S.stash, a % X.team.size)[a] = rm;   // to the CTA that finishes contig a
+            if (QUIET) S.DmKey[a] = rm.D6;
         }
     }
     *reinterpret_cast<int4 *>(X.Sst + tile * ST + lane * 4) = make_int4(Sn[0], Sn[1], Sn[2], Sn[3]);
@@ -566,11 +570,19 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                     // (the first tile of a contig has no upper neighbour but four more conditions: stay_first; the first tile
                     // of a chunk reads the flag its neighbour chunk's owner published with the halo)
                     const bool left_ok = t != t_lo ? (S.tb[t - 1] & PackSmem::TB_Q) != 0 : lq0 != 0u;
-                    mode = (tic + 1 != X.ent[a_t].ntiles && (edge || (t != t_lo && t + 1 != t_hi)) &&
+                    const bool lastt = tic + 1 == X.ent[a_t].ntiles;
+                    mode = ((!lastt || (X.quiet_last && tic != 0)) && (edge || (t != t_lo && t + 1 != t_hi)) &&
                             (tic == 0 ? qn.stay_first != 0 : (left_ok && qn.stay))) ? 0u : 1u;
                     if (mode == 0) {
                         const uint32_t tm = tbv & PackSmem::TB_MASK;
-                        S.tilemax[t] = (tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1];
+                        S.tilemax[t] = tm == 0u ? pk.NEGKEY : ((tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1]);
+                        if (lastt) {   // row m: the candidates the tile would have stashed for the per-contig finish
+                            const ContigEntry &e = X.ent[a_t];
+                            int32_t dmn;
+                            S.stash[a_t] = pk_quiet_rowm(pk, pc, Qp[a_t], S.Jc[a_t], S.SmKey[a_t], S.DmKey[a_t],
+                                                         X.bases[e.seq_off + e.m - 2] == yq[1] ? 0 : 1, X.bases[e.seq_off + e.m - 1] == pc.q, &dmn);
+                            S.DmKey[a_t] = dmn;
+                        }
                     }
                 }
                 S.tb[t] = (uint8_t)((tbv & 63u) | (mode << 6));
@@ -650,7 +662,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                     qnow = pk_tile<true, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
                 else
                     qnow = pk_tile<false, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-                if (QUIET && lane == 0) S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && tic + 1 != en.ntiles) ? PackSmem::TB_Q : 0u));
+                if (QUIET && lane == 0)
+                    S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && (tic + 1 != en.ntiles || (X.quiet_last && tic != 0))) ? PackSmem::TB_Q : 0u));
             }
             last_skipped = (skipm >> 31) != 0;
         }
@@ -816,6 +829,7 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
         const Col0 cmm = col0_at(X.sc, en.m, en.m);
         S.Sm[a] = cmm.S; S.slm[a] = cmm.sl; S.tbm[a] = cmm.s_tb;
         S.SmKey[a] = pk_from_wide(pk, 0, cmm.S, cmm.sl, 0);
+        S.DmKey[a] = pk.NEGKEY + pk.PD6;
     }
     X.team.sync();
 }
@@ -1078,6 +1092,7 @@ __global__ void __launch_bounds__(W * 32, W <= 8 ? 2 : 1) fill_packed_kernel(con
         X.quiet = P.quiet != 0 && team.size == 1 && !X.cluster_smem;
         X.dynamic = X.quiet && P.quiet >= 2 && X.NT < (1u << 30);
         X.quiet_first = X.quiet && P.quiet_first != 0; X.quiet_edge = X.quiet && !X.dynamic && P.quiet_edge != 0;
+        X.quiet_last = X.quiet && !X.dynamic && P.quiet_last != 0;
         if (tid < 2 * W) S.haloF[tid] = 0;
         if (tid == 0) { S.q[0] = 0; S.q[1] = 0; }
         if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
@@ -1091,7 +1106,7 @@ __global__ void __launch_bounds__(W * 32, W <= 8 ? 2 : 1) fill_packed_kernel(con
                 unpack8(*reinterpret_cast<const uint2 *>(X.bases + e.seq_off + r0), xq);
                 uint32_t bits = 0;
                 STITCH_UNROLL
-                for (int k = 0; k < STRIP; ++k) if (r0 + (uint32_t)k < e.m) bits |= pk_base_bit(xq[k]);
+                for (int k = 0; k < STRIP; ++k) if (r0 + (uint32_t)k + 1 < e.m) bits |= pk_base_bit(xq[k]);   // ordinary rows (i < m) only
                 bits = __reduce_or_sync(FULL, bits);
                 if (lane == 0) S.tb[t] = (uint8_t)bits;
             }
@@ -1193,7 +1208,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
-    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.cstate = nullptr; X.cta_lo = nullptr;
+    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P)
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + TILE;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
-        pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.cstate = nullptr; X.cta_lo = nullptr;
+        pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
         ColRec *colrec = P.colrec + jd.colrec_off;
         int32_t *gcol = P.gcol + jd.gcol_off;
         const uint8_t *read = P.reads + jd.read_off;

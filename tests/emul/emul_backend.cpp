@@ -138,13 +138,14 @@ static void emul_column(const ColumnArgs &A) {
 struct EmulBackend : Backend {
     Aligner &al;
     uint32_t dump_seq = 0;
-    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE;
+    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE, QUIET_LAST;
     explicit EmulBackend(Aligner &a) : al(a) {
         K = std::max<uint32_t>(1, env_u32("EMUL_K", 7));          // checkpoint spacing (columns)
         WINDOW = std::max<uint32_t>(1, env_u32("EMUL_WINDOW", 6));  // columns at the end of the read filled by the wide path
         PACKED = env_u32("EMUL_PACKED", 1);                         // 0: wide path only
         QUIET = env_u32("EMUL_QUIET", 1);                           // 0: the bulk pass never skips quiet tiles
         QUIET_EDGE = env_u32("EMUL_QUIET_EDGE", 1);                 // 0: the first and last tile of a warp chunk are always computed
+        QUIET_LAST = env_u32("EMUL_QUIET_LAST", 1);                 // 0: the last tile of a contig (row m) is always computed
     }
     ~EmulBackend() {
         g_quiet_tiles += q_tiles; g_quiet_skipped += q_skipped; g_quiet_mat += q_mat;
@@ -251,7 +252,7 @@ struct EmulBackend : Backend {
     // tiles; a chunk that starts inside a contig recomputes the chain exit of the strip before it (the halo).
     struct PkState {           // rolling packed state of a set of contigs (tile_start relative to these arrays)
         std::vector<int32_t> S[2], D[2];
-        std::vector<int32_t> cm, Sm, SmKey; std::vector<uint32_t> cml, cmk, slm, tbm;
+        std::vector<int32_t> cm, Sm, SmKey, DmKey; std::vector<uint32_t> cml, cmk, slm, tbm;   // DmKey: D key of row m (latest column)
         // quiet tiles (bulk pass only): flag per tile (state of the latest column is in the closed form), base
         // classes present in the tile (bit 0..3 = A C G T, bit 4 = anything else), closed form of the latest column
         bool quiet_on = false;
@@ -263,9 +264,9 @@ struct EmulBackend : Backend {
     void pk_quiet_setup(const PK &pk, const ContigEntry *ent, uint32_t C, uint32_t NT, PkState &st) {
         const uint8_t *bases = al.contigs.blob.data();
         st.quiet_on = QUIET != 0;
-        st.quiet.assign(NT, 0); st.tmask.assign(NT, 0); st.Q.assign(C, pk_quiet_init(pk));
+        st.quiet.assign(NT, 0); st.tmask.assign(NT, 0); st.Q.assign(C, pk_quiet_init(pk)); st.DmKey.assign(C, pk.NEGKEY + pk.PD6);
         for (uint32_t a = 0; a < C; ++a)
-            for (uint32_t i = 1; i <= ent[a].m; ++i) st.tmask[ent[a].tile_start + (i - 1) / TILE] |= (uint8_t)base_bit(bases[ent[a].seq_off + i - 1]);
+            for (uint32_t i = 1; i < ent[a].m; ++i) st.tmask[ent[a].tile_start + (i - 1) / TILE] |= (uint8_t)base_bit(bases[ent[a].seq_off + i - 1]);   // ordinary rows only
     }
     struct PkCol {
         bool allow_skip = false;                            // bulk: this column may skip quiet tiles (not a checkpoint column)
@@ -342,7 +343,7 @@ struct EmulBackend : Backend {
         }
         std::vector<int32_t> Smat(TILE), Dmat(TILE);
         const std::vector<uint8_t> quiet_old = st.quiet;   // flags of column j-1 (what a chunk reads of its left neighbour chunk)
-        const bool edge_on = quiet_on && QUIET_EDGE != 0;
+        const bool edge_on = quiet_on && QUIET_EDGE != 0, last_on = quiet_on && QUIET_LAST != 0;
         for (uint32_t w = 0; w < Weff; ++w) {
             const uint32_t t_lo = (uint32_t)((uint64_t)NT * w / Weff), t_hi = (uint32_t)((uint64_t)NT * (w + 1) / Weff);
             int32_t prev_exit = 0; uint32_t prev_exit_open = 0;
@@ -361,13 +362,20 @@ struct EmulBackend : Backend {
                 qold_left = qold;
                 if (quiet_on) {
                     ++q_tiles;
-                    if (lastt || (first && !Qn[a].stay_first && Qn[a].stay)) ++q_special; else if (!edge_on && (tile == t_lo || tile + 1 == t_hi)) ++q_boundary; else if (!Qn[a].stay) ++q_nostay;
+                    if ((lastt && !(last_on && !first)) || (first && !Qn[a].stay_first && Qn[a].stay)) ++q_special; else if (!edge_on && (tile == t_lo || tile + 1 == t_hi)) ++q_boundary; else if (!Qn[a].stay) ++q_nostay;
                     else if (!qold) ++q_noself; else if (!qleft) ++q_noleft;
                 }
-                if (quiet_on && !lastt && (edge_on || (tile != t_lo && tile + 1 != t_hi)) && qold && (first ? Qn[a].stay_first != 0 : (qleft && Qn[a].stay))) {
+                if (quiet_on && (!lastt || (last_on && !first)) && (edge_on || (tile != t_lo && tile + 1 != t_hi)) && qold &&
+                    (first ? Qn[a].stay_first != 0 : (qleft && Qn[a].stay))) {
                     const uint32_t mb = base_bit(pc.q);
                     const bool hm = (st.tmask[tile] & mb) != 0, hx = (st.tmask[tile] & ~mb) != 0;
-                    tilemax[tile] = hm ? (hx ? pk_max(Qn[a].bk[0], Qn[a].bk[1]) : Qn[a].bk[0]) : Qn[a].bk[1];
+                    tilemax[tile] = st.tmask[tile] == 0 ? pk.NEGKEY : (hm ? (hx ? pk_max(Qn[a].bk[0], Qn[a].bk[1]) : Qn[a].bk[0]) : Qn[a].bk[1]);
+                    if (lastt) {   // row m: the candidates the tile would have stashed for the per-contig finish
+                        int32_t dm_new;
+                        stash[a] = pk_quiet_rowm(pk, pc, st.Q[a], Jc, st.SmKey[a], st.DmKey[a], sidx(bases[en.seq_off + en.m - 2], 1),
+                                                 bases[en.seq_off + en.m - 1] == pc.q, &dm_new);
+                        st.DmKey[a] = dm_new;
+                    }
                     for (uint32_t r = 0; r < (uint32_t)TILE; ++r) { Sc[tile * TILE + r] = POISON; Dc[tile * TILE + r] = POISON; }
                     prev_skipped = true; ++q_skipped;
                     continue;   // stays quiet
@@ -381,6 +389,10 @@ struct EmulBackend : Backend {
                         int sx[PKQ_L + 1]; sv(xb, 1, sx);
                         Smat[r] = pk_quiet_S(Qp, sx[0]);
                         Dmat[r] = pk_quiet_D(pk, Qp, sx);
+                    }
+                    if (lastt) {   // row m is not in the closed form: its keys of column j-1 are kept per contig
+                        const uint32_t rm = en.m - 1 - tic * TILE;
+                        Smat[rm] = st.SmKey[a]; Dmat[rm] = st.DmKey[a];
                     }
                     SpT = Smat.data() - (size_t)tile * TILE; DpT = Dmat.data() - (size_t)tile * TILE;
                 }
@@ -423,7 +435,7 @@ struct EmulBackend : Backend {
                     }
                 }
                 int32_t tmax = pk.NEGKEY;
-                bool tile_quiet = quiet_on && !lastt; uint32_t nfailS = 0;
+                bool tile_quiet = quiet_on && (!lastt || (last_on && !first)); uint32_t nfailS = 0;
                 for (uint32_t lane = 0; lane < 32; ++lane) {
                     const uint32_t row0 = tic * TILE + lane * STRIP + 1;
                     const uint32_t base = tile * TILE + lane * STRIP;
@@ -464,7 +476,7 @@ struct EmulBackend : Backend {
                     }
                     for (int k = 0; k < nvs[lane]; ++k) {
                         Sc[base + k] = S[k]; Dc[base + k] = strips[lane].D6[k];
-                        if (quiet_on && !lastt) {
+                        if (quiet_on && (!lastt || (last_on && !first))) {
                             int sx[PKQ_L + 1]; sv(xs[lane][k], 0, sx);
                             const bool okc = pk_quiet_cell(pk, Qn[a], deadrel, S[k], strips[lane].D6[k], sx);
                             if (!okc) { const bool sOK = S[k] == Qn[a].bk[sx[0]]; ++q_failcells[sOK ? 1 : 0]; if (!sOK) ++nfailS; if (tile_quiet) { if (sOK) ++q_failD; else ++q_failS; } }
@@ -483,6 +495,7 @@ struct EmulBackend : Backend {
                         const int km = nvs[lane];
                         stash[a] = PkRowM{strips[lane].A[km], strips[lane].D6[km], strips[lane].jp[km], I_m, A.tb ? strips[lane].fl[km] : 0u, iext_m};
                         Dc[base + km] = strips[lane].D6[km];
+                        if (quiet_on) st.DmKey[a] = strips[lane].D6[km];
                     }
                     tmax = pk_max(tmax, colmax);
                 }
