@@ -121,6 +121,7 @@ struct CudaBackend : host::Backend {
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
     uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column; 1: quiet tiles with static
                                  // warp chunks (default); 2: quiet tiles, the runs of computed tiles dealt to the warps from a queue (slower)
+    uint32_t quiet_tail = 1;     // STITCH_QUIET_TAIL=0: the tail columns compute every tile
     uint32_t quiet_first = 1, quiet_edge = 1, quiet_last = 1;   // STITCH_QUIET_FIRST / _EDGE / _LAST = 0: those tiles are always computed
     uint32_t pack_warps = 16;    // STITCH_PACK_WARPS=8: 8-warp CTAs, two per SM (one read each), when no cluster is used
     DevBuf<CkSum> d_cksum;
@@ -171,7 +172,7 @@ struct CudaBackend : host::Backend {
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
         quiet_tiles = env_u32("STITCH_QUIET", quiet_tiles);
-        quiet_first = env_u32("STITCH_QUIET_FIRST", 1); quiet_edge = env_u32("STITCH_QUIET_EDGE", 1); quiet_last = env_u32("STITCH_QUIET_LAST", 1);
+        quiet_first = env_u32("STITCH_QUIET_FIRST", 1); quiet_edge = env_u32("STITCH_QUIET_EDGE", 1); quiet_last = env_u32("STITCH_QUIET_LAST", 1); quiet_tail = env_u32("STITCH_QUIET_TAIL", 1);
         pack_warps = env_u32("STITCH_PACK_WARPS", pack_warps) == 8 ? 8 : 16;
     }
     ~CudaBackend() override {
@@ -460,7 +461,7 @@ struct CudaBackend : host::Backend {
         } else if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes;
-            Q.quiet = quiet_tiles; Q.quiet_first = quiet_first; Q.quiet_edge = quiet_edge; Q.quiet_last = quiet_last;
+            Q.quiet = quiet_tiles; Q.quiet_first = quiet_first; Q.quiet_edge = quiet_edge; Q.quiet_last = quiet_last; Q.quiet_tail = quiet_tail;
             const int pw = half_ctas ? 8 : PACK_WARPS;
             size_t psmem = (PackSmem::bytes(cmax, ntmax, pw, pstage) + 15) / 16 * 16;
             if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads

@@ -530,7 +530,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const uint32_t Weff = NT < GW ? NT : GW;
     const PkQuiet *Qp = S.Q + (par ^ 1u) * S.cmax, *Qn = S.Q + par * S.cmax;
     const long long c0 = cs ? clock64() : 0;
-    if (QUIET && X.dynamic) pk_tiles_dynamic<W>(X, S, pc, r0pkey, cr1key, j, O, yq, cs);
+    if (QUIET && !TB && X.dynamic) pk_tiles_dynamic<W>(X, S, pc, r0pkey, cr1key, j, O, yq, cs);
     else if (gw < Weff) {
         const uint32_t t_lo = (uint32_t)((uint64_t)NT * gw / Weff), t_hi = (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
@@ -883,10 +883,25 @@ __device__ __forceinline__ PkColConst pk_col_const(const PK &pk, const Scoring &
 // ---------------------------------------------------------------------------------------------
 // tail: columns (j0, n] again in the traceback variant
 // ---------------------------------------------------------------------------------------------
+// Closed form of a quiet tile of contig `a` in column j (dp_packed.h) and whether quiet tiles of that contig stay quiet;
+// S.Jc / S.SmKey / S.tbm of the contig are up to date.  `allow` = the column may skip tiles at all.
+__device__ __forceinline__ void pk_quiet_contig(const PackCtx &X, PackSmem &S, uint32_t a, uint32_t j, int32_t B, int32_t Bprev, uint8_t q,
+                                                bool allow) {
+    const uint32_t par = j & 1u;
+    const PkColConst ccl = pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, q);
+    PkFirstIn fi;   // what row 1 of this contig sees beyond an ordinary row
+    fi.r0pkey = ccl.r0pkey; fi.cr1key = ccl.cr1key; fi.wbase = pk_wbase(X.pk, S.SmKey[a]);
+    fi.wrap = X.ent[a].circular && S.tbm[a] != TB_XCLIP_SUFFIX;
+    fi.yc1 = X.yclip_mode ? pk_key(X.pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e - B, PP_YC, col0_slen(X.sc, 1, X.ent[a].m)) : X.pk.NEGKEY;
+    S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, ccl.pc, S.Jc[a], S.Q[(par ^ 1u) * S.cmax + a], allow && pk_base_bit(q) != 16u,
+                                          X.quiet_first ? &fi : nullptr);
+}
+
 // Replays the jump records and column bases the bulk pass left (colrec, gcol).
 template <int W>
 __device__ __forceinline__ void pk_replay_consts(const PackCtx &X, PackSmem &S, const ColRec *colrec, const int32_t *gcol,
-                                                 const uint8_t *read, uint32_t j, uint32_t a_global, uint32_t Cglobal, PkColConst *s_cc) {
+                                                 const uint8_t *read, uint32_t j, uint32_t a_global, uint32_t Cglobal, PkColConst *s_cc,
+                                                 bool tail_quiet = false, bool track = false, int32_t track_thr = 0) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const int32_t B = gcol[j - 1], Bprev = j >= 2 ? gcol[j - 2] : 0;
@@ -896,8 +911,19 @@ __device__ __forceinline__ void pk_replay_consts(const PackCtx &X, PackSmem &S, 
         JumpInfo J; J.score = cr.jscore; J.len = cr.jlen; J.idx = cr.jidx; J.from = cr.jfrom;
         S.Jw[a] = J;
         S.Jc[a] = pk_jc(X.pk, pcl, J.score, J.len);
+        if (tail_quiet) {
+            // quiet tiles in the tail: a skipped tile must not hold a cell that can still set a final y-suffix tracker
+            // (SCA:432-447), and column n leaves the records of every cell for the end-of-read fix-up
+            pk_quiet_contig(X, S, a, j, B, Bprev, read[j - 1], j != X.n);
+            PkQuiet &qn = S.Q[(j & 1u) * S.cmax + a];
+            if (track && pk_abs(X.pk, B, pk_max(qn.bk[0], qn.bk[1])) >= track_thr) { qn.stay = 0; qn.stay_first = 0; }
+        }
     }
-    if (tid == 0) *s_cc = pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, read[j - 1]);
+    if (tid == 0) {
+        *s_cc = pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, read[j - 1]);
+        STITCH_UNROLL
+        for (int k = 0; k < PKQ_L + 2; ++k) s_cc->yq[k] = j >= 1u + (uint32_t)k ? read[j - 1 - (uint32_t)k] : (uint8_t)0;
+    }
 }
 
 // The tail of one job on the CTA that ran its bulk pass (s_cc: one shared PkColConst slot).
@@ -930,14 +956,29 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
         }
     }
     pk_init_halos<W>(X, S, j0 & 1u);
+    // quiet tiles in the tail (same closed form as in the bulk pass; no tile is quiet at the checkpoint): the row-m D keys come
+    // from the state just restored
+    const bool tail_quiet = X.quiet && P.quiet_tail != 0 && X.team.size == 1;
+    if (tail_quiet) {
+        for (uint32_t a = tid; a < C; a += W * 32) {
+            const ContigEntry &e = X.ent[a];
+            const uint32_t r = e.m - 1, mt = e.tile_start + r / TILE, ml = (r % TILE) / STRIP, mk = r % STRIP;
+            S.DmKey[a] = X.Dst[mt * ST + (mk >> 2) * 128u + ml * 4u + (mk & 3u)];
+            S.Q[a] = pk_quiet_init(X.pk); S.Q[S.cmax + a] = pk_quiet_init(X.pk);
+        }
+        for (uint32_t t = tid; t < X.NT; t += W * 32) S.tb[t] = (uint8_t)(S.tb[t] & PackSmem::TB_MASK);
+        if (tid < 2 * W) S.haloF[tid] = 0;
+        if (tid == 0) { S.q[0] = 0; S.q[1] = 0; }
+    }
     X.team.sync();   // trackers of every row initialised before any CTA updates them
     for (uint32_t j = j0 + 1; j <= n; ++j) {
-        pk_replay_consts<W>(X, S, colrec, gcol, read, j, 0, C, s_cc);
+        pk_replay_consts<W>(X, S, colrec, gcol, read, j, 0, C, s_cc, tail_quiet, tracked, track_thr);
         __syncthreads();
         const PkColConst cc = *s_cc;
         PkColOut O; O.tb_col = nullptr; O.colrec_col = colrec + (uint64_t)j * C; O.sn = sn; O.last = P.last + jd.cell_off;
         O.track = tracked; O.lastcol = j == n; O.track_thr = track_thr;
-        pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
+        if (tail_quiet) pk_column<W, true, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O, cc.yq);
+        else pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
     }
 }
 
@@ -962,16 +1003,7 @@ __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, 
             }
             const int32_t Jc = pk_jc(X.pk, pcl, J.score, J.len);
             S.Jc[a] = Jc;
-            if (X.quiet) {   // closed form of a quiet tile of this contig in column j, and whether quiet tiles stay quiet
-                const uint8_t q = read[j - 1];
-                const bool allow = !((j % K == 0) && j < X.n) && pk_base_bit(q) != 16u;
-                const PkColConst ccl = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, q);
-                PkFirstIn fi;   // what row 1 of this contig sees beyond an ordinary row
-                fi.r0pkey = ccl.r0pkey; fi.cr1key = ccl.cr1key; fi.wbase = pk_wbase(X.pk, S.SmKey[a]);
-                fi.wrap = X.ent[a].circular && S.tbm[a] != TB_XCLIP_SUFFIX;
-                fi.yc1 = X.yclip_mode ? pk_key(X.pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e - g, PP_YC, col0_slen(X.sc, 1, X.ent[a].m)) : X.pk.NEGKEY;
-                S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, ccl.pc, Jc, S.Q[(par ^ 1u) * S.cmax + a], allow, X.quiet_first ? &fi : nullptr);
-            }
+            if (X.quiet) pk_quiet_contig(X, S, a, j, g, Bprev, read[j - 1], !((j % K == 0) && j < X.n));   // (not at checkpoint columns)
         }
         if (tid == 0) {
             if (writer) gcol[j - 1] = g;

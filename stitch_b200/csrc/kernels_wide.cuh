@@ -79,6 +79,7 @@ struct Params {
     uint32_t stage_bytes;    // packed kernels: size of the front area of their dynamic shared memory (PackSmem)
     uint32_t cluster_state_smem;   // the rolling state lives in the cluster's shared memory (bytes per CTA), 0 = global memory
     uint32_t quiet;          // packed bulk pass: skip quiet tiles (dp_packed.h), single-CTA teams only (2: dynamic scheduling)
+    uint32_t quiet_tail;     // ... and in the tail columns (traceback variant), for tiles below the tracking threshold
     uint32_t quiet_first, quiet_edge, quiet_last;   // ... also the first / last tile of a contig, the first and last tile of a warp chunk
     unsigned long long *qstats;   // [0] tile-columns of the bulk passes, [1] of those skipped as quiet
     uint32_t *tail_j0;       // per job: the checkpointed column the packed tail restarts from

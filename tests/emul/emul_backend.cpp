@@ -270,6 +270,7 @@ struct EmulBackend : Backend {
     }
     struct PkCol {
         bool allow_skip = false;                            // bulk: this column may skip quiet tiles (not a checkpoint column)
+        bool tail_quiet = false;                            // traceback variant (tail): quiet tiles whose cells stay below track_thr are skipped
         const ContigEntry *ent; uint32_t C, NT; const uint32_t *owner;
         const uint8_t *read; uint32_t j, n; int32_t B, Bprev; const JumpInfo *J;
         bool tb; uint8_t *tb_col; ColRec *colrec_col;       // traceback variant: packed bytes, Lx[j] per contig
@@ -320,7 +321,7 @@ struct EmulBackend : Backend {
         const uint32_t Weff = std::min<uint32_t>((uint32_t)W, NT);
         const bool ycmode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
         // quiet tiles: closed form of this column per contig; sub index of a contig base against y_j, y_{j-1}, y_{j-2}, y_{j-3}
-        const bool quiet_on = st.quiet_on && !A.tb;
+        const bool quiet_on = st.quiet_on && (!A.tb || A.tail_quiet);
         const int32_t deadrel = pk_deadrel(sc);
         // sv(xb, back, s): s[k] = sub index of contig base xb against y_{j-back-k}, k = 0 .. PKQ_L
         auto sidx = [&](uint8_t xb, int back) -> int { return ((int)j - back >= 1 && xb == A.read[j - 1 - (uint32_t)back]) ? 0 : 1; };
@@ -336,6 +337,8 @@ struct EmulBackend : Backend {
                 fi.wrap = A.ent[a].circular && st.tbm[a] != TB_XCLIP_SUFFIX;
                 fi.yc1 = ycmode ? pk_key(pk, (int64_t)sc.yp + sc.o + (int64_t)sc.e - B, PP_YC, col0_slen(sc, 1, A.ent[a].m)) : pk.NEGKEY;
                 Qn[a] = pk_quiet_next(pk, sc, pc, pk_jc(pk, pc, A.J[a].score, A.J[a].len), st.Q[a], allow, &fi);
+                // tail: a skipped tile must not hold a cell that can still set a final y-suffix tracker (SCA:432-447)
+                if (A.tb && A.track && pk_abs(pk, B, pk_max(Qn[a].bk[0], Qn[a].bk[1])) >= A.track_thr) { Qn[a].stay = 0; Qn[a].stay_first = 0; }
                 ++q_why[Qn[a].why & 63]; ++q_delta[(uint32_t)(pc.delta + 32) & 63];
                 if (q_age.size() < C) q_age.assign(C, 0);
                 if (!Qn[a].stay) q_age[a] = 0; else if (q_age[a] < 11) ++q_age[a];
@@ -637,6 +640,8 @@ struct EmulBackend : Backend {
             }
         const std::vector<uint32_t> owner = owners_of(L.ent.data(), C, NT);
         std::vector<JumpInfo> J(C);
+        pk_quiet_setup(pk, L.ent.data(), C, NT, st);   // quiet tiles in the tail: no tile is quiet at the checkpoint
+        for (uint32_t a = 0; a < C; ++a) st.DmKey[a] = st.D[j0 & 1][row_linear(L.ent[a], L.ent[a].m)];
         // every row ends with a tracker value >= max_j G(j) - W' (dp_core.h: first_candidate_column): cells below can be skipped
         int32_t thr = MIN_SCORE;
         if (tracked) {
@@ -651,6 +656,7 @@ struct EmulBackend : Backend {
             A.B = F.gcol[j - 1]; A.Bprev = j >= 2 ? F.gcol[j - 2] : 0; A.J = J.data();
             A.tb = true; A.tb_col = nullptr; A.colrec_col = F.colrec.data() + (size_t)j * C;
             A.track = tracked; A.sn = F.sn.data(); A.lastcol = j == n; A.last = F.last.data(); A.track_thr = thr;
+            A.tail_quiet = true; A.allow_skip = j != n;   // column n: every cell leaves its record for the end-of-read fix-up
             packed_column(pk, A, st);
         }
     }
