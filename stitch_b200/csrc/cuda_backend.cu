@@ -91,6 +91,7 @@ struct CudaBackend : host::Backend {
     uint32_t cmax = 1;
     uint32_t K = 256;        // checkpoint spacing (columns) of the current batch
     uint32_t K_base = 256;   // its default; STITCH_CK_EVERY overrides (tests)
+    bool ck_auto = true;     // no override: a batch that fits in one launch with half the spacing uses K_base / 2
     uint32_t WINDOW = 64;    // columns at the end of the read with y-suffix tracking; STITCH_TRACK_WINDOW
     const uint8_t *device_reads = nullptr;   // set for run_device()
 
@@ -159,6 +160,7 @@ struct CudaBackend : host::Backend {
         d_contigs.reserve(al.contigs.blob.size() + 1024);   // strips of the last tile over-read
         CUDA_CHECK(cudaMemcpy(d_contigs.p, al.contigs.blob.data(), al.contigs.blob.size(), cudaMemcpyHostToDevice));
         d_counter.reserve(8);
+        ck_auto = std::getenv("STITCH_CK_EVERY") == nullptr;
         K_base = std::max<uint32_t>(1, env_u32("STITCH_CK_EVERY", K_base));
         K = K_base;
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
@@ -264,13 +266,27 @@ struct CudaBackend : host::Backend {
         // working memory is per CTA and is budgeted in run_chunk); equal-sized chunks so that no chunk is a sliver
         std::vector<uint64_t> bytes(jobs.size());
         uint64_t total = 0;
-        for (size_t k = 0; k < jobs.size(); ++k) {
-            const bool packed = plan_LB(jobs[k]) != 0;
-            bytes[k] = out_bytes(jobs[k]) + ((fused && packed) ? 0 : need_bytes(need_of(jobs[k], packed)));
-            if (bytes[k] > mem_budget) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
-            total += bytes[k];
-        }
         const uint64_t cap = fused ? mem_budget / 2 : mem_budget;
+        auto size_up = [&]() {
+            total = 0;
+            for (size_t k = 0; k < jobs.size(); ++k) {
+                const bool packed = plan_LB(jobs[k]) != 0;
+                bytes[k] = out_bytes(jobs[k]) + ((fused && packed) ? 0 : need_bytes(need_of(jobs[k], packed)));
+                total += bytes[k];
+            }
+        };
+        // a smaller checkpoint spacing (down to half) when the whole batch still fits in one launch: the tail and the unit re-fills of the
+        // walk (about a quarter of the kernel's time once quiet tiles made the bulk pass cheap) shrink with K; measured on
+        // config 2: 450 vs 431 GCUPS at 592 reads, but 390 vs 430 when the doubled checkpoints split 1000 reads into two launches
+        if (ck_auto && K == K_base && K >= 64) {
+            for (K = K_base / 2; K < K_base; K += K_base / 8) {   // the smallest spacing (in eighths of K_base) that keeps one launch
+                size_up();
+                if (total <= cap) break;
+            }
+        }
+        size_up();
+        for (size_t k = 0; k < jobs.size(); ++k)
+            if (bytes[k] > mem_budget) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
         const uint64_t n_chunks = (total + cap - 1) / cap;
         const uint64_t target = total / n_chunks + 1;
         size_t begin = 0;
