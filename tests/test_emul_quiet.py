@@ -74,3 +74,21 @@ def test_quiet_off_is_identical(oracle, emul_lib, monkeypatch):
     got, exp = run_both(oracle, emul_lib, dict(double_strand=True, circular=True), contigs, reads, 8, raw=False)
     compare(got, exp, "quiet off")
     assert counters(emul_lib, 8)[1] == before[1]
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_quiet_special_tiles(oracle, emul_lib, wide_checkpoints, case):
+    """First / last tiles of contigs and of warp chunks under the closed form: contig lengths around the tile size (row m
+    alone in the last tile, m a multiple of the tile), circular wrap into row 1, all four modes, tie-prone alphabet."""
+    rng = random.Random(88000 + case)
+    kw = [dict(double_strand=True, circular=True), dict(mode=3, circular=True), dict(mode=1, double_strand=True, circular=True),
+          dict(mode=2, circular=True, gap_extend=-3, jump_score_same_contig_and_strand=-6, jump_score_inter_contig=-12)][case]
+    alphabet = b"ACGT" if case % 2 == 0 else b"ACG"
+    contigs = [gen.rand_seq(rng, l, alphabet) for l in (1500, 2305, 2560, 300, 769, 1024)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(300, 420), rng.randint(2, 4), strands=bool(kw.get("double_strand")),
+                               wrap=True, alphabet=alphabet) for _ in range(3)]
+    before = counters(emul_lib, 8)
+    got, exp = run_both(oracle, emul_lib, kw, contigs, reads, 8, raw=False)
+    compare(got, exp, f"special tiles case {case}")
+    after = counters(emul_lib, 8)
+    assert after[1] > before[1]

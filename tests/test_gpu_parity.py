@@ -302,7 +302,7 @@ def test_sam_records_on_gpu(oracle):
             assert sam[r] == exp, f"read {r} {kw} {so}"
 
 
-@pytest.mark.parametrize("case", range(4))
+@pytest.mark.parametrize("case", range(8))
 def test_quiet_tiles_on_gpu(oracle, case):
     """Quiet tiles (dp_packed.h): with the default checkpoint spacing the bulk pass skips the warp tiles that are
     provably in the closed form "jump + substitution score" and re-materialises them when needed.  Same chains
@@ -310,8 +310,13 @@ def test_quiet_tiles_on_gpu(oracle, case):
     rng = random.Random(4400 + case)
     kw = [dict(double_strand=True, circular=True), dict(mode=1, double_strand=True), dict(mode=3, circular=True),
           dict(mode=2, double_strand=True, match_score=2, mismatch_score=-3, gap_open=-4, gap_extend=-3,
-               jump_score_same_contig_and_strand=-8, jump_score_same_contig_opposite_strand=-9, jump_score_inter_contig=-11)][case]
-    contigs = [gen.rand_seq(rng, rng.randint(2300, 3500)) for _ in range(4)] + [gen.rand_seq(rng, 700)]
+               jump_score_same_contig_and_strand=-8, jump_score_same_contig_opposite_strand=-9, jump_score_inter_contig=-11),
+          dict(circular=True), dict(mode=3, double_strand=True, circular=True), dict(mode=1, circular=True, suboptimal=True),
+          dict(mode=2, double_strand=True, circular=True, gap_extend=-3, jump_score_same_contig_and_strand=-6, jump_score_inter_contig=-12)][case]
+    # lengths around the 256-row tile size: row m alone in the last tile (m = 256 k + 1), m a multiple of 256, a two-tile contig
+    contigs = [gen.rand_seq(rng, rng.randint(2300, 3500)) for _ in range(3)] + [gen.rand_seq(rng, l) for l in (700, 2305, 2560, 300)]
+    if case >= 4:   # a lower-complexity alphabet makes score / length ties frequent
+        contigs = [gen.rand_seq(rng, len(c), b"ACG") if k % 2 else c for k, c in enumerate(contigs)]
     reads = [gen.chimeric_read(rng, contigs, rng.randint(700, 1100), rng.randint(2, 4), strands=bool(kw.get("double_strand")),
                                wrap=bool(kw.get("circular"))) for _ in range(5)]
     named = [(f"c{k}", s) for k, s in enumerate(contigs)]
