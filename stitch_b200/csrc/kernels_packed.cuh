@@ -84,7 +84,7 @@ struct PackSmem {
         tilemax = DmKey + cmax;
         haloS = tilemax + ntmax;                             // [2][W][9]
         haloD = haloS + 2 * W * 9;                           // [2][W][8]
-        haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W] (unused)
+        haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W]: quiet flag of the last tile of the previous chunk
         q = haloF + 2 * W;
         runq = q + 2;
         Q = reinterpret_cast<PkQuiet *>(runq + ntmax / 2 + W + 4);
