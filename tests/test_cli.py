@@ -154,3 +154,19 @@ def test_cli_rejects_what_it_cannot_do(cli, tmp_path):
     assert p.returncode != 0 and b"exactly one of --reads-fastq or --reads-fasta" in p.stderr
     p = subprocess.run([CLI, "align", "-f", "a.fq", "-r", "x.fa", "-p"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode != 0 and b"--pre-align is not supported" in p.stderr
+
+
+def test_cli_multi_context_order(cli, tmp_path):
+    """--gpus N: one context and one host thread per device, batches dealt round-robin; the records still come out in
+    input order and equal the single-context output."""
+    rng = random.Random(57)
+    contigs = [gen.rand_seq(rng, rng.randint(150, 300)) for _ in range(3)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(50, 150), rng.randint(1, 3), strands=True, wrap=True) for _ in range(17)]
+    ref, fa = tmp_path / "ref.fa", tmp_path / "reads.fa"
+    ref.write_text("".join(f">c{k}\n{c.decode()}\n" for k, c in enumerate(contigs)))
+    fa.write_text("".join(f">q{k}\n{r.decode()}\n" for k, r in enumerate(reads)))
+    one = [l for l in cli(["-a", str(fa), "-r", str(ref), "-d", "--sam"]).decode().splitlines() if not l.startswith("@PG")]
+    many = [l for l in cli(["-a", str(fa), "-r", str(ref), "-d", "--sam", "--gpus", "3", "--batch", "2"]).decode().splitlines() if not l.startswith("@PG")]
+    assert one == many
+    names = [l.split("\t")[0] for l in one if not l.startswith("@")]
+    assert [n for k, n in enumerate(names) if k == 0 or names[k - 1] != n] == [f"q{k}" for k in range(len(reads))]
