@@ -138,7 +138,7 @@ static void emul_column(const ColumnArgs &A) {
 struct EmulBackend : Backend {
     Aligner &al;
     uint32_t dump_seq = 0;
-    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE, QUIET_LAST;
+    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE, QUIET_LAST, CONE_AUDIT;
     explicit EmulBackend(Aligner &a) : al(a) {
         K = std::max<uint32_t>(1, env_u32("EMUL_K", 7));          // checkpoint spacing (columns)
         WINDOW = std::max<uint32_t>(1, env_u32("EMUL_WINDOW", 6));  // columns at the end of the read filled by the wide path
@@ -146,8 +146,13 @@ struct EmulBackend : Backend {
         QUIET = env_u32("EMUL_QUIET", 1);                           // 0: the bulk pass never skips quiet tiles
         QUIET_EDGE = env_u32("EMUL_QUIET_EDGE", 1);                 // 0: the first and last tile of a warp chunk are always computed
         QUIET_LAST = env_u32("EMUL_QUIET_LAST", 1);                 // 0: the last tile of a contig (row m) is always computed
+        CONE_AUDIT = env_u32("EMUL_CONE_AUDIT", 0);                 // 1: audit the dependency cone of the unit re-fills (experiment)
     }
     ~EmulBackend() {
+        if (CONE_AUDIT && cone_units)
+            std::fprintf(stderr, "[emul cone] units %llu, cone cells %llu, differing bytes %llu, rows in the cone %.1f%% of the rows re-filled\n",
+                         (unsigned long long)cone_units, (unsigned long long)cone_cells, (unsigned long long)cone_bad,
+                         100.0 * (double)cone_window_rows / (double)cone_full_rows);
         g_quiet_tiles += q_tiles; g_quiet_skipped += q_skipped; g_quiet_mat += q_mat;
         if (std::getenv("EMUL_QUIET_STATS") && q_tiles) {
             std::fprintf(stderr, "   why:");
@@ -661,8 +666,12 @@ struct EmulBackend : Backend {
         }
     }
 
+    // EMUL_CONE_AUDIT=1 (experiment for the next round): re-fill the unit a second time while rows above the
+    // dependency cone of the entry cell (i_entry, j) - rows < i_entry - slope * (j - jj) at column jj - are left stale, and check
+    // that the traceback bytes inside the cone do not change.
+    uint64_t cone_units = 0, cone_bad = 0, cone_cells = 0, cone_window_rows = 0, cone_full_rows = 0;
     void load_unit_packed(const Job &job, const Layout &L, uint32_t LB, const Fill &F, uint32_t a, uint32_t j, std::vector<uint8_t> &bytes,
-                          std::vector<ColRec> &ucr, TbUnit &u) {
+                          std::vector<ColRec> &ucr, TbUnit &u, uint32_t i_entry = 0) {
         const Scoring &sc = al.opts.sc;
         const uint32_t C = (uint32_t)L.ent.size(), PM = L.PM(), n = job.n;
         const uint32_t b = (j - 1) / K, jb = b * K, je = std::min(jb + K, n);
@@ -689,6 +698,37 @@ struct EmulBackend : Backend {
             packed_column(pk, A, st);
         }
         u.bytes = bytes.data(); u.cr = ucr.data(); u.a = a; u.jb = jb; u.je = je; u.pm = pm;
+        if (CONE_AUDIT && i_entry >= 1 && i_entry < en.m && !(en.circular)) {
+            const uint32_t slope = (uint32_t)(pk_band(sc) / -sc.e) + 2;   // one row per column for the diagonal + the insertion chain's reach
+            PkState st2;
+            if (b == 0) pk_state_init0(pk, &en, 1, pm, st2);
+            else pk_state_from_ck(pk, &en, &en_ck, 1, pm, jb, F.gcol[jb - 1], F.ck_state.data() + (size_t)(b - 1) * PM,
+                                  F.ck_sum.data() + (size_t)(b - 1) * C + a, st2);
+            std::vector<uint8_t> bytes2((size_t)(je - jb) * pm, 0);
+            std::vector<ColRec> ucr2(je - jb);
+            ++cone_units;
+            for (uint32_t jj = jb + 1; jj <= j; ++jj) {
+                const ColRec &cr = F.colrec[(size_t)jj * C + a];
+                JumpInfo J{cr.jscore, cr.jlen, cr.jidx, cr.jfrom};
+                PkCol A{};
+                A.ent = &en; A.C = 1; A.NT = en.ntiles; A.owner = owner.data(); A.read = job.read; A.j = jj; A.n = n;
+                A.B = F.gcol[jj - 1]; A.Bprev = jj >= 2 ? F.gcol[jj - 2] : 0; A.J = &J;
+                A.tb = true; A.tb_col = bytes2.data() + (size_t)(jj - jb - 1) * pm; A.colrec_col = ucr2.data() + (jj - jb - 1);
+                packed_column(pk, A, st2);
+                const int64_t top = (int64_t)i_entry - (int64_t)slope * (int64_t)(j - jj);   // first row (1-based) of the cone at column jj
+                // rows above the cone are "not computed": they keep what they held one column earlier
+                for (int64_t r = 1; r < top && r <= (int64_t)en.m; ++r) {
+                    st2.S[jj & 1][(size_t)r - 1] = st2.S[(jj - 1) & 1][(size_t)r - 1];
+                    st2.D[jj & 1][(size_t)r - 1] = st2.D[(jj - 1) & 1][(size_t)r - 1];
+                }
+                const uint32_t lo = top < 1 ? 1u : (uint32_t)top;
+                cone_window_rows += i_entry - lo + 1; cone_full_rows += en.m;
+                for (uint32_t r = lo; r <= i_entry; ++r) {
+                    ++cone_cells;
+                    if (bytes2[(size_t)(jj - jb - 1) * pm + r - 1] != bytes[(size_t)(jj - jb - 1) * pm + r - 1]) ++cone_bad;
+                }
+            }
+        }
     }
 
     // Returns the length bits of the packed path, or 0 when the read ran on the wide path.
@@ -779,7 +819,7 @@ struct EmulBackend : Backend {
                 walk_begin(v, a_end, rc.ops.data(), c, ws, rc.h);
                 uint32_t s;
                 while ((s = walk_run(v, ws, rc.h)) == WALK_NEED_UNIT) {
-                    if (LB) load_unit_packed(job, L, LB, F, ws.a, ws.j, unit_bytes, unit_cr, v.unit);
+                    if (LB) load_unit_packed(job, L, LB, F, ws.a, ws.j, unit_bytes, unit_cr, v.unit, ws.i);
                     else load_unit(job, L, F, ws.a, ws.j, unit_bytes, unit_cr, v.unit);
                 }
                 if (s != WALK_OVERFLOW) break;
