@@ -31,9 +31,6 @@ ALG_BYTES_PER_CELL = 0.5         # the traceback stream, <
 # what the fill kernel really moves (ncu profiles/): the rolling column state, one S key and one D key
 # per cell, read and written once per column by every tile that is not skipped as quiet, plus checkpoints and jump records
 STATE_BYTES_PER_CELL = 16.0
-# dram__bytes_read.sum + dram__bytes_write.sum per cell update of fill_packed_kernel with quiet tiles (1.32 TB + 1.84 TB for the
-# 4.73e11 cell updates of 148 config-2 reads; profiles/r01_ncu_fill_packed_quiet_details.txt).  Without quiet tiles: 17.2 B.
-DRAM_BYTES_PER_CELL_NCU = 6.67
 
 
 def read_peaks():
@@ -97,28 +94,105 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(kw, named, reads, sample_len=300, max_threads=None):
-    """Times the restated reference (oracle/, 16-byte cells, one aligner per thread) on host cores."""
+CPU_RATE_EST = 2.0e6   # cell updates / s / thread of the restated reference at n = 10 kb (measured: profiles/r02_cpu_port_vs_n.json)
+
+
+def cpu_baseline(kw, named, reads, truth, budget_s=30.0, max_threads=None):
+    """Times the restated reference (oracle/, 16-byte cells in the reference's own matrix layout, one aligner per thread,
+    as fg-stitch-cli/src/commands/align.rs:345-390 runs them) on host cores, on FULL-LENGTH reads of the workload.
+
+    What bounds the sample is the contig axis, not the read: every thread aligns one whole read against one contig-strand
+    it was drawn from (truncated to fewer rows only when even that exceeds the time budget).  The reference's cost per cell
+    update is set by the read length (it walks its (m+1) x (n+1) traceback matrix with a stride of 16 (n+1) bytes), hardly
+    by the number of contig rows, so CUPS measured this way stand for the whole workload; truncating the READS (round 1)
+    flattered the CPU by 3x (profiles/r02_cpu_port_vs_n.json)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from stitch_b200._abi import make_opts
     T = min(host_threads(), max_threads or 64, len(reads))
-    # 16 B x (n+1) x sum(m+1) of traceback per thread (the reference's allocation)
-    cells = sum(len(s) + 1 for _, s in named) * (2 if kw.get("double_strand") else 1) * (sample_len + 1)
-    try:
+    n = max(len(r) for r in reads[:T])
+    m_full = max(len(s) for _, s in named)
+    rows = int(min(m_full, max(256, budget_s * CPU_RATE_EST / n)))
+    try:   # 16 B x (n+1) x (rows+1) of traceback per thread (the reference's allocation)
         avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
-        T = max(1, min(T, int(avail * 0.5 // (16 * cells))))
+        T = max(1, min(T, int(avail * 0.5 // (16 * (n + 1) * (rows + 1)))))
     except Exception:
         pass
-    sample = [r[:sample_len] for r in reads[:T]]
-    o = oracle_lib.OracleAligners(make_opts(**kw), named)
-    _, info = o.batch(sample, raw=False, threads=T)
+    sample = reads[:T]
+    use = named if rows >= m_full else [(nm, s[:rows]) for nm, s in named]
+    subsets = [[truth[r][0]] for r in range(T)]
+    o = oracle_lib.OracleAligners(make_opts(**kw), use)
+    oracle_lib.set_checker_layout(False)   # the reference's layout: this is the baseline, not a parity check
+    _, info = o.batch(sample, subsets=subsets, raw=False, threads=T)
     gcups = info["cells"] / info["seconds"] / 1e9
     return {"value": gcups, "unit": "GCUPS", "cores": T, "kind": "port",
-            "sample": f"{len(sample)} reads truncated to their first {sample_len} bases (same contigs and options), "
-                      f"one restated-reference aligner per thread, {info['fills']} fills, {info['cells']} cells in "
-                      f"{info['seconds']:.1f} s; the Rust reference itself cannot be built here (no cargo)",
+            "sample": f"{len(sample)} full-length reads ({n} b) of the workload, one per thread, each against one contig-strand it was "
+                      f"drawn from ({'whole, ' + str(m_full) if rows >= m_full else 'first ' + str(rows)} rows; same options; origin "
+                      f"re-alignment fills included): {info['fills']} fills, {info['cells']} cells in {info['seconds']:.1f} s; one "
+                      f"restated-reference aligner per thread, the reference's traceback layout; the Rust reference itself cannot be "
+                      f"built here (no cargo)",
             "seconds": info["seconds"], "cells": info["cells"]}
+
+
+def cpu_sweep(kw, named, reads, truth, lengths=(300, 1000, 3000, 10000)):
+    """CUPS of the restated reference against the read length (reads truncated to n, one contig-strand each)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from stitch_b200._abi import make_opts
+    out = []
+    for threads in (1, min(host_threads(), 16)):
+        for n in lengths:
+            T = min(threads, len(reads))
+            o = oracle_lib.OracleAligners(make_opts(**kw), named)
+            _, info = o.batch([r[:n] for r in reads[:T]], subsets=[[truth[r][0]] for r in range(T)], raw=False, threads=T)
+            out.append({"read_len": n, "threads": T, "cells": info["cells"], "seconds": info["seconds"],
+                        "mcups_per_thread": info["cells"] / info["seconds"] / 1e6 / T})
+    return out
+
+
+def parity_check(al, kw, named, reads, truth, e2e_chains, n_check=4, pool=32):
+    """After the timed region: `n_check` reads of the batch the e2e step just aligned, aligned again on the GPU restricted
+    (subset_words) to the contig-strands they use plus two decoys, bit for bit against the oracle on the same subsets
+    (all 40 strands would cost the oracle 51 GB per read); the subset score must equal the score of the timed e2e result."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import random
+    import oracle_lib
+    from stitch_b200._abi import make_opts
+    ns = len(named) * (2 if kw.get("double_strand") else 1)
+    rng = random.Random(1)
+    pool = min(pool, len(reads))
+    subsets = []
+    for r in range(pool):
+        a = e2e_chains[r][0]
+        mine = set(truth[r]) | {a.start_contig_idx, a.end_contig_idx} | {x for k, x, _ in a.ops if k == 6}
+        subsets.append(sorted(mine | set(rng.sample([c for c in range(ns) if c not in mine], 2))))
+    check = sorted(range(pool), key=lambda r: (len(subsets[r]), r))[:n_check]
+    got = al.align_batch([reads[r] for r in check], [subsets[r] for r in check])
+    oracle_lib.set_checker_layout(True)
+    try:
+        exp, info = oracle_lib.OracleAligners(make_opts(**kw), named).batch([reads[r] for r in check], subsets=[subsets[r] for r in check],
+                                                                            raw=False, threads=min(n_check, host_threads()))
+    finally:
+        oracle_lib.set_checker_layout(False)
+    ok = all(len(g) == len(e) and all(x.key() == y.key() for x, y in zip(g, e)) for g, e in zip(got, exp))
+    same_score = all(got[k][0].score == e2e_chains[r][0].score for k, r in enumerate(check))
+    return {"reads": len(check), "ok": bool(ok and same_score), "bit_exact_vs_oracle": bool(ok), "score_equals_timed_e2e_result": bool(same_score),
+            "read_indices": check, "subset_sizes": [len(subsets[r]) for r in check], "oracle_seconds": info["seconds"],
+            "how": "GPU align_batch with per-read subset_words vs oracle/ on the same subsets, every field and operation of every chain"}
+
+
+def workload_config(args, kw, named, world, read_len):
+    """The `config` object of the JSON line: identical for both arms (the arms describe their own samples elsewhere)."""
+    workload = {1: "config1: 10 kb chimeric reads vs 20 plasmids (7-9 kb), single strand, local",
+                2: "config2: 10 kb chimeric reads vs 20 plasmids (7-9 kb), --double-strand --circular, local",
+                3: "config3 slice: 5-20 kb reads vs 128 contigs x 2 strands (reference limit of 256 contig-strands)",
+                4: "config4: 50-100 kb reads vs 50 x 20 kb contigs, --double-strand",
+                6: "config2 reads vs a shared-backbone panel (every contig = 60 % common backbone + 40 % unique insert), -d -C"}[args.config]
+    return {"workload": workload, "reads_per_gpu_per_step": args.reads, "read_len": read_len,
+            "contig_strands": len(named) * (2 if kw.get("double_strand") else 1),
+            "l2": "inputs larger than L2: the rolling state of the reads in flight (148 x 2.6 MB) is streamed by every computed "
+                  "tile-column and a step touches > 100 GB of checkpoints; no flush needed",
+            "parallelism": f"reads sharded over {world} GPU(s), no collective"}
 
 
 def main():
@@ -131,32 +205,35 @@ def main():
     ap.add_argument("--read-len", type=int, default=None)
     ap.add_argument("--impl", default="stitch_b200", choices=["stitch_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-len", type=int, default=300)
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=30.0, help="CPU seconds the cpu_baseline sample is sized for")
+    ap.add_argument("--cpu-sweep", action="store_true", help="print the CPU port's CUPS against the read length and exit")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from stitch_b200 import synth
-    workload = {1: "config1: 10 kb chimeric reads vs 20 plasmids (7-9 kb), single strand, local",
-                2: "config2: 10 kb chimeric reads vs 20 plasmids (7-9 kb), --double-strand --circular, local",
-                3: "config3 slice: 5-20 kb reads vs 128 contigs x 2 strands (reference limit of 256 contig-strands)",
-                4: "config4: 50-100 kb reads vs 50 x 20 kb contigs, --double-strand"}[args.config]
+
+    if args.cpu_sweep:
+        truth = []
+        kw, named, reads = synth.config(args.config, max(host_threads(), 1), args.read_len, truth=truth)
+        print(json.dumps({"cpu_port_vs_read_len": cpu_sweep(kw, named, reads, truth), "host_threads": host_threads(),
+                          "note": "restated reference (oracle/), one read per thread against one contig-strand; reads truncated to read_len"}))
+        return 0
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        kw, named, reads = synth.config(args.config, max(host_threads(), 1), args.read_len)
+        truth = []
+        kw, named, reads = synth.config(args.config, max(host_threads(), 1), args.read_len, truth=truth)
+        n_steps = args.warmup + args.steps
+        budget = max(2.0, min(30.0, 200.0 / max(1, n_steps)))   # the whole run ends within a few minutes
         vals = []
-        base = None
-        for step in range(args.warmup + args.steps):
-            base = cpu_baseline(kw, named, reads, args.cpu_sample_len)
+        for step in range(n_steps):
+            base = cpu_baseline(kw, named, reads, truth, budget)
             if step >= args.warmup:
                 vals.append(base)
-            if base["seconds"] * (args.warmup + args.steps) > 240 and step == 0:
-                # keep the whole run within a few minutes: one measured step stands for all
-                vals = [base]
-                break
         cells = sum(v["cells"] for v in vals)
         secs = sum(v["seconds"] for v in vals)
         g = cells / secs / 1e9
@@ -165,7 +242,9 @@ def main():
         line = {"impl": "reference", "metric": "GCUPS", "value": g, "unit": "GCUPS", "n_gpus": args.gpus,
                 "steps": len(vals), "warmup": args.warmup, "ms_per_step": secs / len(vals) * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": workload, "note": "restated reference on host cores (the Rust reference cannot be built: no cargo/rustc)"},
+                "config": workload_config(args, kw, named, max(1, args.gpus), len(reads[0])),
+                "note": "restated reference on host cores (the Rust reference cannot be built: no cargo/rustc); each step is a bounded "
+                        "sample of the workload (see cpu_baseline.sample)",
                 "reads_per_s_extrapolated": g * 1e9 / cells_per_read,
                 "cpu_baseline": base,
                 "e2e": {"value": g, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -185,9 +264,10 @@ def main():
     from stitch_b200 import _abi, _lib
     lib = _lib.load()
     from stitch_b200 import sharding
-    kw, named, all_reads = synth.config(args.config, args.reads * world, args.read_len)
+    all_truth = []
+    kw, named, all_reads = synth.config(args.config, args.reads * world, args.read_len, truth=all_truth)
     lo, hi = sharding.block_range(len(all_reads), rank, world)   # contiguous block per rank; no data-path collective
-    reads = all_reads[lo:hi]
+    reads, truth = all_reads[lo:hi], all_truth[lo:hi]
     targets = [stitch_b200.TargetSeq(n, s) for n, s in named]
     al = stitch_b200.Builder(**kw).build_aligners(targets, device=local_rank)
 
@@ -210,13 +290,16 @@ def main():
         return al.stats()
 
     host_buf, host_offs = _abi.pack_reads(reads)   # e2e: host buffers in, chains out
+    kept = {"res": None}                            # the results of the latest e2e step (read back after the timed region)
 
     def step_e2e():
         res = C.c_void_p()
         rc = lib.stitch_align_batch(al._h, host_buf, host_offs, len(reads), None, 0, C.byref(res))
         if rc != 0:
             raise RuntimeError(al.last_error())
-        lib.stitch_free_results(res)
+        if kept["res"] is not None:
+            lib.stitch_free_results(kept["res"])
+        kept["res"] = res
         return al.stats()
 
     def barrier():
@@ -272,18 +355,20 @@ def main():
         launches_fill = max(1, agg["packed_launches"])   # fill_packed_kernel launches in the timed region (one per chunk of reads)
         ach = agg["packed_cells"] * ALG_BYTES_PER_CELL / fill_s / 1e9 if fill_s > 0 else 0.0
         skipped_frac = agg["quiet_tile_columns"] / agg["tile_columns"] if agg["tile_columns"] else 0.0
+        # HBM traffic of the fill kernel per launch, from the counters of the run itself: every computed tile-column reads and
+        # writes its 2 KB of rolling state (a materialised tile only writes; counted as read + write: an upper bound), plus the
+        # checkpoints and jump records (traceback_bytes), the tail columns and unit re-fills of the walk not included
+        state_bytes = (agg["tile_columns"] - agg["quiet_tile_columns"]) * 2.0 * 2048.0
+        traffic_est = (state_bytes + agg["tb_bytes"]) / launches_fill
         gops = C.c_double(0)
         lib.stitch_measure_int32_peak(local_rank, C.byref(gops))
+        cfg = workload_config(args, kw, named, world, len(reads[0]))
+        cfg["cells_per_step"] = agg["cells_all"] / args.steps
         line = {
             "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload, "reads_per_gpu_per_step": len(reads), "read_len": len(reads[0]),
-                       "contig_strands": len(named) * (2 if kw.get("double_strand") else 1),
-                       "cells_per_step": agg["cells_all"] / args.steps,
-                       "l2": "inputs larger than L2: the rolling state of the reads in flight (148 x 2.6 MB) is streamed by every computed "
-                             "tile-column and a step touches > 100 GB of checkpoints; no flush needed",
-                       "parallelism": f"reads sharded over {world} GPU(s), no collective"},
+            "config": cfg,
             "reads_per_s": len(reads) * world * args.steps / dt,
             "clocks": clocks,
             "e2e": {"value": gcups_e, "unit": "GCUPS", "reads_per_s": len(reads) * world * args.steps / dt_e,
@@ -291,7 +376,7 @@ def main():
                     "fills_per_step": agg_e["fills"] / args.steps, "ms_per_step": dt_e / args.steps * 1e3},
             "gpu_launches": agg["launches_all"],
             "quiet_tiles": {"tile_columns": agg["tile_columns"], "skipped": agg["quiet_tile_columns"],
-                            "frac_skipped": agg["quiet_tile_columns"] / agg["tile_columns"] if agg["tile_columns"] else 0.0,
+                            "frac_skipped": skipped_frac,
                             "note": "bulk pass of fill_packed_kernel on this rank: (256-row tile, column) pairs proven to be in the closed form "
                                     "jump + substitution score and therefore neither loaded, computed nor stored (dp_packed.h, PkQuiet); "
                                     "GCUPS counts every cell of every fill, as the metric defines it"},
@@ -301,30 +386,39 @@ def main():
                                    "packed_kernel_gcups": (agg["packed_cells"] / (agg["packed_ms"] * 1e-3) / 1e9) if agg["packed_ms"] else None},
             "roofline": {"bound": "hbm", "kernel": "fill_packed_kernel", "achieved": ach, "peak": peaks.get("hbm_gbs"),
                          "unit": "GB/s", "frac": ach / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None,
-                         "traffic": DRAM_BYTES_PER_CELL_NCU * agg["packed_cells"] / launches_fill,
+                         "traffic": traffic_est,
+                         "traffic_source": "derived in this run from the kernel's own counters: computed tile-columns x 4 KB (2 KB of rolling "
+                                           "state read + written) + checkpoint and jump-record bytes; the ncu capture of the same kernel is "
+                                           "under profiles/ (dram__bytes_read + dram__bytes_write per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": ALG_BYTES_PER_CELL,
                          "avg_launch_ms": agg["packed_ms"] / launches_fill if launches_fill else None, "kernel_gcups": fill_gcups,
                          "state_stream_gbs": fill_gcups * STATE_BYTES_PER_CELL * (1.0 - skipped_frac),
                          "state_stream_frac_of_peak": fill_gcups * STATE_BYTES_PER_CELL * (1.0 - skipped_frac) / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None,
                          "note": "achieved = 0.5 B x cell updates / CUDA-event time of fill_packed_kernel (one launch per step; its time "
-                                 "includes the tail columns and the in-kernel fix-up/walk phase). traffic = 6.67 B per cell update (ncu, this "
-                                 "kernel) x cell updates per launch: the rolling column state (16 B per cell update of a computed tile) is "
-                                 "streamed through HBM because a read's state (2.6 MB) does not fit one SM; quiet tiles (about 60 % of the "
-                                 "tile-columns on this workload) are neither loaded nor stored. With them the kernel is no longer HBM-bound "
-                                 "(ncu: DRAM 23 % of peak, issue slots 39 %, top stalls: CTA barriers, fixed-latency dependencies, long "
-                                 "scoreboard): see int_roofline and DESIGN.md section 4"},
+                                 "includes the tail columns and the in-kernel fix-up/walk phase). The rolling column state (16 B per cell "
+                                 "update of a computed tile) is streamed through HBM because a read's state (2.6 MB) does not fit one SM; "
+                                 "quiet tiles are neither loaded nor stored. With them the kernel is not HBM-bound: see int_roofline and "
+                                 "DESIGN.md section 4"},
             "int_roofline": {"bound": "int32", "achieved": fill_gcups * ALG_OPS_PER_CELL, "peak": gops.value,
                              "unit": "Gop/s", "frac": fill_gcups * ALG_OPS_PER_CELL / gops.value if gops.value else None,
                              "ops_per_cell": ALG_OPS_PER_CELL,
                              "peak_source": "stitch_measure_int32_peak (add+max issue-rate microbenchmark, measured in this run)"},
         }
+        if not args.no_parity_check:
+            try:
+                e2e_chains = _lib.read_results(lib, _lib.PRODUCT_RESULTS, kept["res"])
+                line["parity_check"] = parity_check(al, kw, named, reads, truth, e2e_chains)
+            except Exception as e:
+                line["parity_check"] = {"reads": 0, "ok": False, "error": str(e)}
         if not args.no_cpu_baseline and world >= 1:
             try:
-                line["cpu_baseline"] = cpu_baseline(kw, named, all_reads, args.cpu_sample_len)
+                line["cpu_baseline"] = cpu_baseline(kw, named, all_reads, all_truth, args.cpu_budget_s)
             except Exception as e:   # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line))
+    if kept["res"] is not None:
+        lib.stitch_free_results(kept["res"])
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

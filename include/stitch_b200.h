@@ -149,6 +149,12 @@ void stitch_results_read(const stitch_results *r, uint32_t read, uint64_t *first
 const stitch_chain *stitch_results_chains(const stitch_results *r, uint64_t *n_chains);
 const stitch_op *stitch_results_ops(const stitch_results *r, uint64_t *n_ops);
 void stitch_free_results(stitch_results *r);
+/* A results handle holding ONE read with the given chains (copied; ops_offset of chain k indexes `ops`).  Alignment is a
+ * plain public struct in the reference (LIB/align/alignment.rs:16-51) and SamRecordFormatter::format takes any
+ * &[Alignment] (mod.rs:622-627): this is how a caller formats chains it built or edited itself (n_chains = 0: the
+ * unmapped record). */
+int stitch_results_from_chains(const stitch_chain *chains, uint32_t n_chains, const stitch_op *ops, uint64_t n_ops,
+                               stitch_results **out);
 
 /* Options of the SAM record layer: Options.{soft_clip,use_eq_and_x,pick_primary,filter_secondary,filter_secondary_pct},
  * LIB/align/aligners/mod.rs:106-115 (defaults: false, false, query-length, false, 10.0). */

@@ -84,6 +84,8 @@ struct oracle_aligner {
 extern "C" {
 
 const char *oracle_last_error(void) { return g_err.c_str(); }
+// 0 (default): the reference's traceback layout (what the CPU baseline is timed on); 1: column-major (parity checks only)
+void oracle_set_checker_layout(int colmajor) { SingleContig::g_checker_layout = colmajor != 0; }
 
 // scoring = {match, mismatch, gap_open, gap_extend, jump}; mode 0..3 = the SCA mode wrappers
 // (single_contig_aligner.rs:733-872), which also filter the free clip ops.

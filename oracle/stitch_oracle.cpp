@@ -74,6 +74,8 @@ uint32_t Cell::from() const { return (uint32_t)((w1 >> 31) & L27); }
 // ---------------------------------------------------------------------------------------------
 // SingleContig
 // ---------------------------------------------------------------------------------------------
+bool SingleContig::g_checker_layout = false;
+
 void SingleContig::init_matrices(int64_t m, int64_t n) {   // SCA:97-186
     // traceback.init: every cell = START / len 0 / idx 0 / from 0 (traceback/mod.rs:93-100)
     rows = m + 1;

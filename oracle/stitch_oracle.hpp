@@ -93,12 +93,16 @@ struct SingleContig {
     std::vector<int32_t> Sn;
     std::vector<Cell> tb;      // (m+1) x (n+1), row-major in i (traceback/mod.rs:102-114)
     int64_t rows = 0, cols = 0;
+    // The reference stores cell (i, j) at i * cols + j and fills column by column (a stride of 16 (n+1) bytes per inner
+    // step): that is the layout the CPU BASELINE is timed on.  The parity tests on full-length reads set
+    // g_checker_layout (oracle_set_checker_layout): cell (i, j) at j * rows + i, same values, several times faster.
+    static bool g_checker_layout;
     Scoring sc;
     uint32_t contig_idx = 0;
     bool circular = false;
 
-    Cell &cell(int64_t i, int64_t j) { return tb[(size_t)(i * cols + j)]; }
-    const Cell &cell(int64_t i, int64_t j) const { return tb[(size_t)(i * cols + j)]; }
+    Cell &cell(int64_t i, int64_t j) { return tb[(size_t)(g_checker_layout ? j * rows + i : i * cols + j)]; }
+    const Cell &cell(int64_t i, int64_t j) const { return tb[(size_t)(g_checker_layout ? j * rows + i : i * cols + j)]; }
 
     void init_matrices(int64_t m, int64_t n);                                      // :97-186
     void init_column(int64_t j, int curr, int64_t m, int64_t n);                   // :188-239

@@ -148,7 +148,7 @@ class Aligners:
             raise StitchError(f"stitch_align_batch failed ({rc}): {self.last_error()}")
         try:
             chains = _lib.read_results(self._lib, _lib.PRODUCT_RESULTS, res)
-            sam = [_lib.format_sam(self._lib, "stitch_", self._h, res, r, headers[r], bytes(reads[r]).upper(),
+            sam = [_lib.format_sam(self._lib, "stitch_", self._h, res, r, headers[r], bytes(reads[r]),
                                    None if quals is None else quals[r], None, sam_opts) for r in range(len(reads))]
             return chains, sam
         finally:

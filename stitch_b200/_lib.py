@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = [
     "stitch_results_n_reads", "stitch_results_read", "stitch_results_chains", "stitch_results_ops",
     "stitch_free_results", "stitch_get_stats", "stitch_set_max_inflight", "stitch_destroy",
     "stitch_last_error", "stitch_abi_version", "stitch_measure_int32_peak", "stitch_format_sam", "stitch_free_text",
+    "stitch_results_from_chains",
 ]
 
 _lib = None
@@ -39,6 +40,29 @@ def declare_results_api(lib, prefix_map):
     free = getattr(lib, prefix_map["free"])
     free.restype = None
     free.argtypes = [C.c_void_p]
+
+
+def results_from_chains(lib, prefix, chains):
+    """A results handle (one read) holding `chains` (Alignment objects); free it with <prefix>free_results."""
+    n_ops = sum(len(a.ops) for a in chains)
+    ch = (StitchChain * max(1, len(chains)))()
+    ops = (StitchOp * max(1, n_ops))()
+    k = 0
+    for c, a in enumerate(chains):
+        ch[c] = StitchChain(score=a.score, xstart=a.xstart, xend=a.xend, ystart=a.ystart, yend=a.yend, xlen=a.xlen, ylen=a.ylen,
+                            start_contig_idx=a.start_contig_idx, end_contig_idx=a.end_contig_idx, length=a.length,
+                            n_ops=len(a.ops), ops_offset=k)
+        for kind, x, y in a.ops:
+            ops[k] = StitchOp(kind, x, y)
+            k += 1
+    f = getattr(lib, prefix + "results_from_chains")
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    out = C.c_void_p()
+    rc = f(ch, len(chains), ops, n_ops, C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"results_from_chains failed ({rc})")
+    return out
 
 
 def declare_sam_api(lib, prefix):

@@ -85,6 +85,25 @@ const stitch_op *STITCH_API(results_ops)(const stitch_results *r, uint64_t *n) {
     *n = r->res.ops.size(); return r->res.ops.data();
 }
 void STITCH_API(free_results)(stitch_results *r) { delete r; }
+int STITCH_API(results_from_chains)(const stitch_chain *chains, uint32_t n_chains, const stitch_op *ops, uint64_t n_ops, stitch_results **out) {
+    if (!out || (n_chains && !chains) || (n_ops && !ops)) return STITCH_ERR_INVALID;
+    for (uint32_t c = 0; c < n_chains; ++c)
+        if (chains[c].ops_offset > n_ops || chains[c].n_ops > n_ops - chains[c].ops_offset) return STITCH_ERR_INVALID;
+    try {
+        std::unique_ptr<stitch_results> r(new stitch_results());
+        r->res.begin_read();
+        for (uint32_t c = 0; c < n_chains; ++c) {
+            stitch_chain ch = chains[c];
+            const uint64_t src = ch.ops_offset;
+            ch.ops_offset = r->res.ops.size();
+            r->res.ops.insert(r->res.ops.end(), ops + src, ops + src + ch.n_ops);
+            r->res.chains.push_back(ch);
+            r->res.count.back() += 1;
+        }
+        *out = r.release();
+        return STITCH_OK;
+    } catch (const std::exception &) { return STITCH_ERR_NOMEM; }
+}
 
 int STITCH_API(format_sam)(stitch_ctx *ctx, const stitch_results *res, uint32_t read, const char *read_header, const uint8_t *bases,
                            const uint8_t *quals, uint32_t n_bases, int has_pre_align_score, int32_t pre_align_score,

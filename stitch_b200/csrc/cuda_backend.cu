@@ -38,7 +38,6 @@ using host::Error;
 constexpr int FILL_WARPS = 8;
 constexpr int PACK_WARPS = 16;
 constexpr int WALK_WARPS = 16;
-constexpr int FUSED_WARPS = 8;
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -109,22 +108,17 @@ struct CudaBackend : host::Backend {
     DevBuf<unsigned long long> d_dbg, d_qstats;
     bool debug_stats = false;
     DevBuf<ColRec> d_ucr;
-    size_t l2_persist_max = 0, l2_window_max = 0;
-    uint32_t l2_persist = 0;   // STITCH_L2_PERSIST=1: pin the rolling state of the packed kernel in the L2 (measured: no gain)
     uint32_t use_packed = 1;   // STITCH_PACKED=0 forces the wide kernels (tests)
     uint32_t walk_in_kernel = 1;   // STITCH_WALK_IN_KERNEL=0: separate fix-up / walk kernels after the packed fill
-    uint32_t use_fused = 0;    // STITCH_FUSED=1: one persistent kernel per read (fill, tail, fix-up, walk; per-CTA arenas); measured slower
     // STITCH_CLUSTER: CTAs per read in the packed kernel (1, 2, 4, 8, 16); 0 = automatic: one CTA per read when there are
     // enough reads to fill the GPU (measured best on config 2), a cluster per read when there are only a few (the origin
     // re-alignment fills, small batches), with the rolling state in the cluster's shared memory when it fits
     uint32_t cluster_pref = 0;
     uint32_t cluster_min_tiles = 4 * PACK_WARPS;   // STITCH_CLUSTER_MIN_TILES: smaller layouts use one CTA per read
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
-    uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column; 1: quiet tiles with static
-                                 // warp chunks (default); 2: quiet tiles, the runs of computed tiles dealt to the warps from a queue (slower)
+    uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
     uint32_t quiet_tail = 1;     // STITCH_QUIET_TAIL=0: the tail columns compute every tile
     uint32_t quiet_first = 1, quiet_edge = 1, quiet_last = 1;   // STITCH_QUIET_FIRST / _EDGE / _LAST = 0: those tiles are always computed
-    uint32_t pack_warps = 16;    // STITCH_PACK_WARPS=8: 8-warp CTAs, two per SM (one read each), when no cluster is used
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
     DevBuf<ColRec> d_colrec;
@@ -153,8 +147,6 @@ struct CudaBackend : host::Backend {
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
         num_sms = prop.multiProcessorCount;
-        l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-        l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
         d_contigs.reserve(al.contigs.blob.size() + 1024);   // strips of the last tile over-read
@@ -165,17 +157,13 @@ struct CudaBackend : host::Backend {
         K = K_base;
         WINDOW = std::max<uint32_t>(1, env_u32("STITCH_TRACK_WINDOW", WINDOW));
         use_packed = env_u32("STITCH_PACKED", 1);
-        use_fused = env_u32("STITCH_FUSED", 0);
         walk_in_kernel = env_u32("STITCH_WALK_IN_KERNEL", 1);
         debug_stats = env_u32("STITCH_DEBUG_STATS", 0) != 0;
-        l2_persist = env_u32("STITCH_L2_PERSIST", 0);
-        if (l2_persist && l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
         cluster_pref = std::min<uint32_t>(16, env_u32("STITCH_CLUSTER", cluster_pref));
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
         quiet_tiles = env_u32("STITCH_QUIET", quiet_tiles);
         quiet_first = env_u32("STITCH_QUIET_FIRST", 1); quiet_edge = env_u32("STITCH_QUIET_EDGE", 1); quiet_last = env_u32("STITCH_QUIET_LAST", 1); quiet_tail = env_u32("STITCH_QUIET_TAIL", 1);
-        pack_warps = env_u32("STITCH_PACK_WARPS", pack_warps) == 8 ? 8 : 16;
     }
     ~CudaBackend() override {
         cudaSetDevice(device);
@@ -210,6 +198,9 @@ struct CudaBackend : host::Backend {
         uploaded_layouts = Ls.size();
     }
 
+    // opt-in dynamic shared memory of an sm_100 CTA (227 KB) minus the kernels' static shared memory
+    static constexpr size_t SMEM_LIMIT = 227 * 1024 - 2048;
+    static constexpr uint32_t K_MAX = 8192;   // the walk stages 21 bytes per column of a unit in shared memory
     uint32_t blocks_of(uint32_t n) const { return (n + K - 1) / K; }
     uint32_t plan_LB(const host::Job &j) const {   // length bits of the packed path, 0 = wide path
         if (!use_packed) return 0;
@@ -217,12 +208,12 @@ struct CudaBackend : host::Backend {
         uint32_t m_max = 0;
         for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
         const uint32_t LB = pk_plan(al.opts.sc, j.n, m_max);
-        // shared memory of the packed kernels: tile table + cp.async stage buffers + the walk phase's staging of one
-        // contig's bases; otherwise the read takes the (slow, exact) wide path
-        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) + UnitStage::bytes(4 * K_base, m_max / (uint32_t)TILE + 1) > 216 * 1024) return 0;
+        // shared memory of the packed fill: per-contig / per-tile tables + cp.async stage buffers; otherwise the read takes the
+        // (slow, exact) wide path.  The walk phase's staging is optional: run_chunk sizes it with the real K and falls back
+        // to the separate walk kernel (or to unstaged contig bases) when it does not fit.
+        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) > SMEM_LIMIT) return 0;
         return LB;
     }
-    bool fused_path() const { return use_fused && cluster_pref <= 1; }
     // records a read holds from its fill until its walk is done (CellState/ColRec/... counts)
     // ck: wide checkpoints (CellState records); pck: packed checkpoints (raw keys, 2 per cell)
     struct Need { uint64_t colrec, cell, ck, cksum, gcol, pck; };
@@ -253,7 +244,7 @@ struct CudaBackend : host::Backend {
                               d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_pck.cap * 4;
         mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.85);
         // checkpoint spacing: K_base columns, widened so that no read holds more than ~512 MB of checkpoints
-        // (long reads against large references: config 4 is 100 kb x 2 M rows)
+        // (long reads against large references: config 4 is 100 kb x 2 M rows), up to K_MAX
         K = K_base;
         for (const auto &j : jobs) {
             const uint64_t per_ck = (uint64_t)al.layouts.layouts[j.layout].PM() * 8;
@@ -261,17 +252,15 @@ struct CudaBackend : host::Backend {
             const uint64_t need_K = ((uint64_t)j.n + max_cks) / (max_cks + 1);
             if (need_K > K) K = (uint32_t)((need_K + K_base - 1) / K_base * K_base);
         }
-        const bool fused = fused_path();
-        // chunks: per-read records of the reads that are not on the fused path + the outputs of all (the fused path's
-        // working memory is per CTA and is budgeted in run_chunk); equal-sized chunks so that no chunk is a sliver
+        if (K > K_MAX && K_base <= K_MAX) K = K_MAX / K_base * K_base;
+        // equal-sized chunks (so that no chunk is a sliver) of per-read records + outputs
         std::vector<uint64_t> bytes(jobs.size());
         uint64_t total = 0;
-        const uint64_t cap = fused ? mem_budget / 2 : mem_budget;
+        const uint64_t cap = mem_budget;
         auto size_up = [&]() {
             total = 0;
             for (size_t k = 0; k < jobs.size(); ++k) {
-                const bool packed = plan_LB(jobs[k]) != 0;
-                bytes[k] = out_bytes(jobs[k]) + ((fused && packed) ? 0 : need_bytes(need_of(jobs[k], packed)));
+                bytes[k] = out_bytes(jobs[k]) + need_bytes(need_of(jobs[k], plan_LB(jobs[k]) != 0));
                 total += bytes[k];
             }
         };
@@ -296,6 +285,7 @@ struct CudaBackend : host::Backend {
                 if (end > begin && (used + bytes[end] > cap || used >= target || (max_inflight && end - begin >= max_inflight))) break;
                 used += bytes[end]; ++end;
             }
+            struct ScaleGuard { uint32_t &s; ~ScaleGuard() { s = 1; } } guard{ops_scale};   // (also when a retry throws)
             run_chunk(jobs, begin, end, out);
             begin = end;
         }
@@ -304,6 +294,7 @@ struct CudaBackend : host::Backend {
 
     template <typename KernelT>
     void set_smem(KernelT kernel, size_t smem) {
+        if (smem > SMEM_LIMIT + 2048) throw Error(STITCH_ERR_LIMIT, "shared memory of a kernel exceeds 227 KB (contig table or checkpoint spacing too large)");
         if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
 
@@ -312,9 +303,8 @@ struct CudaBackend : host::Backend {
         const auto &Ls = al.layouts.layouts;
         h_jobs.reserve(nj); h_order.reserve(4 * (size_t)nj + 16);
         const bool tracked = al.opts.sc.ys != MIN_SCORE;
-        const bool fused = fused_path();
-        uint64_t reads_b = 0, ops_n = 0, chains_n = 0, pm_max = 0, unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0, per_job_bytes = 0;
-        Need tot{0, 0, 0, 0, 0, 0}, arena{0, 0, 0, 0, 0, 0};
+        uint64_t reads_b = 0, ops_n = 0, chains_n = 0, pm_max = 0, unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0;
+        Need tot{0, 0, 0, 0, 0, 0};
         uint32_t n_packed = 0, ntmax = 1, max_ctiles = 1;
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
@@ -340,14 +330,9 @@ struct CudaBackend : host::Backend {
                 stats.packed_cells += L.cells_per_col * j.n; ++n_packed;
                 ntmax = std::max(ntmax, L.n_tiles); ppm_max = std::max<uint64_t>(ppm_max, L.PM());
             }
-            if (d.LB && fused) {   // records live in the CTA's arena
-                arena.colrec = std::max(arena.colrec, nd.colrec); arena.cell = std::max(arena.cell, nd.cell); arena.pck = std::max(arena.pck, nd.pck);
-                arena.cksum = std::max(arena.cksum, nd.cksum); arena.gcol = std::max(arena.gcol, nd.gcol);
-            } else {
-                tot.colrec += nd.colrec; tot.cell += nd.cell; tot.ck += nd.ck; tot.pck += nd.pck; tot.cksum += nd.cksum; tot.gcol += nd.gcol;
-                handsum_n += C; per_job_bytes += need_bytes(nd);
-                pm_max = std::max<uint64_t>(pm_max, L.PM());
-            }
+            tot.colrec += nd.colrec; tot.cell += nd.cell; tot.ck += nd.ck; tot.pck += nd.pck; tot.cksum += nd.cksum; tot.gcol += nd.gcol;
+            handsum_n += C;
+            pm_max = std::max<uint64_t>(pm_max, L.PM());
             h_jobs.p[k] = d;
             reads_b += round_up(j.n, 16);
             ops_n += d.ops_cap; chains_n += d.max_chains;
@@ -364,25 +349,18 @@ struct CudaBackend : host::Backend {
         uint32_t *po = h_order.p + nj, *wo = po + n_packed, *ro = wo + n_wide;
         { uint32_t a = 0, b = 0; for (uint32_t k = 0; k < nj; ++k) { if (h_jobs.p[h_order.p[k]].LB) po[a++] = h_order.p[k]; else wo[b++] = h_order.p[k]; } }
 
-        // grids.  Fused path: two 8-warp CTAs per SM, each with its own arena; clustered path: one team per read.
-        const uint32_t wgrid = std::min<uint32_t>(nj, (uint32_t)num_sms);   // walk / wide kernels
+        // grids: one CTA (or one thread-block cluster) per packed read; two 8-warp CTAs per SM for the wide fill
+        const uint32_t wgrid = std::min<uint32_t>(nj, (uint32_t)num_sms);                     // walk kernel
+        const uint32_t wide_grid = std::min<uint32_t>(n_wide, 2 * (uint32_t)num_sms);         // wide fill (and its re-runs: n_redo <= n_wide)
         uint32_t cluster = cluster_pref;
         if (cluster == 0) {   // automatic: the largest cluster that still gives every read its own team in one wave
             cluster = 1;
-            if (!fused) while (cluster < 16 && (uint64_t)n_packed * cluster * 2 <= (uint64_t)num_sms * 3 / 4) cluster *= 2;
+            while (cluster < 16 && (uint64_t)n_packed * cluster * 2 <= (uint64_t)num_sms * 3 / 4) cluster *= 2;
         }
         if (ntmax < cluster_min_tiles) cluster = 1;
-        uint32_t fgrid = 0, pteams = 0;
+        uint32_t pteams = 0;
         size_t cstate_bytes = 0, pstage = PackSmem::default_stage(PACK_WARPS);
-        const size_t fsmem_tables = (PackSmem::bytes(cmax, ntmax, FUSED_WARPS, PackSmem::default_stage(FUSED_WARPS)) + 15) / 16 * 16;
-        const size_t fsmem = fsmem_tables + UnitStage::bytes(K, max_ctiles);
-        if (n_packed && fused) {
-            fgrid = std::min<uint32_t>(n_packed, (uint32_t)num_sms * (fsmem <= 110 * 1024 ? 2 : 1));
-            const uint64_t per_cta = need_bytes(arena) + 2 * ppm_max * 4 + unit_max + 2 * (uint64_t)max_ctiles * TILE * 4 + K * sizeof(ColRec);
-            const uint64_t avail = mem_budget > per_job_bytes + ops_n * sizeof(OutOp) ? mem_budget - per_job_bytes - ops_n * sizeof(OutOp) : 0;
-            if (per_cta > avail) throw Error(STITCH_ERR_NOMEM, "one read's checkpoints do not fit in device memory");
-            fgrid = (uint32_t)std::min<uint64_t>(fgrid, avail / per_cta);
-        } else if (n_packed) {
+        if (n_packed) {
             pteams = std::min<uint32_t>(n_packed, (uint32_t)num_sms / cluster);
             if (cluster > 1) {
                 cudaLaunchConfig_t cfg = {};
@@ -406,29 +384,32 @@ struct CudaBackend : host::Backend {
                 if (debug_stats) std::fprintf(stderr, "[stitch dbg] cluster %u: max active clusters %d, state in smem %zu B/CTA\n", cluster, max_clusters, cstate_bytes);
             }
         }
-        const bool packed_walks_in_kernel = !fused && walk_in_kernel && cluster == 1 && n_packed > 0;
-        // 8-warp CTAs, two per SM: while one read is in the serial phases of a column (jump selection, per-contig finish,
-        // barriers) the other one's tiles keep the SM busy
-        bool half_ctas = false;
-        if (!fused && n_packed && cluster == 1 && pack_warps == 8) {
-            const size_t st8 = PackSmem::default_stage(8);
-            const size_t sm8 = (PackSmem::bytes(cmax, ntmax, 8, st8) + 15) / 16 * 16 + (packed_walks_in_kernel ? UnitStage::bytes(K, max_ctiles) : 0);
-            if (2 * (sm8 + 1024) <= 227 * 1024) { half_ctas = true; pstage = st8; pteams = std::min<uint32_t>(n_packed, 2u * (uint32_t)num_sms); }
+        // shared memory of the packed fill, and of its walk phase (per-unit staging of K columns + the unit's contig bases) when
+        // that fits beside it with the real K and the longest contig of this chunk; otherwise the separate walk kernel runs
+        size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS, pstage) + 15) / 16 * 16;
+        bool packed_walks_in_kernel = walk_in_kernel && cluster == 1 && n_packed > 0;
+        bool pstage_bases = true;
+        if (packed_walks_in_kernel) {
+            if (psmem + UnitStage::bytes(K, max_ctiles, true) > SMEM_LIMIT) pstage_bases = false;
+            if (psmem + UnitStage::bytes(K, max_ctiles, pstage_bases) > SMEM_LIMIT) packed_walks_in_kernel = false;
         }
-        const uint32_t bufgrid = std::max(std::max(wgrid, fgrid), packed_walks_in_kernel ? pteams : 0u);   // CTAs that own walk buffers
+        const uint32_t n_post = packed_walks_in_kernel ? n_wide : nj;   // reads walked by the separate fix-up / walk kernels
+        const uint32_t bufgrid = std::max(n_post ? wgrid : 0u, packed_walks_in_kernel ? pteams : 0u);   // CTAs that own walk buffers
         d_jobs.reserve(nj); d_order.reserve(4 * (size_t)nj + 16);
-        d_colrec.reserve(tot.colrec + (uint64_t)fgrid * arena.colrec); d_last.reserve(tot.cell + (uint64_t)fgrid * arena.cell);
-        d_sn.reserve(tot.cell + (uint64_t)fgrid * arena.cell); d_ck.reserve(tot.ck + 64); d_pck.reserve(tot.pck + (uint64_t)fgrid * arena.pck + 64);
-        d_cksum.reserve(tot.cksum + (uint64_t)fgrid * arena.cksum); d_gcol.reserve(tot.gcol + (uint64_t)fgrid * arena.gcol);
+        d_colrec.reserve(tot.colrec); d_last.reserve(tot.cell);
+        d_sn.reserve(tot.cell); d_ck.reserve(tot.ck + 64); d_pck.reserve(tot.pck + 64);
+        d_cksum.reserve(tot.cksum); d_gcol.reserve(tot.gcol);
         d_ops.reserve(ops_n); d_chains.reserve(chains_n); d_jobout.reserve(nj);
-        d_state.reserve((uint64_t)wgrid * 2 * pm_max + 64);
+        // wide rolling state: one pair of column buffers per CTA of the LARGEST grid that indexes it (wide fill / re-runs by
+        // blockIdx, wide unit re-fills of the walk kernel)
+        d_state.reserve((uint64_t)std::max(wide_grid, n_wide ? wgrid : 0u) * 2 * pm_max + 64);
         d_hand.reserve(64); d_handsum.reserve(handsum_n + 64);   // (hand-over buffers of the retired packed -> wide tail)
-        d_pstate.reserve((uint64_t)std::max(fgrid, pteams) * 2 * ppm_max + 64);
+        d_pstate.reserve((uint64_t)pteams * 2 * ppm_max + 64);
         d_tailj0.reserve(nj);
         const uint64_t wps_half = (uint64_t)max_ctiles * TILE;
         d_wpstate.reserve((uint64_t)bufgrid * 2 * wps_half + 64);
         d_ucr.reserve((uint64_t)bufgrid * K + 64);
-        d_unit.reserve((uint64_t)bufgrid * round_up(unit_max, 256));
+        d_unit.reserve((uint64_t)bufgrid * round_up(unit_max, 256) + 64);
         if (!device_reads) { d_reads.reserve(reads_b); h_reads.reserve(reads_b); }
         h_ops.reserve(ops_n); h_chains.reserve(chains_n); h_jobout.reserve(nj);
 
@@ -458,74 +439,46 @@ struct CudaBackend : host::Backend {
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
         P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1;
-        P.arena.colrec_base = tot.colrec; P.arena.colrec_stride = arena.colrec; P.arena.cell_base = tot.cell; P.arena.cell_stride = arena.cell;
-        P.arena.ck_base = tot.pck; P.arena.ck_stride = arena.pck; P.arena.cksum_base = tot.cksum; P.arena.cksum_stride = arena.cksum;
-        P.arena.gcol_base = tot.gcol; P.arena.gcol_stride = arena.gcol;
         if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
         set_smem(fill_wide_kernel<FILL_WARPS>, smem);
         mark(T_PACKED);
-        if (n_packed && fused) {
-            // the whole pipeline of the packed reads in one persistent kernel (fill, tail, fix-up, walk)
-            Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
-            Q.walk_stage_smem_off = (uint32_t)fsmem_tables; Q.stage_bytes = (uint32_t)PackSmem::default_stage(FUSED_WARPS);
-            set_smem(align_packed_kernel<FUSED_WARPS>, fsmem);
-            align_packed_kernel<FUSED_WARPS><<<fgrid, FUSED_WARPS * 32, fsmem, stream>>>(Q);
-            CUDA_CHECK(cudaGetLastError());
-            stats.launches += 1; stats.packed_launches += 1;
-        } else if (n_packed) {
+        if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
             Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes;
             Q.quiet = quiet_tiles; Q.quiet_first = quiet_first; Q.quiet_edge = quiet_edge; Q.quiet_last = quiet_last; Q.quiet_tail = quiet_tail;
-            const int pw = half_ctas ? 8 : PACK_WARPS;
-            size_t psmem = (PackSmem::bytes(cmax, ntmax, pw, pstage) + 15) / 16 * 16;
             if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads
                 d_done.reserve(nj);
                 CUDA_CHECK(cudaMemsetAsync(d_done.p, 0, nj * sizeof(uint32_t), stream));
                 Q.done = d_done.p;
-                Q.walk_stage_smem_off = (uint32_t)psmem;
-                psmem += UnitStage::bytes(K, max_ctiles);
+                Q.walk_stage_smem_off = (uint32_t)psmem; Q.unit_stage_bases = pstage_bases ? 1u : 0u;
+                psmem += UnitStage::bytes(K, max_ctiles, pstage_bases);
             }
-            if (half_ctas) set_smem(fill_packed_kernel<8>, psmem); else set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
+            set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(pw * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
-            cudaLaunchAttribute at[2];
+            cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(PACK_WARPS * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;
+            cudaLaunchAttribute at[1];
             unsigned na = 0;
             if (cluster > 1) {
                 at[na].id = cudaLaunchAttributeClusterDimension;
                 at[na].val.clusterDim.x = cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
                 ++na;
             }
-            if (l2_persist && l2_persist_max && l2_window_max) {
-                // pin (a fraction of) the rolling column state in the L2 (measured: no gain on B200)
-                const size_t bytes = (size_t)pteams * 2 * ppm_max * sizeof(int32_t);
-                const size_t win = std::min(bytes, l2_window_max);
-                at[na].id = cudaLaunchAttributeAccessPolicyWindow;
-                at[na].val.accessPolicyWindow.base_ptr = d_pstate.p;
-                at[na].val.accessPolicyWindow.num_bytes = win;
-                at[na].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)l2_persist_max * 0.9 / (double)win);
-                at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                ++na;
-            }
             cfg.attrs = at; cfg.numAttrs = na;
-            if (half_ctas) CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<8>, Q));
-            else CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, fill_packed_kernel<PACK_WARPS>, Q));
             stats.launches += 1; stats.packed_launches += 1;
         }
         mark(T_WIDE);
         if (n_wide) {
             // jobs outside the packed regime run on the wide kernel
             Params Q = P; Q.order = d_order.p + nj + n_packed; Q.n_jobs = n_wide;
-            fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_wide, 2 * (uint32_t)num_sms), FILL_WARPS * 32, smem, stream>>>(Q);
+            fill_wide_kernel<FILL_WARPS><<<wide_grid, FILL_WARPS * 32, smem, stream>>>(Q);
             CUDA_CHECK(cudaGetLastError());
             stats.launches += 1;
         }
         // fix-up and walk kernels: the wide reads, plus the packed ones when their kernel did not do it itself
-        const bool packed_done = fused || packed_walks_in_kernel;
-        const uint32_t n_post = packed_done ? n_wide : nj;
-        const uint32_t *post_order = packed_done ? d_order.p + nj + n_packed : d_order.p;
+        const uint32_t *post_order = packed_walks_in_kernel ? d_order.p + nj + n_packed : d_order.p;
         mark(T_FIXUP);
         if (n_post) {
             Params Q = P; Q.order = post_order; Q.n_jobs = n_post;
@@ -556,7 +509,7 @@ struct CudaBackend : host::Backend {
                 CUDA_CHECK(cudaMemcpyAsync(d_redo.p, h_redo.p, nj * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
                 Params Q = P; Q.order = d_order.p + 2 * (size_t)nj; Q.n_jobs = n_redo; Q.force_full = 1; Q.counter = d_counter.p + 1;
                 Q.redo_j0 = d_redo.p;
-                fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_redo, 2 * (uint32_t)num_sms), FILL_WARPS * 32, smem, stream>>>(Q);
+                fill_wide_kernel<FILL_WARPS><<<std::min<uint32_t>(n_redo, wide_grid), FILL_WARPS * 32, smem, stream>>>(Q);
                 CUDA_CHECK(cudaGetLastError());
                 fixup_kernel<<<n_redo, 64, 0, stream>>>(Q);
                 CUDA_CHECK(cudaGetLastError());
@@ -569,7 +522,11 @@ struct CudaBackend : host::Backend {
             size_t wsmem = std::max(WideSmem<WALK_WARPS>::bytes(1), PackSmem::bytes(1, max_ctiles, WALK_WARPS, 0));
             wsmem = (wsmem + 15) / 16 * 16;
             Wp.walk_stage_smem_off = (uint32_t)wsmem;
-            wsmem += (UnitStage::bytes(K, max_ctiles) + 15) / 16 * 16;
+            // the per-unit staging: K columns of records always (K <= K_MAX), the contig's bases only when they fit (only packed
+            // re-fills read them; a contig beyond ~190 kb is read from global memory instead)
+            const bool wstage_bases = n_post > n_wide && wsmem + UnitStage::bytes(K, max_ctiles, true) <= SMEM_LIMIT;
+            Wp.unit_stage_bases = wstage_bases ? 1u : 0u;
+            wsmem += (UnitStage::bytes(K, max_ctiles, wstage_bases) + 15) / 16 * 16;
             const size_t state_b = 2 * wps_half * sizeof(int32_t);
             if (wsmem + state_b <= 160 * 1024) { Wp.walk_state_smem_off = (uint32_t)wsmem; wsmem += state_b; }
             set_smem(walk_kernel<WALK_WARPS>, wsmem);
@@ -592,13 +549,13 @@ struct CudaBackend : host::Backend {
         if (debug_stats) {
             unsigned long long h[16];
             cudaMemcpy(h, d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
-            std::fprintf(stderr, "[stitch dbg] jobs %u (fused grid %u): tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, "
-                         "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, fgrid, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
+            std::fprintf(stderr, "[stitch dbg] jobs %u (K %u): tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, "
+                         "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, K, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
                          h[4] * 1e-6, h[5] * 1e-6);
             std::fprintf(stderr, "[stitch dbg] bulk columns, Mcycles summed over reads: select %.1f, tile phase %.1f (mean warp busy %.1f), per-contig finish %.1f (warp 0: tile maxima reduced at %.1f, look-ups done at %.1f, row m done at %.1f)\n",
                          h[7] * 1e-6, h[8] * 1e-6, h[10] * 1e-6, h[9] * 1e-6, h[13] * 1e-6, h[11] * 1e-6, h[12] * 1e-6);
         }
-        stats.tb_bytes += tot.ck * sizeof(CellState) + (tot.pck + (uint64_t)fgrid * arena.pck) * 4 + (tot.colrec + (uint64_t)fgrid * arena.colrec) * sizeof(ColRec);
+        stats.tb_bytes += tot.ck * sizeof(CellState) + tot.pck * 4 + tot.colrec * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);
 
         bool overflow = false;
@@ -609,10 +566,9 @@ struct CudaBackend : host::Backend {
         }
         if (overflow) {
             if (ops_scale >= 64) throw Error(STITCH_ERR_INTERNAL, "operation buffer overflow");
-            ops_scale *= 4;   // rare: rerun the chunk with larger operation buffers
+            ops_scale *= 4;   // rare: rerun the chunk with larger operation buffers (run() resets the scale after the chunk)
             for (size_t k = begin; k < end; ++k) out[k] = host::JobResult();
             run_chunk(jobs, begin, end, out);
-            ops_scale = 1;
             return;
         }
         for (uint32_t k = 0; k < nj; ++k) {

@@ -56,7 +56,6 @@ struct PackSmem {
     // bits 6..7 what the tile does in the current column (0 skip, 1 materialise, 2 load); owned by the tile's warp
     uint8_t *tb;
     static constexpr uint32_t TB_MASK = 31u, TB_Q = 32u;
-    uint32_t *runq, *q;     // dynamic tile scheduling: first tiles of the runs of computed tiles of a column; q[0] = runs, q[1] = cursor
     ContigEntry *ent_s;     // [cmax]: the layout's contig table (bulk pass: no global loads in the per-column serial phases)
     uint16_t *owner_s;      // [ntmax]: contig position of every tile
     uint32_t cmax;
@@ -67,8 +66,7 @@ struct PackSmem {
     static size_t default_stage(int W) { return (size_t)W * 2 * STAGE_BYTES; }
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
         return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 9 + ntmax + 2 * W * 18) +
-               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 3 * (size_t)ntmax +
-               4 * ((size_t)ntmax / 2 + W + 8) + 64;
+               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 3 * (size_t)ntmax + 4 * 8 + 64;
     }
     __device__ void carve(unsigned char *raw, uint32_t cmax_, uint32_t ntmax, int W, size_t stage_bytes) {
         const uint32_t cmax = cmax_;
@@ -85,9 +83,7 @@ struct PackSmem {
         haloS = tilemax + ntmax;                             // [2][W][9]
         haloD = haloS + 2 * W * 9;                           // [2][W][8]
         haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W]: quiet flag of the last tile of the previous chunk
-        q = haloF + 2 * W;
-        runq = q + 2;
-        Q = reinterpret_cast<PkQuiet *>(runq + ntmax / 2 + W + 4);
+        Q = reinterpret_cast<PkQuiet *>(haloF + 2 * W + 2);
         ent_s = reinterpret_cast<ContigEntry *>(Q + 2 * cmax);
         owner_s = reinterpret_cast<uint16_t *>(ent_s + cmax);
         tb = reinterpret_cast<uint8_t *>(owner_s + ntmax);
@@ -118,7 +114,6 @@ struct PackCtx {            // uniform per (job, set of contigs)
     uint32_t own_lo, own_hi, warps;
     bool cluster_smem;
     bool quiet;             // the bulk pass may skip quiet tiles (single-CTA teams with the state in global memory)
-    bool dynamic;           // ... and deals the runs of computed tiles of a column to the warps from a queue
     bool quiet_first, quiet_edge, quiet_last;   // the first / last tile of a contig, the first and last tile of a warp chunk may be skipped too
     int32_t *cstate;
     const uint32_t *cta_lo;   // shared memory: first tile of every CTA of the team, [size + 1]
@@ -361,163 +356,6 @@ __device__ void pk_init_halos(const PackCtx &X, PackSmem &S, uint32_t slot) {
 // S.Sm/slm/tbm/SmKey describe column j and the CTA is synchronised.
 __device__ __forceinline__ uint32_t pk_base_bit(uint8_t b) { return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 16u; }
 
-// Tile phase of one column with quiet tiles and dynamic scheduling (single-CTA teams, state in global memory).
-// Every warp plans its static chunk of tiles (one tile per lane: skip / materialise / load, as in pk_column) and posts the
-// first tile of every RUN of consecutive computed tiles to a queue; after a CTA barrier the warps pull runs from the queue.
-// A run is independent of everything to its left: it starts at a chunk start (halo of the previous column in shared
-// memory), at the first tile of a contig, or after a skipped tile (closed form of the neighbour, dead chain).  Within a
-// run the tiles are walked in order with the diagonal / chain carried in registers.  The warp that computes the last
-// tile of a chunk publishes the halo of the next chunk.  Which tiles are skipped does not depend on the scheduling.
-template <int W>
-__device__ __forceinline__ void pk_tiles_dynamic(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t r0pkey, int32_t cr1key, uint32_t j,
-                                                 const PkColOut &O, const uint8_t *yq, PkColStat *cs) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t NT = X.NT, par = j & 1u;
-    const uint32_t Weff = NT < (uint32_t)W ? NT : (uint32_t)W;
-    const PkQuiet *Qp = S.Q + (par ^ 1u) * S.cmax, *Qn = S.Q + par * S.cmax;
-    constexpr uint32_t NONE = 0xffffffffu;
-    // ---- plan ----
-    if (warp < Weff) {
-        const uint32_t t_lo = (uint32_t)((uint64_t)NT * warp / Weff), t_hi = (uint32_t)((uint64_t)NT * (warp + 1) / Weff);
-        const uint32_t mb = pk_base_bit(pc.q);
-        for (uint32_t t = t_lo + lane; t < t_hi; t += 32) {
-            uint32_t mode = 2;
-            const uint32_t tbv = S.tb[t];
-            if (tbv & PackSmem::TB_Q) {
-                const uint32_t a_t = X.owner[t];
-                const uint32_t tic = t - X.ent[a_t].tile_start;
-                const PkQuiet &qn = Qn[a_t];
-                // (the first tile of a contig has no upper neighbour but four more conditions: stay_first)
-                mode = (tic + 1 != X.ent[a_t].ntiles && t != t_lo && t + 1 != t_hi &&
-                        (tic == 0 ? qn.stay_first != 0 : ((S.tb[t - 1] & PackSmem::TB_Q) && qn.stay))) ? 0u : 1u;
-                if (mode == 0) {
-                    const uint32_t tm = tbv & PackSmem::TB_MASK;
-                    S.tilemax[t] = (tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1];
-                }
-            }
-            S.tb[t] = (uint8_t)((tbv & 63u) | (mode << 6));
-        }
-        __syncwarp();
-        uint32_t nskipped = 0, prev_dense = 0;
-        for (uint32_t base = t_lo; base < t_hi; base += 32) {
-            const uint32_t nb = t_hi - base, validm = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-            const uint32_t m0 = base + lane < t_hi ? (uint32_t)S.tb[base + lane] >> 6 : 0u;
-            const uint32_t dm = __ballot_sync(FULL, m0 != 0u) & validm;
-            nskipped += __popc(~dm & validm);
-            const uint32_t starts = dm & ~((dm << 1) | prev_dense);
-            const uint32_t ns = __popc(starts);
-            if (ns) {
-                uint32_t slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&S.q[0], ns);
-                slot0 = __shfl_sync(FULL, slot0, 0);
-                if (lane < ns) S.runq[slot0 + lane] = base + __fns(starts, 0, (int)lane + 1);
-            }
-            prev_dense = dm >> 31;
-        }
-        if (cs && lane == 0 && nskipped) atomicAdd(&cs->skipped, nskipped);
-    }
-    __syncthreads();
-    // ---- pull ----
-    const uint32_t q_n = S.q[0];
-    const bool staged = X.staged;
-    unsigned char *stg0 = S.stage + (size_t)warp * 2 * PackSmem::STAGE_BYTES;
-    auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot) {
-        unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
-        __pipeline_memcpy_async(d + lane * 16, X.Sst + t * ST + lane * 4, 16);
-        __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * ST + 128 + lane * 4, 16);
-        __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * ST + lane * 4, 16);
-        __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * ST + 128 + lane * 4, 16);
-        __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
-        __pipeline_commit();
-    };
-    auto pull = [&]() -> uint32_t {
-        uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(&S.q[1], 1u);
-        return __shfl_sync(FULL, r, 0);
-    };
-    auto leading_ones = [](uint32_t m) -> uint32_t { return m == 0xffffffffu ? 32u : (uint32_t)__ffs((int)~m) - 1u; };
-    PkQuietArgs qz; qz.mat = false; qz.prev_skipped = false; qz.Qp = Qp; qz.Qn = Qn; qz.yq = yq; qz.deadrel = pk_deadrel(X.sc);
-    uint32_t a = 0;
-    ContigEntry en = X.ent[0];
-    int32_t Jc = S.Jc[0];
-    uint32_t pf_tile = NONE, pf_slot = 1;   // the latest prefetch: tile and stage slot
-    uint32_t r_cur = pull();
-    while (r_cur < q_n) {
-        const uint32_t r_next = pull();   // one run ahead: its first tile is prefetched while this run ends
-        uint32_t next_first_load = NONE;
-        if (r_next < q_n) { const uint32_t tn = S.runq[r_next]; if (((uint32_t)S.tb[tn] >> 6) == 2u) next_first_load = tn; }
-        const uint32_t ts = S.runq[r_cur];
-        const uint32_t c = (uint32_t)((((uint64_t)ts + 1) * Weff - 1) / NT);   // the static chunk the run lies in
-        const uint32_t c_lo = (uint32_t)((uint64_t)NT * c / Weff), c_hi = (uint32_t)((uint64_t)NT * (c + 1) / Weff);
-        const int32_t *hS = S.haloS + ((par ^ 1u) * W + c) * 9, *hD = S.haloD + ((par ^ 1u) * W + c) * 8;
-        int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
-        bool run_on = true;
-        for (uint32_t base = ts; run_on && base < c_hi; base += 32) {
-            const uint32_t nb = c_hi - base, validm = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-            const uint32_t m0 = base + lane < c_hi ? (uint32_t)S.tb[base + lane] >> 6 : 0u;
-            const uint32_t m1 = base + 32 + lane < c_hi ? (uint32_t)S.tb[base + 32 + lane] >> 6 : 0u;
-            const uint32_t dm = __ballot_sync(FULL, m0 != 0u) & validm, dm1 = __ballot_sync(FULL, m1 != 0u);
-            const uint32_t rl = leading_ones(dm);                       // tiles of the run in this block
-            const uint32_t runm = rl == 32u ? 0xffffffffu : ((1u << rl) - 1u);
-            const uint32_t loadm = __ballot_sync(FULL, m0 == 2u) & runm;
-            uint32_t loadm_next = __ballot_sync(FULL, m1 == 2u);
-            if (rl == 32u) { const uint32_t rl1 = leading_ones(dm1); loadm_next &= rl1 == 32u ? 0xffffffffu : ((1u << rl1) - 1u); }
-            else { loadm_next = 0; run_on = false; }
-            for (uint32_t b = 0; b < rl; ++b) {
-                const uint32_t tile = base + b;
-                const bool is_load = (loadm >> b) & 1u;
-                qz.prev_skipped = tile == ts && ts != c_lo;   // (the first tile of a contig ignores it)
-                if (tile < en.tile_start || tile >= en.tile_start + en.ntiles) { a = X.owner[tile]; en = X.ent[a]; Jc = S.Jc[a]; }
-                uint32_t cur_slot = 0;
-                if (staged && is_load) {
-                    if (pf_tile != tile) { pf_slot ^= 1u; prefetch(tile, en, pf_slot); pf_tile = tile; }
-                    cur_slot = pf_slot;
-                }
-                bool issued = false;
-                if (staged) {
-                    const uint32_t rest = b == 31u ? 0u : (loadm & ~((2u << b) - 1u));
-                    uint32_t nl = NONE;
-                    if (rest) nl = base + (uint32_t)__ffs((int)rest) - 1u;
-                    else if (loadm_next) nl = base + 32u + (uint32_t)__ffs((int)loadm_next) - 1u;
-                    else if (!run_on || base + 32u >= c_hi) nl = next_first_load;
-                    if (nl != NONE && nl != pf_tile) {
-                        pf_slot ^= 1u;
-                        if (nl >= en.tile_start && nl < en.tile_start + en.ntiles) prefetch(nl, en, pf_slot);
-                        else { const ContigEntry e2 = X.ent[X.owner[nl]]; prefetch(nl, e2, pf_slot); }
-                        pf_tile = nl; issued = true;
-                    }
-                }
-                const unsigned char *stg = nullptr;
-                if (staged && is_load) {
-                    if (issued) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-                    stg = stg0 + cur_slot * PackSmem::STAGE_BYTES;
-                }
-                qz.mat = !is_load;
-                qz.Qp = Qp + a; qz.Qn = Qn + a;
-                const uint32_t tic = tile - en.tile_start;
-                bool qnow;
-                if (tic == 0 || tic + 1 == en.ntiles)
-                    qnow = pk_tile<true, false, true>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == c_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-                else
-                    qnow = pk_tile<false, false, true>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == c_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-                if (lane == 0) S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && tic + 1 != en.ntiles) ? PackSmem::TB_Q : 0u));
-                if (tile + 1 == c_hi && c + 1 < Weff) {   // halo of the next chunk for the next column, read back from the state just written
-                    int32_t *nS = S.haloS + (par * W + c + 1) * 9, *nD = S.haloD + (par * W + c + 1) * 8;
-                    const int32_t *tp = X.Sst + tile * ST;
-                    if (lane == 31) {
-                        const int4 s0 = *reinterpret_cast<const int4 *>(tp + 31 * 4), s1 = *reinterpret_cast<const int4 *>(tp + 128 + 31 * 4);
-                        const int4 d0 = *reinterpret_cast<const int4 *>(tp + TILE + 31 * 4), d1 = *reinterpret_cast<const int4 *>(tp + TILE + 128 + 31 * 4);
-                        nS[1] = s0.x; nS[2] = s0.y; nS[3] = s0.z; nS[4] = s0.w; nS[5] = s1.x; nS[6] = s1.y; nS[7] = s1.z; nS[8] = s1.w;
-                        nD[0] = d0.x; nD[1] = d0.y; nD[2] = d0.z; nD[3] = d0.w; nD[4] = d1.x; nD[5] = d1.y; nD[6] = d1.z; nD[7] = d1.w;
-                    }
-                    if (lane == 30) nS[0] = tp[128 + 30 * 4 + 3];
-                }
-            }
-        }
-        r_cur = r_next;
-    }
-}
-
 template <int W, bool TB, bool QUIET = false>
 __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t r0pkey, int32_t cr1key, uint32_t j,
                           const PkColOut &O, const uint8_t *yq = nullptr, PkColStat *cs = nullptr) {
@@ -530,8 +368,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const uint32_t Weff = NT < GW ? NT : GW;
     const PkQuiet *Qp = S.Q + (par ^ 1u) * S.cmax, *Qn = S.Q + par * S.cmax;
     const long long c0 = cs ? clock64() : 0;
-    if (QUIET && !TB && X.dynamic) pk_tiles_dynamic<W>(X, S, pc, r0pkey, cr1key, j, O, yq, cs);
-    else if (gw < Weff) {
+    if (gw < Weff) {
         const uint32_t t_lo = (uint32_t)((uint64_t)NT * gw / Weff), t_hi = (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
         int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
@@ -799,7 +636,6 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     }
     if (cs && tid == 0) cs->t_f2 += (unsigned long long)(clock64() - c1);
     team.sync();
-    if (QUIET && tid == 0) { S.q[0] = 0; S.q[1] = 0; }   // (the next column posts its runs after the barrier of its jump selection)
     if (cs && tid == 0) { cs->t_tiles += (unsigned long long)(c1 - c0); cs->t_finish += (unsigned long long)(clock64() - c1); }
 }
 
@@ -968,7 +804,6 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
         }
         for (uint32_t t = tid; t < X.NT; t += W * 32) S.tb[t] = (uint8_t)(S.tb[t] & PackSmem::TB_MASK);
         if (tid < 2 * W) S.haloF[tid] = 0;
-        if (tid == 0) { S.q[0] = 0; S.q[1] = 0; }
     }
     X.team.sync();   // trackers of every row initialised before any CTA updates them
     for (uint32_t j = j0 + 1; j <= n; ++j) {
@@ -1060,7 +895,7 @@ template <int W> __device__ __noinline__ void pk_walk_phase(const Params P, unsi
 // bulk fill
 // ---------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(W * 32, W <= 8 ? 2 : 1) fill_packed_kernel(const Params P) {
+__global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
     __shared__ uint32_t sJob;
@@ -1122,11 +957,9 @@ __global__ void __launch_bounds__(W * 32, W <= 8 ? 2 : 1) fill_packed_kernel(con
         pk_init_halos<W>(X, S, 0);
         if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
         X.quiet = P.quiet != 0 && team.size == 1 && !X.cluster_smem;
-        X.dynamic = X.quiet && P.quiet >= 2 && X.NT < (1u << 30);
-        X.quiet_first = X.quiet && P.quiet_first != 0; X.quiet_edge = X.quiet && !X.dynamic && P.quiet_edge != 0;
-        X.quiet_last = X.quiet && !X.dynamic && P.quiet_last != 0;
+        X.quiet_first = X.quiet && P.quiet_first != 0; X.quiet_edge = X.quiet && P.quiet_edge != 0;
+        X.quiet_last = X.quiet && P.quiet_last != 0;
         if (tid < 2 * W) S.haloF[tid] = 0;
-        if (tid == 0) { S.q[0] = 0; S.q[1] = 0; }
         if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
         if (X.quiet) {   // quiet tiles: no tile is quiet yet; base classes of every tile
             for (uint32_t a = tid; a < C; a += W * 32) S.Q[a] = pk_quiet_init(X.pk);
@@ -1200,10 +1033,11 @@ struct UnitStage {
     JumpInfo *J;        // [K]
     int32_t *B;         // [K + 1]: B[t] = base of column jb + t  (B[0] = base of the checkpointed column jb)
     uint8_t *q;         // [K]
-    uint8_t *bases;     // contig bases (+ 16 bytes of padding for the strip over-read)
+    uint8_t *bases;     // contig bases (+ 16 bytes of padding for the strip over-read); only when Params::unit_stage_bases
     static __host__ __device__ size_t r16(size_t v) { return (v + 15) / 16 * 16; }
-    static size_t bytes(uint32_t K, uint32_t max_ctiles) {
-        return r16(sizeof(JumpInfo) * K) + r16(sizeof(int32_t) * (K + 1)) + r16(K) + r16((size_t)max_ctiles * TILE + 16);
+    // `stage_bases` = false: the longest contig does not fit beside the rest; the re-fill reads bases from global memory
+    static size_t bytes(uint32_t K, uint32_t max_ctiles, bool stage_bases) {
+        return r16(sizeof(JumpInfo) * K) + r16(sizeof(int32_t) * (K + 1)) + r16(K) + (stage_bases ? r16((size_t)max_ctiles * TILE + 16) : 0);
     }
     __device__ void carve(unsigned char *raw, uint32_t K) {   // raw is 16-byte aligned; every part stays 16-byte aligned
         J = reinterpret_cast<JumpInfo *>(raw);
@@ -1226,7 +1060,8 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     const int32_t *gcol = P.gcol + jd.gcol_off;
     const ColRec *colrec = P.colrec + jd.colrec_off;
     const uint8_t *read = P.reads + jd.read_off;
-    if (tid == 0) { *s_en = gen; s_en->tile_start = 0; s_en->seq_off = 0; }
+    const bool stage_bases = P.unit_stage_bases != 0;
+    if (tid == 0) { *s_en = gen; s_en->tile_start = 0; if (stage_bases) s_en->seq_off = 0; }
     for (uint32_t t = tid; t < je - jb; t += T) {
         const ColRec cr = colrec[(uint64_t)(jb + 1 + t) * C + a];
         JumpInfo J; J.score = cr.jscore; J.len = cr.jlen; J.idx = cr.jidx; J.from = cr.jfrom;
@@ -1234,13 +1069,13 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
         U.q[t] = read[jb + t];
     }
     for (uint32_t t = tid; t <= je - jb; t += T) U.B[t] = (jb + t >= 1) ? gcol[jb + t - 1] : 0;
-    for (uint32_t t = tid; t < pm + 16; t += T) U.bases[t] = t < gen.m ? P.contig_bases[gen.seq_off + t] : (uint8_t)0;
+    if (stage_bases) for (uint32_t t = tid; t < pm + 16; t += T) U.bases[t] = t < gen.m ? P.contig_bases[gen.seq_off + t] : (uint8_t)0;
     __syncthreads();
     PackCtx X;
-    X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = U.bases;
+    X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = stage_bases ? U.bases : P.contig_bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
     X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
-    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
+    pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);

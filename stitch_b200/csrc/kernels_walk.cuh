@@ -1,15 +1,11 @@
-// kernels_walk.cuh — end-contig selection + pointer walk (traceback/mod.rs:129-373 of the reference) and the
-// fused per-read kernel of the packed path.
+// kernels_walk.cuh — end-contig selection + pointer walk (traceback/mod.rs:129-373 of the reference).
 //
 //   walk_job             thread 0 walks; whenever the walk needs packed traceback bytes that are not loaded the whole
 //                        CTA re-fills that unit (one contig over one block of K columns) from the column-state
 //                        checkpoint before it, with the packed-key columns (kernels_packed.cuh) or, for scorings
 //                        outside their regime, the wide ones.
 //   walk_kernel          walk_job for the reads of the wide path (their fill ran in fill_wide_kernel).
-//   align_packed_kernel  the whole per-read pipeline of the packed path in ONE persistent kernel: a CTA pulls a
-//                        read, runs its bulk fill, tail, end-of-read fix-up and walk, then pulls the next read.
-//                        Two CTAs share an SM, so the latency-bound phases of one read (walk, fix-up) overlap the
-//                        bandwidth-bound fill of another; all working memory is per CTA, not per read.
+//   pk_walk_phase        walk_job for the reads of the packed path, as the second phase of fill_packed_kernel.
 #pragma once
 #include "kernels_packed.cuh"
 #include "kernels_wide.cuh"
@@ -31,7 +27,7 @@ struct WalkBufs {           // per CTA
     uint8_t *ubytes; ColRec *ucr;
 };
 
-// `jd` carries the offsets of the read's records (per read for the wide path, per CTA arena for the fused kernel).
+// `jd` carries the offsets of the read's records.
 template <int W, bool PACKED_ONLY>
 __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDesc &jd, const LayoutDesc &ld, WideSmem<W> *WS, PackSmem &PS,
                          UnitStage &US, WalkShared &sh, const WalkBufs &B) {
@@ -138,36 +134,6 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
     }
 }
 
-// Everything after the bulk pass of one read of the fused kernel: tail, end-of-read fix-up, walk.
-template <int W>
-__device__ __noinline__ void finish_job(const Params &P, uint32_t job, const JobDesc &jd, const LayoutDesc &ld, PackCtx &X, PackSmem &S,
-                                        UnitStage &US, WalkShared &sh, const WalkBufs &B, PkColConst *s_cc, int32_t *s_gmax, uint32_t *s_first,
-                                        long long t_bulk0) {
-    const uint32_t tid = threadIdx.x;
-    constexpr uint32_t T = W * 32;
-    const Scoring &sc = X.sc;
-    const uint32_t C = ld.C, n = jd.n, K = P.K;
-    ColRec *colrec = P.colrec + jd.colrec_off;
-    int32_t *gcol = P.gcol + jd.gcol_off;
-    int32_t track_thr = MIN_SCORE;
-    const uint32_t j0 = pk_tail_start<W>(P, S, sc, gcol, n, C, K, s_gmax, s_first, track_thr, true);
-    // ---- tail: the last columns again, traceback variant with trackers ----
-    const long long t_tail0 = clock64();
-    pk_tail<W>(P, jd, ld, X, S, s_cc, j0, track_thr);
-    if (P.dbg && tid == 0) {
-        atomicAdd(P.dbg + 0, (unsigned long long)(n - j0));
-        atomicAdd(P.dbg + 1, (unsigned long long)(clock64() - t_tail0));
-        atomicAdd(P.dbg + 2, (unsigned long long)(t_tail0 - t_bulk0));
-    }
-    // ---- end-of-read fix-up (SCA:453-555), one thread per contig-strand ----
-    __syncthreads();
-    for (uint32_t a = tid; a < C; a += T)
-        fixup_contig(sc, X.ent[a], n, P.last + jd.cell_off, P.sn + jd.cell_off, P.tracked_mode != 0, &colrec[(uint64_t)n * C + a].lx);
-    __syncthreads();
-    // ---- walk ----
-    walk_job<W, true>(P, job, jd, ld, nullptr, S, US, sh, B);
-}
-
 // Walk phase of fill_packed_kernel (see there).  Shared memory: the tables of PackSmem as carved by the kernel, the
 // per-unit staging area after them, and the re-fill state of one contig in the (now idle) cp.async stage buffers.
 template <int W>
@@ -203,87 +169,6 @@ __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_r
                          &P.colrec[jd.colrec_off + (uint64_t)jd.n * ld.C + a].lx);
         __syncthreads();
         walk_job<W, true>(P, job, jd, ld, nullptr, PS, US, sh, B);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// the fused per-read kernel of the packed path
-// ---------------------------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(W * 32, 2) align_packed_kernel(const Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
-    UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
-    __shared__ uint32_t sJob;
-    __shared__ PkColConst s_cc[2];
-    __shared__ int32_t s_gmax;
-    __shared__ uint32_t s_first;
-    __shared__ WalkShared sh;
-    const uint32_t tid = threadIdx.x;
-    constexpr uint32_t T = W * 32;
-    const Scoring sc = P.sc;
-    Team team; team.rank = 0; team.size = 1;
-    WalkBufs B;
-    B.st0 = nullptr; B.st1 = nullptr;
-    B.ubytes = P.unit_bytes + (uint64_t)blockIdx.x * P.unit_stride;
-    B.ucr = P.unit_cr + (uint64_t)blockIdx.x * P.K;
-    B.wps_smem = false;
-    B.wps = P.wpstate + (uint64_t)blockIdx.x * P.wpstate_stride;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) sJob = atomicAdd(P.counter, 1u);
-        __syncthreads();
-        if (sJob >= P.n_jobs) break;
-        const uint32_t job = P.order[sJob];
-        JobDesc jd = P.jobs[job];
-        // all records of the read live in this CTA's arena
-        jd.colrec_off = P.arena.colrec_base + (uint64_t)blockIdx.x * P.arena.colrec_stride;
-        jd.cell_off = P.arena.cell_base + (uint64_t)blockIdx.x * P.arena.cell_stride;
-        jd.ck_off = P.arena.ck_base + (uint64_t)blockIdx.x * P.arena.ck_stride;
-        jd.cksum_off = P.arena.cksum_base + (uint64_t)blockIdx.x * P.arena.cksum_stride;
-        jd.gcol_off = P.arena.gcol_base + (uint64_t)blockIdx.x * P.arena.gcol_stride;
-        const LayoutDesc ld = P.layouts[jd.layout];
-        const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
-        PackCtx X;
-        X.team = team;
-        X.pk = pk_make(sc, jd.LB); X.sc = sc; X.ent = P.ents + ld.ent_off; X.owner = P.owners + ld.owner_off;
-        X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
-        X.Sst = P.pstate + (uint64_t)blockIdx.x * P.pstate_stride; X.Dst = X.Sst + TILE;
-        X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE; X.state_smem = false; X.staged = true;
-        pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.dynamic = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
-        ColRec *colrec = P.colrec + jd.colrec_off;
-        int32_t *gcol = P.gcol + jd.gcol_off;
-        const uint8_t *read = P.reads + jd.read_off;
-        PkColOut O; O.tb_col = nullptr; O.colrec_col = nullptr; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false;
-        O.track_thr = MIN_SCORE;
-
-        // ---- bulk: all n columns ----
-        const long long t_bulk0 = clock64();
-        pk_state_init0<W>(X, S);
-        pk_init_halos<W>(X, S, 0);
-        for (uint32_t a = tid; a < C; a += T) {   // column-0 record: Lx[0]
-            int32_t t; uint32_t lx; col0_tracker(sc, X.ent[a].m, t, lx);
-            ColRec cr; cr.jscore = 0; cr.jlen = 0; cr.jidx = 0; cr.jfrom = 0; cr.lx = lx; cr.pad0 = cr.pad1 = cr.pad2 = 0;
-            colrec[a] = cr;
-        }
-        if (tid == 0) { s_cc[0].pc.B = 0; s_cc[0].pc.delta = 0; }
-        __syncthreads();
-        for (uint32_t j = 1; j <= n; ++j) {
-            const uint32_t par = j & 1u;
-            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, true, P.K);
-            __syncthreads();
-            const PkColConst cc = s_cc[par];
-            pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
-            if ((j % K == 0) && j < n)
-                pk_write_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j / K - 1) * 2 * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
-        }
-        // ---- tail, fix-up, walk: a real call on copies, so that the bulk loop above keeps its pointer tables in
-        // registers and its register allocation to itself ----
-        {
-            PackCtx X2 = X; PackSmem S2 = S; UnitStage US2 = US; WalkBufs B2 = B; JobDesc jd2 = jd; LayoutDesc ld2 = ld;
-            finish_job<W>(P, job, jd2, ld2, X2, S2, US2, sh, B2, &s_cc[0], &s_gmax, &s_first, t_bulk0);
-        }
     }
 }
 

@@ -44,12 +44,8 @@ struct LayoutDesc { uint32_t ent_off, C, n_tiles, owner_off, posof_off, PM, max_
 enum : uint32_t { JOB_OK = 0, JOB_NEED_FULL_TRACK = 100 };
 struct JobOut { uint32_t n_chains, status; };
 
-// Per-CTA working memory of the fused kernel: record offsets = base + blockIdx.x * stride (in records).
-struct Arena { uint64_t colrec_base, colrec_stride, cell_base, cell_stride, ck_base, ck_stride, cksum_base, cksum_stride, gcol_base, gcol_stride; };
-
 struct Params {
     Scoring sc;
-    Arena arena;
     const JobDesc *jobs;
     const uint32_t *order;
     uint32_t n_jobs, cmax;
@@ -78,7 +74,7 @@ struct Params {
     uint32_t cluster_size;   // packed kernel: CTAs per read (thread-block cluster), 1 = no cluster
     uint32_t stage_bytes;    // packed kernels: size of the front area of their dynamic shared memory (PackSmem)
     uint32_t cluster_state_smem;   // the rolling state lives in the cluster's shared memory (bytes per CTA), 0 = global memory
-    uint32_t quiet;          // packed bulk pass: skip quiet tiles (dp_packed.h), single-CTA teams only (2: dynamic scheduling)
+    uint32_t quiet;          // packed bulk pass: skip quiet tiles (dp_packed.h), single-CTA teams only
     uint32_t quiet_tail;     // ... and in the tail columns (traceback variant), for tiles below the tracking threshold
     uint32_t quiet_first, quiet_edge, quiet_last;   // ... also the first / last tile of a contig, the first and last tile of a warp chunk
     unsigned long long *qstats;   // [0] tile-columns of the bulk passes, [1] of those skipped as quiet
@@ -91,6 +87,7 @@ struct Params {
     uint32_t *done;          // packed kernel with the in-kernel walk phase: per job, 1 once its fill and tail are complete
     uint32_t walk_stage_smem_off;   // walk kernel: byte offset of the per-unit staging area in dynamic shared memory
     uint32_t walk_state_smem_off;   // walk kernel: byte offset of the packed unit state in dynamic shared memory (0: global)
+    uint32_t unit_stage_bases;      // walk: the per-unit staging area holds the contig's bases (they fit); 0: read from global memory
     int32_t *gcol;
     OutOp *ops;
     ChainHdr *chains;

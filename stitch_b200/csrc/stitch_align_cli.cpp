@@ -248,7 +248,8 @@ std::vector<uint8_t> bam_record(const std::string &line, const std::vector<std::
     for (uint32_t c : cigar) put32(r, c);
     static const char *NT16 = "=ACMGRSVTWYHKDBN";
     for (uint32_t k = 0; k < l_seq; k += 2) {
-        auto code = [&](char c) -> uint8_t { const char *p = std::strchr(NT16, c); return (uint8_t)(p && c ? p - NT16 : 15); };
+        // (the 4-bit codes have no case: soft-masked bases encode as their upper-case letters, as in htslib)
+        auto code = [&](char c) -> uint8_t { if (c >= 'a' && c <= 'z') c = (char)(c - 32); const char *p = std::strchr(NT16, c); return (uint8_t)(p && c ? p - NT16 : 15); };
         r.push_back((uint8_t)((code(seq[k]) << 4) | (k + 1 < l_seq ? code(seq[k + 1]) : 0)));
     }
     if (qual == "*") r.insert(r.end(), l_seq, 0xff);
@@ -424,10 +425,10 @@ void run_batch(const Api &api, stitch_ctx *ctx, const stitch_sam_opts &so, Batch
     for (size_t k = 0; k < b.recs.size(); ++k) {
         const Record &r = b.recs[k];
         char *text = nullptr;
-        // SEQ of the records is the read as given, upper-cased (io.rs:64); qualities as given
-        const std::string &u = seqs[uniq_of[k]];
-        if (api.format_sam(ctx, res, uniq_of[k], r.head.c_str(), reinterpret_cast<const uint8_t *>(u.data()),
-                           r.has_qual ? reinterpret_cast<const uint8_t *>(r.qual.data()) : nullptr, (uint32_t)u.size(), 0, 0, &so, &text) != STITCH_OK) {
+        // SEQ / QUAL of the records are the read as given (SamRecordFormatter::format uses fastq.seq(), mod.rs:630; only the
+        // alignment sees the upper-cased copy, mod.rs:243)
+        if (api.format_sam(ctx, res, uniq_of[k], r.head.c_str(), reinterpret_cast<const uint8_t *>(r.seq.data()),
+                           r.has_qual ? reinterpret_cast<const uint8_t *>(r.qual.data()) : nullptr, (uint32_t)r.seq.size(), 0, 0, &so, &text) != STITCH_OK) {
             b.error = api.last_error(ctx);
             api.free_results(res);
             return;

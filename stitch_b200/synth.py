@@ -39,7 +39,8 @@ def _noise(rng, s, sub=0.03, ins=0.01, dele=0.01, p_geo=0.7):
     return np.concatenate(out) if out else _rand_bases(rng, 1)
 
 
-def make_read(rng, contigs, length, seg_lo, seg_hi, strands=False, wrap=False):
+def make_read(rng, contigs, length, seg_lo, seg_hi, strands=False, wrap=False, truth=None):
+    """`truth` (a list) receives the contig-strand index of every segment: contig k forward = k, reverse = len(contigs) + k."""
     nseg = int(rng.integers(seg_lo, seg_hi + 1))
     cuts = np.sort(rng.integers(1, length, size=nseg - 1)) if nseg > 1 else np.array([], dtype=np.int64)
     bounds = np.concatenate(([0], cuts, [length]))
@@ -48,7 +49,8 @@ def make_read(rng, contigs, length, seg_lo, seg_hi, strands=False, wrap=False):
         l = int(bounds[k + 1] - bounds[k])
         if l <= 0:
             continue
-        c = contigs[int(rng.integers(0, len(contigs)))]
+        ci = int(rng.integers(0, len(contigs)))
+        c = contigs[ci]
         l = min(l, len(c))
         if wrap:
             start = int(rng.integers(0, len(c)))
@@ -56,8 +58,11 @@ def make_read(rng, contigs, length, seg_lo, seg_hi, strands=False, wrap=False):
         else:
             start = int(rng.integers(0, len(c) - l + 1))
             piece = c[start:start + l]
-        if strands and rng.random() < 0.5:
+        flipped = bool(strands and rng.random() < 0.5)
+        if flipped:
             piece = _COMP[piece][::-1]
+        if truth is not None:
+            truth.append(ci + (len(contigs) if flipped else 0))
         parts.append(piece)
     clean = np.concatenate(parts)
     noisy = _noise(rng, clean)
@@ -67,26 +72,38 @@ def make_read(rng, contigs, length, seg_lo, seg_hi, strands=False, wrap=False):
     return np.concatenate((noisy, _rand_bases(rng, length - len(noisy))))
 
 
-def config(number, n_reads, read_len=None):
-    """Returns (opts kwargs, [(name, bytes)] contigs, [bytes] reads) for BASELINE config `number`."""
+def config(number, n_reads, read_len=None, truth=None):
+    """Returns (opts kwargs, [(name, bytes)] contigs, [bytes] reads) for BASELINE config `number`.
+    `truth` (a list) receives, per read, the contig-strand indices its segments were drawn from."""
     rng = np.random.default_rng(20240 + number)
+    tr = [[] for _ in range(n_reads)]
     if number in (1, 2, 5):
         contigs = make_contigs(rng, 20, 7000, 9000)
         L = read_len or 10000
         two = number == 2
-        reads = [make_read(rng, contigs, L, 3, 6, strands=two, wrap=two) for _ in range(n_reads)]
+        reads = [make_read(rng, contigs, L, 3, 6, strands=two, wrap=two, truth=tr[k]) for k in range(n_reads)]
         kw = dict(double_strand=True, circular=True) if two else {}
+    elif number == 6:   # not a BASELINE config: the floor of the quiet-tile skipping.  Real plasmid panels share backbones (origin,
+        # resistance cassette): every contig = one common 4.8 kb backbone (60 %) with a unique 2.2-4.2 kb insert at the same
+        # site, so that a read segment drawn from the backbone has 20 equally good contigs; reads as config 2
+        backbone = _rand_bases(rng, 4800)
+        contigs = [np.concatenate((backbone[:2400], _rand_bases(rng, int(rng.integers(2200, 4201))), backbone[2400:])) for _ in range(20)]
+        L = read_len or 10000
+        reads = [make_read(rng, contigs, L, 3, 6, strands=True, wrap=True, truth=tr[k]) for k in range(n_reads)]
+        kw = dict(double_strand=True, circular=True)
     elif number == 3:   # 256-contig-strand slice of the construct database (the reference's own limit)
         contigs = make_contigs(rng, 128, 5000, 10000)
-        reads = [make_read(rng, contigs, read_len or int(rng.integers(5000, 20001)), 3, 8, strands=True)
-                 for _ in range(n_reads)]
+        reads = [make_read(rng, contigs, read_len or int(rng.integers(5000, 20001)), 3, 8, strands=True, truth=tr[k])
+                 for k in range(n_reads)]
         kw = dict(double_strand=True)
     elif number == 4:
         contigs = make_contigs(rng, 50, 20000, 20000)
-        reads = [make_read(rng, contigs, read_len or int(rng.integers(50000, 100001)), 10, 30, strands=True)
-                 for _ in range(n_reads)]
+        reads = [make_read(rng, contigs, read_len or int(rng.integers(50000, 100001)), 10, 30, strands=True, truth=tr[k])
+                 for k in range(n_reads)]
         kw = dict(double_strand=True)
     else:
         raise ValueError(number)
+    if truth is not None:
+        truth.extend(sorted(set(t)) for t in tr)
     named = [(f"contig{k}", c.tobytes()) for k, c in enumerate(contigs)]
     return kw, named, [r.tobytes() for r in reads]

@@ -86,7 +86,7 @@ class EmulAligners:
             raise EmulError(f"batch failed ({rc}): {self.e.emul_last_error(self._h).decode()}")
         try:
             chains = _lib.read_results(self.e, EMUL_RESULTS, res)
-            sam = [_lib.format_sam(self.e, "emul_", self._h, res, r, headers[r], bytes(reads[r]).upper(),
+            sam = [_lib.format_sam(self.e, "emul_", self._h, res, r, headers[r], bytes(reads[r]),
                                    None if quals is None else quals[r], None, sam_opts) for r in range(len(reads))]
             return chains, sam
         finally:

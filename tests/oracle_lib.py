@@ -60,8 +60,16 @@ def lib():
     o.oracle_result_fills.argtypes = [C.c_void_p]
     o.oracle_result_seconds.restype = C.c_double
     o.oracle_result_seconds.argtypes = [C.c_void_p]
+    o.oracle_set_checker_layout.restype = None
+    o.oracle_set_checker_layout.argtypes = [C.c_int]
     _o = o
     return o
+
+
+def set_checker_layout(colmajor: bool):
+    """Traceback matrix layout of the oracle: False = the reference's (i * cols + j; what the CPU baseline is timed on),
+    True = column-major (same values, several times faster on full-length reads; parity checks only)."""
+    lib().oracle_set_checker_layout(int(bool(colmajor)))
 
 
 class OracleError(RuntimeError):

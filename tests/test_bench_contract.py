@@ -10,13 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_line():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-sample-len", "12"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+                        "--read-len", "300"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     line = json.loads(p.stdout.decode().strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "GCUPS" and line["unit"] == "GCUPS" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["n_gpus"] == 1 and "workload" in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "reads truncated" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "full-length reads (300 b)" in cb["sample"]
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["unit"] == "GCUPS" and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
 

@@ -126,7 +126,7 @@ def test_cli_sam_and_bam(cli, tmp_path):
                   default_jump_score=-9, jump_score_inter_contig=-11), dict(pick_primary=1, filter_secondary=True, filter_secondary_pct=40.0))):
         named = [(f"ctg{k}", c) for k, c in enumerate(contigs)]
         e = emul_lib.EmulAligners(make_opts(**kw), named, strip=8)
-        _, exp = e.batch_sam([r.upper() for r in reads], heads, quals=[q.encode() for q in quals], sam_opts=sam_opts)
+        _, exp = e.batch_sam(reads, heads, quals=[q.encode() for q in quals], sam_opts=sam_opts)
         e.close()
         exp_lines = [l for per_read in exp for l in per_read]
         # SAM text, reads from gzip FASTQ, batches of 4 records (runs of identical sequences stay together)
@@ -140,10 +140,11 @@ def test_cli_sam_and_bam(cli, tmp_path):
         assert tail == bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
         text, refs, lines = bam_to_sam(raw)
         assert refs == [(f"ctg{k}", len(c)) for k, c in enumerate(contigs)] and text.startswith("@HD")
-        assert lines == exp_lines
+        # (BAM's 4-bit base codes carry no case: the soft-masked read comes back upper-cased)
+        assert lines == ["\t".join(f.upper() if k == 9 else f for k, f in enumerate(l.split("\t"))) for l in exp_lines]
         # FASTA reads: no qualities
         e = emul_lib.EmulAligners(make_opts(**kw), named, strip=8)
-        _, exp = e.batch_sam([r.upper() for r in reads], heads, quals=None, sam_opts=sam_opts)
+        _, exp = e.batch_sam(reads, heads, quals=None, sam_opts=sam_opts)
         e.close()
         out = cli(["-a", str(fa), "-r", str(ref), "--sam"] + extra).decode().splitlines()
         assert [l for l in out if not l.startswith("@")] == [l for per_read in exp for l in per_read]

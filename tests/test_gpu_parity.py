@@ -18,7 +18,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # blocks, re-filled units and window re-runs (the library reads these when a context is created).
 TUNING = {"STITCH_CK_EVERY": "7", "STITCH_TRACK_WINDOW": "6"}
 ALL_TUNING_KEYS = ("STITCH_CK_EVERY", "STITCH_TRACK_WINDOW", "STITCH_CLUSTER", "STITCH_CLUSTER_MIN_TILES", "STITCH_PACKED",
-                   "STITCH_FUSED", "STITCH_CLUSTER_SMEM", "STITCH_QUIET")
+                   "STITCH_CLUSTER_SMEM", "STITCH_QUIET", "STITCH_WALK_IN_KERNEL")
 
 
 def cluster_tuning(seed, base=None):
@@ -28,7 +28,7 @@ def cluster_tuning(seed, base=None):
     t["STITCH_CLUSTER_MIN_TILES"] = "1"
     t["STITCH_CLUSTER_SMEM"] = str(seed % 2)              # rolling state in the cluster's shared memory / in global memory
     if seed % 6 == 3:
-        t["STITCH_FUSED"] = "1"                           # one CTA per read: the fused per-read kernel (per-CTA arenas)
+        t["STITCH_WALK_IN_KERNEL"] = "0"                  # separate fix-up / walk kernels also for one CTA per read
     return t
 
 
@@ -297,7 +297,7 @@ def test_sam_records_on_gpu(oracle):
         al.close()
         compare(chains, exp_chains, f"sam {kw}")
         for r in range(len(reads)):
-            exp = sam_oracle.format_sam(headers[r], reads[r].upper(), quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
+            exp = sam_oracle.format_sam(headers[r], reads[r], quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
                                         (o.match_score, o.mismatch_score, o.gap_open, o.gap_extend), **so)
             assert sam[r] == exp, f"read {r} {kw} {so}"
 
@@ -322,17 +322,12 @@ def test_quiet_tiles_on_gpu(oracle, case):
     named = [(f"c{k}", s) for k, s in enumerate(contigs)]
     exp, _ = oracle.OracleAligners(make_opts(**kw), named).batch(reads, raw=False)
     # (few reads would otherwise get a cluster per read: no quiet tiles there)
-    for quiet in ("2", "1"):   # 2: runs of computed tiles dealt to the warps from a queue, 1: static warp chunks (default)
-        al = gpu_aligners(kw, named, tuning={"STITCH_CLUSTER": "1", "STITCH_QUIET": quiet})
-        got = al.align_batch(reads)
-        st = al.stats()
-        al.close()
-        compare(got, exp, f"quiet {quiet} case {case}")
-        assert st.tile_columns > 0 and st.quiet_tile_columns > 0.1 * st.tile_columns, (st.tile_columns, st.quiet_tile_columns)
-        if quiet == "2":
-            skipped = st.quiet_tile_columns
-        else:
-            assert st.quiet_tile_columns >= skipped   # (static chunks also skip the first / last tile of a chunk)
+    al = gpu_aligners(kw, named, tuning={"STITCH_CLUSTER": "1"})
+    got = al.align_batch(reads)
+    st = al.stats()
+    al.close()
+    compare(got, exp, f"quiet case {case}")
+    assert st.tile_columns > 0 and st.quiet_tile_columns > 0.1 * st.tile_columns, (st.tile_columns, st.quiet_tile_columns)
     al = gpu_aligners(kw, named, tuning={"STITCH_QUIET": "0", "STITCH_CLUSTER": "1"})
     got0 = al.align_batch(reads)
     st0 = al.stats()
@@ -367,7 +362,7 @@ def test_cli_on_gpu(oracle, tmp_path):
     exp_chains, _ = oracle.OracleAligners(o, named).batch(reads, raw=False)
     exp = []
     for r in range(len(reads)):
-        exp += sam_oracle.format_sam(heads[r], reads[r].upper(), quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
+        exp += sam_oracle.format_sam(heads[r], reads[r], quals[r], exp_chains[r], [(n, len(s)) for n, s in named],
                                      (o.match_score, o.mismatch_score, o.gap_open, o.gap_extend))
     env = {k: v for k, v in os.environ.items() if k not in ("STITCH_B200_LIB", "STITCH_B200_PREFIX")}
     p = subprocess.run([cli, "align", "-f", str(fq), "-r", str(ref), "-d", "-C", "--sam", "--batch", "3"], env=env,
@@ -375,3 +370,125 @@ def test_cli_on_gpu(oracle, tmp_path):
     assert p.returncode == 0, p.stderr.decode()
     got = [l for l in p.stdout.decode().splitlines() if not l.startswith("@")]
     assert got == exp
+
+
+def _oracle_threads(bytes_per_read):
+    try:
+        avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
+    except Exception:
+        avail = 32 << 30
+    return int(max(1, min(os.cpu_count() or 1, 8, avail * 0.6 // max(1, bytes_per_read))))
+
+
+def _full_size_case(oracle, config, n_batch, n_check, read_len=None, pick=None):
+    """`n_batch` full-size reads of a BASELINE config through the GPU with PRODUCTION defaults (no tuning knob set: default
+    checkpoint spacing, one CTA per read, quiet tiles), then `n_check` of them again with each read restricted
+    (subset_words) to the contig-strands its segments were drawn from plus two decoys, bit for bit against the oracle on
+    the same subsets (the oracle's 16-byte cells make all contigs unaffordable: a 10 kb read against 7 strands is 9 GB)."""
+    import stitch_b200
+    from stitch_b200 import synth
+    truth = []
+    kw, named, reads = synth.config(config, n_batch, read_len, truth=truth)
+    ns = len(named) * (2 if kw.get("double_strand") else 1)
+    rng = random.Random(config)
+    al = gpu_aligners(kw, named)          # production defaults
+    full = al.align_batch(reads)
+    st = al.stats()
+    assert st.packed_cells > 0 and st.quiet_tile_columns > 0.3 * st.tile_columns, (st.tile_columns, st.quiet_tile_columns)
+    subsets = []
+    for r in range(n_batch):
+        # (a spurious short hit of the read's random tail may add a contig the segments were not drawn from)
+        used = {full[r][0].start_contig_idx, full[r][0].end_contig_idx} | {a for k, a, _ in full[r][0].ops if k == 6}
+        mine = set(truth[r]) | used
+        decoys = rng.sample([c for c in range(ns) if c not in mine], 2)
+        subsets.append(sorted(mine | set(decoys)))
+    check = sorted(range(n_batch), key=lambda r: (len(subsets[r]), r))[:n_check] if pick is None else pick
+    sub = al.align_batch(reads, subsets)
+    st2 = al.stats()
+    assert st2.quiet_tile_columns > 0.1 * st2.tile_columns, (st2.tile_columns, st2.quiet_tile_columns)
+    al.close()
+    for r in range(n_batch):   # the subset holds every contig of the read: same optimum as against all contigs
+        assert full[r][0].score == sub[r][0].score, f"config {config} read {r}: {full[r][0].score} vs {sub[r][0].score}"
+    rows = max(sum(len(named[c % len(named)][1]) + 1 for c in subsets[r]) for r in check)
+    per_read = 16 * rows * (max(len(reads[r]) for r in check) + 1)
+    oracle.set_checker_layout(True)
+    try:
+        exp, info = oracle.OracleAligners(make_opts(**kw), named).batch([reads[r] for r in check], subsets=[subsets[r] for r in check],
+                                                                         raw=False, threads=_oracle_threads(per_read))
+    finally:
+        oracle.set_checker_layout(False)
+    compare([sub[r] for r in check], exp, f"config {config} full size")
+    return info
+
+
+def test_full_size_config2_vs_oracle(oracle):
+    """BASELINE config 2 at the size the headline is quoted on: noisy 10 kb reads, --double-strand --circular (origin
+    re-alignment fills included), 64 reads so that the backend runs one CTA per read with quiet tiles."""
+    _full_size_case(oracle, 2, 64, 6)
+
+
+def test_full_size_config1_vs_oracle(oracle):
+    _full_size_case(oracle, 1, 64, 4)
+
+
+def test_full_size_config3_slice_vs_oracle(oracle):
+    """A config-3-slice read of 20 kb (256 contig-strands in the table, 17 length bits)."""
+    _full_size_case(oracle, 3, 60, 1, read_len=20000)
+
+
+def test_many_reads_on_the_wide_path(oracle):
+    """More reads than 2 x SM count on the wide kernels (scorings outside the packed regime, here gap_extend = -1 with the
+    default jump score: insertion-chain reach 16 > 8): every CTA of the wide fill's grid owns its own rolling state."""
+    rng = random.Random(811)
+    contigs = [gen.rand_seq(rng, rng.randint(60, 300)) for _ in range(3)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(30, 90), rng.randint(1, 3), strands=True) for _ in range(400)]
+    reads = [r if r else b"A" for r in reads]
+    for kw, tuning in ((dict(double_strand=True, gap_extend=-1), None), (dict(double_strand=True, mode=1), {"STITCH_PACKED": "0"})):
+        got, exp = run_both(oracle, kw, contigs, reads, raw=False, tuning=tuning)
+        compare(got, exp, f"wide path {kw}")
+
+
+def test_config4_many_long_reads():
+    """BASELINE config 4 at its stated size on the in-kernel walk path (>= 56 reads, so one CTA per read): 60 reads of 70-100 kb
+    against 50 x 20 kb contigs, both strands.  The checkpoint spacing widens past 2 k columns; the walk phase's shared-memory
+    staging is sized with that spacing (it used to exceed the 227 KB limit).  Exact-concatenation reads: score, span, jumps."""
+    rng = random.Random(44)
+    contigs = [gen.rand_seq(rng, 20000) for _ in range(50)]
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    nseg = [rng.randint(10, 14) for _ in range(60)]
+    reads = [_exact_read(rng, contigs, k, rng.randint(6000, 7000)) for k in nseg]
+    al = gpu_aligners(dict(double_strand=True), named)
+    res = al.align_batch(reads)
+    st = al.stats()
+    al.close()
+    for k, read, chains in zip(nseg, reads, res):
+        a = chains[0]
+        assert (a.score, a.length, a.ystart, a.yend) == (len(read) - (k - 1) * 10, len(read), 0, len(read))
+        a.validate()
+    assert st.packed_cells == st.cells
+
+
+def test_contig_longer_than_the_staging_area(oracle):
+    """A 300 kb contig: its bases do not fit the walk's shared-memory staging area and are read from global memory
+    instead (packed path), and the wide path's walk never stages them."""
+    rng = random.Random(45)
+    contigs = [gen.rand_seq(rng, 300000)] + [gen.rand_seq(rng, rng.randint(500, 900)) for _ in range(2)]
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    reads = []
+    for _ in range(4):
+        s = rng.randrange(0, 300000 - 700)
+        piece = contigs[0][s:s + 700]
+        other = contigs[1][100:400]
+        reads.append(piece + (gen.revcomp(other) if rng.random() < 0.5 else other))
+    for tuning in (None, {"STITCH_WALK_IN_KERNEL": "0"}, {"STITCH_PACKED": "0"}):
+        al = gpu_aligners(dict(double_strand=True), named, tuning=tuning)
+        res = al.align_batch(reads)
+        al.close()
+        for read, chains in zip(reads, res):
+            a = chains[0]
+            assert (a.score, a.length, a.ystart, a.yend) == (1000 - 10, 1000, 0, 1000), tuning
+            a.validate()
+    # one noisy read against the oracle (16 B x 300 kb x 400 columns = 2 GB)
+    noisy = [gen.noisy(rng, reads[0][:400])]
+    got, exp = run_both(oracle, dict(double_strand=False), contigs, noisy, raw=False)
+    compare(got, exp, "long contig")

@@ -20,7 +20,7 @@ def oracle_sam(oracle, kw, named, reads, headers, quals, sam_opts):
     chains, _ = oracle.OracleAligners(o, named).batch(reads, raw=False)
     targets = [(n, len(s)) for n, s in named]
     scoring = (o.match_score, o.mismatch_score, o.gap_open, o.gap_extend)
-    return [sam_oracle.format_sam(headers[r], bytes(reads[r]).upper(), None if quals is None else quals[r], chains[r], targets, scoring,
+    return [sam_oracle.format_sam(headers[r], bytes(reads[r]), None if quals is None else quals[r], chains[r], targets, scoring,
                                   **sam_opts) for r in range(len(reads))]
 
 
