@@ -49,7 +49,7 @@ enum {
     STITCH_ERR_INVALID = -1,   /* bad argument / option out of the supported range        */
     STITCH_ERR_CUDA = -2,      /* CUDA runtime failure (no CPU fallback exists)            */
     STITCH_ERR_NOMEM = -3,     /* device or host allocation failed                          */
-    STITCH_ERR_LIMIT = -4,     /* > 256 contig-strands or contig >= 2^27 (packed cell limit) */
+    STITCH_ERR_LIMIT = -4,     /* > 256 contig-strands for ONE read, > 65536 in the table, contig >= 2^27 */
     STITCH_ERR_INTERNAL = -5   /* traceback reached a state the reference would panic on   */
 };
 
@@ -69,6 +69,13 @@ typedef struct stitch_opts {
     uint8_t reserved0;
     uint32_t circular_slop;       /* default 20                                              */
     float suboptimal_pct;         /* default 20.0                                            */
+    /* Pre-alignment contig selection (Options.pre_align .. pre_align_subset_contigs, mod.rs:76-86; align.rs:119-146). */
+    uint8_t pre_align;            /* -p: only reads with a pre-alignment score >= pre_align_min_score are aligned   */
+    uint8_t pre_align_subset_contigs; /* -x: align such a read to the contig-strands that reached the score only     */
+    uint8_t reserved1[2];
+    uint32_t kmer_size;           /* -k, default 12                                          */
+    uint32_t band_width;          /* -w, default 50                                          */
+    int32_t pre_align_min_score;  /* -s, default 100                                         */
 } stitch_opts;
 
 /* One target sequence (TargetSeq, LIB/util/target_seq.rs:15): upper-cased forward bases.
@@ -113,6 +120,8 @@ typedef struct stitch_stats {
     uint64_t packed_launches;     /* launches of the packed-key kernel (one per chunk of reads)        */
     uint64_t tile_columns;        /* packed bulk pass: (256-row tile, column) pairs of the batch               */
     uint64_t quiet_tile_columns;  /* of those: skipped because the tile was provably quiet (dp_packed.h)       */
+    double prealign_ms;           /* CUDA-event time of the pre-alignment (copies + prealign_kernel)           */
+    uint64_t prealign_reads;      /* reads that went through the pre-alignment                                   */
 } stitch_stats;
 
 typedef struct stitch_ctx stitch_ctx;
@@ -127,7 +136,9 @@ int stitch_create(const stitch_opts *opts, const stitch_contig *contigs, uint32_
  * (already upper-cased is not required: the library upper-cases, io.rs:64), read r is
  * bases[offsets[r] .. offsets[r+1]).  `subset_words` is NULL or n_reads * subset_stride
  * 32-bit words; bit c of read r's words selects contig-strand c (the pre-align subset,
- * mod.rs:287-295); an all-zero row means "all contigs". */
+ * mod.rs:287-295); an all-zero row means "all contigs".  With opts.pre_align and subset_words == NULL the library
+ * runs its own pre-alignment (k-mer seeding on the GPU) and selects the contig-strands itself; a
+ * read that reaches the minimum score nowhere comes back with no chain (unmapped). */
 int stitch_align_batch(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets,
                        uint32_t n_reads, const uint32_t *subset_words, uint32_t subset_stride,
                        stitch_results **out);
@@ -137,6 +148,13 @@ int stitch_align_batch(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *of
 int stitch_custom_batch(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets,
                         uint32_t n_reads, const uint32_t *subset_words, uint32_t subset_stride,
                         stitch_results **out);
+
+/* The pre-alignment alone (needs opts.pre_align): per read the selected contig-strands as subset_words (the BitSet
+ * `contigs_to_align` of mod.rs:287-295; an all-zero row: no contig-strand reached pre_align_min_score, the read would not
+ * be aligned) and, in best_scores (may be NULL), the best score among them (0 when none).  Feeding the words back to
+ * stitch_align_batch gives the chains stitch_align_batch computes by itself with opts.pre_align_subset_contigs. */
+int stitch_prealign_batch(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
+                          uint32_t *subset_words, uint32_t subset_stride, int32_t *best_scores);
 
 /* Same as stitch_align_batch / stitch_custom_batch but with reads already resident in
  * device memory (device pointers); used to time the path without host copies. */
@@ -149,6 +167,10 @@ void stitch_results_read(const stitch_results *r, uint32_t read, uint64_t *first
 const stitch_chain *stitch_results_chains(const stitch_results *r, uint64_t *n_chains);
 const stitch_op *stitch_results_ops(const stitch_results *r, uint64_t *n_ops);
 void stitch_free_results(stitch_results *r);
+/* The Option<i32> of Aligners::align's return value (mod.rs:338-339): the best pre-alignment score of read `read`.
+ * Returns 1 and sets *score when there is one (pre_align on and the read reached pre_align_min_score on some
+ * contig-strand), 0 for None. */
+int stitch_results_prealign(const stitch_results *r, uint32_t read, int32_t *score);
 /* A results handle holding ONE read with the given chains (copied; ops_offset of chain k indexes `ops`).  Alignment is a
  * plain public struct in the reference (LIB/align/alignment.rs:16-51) and SamRecordFormatter::format takes any
  * &[Alignment] (mod.rs:622-627): this is how a caller formats chains it built or edited itself (n_chains = 0: the

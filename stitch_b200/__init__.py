@@ -70,7 +70,8 @@ class Builder:
                    default_jump_score=-10, jump_score_same_contig_and_strand=None,
                    jump_score_same_contig_opposite_strand=None, jump_score_inter_contig=None,
                    double_strand=False, circular=False, circular_slop=20, suboptimal=False,
-                   suboptimal_pct=20.0)
+                   suboptimal_pct=20.0, pre_align=False, pre_align_subset_contigs=True, kmer_size=12, band_width=50,
+                   pre_align_min_score=100)
 
     def __init__(self, **kw):
         self._v = dict(self._FIELDS)
@@ -125,7 +126,9 @@ class Aligners:
         if rc != 0:
             raise StitchError(f"{fn.__name__} failed ({rc}): {self.last_error()}")
         try:
-            return _lib.read_results(self._lib, _lib.PRODUCT_RESULTS, res)
+            out = _lib.read_results(self._lib, _lib.PRODUCT_RESULTS, res)
+            self.last_prealign_scores = _lib.read_prealign(self._lib, "stitch_", res, len(reads))
+            return out
         finally:
             self._lib.stitch_free_results(res)
 
@@ -148,8 +151,10 @@ class Aligners:
             raise StitchError(f"stitch_align_batch failed ({rc}): {self.last_error()}")
         try:
             chains = _lib.read_results(self._lib, _lib.PRODUCT_RESULTS, res)
+            pre = _lib.read_prealign(self._lib, "stitch_", res, len(reads))
+            self.last_prealign_scores = pre
             sam = [_lib.format_sam(self._lib, "stitch_", self._h, res, r, headers[r], bytes(reads[r]),
-                                   None if quals is None else quals[r], None, sam_opts) for r in range(len(reads))]
+                                   None if quals is None else quals[r], pre[r], sam_opts) for r in range(len(reads))]
             return chains, sam
         finally:
             self._lib.stitch_free_results(res)
@@ -164,9 +169,16 @@ class Aligners:
 
     # -- reference-shaped single-read call ---------------------------------------------------
     def align(self, record, target_seqs=None, target_hashes=None):
-        """(Vec<Alignment>, Option<i32>) of Aligners::align; pre-alignment is not on this path."""
+        """(Vec<Alignment>, Option<i32>) of Aligners::align (with opts.pre_align: the library's own pre-alignment)."""
         seq = record.seq if isinstance(record, FastxOwnedRecord) else bytes(record)
-        return self.align_batch([seq])[0], None
+        chains = self.align_batch([seq])[0]
+        return chains, self.last_prealign_scores[0]
+
+    def prealign_batch(self, reads: Sequence[bytes]):
+        """The pre-alignment alone: (selected contig-strands per read, best score per read)."""
+        from . import _lib
+        n_strands = len(self.target_seqs) * (2 if self.opts.double_strand else 1)
+        return _lib.prealign_batch(self._lib, "stitch_", self._h, reads, n_strands)
 
     def stats(self) -> StitchStats:
         s = StitchStats()

@@ -20,6 +20,8 @@ class StitchOpts(C.Structure):
         ("jump_same", C.c_int32), ("jump_opp", C.c_int32), ("jump_inter", C.c_int32),
         ("double_strand", C.c_uint8), ("circular", C.c_uint8), ("suboptimal", C.c_uint8), ("reserved0", C.c_uint8),
         ("circular_slop", C.c_uint32), ("suboptimal_pct", C.c_float),
+        ("pre_align", C.c_uint8), ("pre_align_subset_contigs", C.c_uint8), ("reserved1", C.c_uint8 * 2),
+        ("kmer_size", C.c_uint32), ("band_width", C.c_uint32), ("pre_align_min_score", C.c_int32),
     ]
 
 
@@ -48,6 +50,7 @@ class StitchStats(C.Structure):
         ("packed_fill_ms", C.c_double), ("wide_fill_ms", C.c_double), ("redo_fill_ms", C.c_double),
         ("packed_cells", C.c_uint64), ("redo_fills", C.c_uint64), ("tail_fill_ms", C.c_double), ("packed_launches", C.c_uint64),
         ("tile_columns", C.c_uint64), ("quiet_tile_columns", C.c_uint64),
+        ("prealign_ms", C.c_double), ("prealign_reads", C.c_uint64),
     ]
 
 
@@ -60,7 +63,8 @@ def make_opts(mode=MODE_LOCAL, match_score=1, mismatch_score=-4, gap_open=-6, ga
               default_jump_score=-10, jump_score_same_contig_and_strand=None,
               jump_score_same_contig_opposite_strand=None, jump_score_inter_contig=None,
               double_strand=False, circular=False, circular_slop=20, suboptimal=False,
-              suboptimal_pct=20.0) -> StitchOpts:
+              suboptimal_pct=20.0, pre_align=False, pre_align_subset_contigs=True, kmer_size=12, band_width=50,
+              pre_align_min_score=100) -> StitchOpts:
     """Options with the reference's defaults (aligners/mod.rs:67-116, 143-152)."""
     if isinstance(mode, str):
         mode = MODE_NAMES[mode.lower()]
@@ -70,7 +74,9 @@ def make_opts(mode=MODE_LOCAL, match_score=1, mismatch_score=-4, gap_open=-6, ga
         gap_extend=gap_extend, jump_same=pick(jump_score_same_contig_and_strand),
         jump_opp=pick(jump_score_same_contig_opposite_strand), jump_inter=pick(jump_score_inter_contig),
         double_strand=int(bool(double_strand)), circular=int(bool(circular)), suboptimal=int(bool(suboptimal)),
-        reserved0=0, circular_slop=int(circular_slop), suboptimal_pct=float(suboptimal_pct))
+        reserved0=0, circular_slop=int(circular_slop), suboptimal_pct=float(suboptimal_pct),
+        pre_align=int(bool(pre_align)), pre_align_subset_contigs=int(bool(pre_align_subset_contigs)), kmer_size=int(kmer_size),
+        band_width=int(band_width), pre_align_min_score=int(pre_align_min_score))
 
 
 def make_contigs(contigs):

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "stitch_results_n_reads", "stitch_results_read", "stitch_results_chains", "stitch_results_ops",
     "stitch_free_results", "stitch_get_stats", "stitch_set_max_inflight", "stitch_destroy",
     "stitch_last_error", "stitch_abi_version", "stitch_measure_int32_peak", "stitch_format_sam", "stitch_free_text",
-    "stitch_results_from_chains",
+    "stitch_results_from_chains", "stitch_results_prealign", "stitch_prealign_batch",
 ]
 
 _lib = None
@@ -120,6 +120,44 @@ def read_results(lib, prefix_map, handle):
             lst.append(Alignment(c.score, c.xstart, c.xend, c.ystart, c.yend, c.xlen, c.ylen,
                                  c.start_contig_idx, c.end_contig_idx, c.length, o))
         out.append(lst)
+    return out
+
+
+def prealign_batch(lib, prefix, ctx, reads, n_strands):
+    """stitch_prealign_batch: -> (selected contig-strands per read, best score per read)."""
+    from ._abi import pack_reads
+    f = getattr(lib, prefix + "prealign_batch")
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_int32)]
+    buf, offs = pack_reads(reads)
+    stride = (n_strands + 31) // 32
+    words = (C.c_uint32 * max(1, stride * len(reads)))()
+    best = (C.c_int32 * max(1, len(reads)))()
+    rc = f(ctx, buf, offs, len(reads), words, stride, best)
+    if rc != 0:
+        raise RuntimeError(f"prealign_batch failed ({rc}): {getattr(lib, prefix + 'last_error')(ctx).decode()}")
+    sel = []
+    for r in range(len(reads)):
+        row = []
+        for w in range(stride):
+            bits = words[r * stride + w]
+            while bits:
+                low = bits & -bits
+                row.append(w * 32 + low.bit_length() - 1)
+                bits ^= low
+        sel.append(row)
+    return sel, [int(best[r]) for r in range(len(reads))]
+
+
+def read_prealign(lib, prefix, handle, n_reads):
+    """The Option<i32> pre-alignment score of every read of a results handle (None = no score)."""
+    f = getattr(lib, prefix + "results_prealign")
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]
+    out = []
+    v = C.c_int32()
+    for r in range(n_reads):
+        out.append(int(v.value) if f(handle, r, C.byref(v)) else None)
     return out
 
 

@@ -74,6 +74,19 @@ int STITCH_API(custom_batch)(stitch_ctx *ctx, const uint8_t *bases, const uint64
     return run_batch(ctx, bases, offsets, n_reads, subset_words, subset_stride, out, true);
 }
 
+int STITCH_API(prealign_batch)(stitch_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads,
+                               uint32_t *subset_words, uint32_t subset_stride, int32_t *best_scores) {
+    if (!ctx) return STITCH_ERR_INVALID;
+    STITCH_GUARD_BEGIN
+    if (n_reads && (!bases || !offsets || !subset_words)) throw stitch::host::Error(STITCH_ERR_INVALID, "null argument");
+    if (!ctx->al.opts.pre_align) throw stitch::host::Error(STITCH_ERR_INVALID, "the context was created without pre_align");
+    if ((uint64_t)subset_stride * 32 < ctx->al.contigs.n_strands) throw stitch::host::Error(STITCH_ERR_INVALID, "subset_stride too small");
+    ctx->al.backend->stats.reset();
+    ctx->al.prealign_batch(bases, offsets, n_reads, subset_words, subset_stride, best_scores);
+    return STITCH_OK;
+    STITCH_GUARD_END(ctx)
+}
+
 uint32_t STITCH_API(results_n_reads)(const stitch_results *r) { return (uint32_t)r->res.first.size(); }
 void STITCH_API(results_read)(const stitch_results *r, uint32_t read, uint64_t *first, uint32_t *count) {
     *first = r->res.first[read]; *count = r->res.count[read];
@@ -85,6 +98,11 @@ const stitch_op *STITCH_API(results_ops)(const stitch_results *r, uint64_t *n) {
     *n = r->res.ops.size(); return r->res.ops.data();
 }
 void STITCH_API(free_results)(stitch_results *r) { delete r; }
+int STITCH_API(results_prealign)(const stitch_results *r, uint32_t read, int32_t *score) {
+    if (!r || read >= r->res.has_pre.size() || !r->res.has_pre[read]) return 0;
+    if (score) *score = r->res.pre_score[read];
+    return 1;
+}
 int STITCH_API(results_from_chains)(const stitch_chain *chains, uint32_t n_chains, const stitch_op *ops, uint64_t n_ops, stitch_results **out) {
     if (!out || (n_chains && !chains) || (n_ops && !ops)) return STITCH_ERR_INVALID;
     for (uint32_t c = 0; c < n_chains; ++c)
@@ -138,6 +156,7 @@ int STITCH_API(get_stats)(const stitch_ctx *ctx, stitch_stats *out) {
     out->packed_fill_ms = s.packed_ms; out->wide_fill_ms = s.wide_ms; out->redo_fill_ms = s.redo_ms; out->tail_fill_ms = s.tail_ms; out->packed_launches = s.packed_launches;
     out->packed_cells = s.packed_cells; out->redo_fills = s.refills;
     out->tile_columns = s.tile_columns; out->quiet_tile_columns = s.quiet_tile_columns;
+    out->prealign_ms = s.pre_ms; out->prealign_reads = s.pre_reads;
     return STITCH_OK;
 }
 
@@ -153,6 +172,6 @@ const char *STITCH_API(last_error)(const stitch_ctx *ctx) {
     return ctx ? ctx->al.last_error.c_str() : g_create_error.c_str();
 }
 
-uint32_t STITCH_API(abi_version)(void) { return 2; }
+uint32_t STITCH_API(abi_version)(void) { return 3; }
 
 }  // extern "C"

@@ -21,6 +21,7 @@
 #include "kernels_wide.cuh"
 #include "kernels_packed.cuh"
 #include "kernels_walk.cuh"
+#include "kernels_prealign.cuh"
 
 namespace stitch {
 namespace gpu {
@@ -87,7 +88,7 @@ struct CudaBackend : host::Backend {
     int num_sms = 0;
     uint32_t max_inflight = 0;
     size_t uploaded_layouts = 0;
-    uint32_t cmax = 1;
+    uint64_t uploaded_generation = ~0ull;
     uint32_t K = 256;        // checkpoint spacing (columns) of the current batch
     uint32_t K_base = 256;   // its default; STITCH_CK_EVERY overrides (tests)
     bool ck_auto = true;     // no override: a batch that fits in one launch with half the spacing uses K_base / 2
@@ -97,7 +98,6 @@ struct CudaBackend : host::Backend {
     DevBuf<uint8_t> d_contigs, d_reads, d_unit;
     DevBuf<ContigEntry> d_ents;
     DevBuf<uint16_t> d_owners;
-    DevBuf<int16_t> d_posof;
     DevBuf<LayoutDesc> d_layouts;
     DevBuf<JobDesc> d_jobs;
     DevBuf<uint32_t> d_order;
@@ -174,26 +174,23 @@ struct CudaBackend : host::Backend {
 
     void upload_layouts() {
         const auto &Ls = al.layouts.layouts;
-        if (uploaded_layouts == Ls.size()) return;
-        std::vector<ContigEntry> ents; std::vector<uint16_t> owners; std::vector<int16_t> posof; std::vector<LayoutDesc> descs;
-        cmax = 1;
+        if (uploaded_layouts == Ls.size() && uploaded_generation == al.layouts.generation) return;
+        uploaded_generation = al.layouts.generation;
+        std::vector<ContigEntry> ents; std::vector<uint16_t> owners; std::vector<LayoutDesc> descs;
         for (const auto &L : Ls) {
             LayoutDesc d{};
             d.ent_off = (uint32_t)ents.size(); d.C = (uint32_t)L.ent.size(); d.n_tiles = L.n_tiles;
-            d.owner_off = (uint32_t)owners.size(); d.posof_off = (uint32_t)posof.size(); d.PM = L.PM();
-            cmax = std::max(cmax, d.C);
+            d.owner_off = (uint32_t)owners.size(); d.PM = L.PM();
             for (uint32_t a = 0; a < d.C; ++a) {
                 ents.push_back(L.ent[a]);
                 d.max_ctiles = std::max(d.max_ctiles, L.ent[a].ntiles);
                 for (uint32_t t = 0; t < L.ent[a].ntiles; ++t) owners.push_back((uint16_t)a);
             }
-            posof.insert(posof.end(), L.pos_of.begin(), L.pos_of.end());
             descs.push_back(d);
         }
-        d_ents.reserve(ents.size()); d_owners.reserve(owners.size()); d_posof.reserve(posof.size()); d_layouts.reserve(descs.size());
+        d_ents.reserve(ents.size()); d_owners.reserve(owners.size()); d_layouts.reserve(descs.size());
         CUDA_CHECK(cudaMemcpy(d_ents.p, ents.data(), ents.size() * sizeof(ContigEntry), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d_owners.p, owners.data(), owners.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d_posof.p, posof.data(), posof.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(d_layouts.p, descs.data(), descs.size() * sizeof(LayoutDesc), cudaMemcpyHostToDevice));
         uploaded_layouts = Ls.size();
     }
@@ -211,7 +208,7 @@ struct CudaBackend : host::Backend {
         // shared memory of the packed fill: per-contig / per-tile tables + cp.async stage buffers; otherwise the read takes the
         // (slow, exact) wide path.  The walk phase's staging is optional: run_chunk sizes it with the real K and falls back
         // to the separate walk kernel (or to unstaged contig bases) when it does not fit.
-        if (LB && PackSmem::bytes(cmax, L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) > SMEM_LIMIT) return 0;
+        if (LB && PackSmem::bytes((uint32_t)L.ent.size(), L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) > SMEM_LIMIT) return 0;
         return LB;
     }
     // records a read holds from its fill until its walk is done (CellState/ColRec/... counts)
@@ -305,7 +302,18 @@ struct CudaBackend : host::Backend {
         const bool tracked = al.opts.sc.ys != MIN_SCORE;
         uint64_t reads_b = 0, ops_n = 0, chains_n = 0, pm_max = 0, unit_max = 0, cells = 0, handsum_n = 0, ppm_max = 0;
         Need tot{0, 0, 0, 0, 0, 0};
-        uint32_t n_packed = 0, ntmax = 1, max_ctiles = 1;
+        uint32_t n_packed = 0, ntmax = 1, max_ctiles = 1, cmax = 1;
+        // the kernels of a chunk carve their shared-memory tables for the chunk's largest contig count and tile count: packed jobs
+        // whose combination does not fit (many contigs in one job, many tiles in another) go to the wide path, largest first
+        std::vector<uint32_t> LBs(nj);
+        for (uint32_t k = 0; k < nj; ++k) { LBs[k] = plan_LB(jobs[begin + k]); cmax = std::max<uint32_t>(cmax, (uint32_t)Ls[jobs[begin + k].layout].ent.size()); }
+        for (;;) {
+            uint32_t nt = 1, big = nj;
+            for (uint32_t k = 0; k < nj; ++k)
+                if (LBs[k] && Ls[jobs[begin + k].layout].n_tiles >= nt) { nt = Ls[jobs[begin + k].layout].n_tiles; big = k; }
+            if (big == nj || PackSmem::bytes(cmax, nt, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) <= SMEM_LIMIT) break;
+            LBs[big] = 0;
+        }
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
             const host::Layout &L = Ls[j.layout];
@@ -320,7 +328,7 @@ struct CudaBackend : host::Backend {
             d.chain_first = (uint32_t)chains_n;
             d.track_from = tracked ? (j.n > WINDOW ? j.n - WINDOW + 1 : 1) : j.n + 1;
             d.hand_off = tot.cell; d.handsum_off = handsum_n;
-            d.LB = plan_LB(j); d.j0 = 0;
+            d.LB = LBs[k]; d.j0 = 0;
             d.ck_off = d.LB ? tot.pck : tot.ck;
             const Need nd = need_of(j, d.LB != 0);
             uint32_t mct = 0;
@@ -428,7 +436,7 @@ struct CudaBackend : host::Backend {
 
         Params P{};
         P.sc = al.opts.sc; P.jobs = d_jobs.p; P.order = d_order.p; P.n_jobs = nj; P.cmax = cmax;
-        P.layouts = d_layouts.p; P.ents = d_ents.p; P.owners = d_owners.p; P.posof = d_posof.p;
+        P.layouts = d_layouts.p; P.ents = d_ents.p; P.owners = d_owners.p;
         P.contig_bases = d_contigs.p; P.reads = device_reads ? device_reads : d_reads.p;
         P.state = d_state.p; P.state_stride = 2 * pm_max; P.state_half = pm_max;
         P.unit_bytes = d_unit.p; P.unit_stride = round_up(unit_max, 256);
@@ -583,8 +591,65 @@ struct CudaBackend : host::Backend {
             }
         }
     }
+    // ---- pre-alignment contig selection (prealign_core.h, kernels_prealign.cuh) ----
+    host::KmerIndex kindex;
+    DevBuf<uint32_t> d_koff, d_kpos, d_seqoff, d_slen, d_pcnt, d_pbins, d_poutn, d_prlen;
+    DevBuf<uint64_t> d_proff;
+    DevBuf<PreHit> d_pout;
+    void prealign(const std::vector<host::Job> &reads, std::vector<std::vector<PreHit>> &out) override {
+        CUDA_CHECK(cudaSetDevice(device));
+        out.assign(reads.size(), std::vector<PreHit>());
+        if (reads.empty()) return;
+        const host::Opts &o = al.opts;
+        const host::Contigs &c = al.contigs;
+        if (kindex.K != o.kmer) {   // built once per context (the reference hashes every target at start-up, align.rs:333-336)
+            kindex.build(c, o.kmer);
+            d_koff.reserve(kindex.off.size()); d_kpos.reserve(kindex.pos.size() + 1); d_seqoff.reserve(c.n_strands); d_slen.reserve(c.n_strands);
+            CUDA_CHECK(cudaMemcpy(d_koff.p, kindex.off.data(), kindex.off.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d_kpos.p, kindex.pos.data(), kindex.pos.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d_seqoff.p, c.seq_off.data(), c.n_strands * 4, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(d_slen.p, c.len.data(), c.n_strands * 4, cudaMemcpyHostToDevice));
+        }
+        cudaEvent_t e0 = ev[14], e1 = ev[15];
+        const size_t CH = 16384;   // reads per launch (2 KB of output each)
+        std::vector<uint64_t> offs; std::vector<uint32_t> lens; std::vector<PreHit> hout; std::vector<uint32_t> hn;
+        for (size_t begin = 0; begin < reads.size(); begin += CH) {
+            const size_t end = std::min(reads.size(), begin + CH), nr = end - begin;
+            uint64_t bytes = 0; uint32_t max_n = 1;
+            offs.assign(nr, 0); lens.assign(nr, 0);
+            for (size_t k = 0; k < nr; ++k) { offs[k] = bytes; lens[k] = reads[begin + k].n; bytes += round_up(reads[begin + k].n, 16); max_n = std::max(max_n, reads[begin + k].n); }
+            h_reads.reserve(bytes); d_reads.reserve(bytes);
+            for (size_t k = 0; k < nr; ++k) std::memcpy(h_reads.p + offs[k], reads[begin + k].read, reads[begin + k].n);
+            const uint32_t grid = (uint32_t)std::min<size_t>(nr, 2 * (size_t)num_sms);
+            const uint32_t n_bins = (max_n + c.max_len) / o.band + 2;
+            d_proff.reserve(nr); d_prlen.reserve(nr); d_pout.reserve(nr * MAX_STRANDS); d_poutn.reserve(nr);
+            d_pcnt.reserve((size_t)grid * c.n_strands); d_pbins.reserve((size_t)grid * PRE_MAX_CAND * n_bins);
+            CUDA_CHECK(cudaEventRecord(e0, stream));
+            CUDA_CHECK(cudaMemcpyAsync(d_reads.p, h_reads.p, bytes, cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(d_proff.p, offs.data(), nr * 8, cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(d_prlen.p, lens.data(), nr * 4, cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 8 * sizeof(uint32_t), stream));
+            PreKParams P{};
+            P.off = d_koff.p; P.pos = d_kpos.p; P.blob = d_contigs.p; P.seq_off = d_seqoff.p; P.strand_len = d_slen.p;
+            P.n_strands = c.n_strands; P.K = o.kmer; P.W = o.band; P.n_bins = n_bins; P.match = o.sc.match; P.min_score = o.pre_min_score;
+            P.reads = d_reads.p; P.read_off = d_proff.p; P.read_len = d_prlen.p; P.n_reads = (uint32_t)nr;
+            P.counter = d_counter.p; P.cnt = d_pcnt.p; P.bins = d_pbins.p; P.out = d_pout.p; P.out_n = d_poutn.p;
+            prealign_kernel<<<grid, PRE_THREADS, 0, stream>>>(P);
+            CUDA_CHECK(cudaGetLastError());
+            hout.resize(nr * MAX_STRANDS); hn.resize(nr);
+            CUDA_CHECK(cudaMemcpyAsync(hn.data(), d_poutn.p, nr * 4, cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(hout.data(), d_pout.p, nr * MAX_STRANDS * sizeof(PreHit), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaEventRecord(e1, stream));
+            sync("prealign");
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            stats.pre_ms += ms; stats.total_ms += ms; stats.launches += 1; stats.pre_reads += nr;
+            stats.h2d += bytes + nr * 12; stats.d2h += nr * (4 + MAX_STRANDS * sizeof(PreHit));
+            for (size_t k = 0; k < nr; ++k) out[begin + k].assign(hout.begin() + k * MAX_STRANDS, hout.begin() + k * MAX_STRANDS + hn[k]);
+        }
+    }
+
     void mark(int tag) {
-        if (n_marks >= 16) return;
+        if (n_marks >= 14) return;   // (events 14 and 15 time the pre-alignment)
         CUDA_CHECK(cudaEventRecord(ev[n_marks], stream));
         marks[n_marks++] = tag;
     }

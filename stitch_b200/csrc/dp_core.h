@@ -37,7 +37,9 @@ constexpr int32_t MIN_SCORE = -858993459;   // aligners/constants.rs:7
 #endif
 constexpr int STRIP = STITCH_STRIP;          // rows per lane (tests shrink it to force multi-tile contigs)
 constexpr int TILE = 32 * STRIP;             // rows per warp tile
-constexpr uint32_t MAX_STRANDS = 256;        // packed_length_cell.rs:112-114 (8-bit contig index)
+constexpr uint32_t MAX_STRANDS = 256;        // contig-strands ONE READ may be aligned against: packed_length_cell.rs:112-114 (8-bit
+                                             // contig index of the reference's cell); the layout position of a contig is 8-bit here too
+constexpr uint32_t MAX_TABLE_STRANDS = 65536;   // contig-strands the table may hold (a read then needs a subset: pre-alignment)
 constexpr uint32_t MAX_CONTIG_LEN = 134217727u;
 
 // Reference traceback codes (TB:47-57).
@@ -663,8 +665,14 @@ struct ReadView {
     const SnRec *sn;            // tile-transposed order
     const uint8_t *contig_bases;
     const uint8_t *read;
-    const int16_t *pos_of;      // contig_idx -> layout position or -1 (MAX_STRANDS entries)
     TbUnit unit;
+
+    // layout position of contig-strand `idx`, or -1 (the layout's contigs are in ascending contig_idx order, MCA:178-223)
+    SHD int32_t pos_of(uint32_t idx) const {
+        uint32_t lo = 0, hi = C;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ent[mid].contig_idx < idx) lo = mid + 1; else hi = mid; }
+        return lo < C && ent[lo].contig_idx == idx ? (int32_t)lo : -1;
+    }
 
     SHD uint32_t pidx(uint32_t a, uint32_t i) const { return row_index(ent[a], i); }
     SHD bool is_match(uint32_t a, uint32_t i, uint32_t j) const {
@@ -776,7 +784,7 @@ SHD uint32_t walk_run(const ReadView &v, WalkState &st, ChainHdr &h) {
             if (sidx != cur_idx || sfrom != i - 1) {
                 w.push(OP_XJUMP, cur_idx, i - 1);
                 cur_idx = sidx;
-                const int16_t na = sidx < MAX_STRANDS ? v.pos_of[sidx] : (int16_t)-1;
+                const int32_t na = v.pos_of(sidx);
                 if (na < 0) { status = WALK_NONE; break; }
                 a = (uint32_t)na;
             }
@@ -808,7 +816,7 @@ SHD uint32_t walk_run(const ReadView &v, WalkState &st, ChainHdr &h) {
             const LastCell &c = v.last[v.pidx(a, i)];                              // only (m, n) holds this move
             w.push(OP_XJUMP, cur_idx, i);
             cur_idx = c.idx;
-            const int16_t na = c.idx < MAX_STRANDS ? v.pos_of[c.idx] : (int16_t)-1;
+            const int32_t na = v.pos_of(c.idx);
             if (na < 0) { status = WALK_NONE; break; }
             a = (uint32_t)na;
             i = c.from;

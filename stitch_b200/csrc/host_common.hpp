@@ -17,12 +17,14 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/stitch_b200.h"
 #include "dp_core.h"
+#include "prealign_core.h"
 
 namespace stitch {
 namespace host {
@@ -38,6 +40,9 @@ struct Opts {
     bool double_strand = false, circular = false, suboptimal = false;
     uint32_t slop = 20;
     float sub_pct = 20.0f;
+    bool pre_align = false, pre_subset = true;   // mod.rs:76-86
+    uint32_t kmer = 12, band = 50;
+    int32_t pre_min_score = 100;
 };
 
 inline Opts make_opts(const stitch_opts &o) {
@@ -61,6 +66,12 @@ inline Opts make_opts(const stitch_opts &o) {
     }
     p.double_strand = o.double_strand != 0; p.circular = o.circular != 0; p.suboptimal = o.suboptimal != 0;
     p.slop = o.circular_slop; p.sub_pct = o.suboptimal_pct;
+    p.pre_align = o.pre_align != 0; p.pre_subset = o.pre_align_subset_contigs != 0;
+    p.kmer = o.kmer_size; p.band = o.band_width; p.pre_min_score = o.pre_align_min_score;
+    if (p.pre_align) {
+        if (p.kmer < 4 || p.kmer > 31) throw Error(STITCH_ERR_INVALID, "k-mer size must be 4..31");
+        if (p.band < 1) throw Error(STITCH_ERR_INVALID, "band width must be positive");
+    }
     return p;
 }
 
@@ -97,16 +108,18 @@ struct Contigs {
     void build(const stitch_contig *c, uint32_t n, bool double_strand) {
         if (n == 0) throw Error(STITCH_ERR_INVALID, "no contigs");
         n_targets = n; n_strands = double_strand ? 2 * n : n;
-        if (n_strands > MAX_STRANDS)
-            throw Error(STITCH_ERR_LIMIT, "more than 256 contig-strands (8-bit contig index of the reference's traceback cell)");
+        // the reference asserts <= 256 contig-strands on the TABLE (8-bit contig index of its traceback cell,
+        // packed_length_cell.rs:139-140); here the table may hold MAX_TABLE_STRANDS and the limit applies to the
+        // contig-strands one read is aligned against (Layout): larger tables need a per-read subset (pre-alignment)
+        if (n_strands > MAX_TABLE_STRANDS) throw Error(STITCH_ERR_LIMIT, "more than 65536 contig-strands");
         std::vector<std::vector<uint8_t>> fwd(n);
+        std::set<std::string> seen_names;
         for (uint32_t k = 0; k < n; ++k) {
             if (!c[k].name || (!c[k].fwd && c[k].len)) throw Error(STITCH_ERR_INVALID, "null contig");
             if (c[k].len == 0) throw Error(STITCH_ERR_INVALID, "empty contig");
             if (c[k].len > MAX_CONTIG_LEN) throw Error(STITCH_ERR_LIMIT, "contig longer than 2^27-1");
             names.emplace_back(c[k].name);
-            for (uint32_t q = 0; q < k; ++q)
-                if (names[q] == names[k]) throw Error(STITCH_ERR_INVALID, "Contig already added! name: " + names[k]);   // MCA:101-104
+            if (!seen_names.insert(names[k]).second) throw Error(STITCH_ERR_INVALID, "Contig already added! name: " + names[k]);   // MCA:101-104
             fwd[k].assign(c[k].fwd, c[k].fwd + c[k].len);
             for (auto &b : fwd[k]) if (b >= 'a' && b <= 'z') b = (uint8_t)(b - 32);   // target_seq.rs:111-115
         }
@@ -124,8 +137,7 @@ struct Contigs {
 
 // The contig subset a fill runs over (MCA::custom_with_subset keeps ascending contig order).
 struct Layout {
-    std::vector<ContigEntry> ent;
-    std::vector<int16_t> pos_of;   // MAX_STRANDS entries
+    std::vector<ContigEntry> ent;   // ascending contig_idx
     uint32_t n_tiles = 0;
     uint64_t cells_per_col = 0;    // sum of m_c
     uint32_t PM() const { return n_tiles * (uint32_t)TILE; }
@@ -136,25 +148,36 @@ struct LayoutCache {
     bool circular = false;
     std::vector<Layout> layouts;
     std::map<std::vector<uint32_t>, uint32_t> index;
+    uint64_t generation = 0;       // bumped when the cache is emptied (layout ids are only valid within one batch)
+
+    // Called between batches: with per-read subsets (pre-alignment) every batch brings new layouts.
+    void trim(size_t keep_below = 4096) {
+        if (layouts.size() < keep_below) return;
+        layouts.clear(); index.clear(); ++generation;
+    }
 
     uint32_t get(const std::vector<uint32_t> &strands /* ascending contig-strand indices */) {
         auto it = index.find(strands);
         if (it != index.end()) return it->second;
+        if (strands.size() > MAX_STRANDS)
+            throw Error(STITCH_ERR_LIMIT, "a read would be aligned against more than 256 contig-strands (the reference's limit, "
+                                          "packed_length_cell.rs:139-140): select contigs per read (pre-alignment / subset_words)");
         Layout L;
-        L.pos_of.assign(MAX_STRANDS, (int16_t)-1);
         const uint32_t T = contigs->n_targets;
+        std::map<uint32_t, int32_t> pos_of;
         for (uint32_t c : strands) {
             ContigEntry e{};
             e.contig_idx = c; e.m = contigs->len[c];
             e.tile_start = L.n_tiles; e.ntiles = (e.m + TILE - 1) / TILE;
             e.opp = -1; e.seq_off = contigs->seq_off[c]; e.circular = circular ? 1u : 0u;
-            L.pos_of[c] = (int16_t)L.ent.size();
+            pos_of[c] = (int32_t)L.ent.size();
             L.n_tiles += e.ntiles; L.cells_per_col += e.m;
             L.ent.push_back(e);
         }
         for (auto &e : L.ent) {   // opposite strand = same name, other strand, if present (MCA:241-262)
             const uint32_t o = e.contig_idx < T ? e.contig_idx + T : e.contig_idx - T;
-            if (o < contigs->n_strands && L.pos_of[o] >= 0) e.opp = L.pos_of[o];
+            const auto it = o < contigs->n_strands ? pos_of.find(o) : pos_of.end();
+            if (it != pos_of.end()) e.opp = it->second;
         }
         layouts.push_back(std::move(L));
         const uint32_t id = (uint32_t)layouts.size() - 1;
@@ -187,12 +210,41 @@ struct JobResult { std::vector<RawChain> chains; };
 struct BackendStats {
     uint64_t cells = 0, fills = 0, launches = 0, h2d = 0, d2h = 0, tb_bytes = 0, refills = 0;
     double fill_ms = 0, tb_ms = 0, total_ms = 0, packed_ms = 0, wide_ms = 0, redo_ms = 0, tail_ms = 0;
-    uint64_t packed_cells = 0, packed_launches = 0, tile_columns = 0, quiet_tile_columns = 0;
+    uint64_t packed_cells = 0, packed_launches = 0, tile_columns = 0, quiet_tile_columns = 0, pre_reads = 0;
+    double pre_ms = 0;
     void reset() { *this = BackendStats(); }
+};
+
+// K-mer index of every contig-strand for the pre-alignment (prealign_core.h): the positions (offsets into the contig
+// blob) of every valid k-mer, grouped by bucket (counting sort).  Replaces the per-target hash maps of
+// TargetSeq::build_target_hash (util/target_seq.rs:50-56).
+struct KmerIndex {
+    uint32_t K = 0;
+    std::vector<uint32_t> off;   // [n_buckets + 1]
+    std::vector<uint32_t> pos;   // blob offsets, grouped by bucket
+    void build(const Contigs &c, uint32_t k) {
+        K = k;
+        const uint32_t nb = pre_n_buckets(K);
+        off.assign((size_t)nb + 1, 0);
+        auto each = [&](auto &&fn) {
+            for (uint32_t s = 0; s < c.n_strands; ++s) {
+                if (c.len[s] < K) continue;
+                const uint8_t *b = c.blob.data() + c.seq_off[s];
+                for (uint32_t p = 0; p + K <= c.len[s]; ++p) { uint64_t code; if (pre_kmer_code(b + p, K, code)) fn(pre_bucket(code, K), c.seq_off[s] + p); }
+            }
+        };
+        each([&](uint32_t bucket, uint32_t) { ++off[(size_t)bucket + 1]; });
+        for (size_t b = 0; b < nb; ++b) off[b + 1] += off[b];
+        pos.assign(off[nb], 0);
+        std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+        each([&](uint32_t bucket, uint32_t p) { pos[cur[bucket]++] = p; });
+    }
 };
 
 struct Backend {
     virtual ~Backend() {}
+    // Pre-alignment (prealign_core.h): per read, the selected contig-strands in ascending order with their scores.
+    virtual void prealign(const std::vector<Job> &reads, std::vector<std::vector<PreHit>> &out) = 0;
     // `device_reads`: reads already resident on the device (d_bases base pointer + per-job offsets
     // in Job::read interpreted as offsets); only the CUDA backend supports it.
     virtual void run(const std::vector<Job> &jobs, std::vector<JobResult> &out) = 0;
@@ -329,7 +381,10 @@ struct Results {
     std::vector<stitch_op> ops;
     std::vector<uint64_t> first;
     std::vector<uint32_t> count;
-    void begin_read() { first.push_back(chains.size()); count.push_back(0); }
+    std::vector<uint8_t> has_pre;     // per read: Some / None of the pre-alignment score (mod.rs:338-339)
+    std::vector<int32_t> pre_score;
+    void begin_read() { first.push_back(chains.size()); count.push_back(0); has_pre.push_back(0); pre_score.push_back(0); }
+    void set_pre(int32_t score) { has_pre.back() = 1; pre_score.back() = score; }
     void add(const HAlign &a) {
         stitch_chain c{};
         c.score = a.score; c.xstart = (uint32_t)a.xstart; c.xend = (uint32_t)a.xend;
@@ -357,7 +412,7 @@ struct Aligner {
         contigs.build(c, n, opts.double_strand);
         layouts.contigs = &contigs;
         layouts.circular = opts.circular;
-        layouts.all();
+        if (contigs.n_strands <= MAX_STRANDS) layouts.all();
     }
 
     void check_ranges(uint64_t max_n) const {
@@ -372,8 +427,11 @@ struct Aligner {
     uint32_t layout_for(const uint32_t *words, uint32_t stride) {
         if (!words) return layouts.all();
         std::vector<uint32_t> s;
-        for (uint32_t c = 0; c < contigs.n_strands && c / 32 < stride; ++c)
-            if ((words[c / 32] >> (c % 32)) & 1u) s.push_back(c);
+        for (uint32_t w = 0; w < stride && w * 32 < contigs.n_strands; ++w)
+            for (uint32_t bits = words[w]; bits; bits &= bits - 1) {
+                const uint32_t c = w * 32 + (uint32_t)__builtin_ctz(bits);
+                if (c < contigs.n_strands) s.push_back(c);
+            }
         if (s.empty()) return layouts.all();
         return layouts.get(s);
     }
@@ -387,6 +445,7 @@ struct Aligner {
     // MultiContigAligner::custom_with_subset per read (raw chain, clips kept).
     void custom_batch(const uint8_t *bases, const uint64_t *offs, uint32_t n_reads, const uint32_t *subset,
                       uint32_t stride, Results &res) {
+        layouts.trim();
         std::vector<std::vector<uint8_t>> q(n_reads);
         std::vector<Job> jobs(n_reads);
         uint64_t max_n = 0;
@@ -467,27 +526,93 @@ struct Aligner {
     }
 
     // Aligners::align per read.
+    // mod.rs:243-295: which contig-strands a read is aligned against, from its pre-alignment hits.  Returns false when
+    // the read is not aligned at all (no contig-strand reached the minimum score: (Vec::new(), None), mod.rs:282-284).
+    bool prealign_select(const std::vector<PreHit> &hits, std::vector<uint32_t> &strands, int32_t &score) {
+        strands.clear();
+        if (hits.empty()) return false;
+        const uint32_t T = contigs.n_targets;
+        if (opts.pre_subset) {   // every contig-strand that reached the score (mod.rs:287-292)
+            score = hits[0].score;
+            for (const PreHit &h : hits) { strands.push_back(h.strand); score = std::max(score, h.score); }
+            return true;
+        }
+        // all contigs are aligned anyhow: the reference stops at the first target (in input order) with a passing strand
+        // and reports the best score of THAT target's strands (mod.rs:274-277, 338)
+        uint32_t first_t = 0xffffffffu;
+        for (const PreHit &h : hits) first_t = std::min(first_t, h.strand % T);
+        bool any = false;
+        for (const PreHit &h : hits) if (h.strand % T == first_t) { score = any ? std::max(score, h.score) : h.score; any = true; }
+        return true;   // strands stays empty: all contigs
+    }
+
+    void prealign_batch(const uint8_t *bases, const uint64_t *offs, uint32_t n_reads, uint32_t *words, uint32_t stride, int32_t *best) {
+        std::vector<std::vector<uint8_t>> q(n_reads);
+        std::vector<Job> pj(n_reads);
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            q[r] = upper(bases + offs[r], offs[r + 1] - offs[r]);
+            pj[r].read = q[r].data(); pj[r].n = (uint32_t)q[r].size();
+        }
+        std::vector<std::vector<PreHit>> hits;
+        backend->prealign(pj, hits);
+        std::fill(words, words + (size_t)n_reads * stride, 0u);
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            int32_t b = 0;
+            for (const PreHit &h : hits[r]) { words[(size_t)r * stride + h.strand / 32] |= 1u << (h.strand % 32); b = std::max(b, h.score); }
+            if (best) best[r] = b;
+        }
+    }
+
+    // Aligners::align per read.
     void align_batch(const uint8_t *bases, const uint64_t *offs, uint32_t n_reads, const uint32_t *subset,
                      uint32_t stride, Results &res) {
+        layouts.trim();
         std::vector<std::vector<uint8_t>> q(n_reads);
-        std::vector<Job> jobs(n_reads);
         uint64_t max_n = 0;
         for (uint32_t r = 0; r < n_reads; ++r) {
             q[r] = upper(bases + offs[r], offs[r + 1] - offs[r]);
             max_n = std::max<uint64_t>(max_n, q[r].size());
-            jobs[r].read = q[r].data(); jobs[r].n = (uint32_t)q[r].size();
-            jobs[r].layout = layout_for(subset ? subset + (size_t)r * stride : nullptr, stride);
-            jobs[r].walk = opts.suboptimal ? WALK_ALL : WALK_BEST;
         }
         check_ranges(max_n);
-        std::vector<JobResult> out;
-        backend->run(jobs, out);
+        // stage 0: pre-alignment contig selection (only when the caller does not bring its own subsets)
+        const bool pre = opts.pre_align && !subset;
+        std::vector<uint8_t> has_pre(n_reads, 0), dropped(n_reads, 0);
+        std::vector<int32_t> pre_score(n_reads, 0);
+        std::vector<std::vector<uint32_t>> pre_strands(n_reads);
+        if (pre) {
+            std::vector<Job> pj(n_reads);
+            for (uint32_t r = 0; r < n_reads; ++r) { pj[r].read = q[r].data(); pj[r].n = (uint32_t)q[r].size(); }
+            std::vector<std::vector<PreHit>> hits;
+            backend->prealign(pj, hits);
+            for (uint32_t r = 0; r < n_reads; ++r) {
+                if (prealign_select(hits[r], pre_strands[r], pre_score[r])) has_pre[r] = 1;
+                else dropped[r] = 1;
+            }
+        }
+        // stage 1: one fill + traceback per read that is aligned
+        std::vector<Job> jobs;
+        std::vector<int64_t> job_of(n_reads, -1);
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            if (dropped[r]) continue;
+            Job j;
+            j.read = q[r].data(); j.n = (uint32_t)q[r].size();
+            if (pre && !pre_strands[r].empty()) j.layout = layouts.get(pre_strands[r]);
+            else j.layout = layout_for(subset ? subset + (size_t)r * stride : nullptr, stride);
+            j.walk = opts.suboptimal ? WALK_ALL : WALK_BEST;
+            job_of[r] = (int64_t)jobs.size();
+            jobs.push_back(j);
+        }
+        std::vector<JobResult> out1;
+        backend->run(jobs, out1);
+        std::vector<JobResult> out(n_reads);
+        for (uint32_t r = 0; r < n_reads; ++r) if (job_of[r] >= 0) out[r] = std::move(out1[(size_t)job_of[r]]);
 
         // stage 2: origin re-alignment jobs for every chain
         std::vector<std::vector<HAlign>> chains(n_reads);
         std::vector<std::vector<RealignPlan>> plans(n_reads);
         std::vector<Job> jobs2;
         for (uint32_t r = 0; r < n_reads; ++r) {
+            if (dropped[r]) continue;
             if (!opts.suboptimal && out[r].chains.size() != 1) throw Error(STITCH_ERR_INTERNAL, "traceback_from returned None");
             for (const RawChain &rc : out[r].chains) chains[r].push_back(remove_clipping(opts, from_raw(rc)));
             plans[r].resize(chains[r].size());
@@ -529,6 +654,7 @@ struct Aligner {
             }
             res.begin_read();
             for (auto &a : finals) res.add(a);
+            if (has_pre[r]) res.set_pre(pre_score[r]);
         }
     }
 };

@@ -42,7 +42,7 @@ __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDe
     if (tid == 0) {
         v.sc = P.sc; v.ent = P.ents + ld.ent_off; v.C = ld.C; v.n = jd.n;
         v.colrec = P.colrec + jd.colrec_off; v.last = P.last + jd.cell_off; v.sn = P.sn + jd.cell_off;
-        v.contig_bases = P.contig_bases; v.read = P.reads + jd.read_off; v.pos_of = P.posof + ld.posof_off;
+        v.contig_bases = P.contig_bases; v.read = P.reads + jd.read_off;
         v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
         if (jd.walk == host::WALK_ALL) for (uint32_t a = 0; a < ld.C; ++a) sh.seen[a] = 0;
     }
@@ -54,7 +54,7 @@ __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDe
                     int a_end = -1;
                     if (jd.walk == host::WALK_BEST) { if (n_chains == 0 && used == 0) a_end = (int)pick_end(v, nullptr); }
                     else if (jd.walk == host::WALK_FROM) {
-                        if (n_chains == 0 && used == 0) a_end = jd.from_contig < MAX_STRANDS ? v.pos_of[jd.from_contig] : -1;
+                        if (n_chains == 0 && used == 0) a_end = v.pos_of(jd.from_contig);
                     } else if (n_seen < ld.C) a_end = (int)pick_end(v, sh.seen);
                     if (a_end < 0) { finished = true; break; }
                     a_cur = (uint32_t)a_end;
@@ -65,7 +65,7 @@ __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDe
                 if (s == WALK_NEED_UNIT) { sh.cmd = WCMD_UNIT; sh.ua = ws.a; sh.uj = ws.j; break; }
                 walking = false;
                 auto mark = [&](uint32_t idx) {
-                    const int p = idx < MAX_STRANDS ? v.pos_of[idx] : -1;
+                    const int p = v.pos_of(idx);
                     if (p >= 0 && !sh.seen[p]) { sh.seen[p] = 1; ++n_seen; }
                 };
                 if (jd.walk == host::WALK_ALL) {

@@ -39,7 +39,7 @@ struct JobDesc {
     uint32_t ops_cap, chain_first, max_chains, track_from;
 };
 
-struct LayoutDesc { uint32_t ent_off, C, n_tiles, owner_off, posof_off, PM, max_ctiles, pad1; };
+struct LayoutDesc { uint32_t ent_off, C, n_tiles, owner_off, pad0, PM, max_ctiles, pad1; };
 
 enum : uint32_t { JOB_OK = 0, JOB_NEED_FULL_TRACK = 100 };
 struct JobOut { uint32_t n_chains, status; };
@@ -52,7 +52,6 @@ struct Params {
     const LayoutDesc *layouts;
     const ContigEntry *ents;
     const uint16_t *owners;
-    const int16_t *posof;
     const uint8_t *contig_bases;
     const uint8_t *reads;
     CellState *state;        // per CTA: two rolling column buffers

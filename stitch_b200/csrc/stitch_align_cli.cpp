@@ -8,7 +8,12 @@
 // the C ABI of include/stitch_b200.h (stitch_create / stitch_align_batch / stitch_format_sam): this file
 // contains no alignment arithmetic and there is no CPU fallback.
 //
-// Not supported (the reference delegates it to the `bio` crate): --pre-align.
+// Pipeline (align.rs:338-441, io.rs:149-246 of the reference: a reader thread, aligner threads, an ordered writer): a
+// reader thread parses and groups the input into batches and feeds a bounded queue; one worker thread per device context
+// pulls batches as it becomes free (no lock-step rounds), aligns and formats them; the writer thread puts the finished
+// batches back into input order, encodes BAM / BGZF and writes.  GPUs never wait for parsing, compression or each other.
+// --pre-align runs the library's own pre-alignment (k-mer seeding on the GPU; the reference delegates it to the `bio`
+// crate: parity unpinned).
 // The library is loaded at run time (STITCH_B200_LIB / STITCH_B200_PREFIX select another build of the same
 // ABI: the CPU tests point it at the emulator of the kernels, tests/emul).
 #include <dlfcn.h>
@@ -18,7 +23,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -45,6 +55,7 @@ struct Api {
     decltype(&stitch_free_results) free_results;
     decltype(&stitch_destroy) destroy;
     decltype(&stitch_last_error) last_error;
+    decltype(&stitch_results_prealign) results_prealign;
     template <typename F> void bind(F &f, const std::string &prefix, const char *name) {
         f = reinterpret_cast<F>(dlsym(h, (prefix + name).c_str()));
         if (!f) die("symbol " + prefix + name + " not found in the alignment library");
@@ -66,7 +77,7 @@ struct Api {
         const std::string prefix = pe ? pe : "stitch_";
         bind(create, prefix, "create"); bind(align_batch, prefix, "align_batch"); bind(format_sam, prefix, "format_sam");
         bind(free_text, prefix, "free_text"); bind(free_results, prefix, "free_results"); bind(destroy, prefix, "destroy");
-        bind(last_error, prefix, "last_error");
+        bind(last_error, prefix, "last_error"); bind(results_prealign, prefix, "results_prealign");
     }
 };
 
@@ -289,13 +300,14 @@ std::vector<uint8_t> bam_record(const std::string &line, const std::vector<std::
 // ---------------------------------------------------------------------------------------------
 struct Args {
     std::string reads_fastq, reads_fasta, ref_fasta;
-    bool double_strand = false, decompress = false, pre_align = false, soft_clip = false, use_eq_and_x = false, circular = false,
+    bool double_strand = false, decompress = false, pre_align = false, pre_align_subset = true, soft_clip = false, use_eq_and_x = false, circular = false,
          filter_secondary = false, suboptimal = false, sam = false;
     int threads = 2, match_score = 1, mismatch_score = -4, gap_open = -6, gap_extend = -2, jump_score = -10, mode = STITCH_MODE_LOCAL,
         pick_primary = 0, compression = 0, gpus = 1, device = 0;
     bool has_same = false, has_opp = false, has_inter = false;
     int jump_same = 0, jump_opp = 0, jump_inter = 0;
-    unsigned circular_slop = 20, batch = 2048;
+    unsigned circular_slop = 20, batch = 2048, kmer = 12, band = 50;
+    int pre_align_min_score = 100;
     float filter_secondary_pct = 10.0f, suboptimal_pct = 20.0f;
     std::string command_line;
 };
@@ -329,7 +341,8 @@ void usage() {
         "  --filter-secondary [--filter-secondary-pct <10>]  --suboptimal [--suboptimal-pct <20>]\n"
         "  -c, --compression <0>            BGZF level of the BAM written to stdout\n"
         "  -t, --threads <2>                accepted for compatibility (alignment runs on the GPU)\n"
-        "  -p, --pre-align                  not supported\n"
+        "  -p, --pre-align                  pre-align reads (k-mer seeding on the GPU) and align only those reaching the score\n"
+        "  -k, --k <12>  -w, --w <50>  -s, --pre-align-min-score <100>  -x, --pre-align-subset-contigs <true>\n"
         "extras: --sam (SAM text instead of BAM)  --gpus <1>  --device <0>  --batch <2048>\n", stderr);
 }
 
@@ -361,8 +374,10 @@ Args parse(int argc, char **argv) {
         else if (arg == "-t" || arg == "--threads") a.threads = std::stoi(value(arg, inl, has_inl));
         else if (arg == "-z" || arg == "--decompress") flag(a.decompress);
         else if (arg == "-p" || arg == "--pre-align") flag(a.pre_align);
-        else if (arg == "-k" || arg == "--k" || arg == "-w" || arg == "--w" || arg == "-s" || arg == "--pre-align-min-score" ||
-                 arg == "-x" || arg == "--pre-align-subset-contigs") (void)value(arg, inl, has_inl);
+        else if (arg == "-k" || arg == "--k") a.kmer = (unsigned)std::stoul(value(arg, inl, has_inl));
+        else if (arg == "-w" || arg == "--w") a.band = (unsigned)std::stoul(value(arg, inl, has_inl));
+        else if (arg == "-s" || arg == "--pre-align-min-score") a.pre_align_min_score = std::stoi(value(arg, inl, has_inl));
+        else if (arg == "-x" || arg == "--pre-align-subset-contigs") a.pre_align_subset = parse_bool(value(arg, inl, has_inl));   // takes a value (align.rs:144-146)
         else if (arg == "-S" || arg == "--soft-clip") flag(a.soft_clip);
         else if (arg == "-X" || arg == "--use-eq-and-x") flag(a.use_eq_and_x);
         else if (arg == "-A" || arg == "--match-score") a.match_score = std::stoi(value(arg, inl, has_inl));
@@ -394,7 +409,6 @@ Args parse(int argc, char **argv) {
     }
     if (a.reads_fastq.empty() == a.reads_fasta.empty()) die("Must specify exactly one of --reads-fastq or --reads-fasta");
     if (a.ref_fasta.empty()) die("--ref-fasta is required");
-    if (a.pre_align) die("--pre-align is not supported by this build (the reference delegates it to the `bio` crate)");
     if (a.match_score <= 0) die("--match-score must be positive");
     if (a.mismatch_score >= 0 || a.gap_open >= 0 || a.gap_extend >= 0 || a.jump_score >= 0) die("mismatch, gap and jump scores must be negative");
     if (a.compression < 0 || a.compression > 9) die("--compression must be 0..9");
@@ -403,7 +417,7 @@ Args parse(int argc, char **argv) {
 }
 
 // One batch of input records on one device context: align the unique sequences, format every record.
-struct Batch { std::vector<Record> recs; std::vector<std::string> lines; std::string error; };
+struct Batch { uint64_t seq_no = 0; std::vector<Record> recs; std::vector<std::string> lines; std::string error; };
 
 void run_batch(const Api &api, stitch_ctx *ctx, const stitch_sam_opts &so, Batch &b) {
     // a run of consecutive records with the same (upper-cased) sequence is aligned once (align.rs:364-375)
@@ -425,10 +439,12 @@ void run_batch(const Api &api, stitch_ctx *ctx, const stitch_sam_opts &so, Batch
     for (size_t k = 0; k < b.recs.size(); ++k) {
         const Record &r = b.recs[k];
         char *text = nullptr;
+        int32_t pre_score = 0;
+        const int has_pre = api.results_prealign(res, uniq_of[k], &pre_score);   // the Option<i32> of Aligners::align (mod.rs:338-339)
         // SEQ / QUAL of the records are the read as given (SamRecordFormatter::format uses fastq.seq(), mod.rs:630; only the
         // alignment sees the upper-cased copy, mod.rs:243)
         if (api.format_sam(ctx, res, uniq_of[k], r.head.c_str(), reinterpret_cast<const uint8_t *>(r.seq.data()),
-                           r.has_qual ? reinterpret_cast<const uint8_t *>(r.qual.data()) : nullptr, (uint32_t)r.seq.size(), 0, 0, &so, &text) != STITCH_OK) {
+                           r.has_qual ? reinterpret_cast<const uint8_t *>(r.qual.data()) : nullptr, (uint32_t)r.seq.size(), has_pre, pre_score, &so, &text) != STITCH_OK) {
             b.error = api.last_error(ctx);
             api.free_results(res);
             return;
@@ -445,6 +461,35 @@ void run_batch(const Api &api, stitch_ctx *ctx, const stitch_sam_opts &so, Batch
     }
     api.free_results(res);
 }
+
+// Bounded hand-over between the pipeline stages.
+template <typename T>
+class Channel {
+  public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    void push(T v) {
+        std::unique_lock<std::mutex> l(m_);
+        not_full_.wait(l, [&] { return q_.size() < cap_; });
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+    }
+    bool pop(T &v) {   // false: closed and drained
+        std::unique_lock<std::mutex> l(m_);
+        not_empty_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = std::move(q_.front()); q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+    void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; not_empty_.notify_all(); }
+
+  private:
+    std::mutex m_;
+    std::condition_variable not_full_, not_empty_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
 
 }  // namespace
 
@@ -473,6 +518,8 @@ int main(int argc, char **argv) {
     o.jump_inter = a.has_inter ? a.jump_inter : a.jump_score;
     o.double_strand = a.double_strand; o.circular = a.circular; o.suboptimal = a.suboptimal;
     o.circular_slop = a.circular_slop; o.suboptimal_pct = a.suboptimal_pct;
+    o.pre_align = a.pre_align; o.pre_align_subset_contigs = a.pre_align_subset; o.kmer_size = a.kmer; o.band_width = a.band;
+    o.pre_align_min_score = a.pre_align_min_score;
     stitch_sam_opts so{};
     so.soft_clip = a.soft_clip; so.use_eq_and_x = a.use_eq_and_x; so.pick_primary = (uint8_t)a.pick_primary;
     so.filter_secondary = a.filter_secondary; so.filter_secondary_pct = a.filter_secondary_pct;
@@ -499,39 +546,67 @@ int main(int argc, char **argv) {
         bg.write(h.data(), h.size());
     }
 
-    FastxReader reads(a.reads_fastq.empty() ? a.reads_fasta : a.reads_fastq, !a.reads_fastq.empty());
-    Record carry; bool have_carry = false, eof = false;
-    uint64_t n_reads = 0;
-    while (!eof) {
-        // one batch per device; a run of identical sequences is never split across batches (io.rs:126-146)
-        std::vector<Batch> batches((size_t)a.gpus);
-        size_t used = 0;
-        for (; used < batches.size() && !eof; ++used) {
-            Batch &b = batches[used];
-            if (have_carry) { b.recs.push_back(std::move(carry)); have_carry = false; }
+    Channel<std::unique_ptr<Batch>> to_align((size_t)a.gpus * 2), to_write((size_t)a.gpus * 4 + 4);
+    std::mutex err_m;
+    std::string first_error;
+    auto fail = [&](const std::string &e) { std::lock_guard<std::mutex> l(err_m); if (first_error.empty()) first_error = e; };
+
+    // reader: batches of >= --batch records; a run of identical sequences is never split across batches (io.rs:126-146)
+    std::thread reader([&] {
+        FastxReader reads(a.reads_fastq.empty() ? a.reads_fasta : a.reads_fastq, !a.reads_fastq.empty());
+        Record carry; bool have_carry = false, eof = false;
+        uint64_t seq_no = 0;
+        while (!eof) {
+            std::unique_ptr<Batch> b(new Batch());
+            b->seq_no = seq_no++;
+            if (have_carry) { b->recs.push_back(std::move(carry)); have_carry = false; }
             Record r;
             for (;;) {
                 if (!reads.next(r)) { eof = true; break; }
-                if (b.recs.size() >= a.batch && upper(r.seq) != upper(b.recs.back().seq)) { carry = std::move(r); have_carry = true; break; }
-                b.recs.push_back(std::move(r));
+                if (b->recs.size() >= a.batch && upper(r.seq) != upper(b->recs.back().seq)) { carry = std::move(r); have_carry = true; break; }
+                b->recs.push_back(std::move(r));
+            }
+            if (!b->recs.empty()) to_align.push(std::move(b)); else --seq_no;
+        }
+        to_align.close();
+    });
+    // workers: one per device context, each pulls the next batch as soon as it is free
+    std::vector<std::thread> workers;
+    for (int g = 0; g < a.gpus; ++g)
+        workers.emplace_back([&, g] {
+            std::unique_ptr<Batch> b;
+            while (to_align.pop(b)) {
+                run_batch(api, ctxs[(size_t)g], so, *b);
+                if (!b->error.empty()) fail(b->error);
+                std::vector<Record>().swap(b->recs);
+                to_write.push(std::move(b));
+            }
+        });
+    // writer: input order restored, BAM encoding and BGZF off the aligners' threads
+    uint64_t n_lines = 0, n_batches = 0;
+    std::thread writer([&] {
+        std::map<uint64_t, std::unique_ptr<Batch>> pending;
+        uint64_t next = 0;
+        std::unique_ptr<Batch> b;
+        while (to_write.pop(b)) {
+            pending[b->seq_no] = std::move(b);
+            for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
+                for (const std::string &line : it->second->lines) {
+                    if (a.sam) { std::fputs(line.c_str(), stdout); std::fputc('\n', stdout); }
+                    else { const std::vector<uint8_t> rec = bam_record(line, names); bg.write(rec.data(), rec.size()); }
+                }
+                n_lines += it->second->lines.size(); ++n_batches;
+                pending.erase(it); ++next;
             }
         }
-        std::vector<std::thread> th;
-        for (size_t g = 0; g < used; ++g)
-            if (!batches[g].recs.empty()) th.emplace_back([&, g] { run_batch(api, ctxs[g], so, batches[g]); });
-        for (auto &t : th) t.join();
-        for (size_t g = 0; g < used; ++g) {
-            if (!batches[g].error.empty()) die("alignment failed: " + batches[g].error);
-            n_reads += batches[g].recs.size();
-            for (const std::string &line : batches[g].lines) {
-                if (a.sam) { std::fputs(line.c_str(), stdout); std::fputc('\n', stdout); }
-                else { const std::vector<uint8_t> rec = bam_record(line, names); bg.write(rec.data(), rec.size()); }
-            }
-        }
-        if (a.sam) std::fflush(stdout); else bg.flush();
-    }
-    if (!a.sam) bg.finish();
+    });
+    reader.join();
+    for (auto &t : workers) t.join();
+    to_write.close();
+    writer.join();
+    if (!first_error.empty()) die("alignment failed: " + first_error);
+    if (a.sam) std::fflush(stdout); else bg.finish();
     for (stitch_ctx *c : ctxs) api.destroy(c);
-    std::fprintf(stderr, "stitch-b200: processed %llu reads\n", (unsigned long long)n_reads);
+    std::fprintf(stderr, "stitch-b200: wrote %llu records of %llu batches\n", (unsigned long long)n_lines, (unsigned long long)n_batches);
     return 0;
 }

@@ -807,7 +807,6 @@ struct EmulBackend : Backend {
         ReadView v;
         v.sc = sc; v.ent = L.ent.data(); v.C = C; v.n = n; v.colrec = F.colrec.data();
         v.last = F.last.data(); v.sn = F.sn.data(); v.contig_bases = al.contigs.blob.data(); v.read = job.read;
-        v.pos_of = L.pos_of.data();
         v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
         std::vector<uint8_t> unit_bytes; std::vector<ColRec> unit_cr;
         const uint32_t cap = 2 * n + 4 * C + 64;
@@ -834,7 +833,7 @@ struct EmulBackend : Backend {
             if (s == WALK_PANIC) throw Error(STITCH_ERR_INTERNAL, "traceback reached a state the reference panics on");
             if (s == WALK_OK) res.chains.push_back(std::move(rc));
         } else if (job.walk == WALK_FROM) {
-            const int16_t a_end = L.pos_of[job.from_contig];
+            const int32_t a_end = v.pos_of(job.from_contig);
             if (a_end >= 0) {
                 RawChain rc;
                 uint32_t s = do_walk((uint32_t)a_end, rc);
@@ -845,7 +844,7 @@ struct EmulBackend : Backend {
             std::vector<uint8_t> seen(C, 0);
             uint32_t n_seen = 0;
             auto mark = [&](uint32_t idx) {
-                const int16_t p = idx < MAX_STRANDS ? L.pos_of[idx] : (int16_t)-1;
+                const int32_t p = v.pos_of(idx);
                 if (p >= 0 && !seen[(size_t)p]) { seen[(size_t)p] = 1; ++n_seen; }
             };
             while (n_seen < C) {
@@ -858,6 +857,57 @@ struct EmulBackend : Backend {
                 for (const OutOp &o : rc.ops) if (o.kind == OP_XJUMP) mark(o.a);
                 res.chains.push_back(std::move(rc));
             }
+        }
+    }
+
+    // Pre-alignment contig selection exactly as prealign_core.h defines it (the CUDA kernel's outputs are compared with
+    // these in the gpu tier), sequentially.
+    KmerIndex kindex;
+    void prealign(const std::vector<Job> &reads, std::vector<std::vector<PreHit>> &out) override {
+        const Opts &o = al.opts;
+        const Contigs &c = al.contigs;
+        if (kindex.K != o.kmer) kindex.build(c, o.kmer);
+        out.assign(reads.size(), std::vector<PreHit>());
+        const uint32_t K = o.kmer, W = o.band;
+        for (size_t r = 0; r < reads.size(); ++r) {
+            const uint8_t *read = reads[r].read; const uint32_t n = reads[r].n;
+            std::vector<uint32_t> cnt(c.n_strands, 0);
+            std::vector<std::pair<uint32_t, uint32_t>> hits;   // (strand, shifted diagonal)
+            for (uint32_t j = 0; j + K <= n; ++j) {
+                uint64_t code;
+                if (!pre_kmer_code(read + j, K, code)) continue;
+                const uint32_t b = pre_bucket(code, K);
+                for (uint32_t e = kindex.off[b]; e < kindex.off[b + 1]; ++e) {
+                    const uint32_t p = kindex.pos[e];
+                    if (K > PRE_DIRECT_K && !pre_same_kmer(c.blob.data() + p, read + j, K)) continue;
+                    const uint32_t s = pre_strand_of(c.seq_off.data(), c.n_strands, p);
+                    ++cnt[s]; hits.emplace_back(s, (p - c.seq_off[s]) + n - j);
+                }
+            }
+            uint32_t need = pre_need(o.pre_min_score, o.sc.match, K);
+            std::vector<uint32_t> cand;
+            for (;;) {
+                cand.clear();
+                for (uint32_t s = 0; s < c.n_strands; ++s) if (cnt[s] >= need) cand.push_back(s);
+                if (cand.size() <= PRE_MAX_CAND) break;
+                need *= 2;
+            }
+            const uint32_t n_bins = (n + c.max_len) / W + 2;
+            std::vector<PreHit> kept;
+            for (uint32_t s : cand) {
+                std::vector<uint32_t> bins(n_bins, 0);
+                for (const auto &h : hits) if (h.first == s && h.second / W < n_bins) ++bins[h.second / W];
+                uint32_t best = 0;
+                for (uint32_t b = 0; b < n_bins; ++b) best = std::max(best, bins[b] + (b + 1 < n_bins ? bins[b + 1] : 0u));
+                const int32_t sc = pre_score_of(o.sc.match, best, K);
+                if (sc >= o.pre_min_score) kept.push_back(PreHit{s, sc});
+            }
+            if (kept.size() > MAX_STRANDS) {
+                std::stable_sort(kept.begin(), kept.end(), [](const PreHit &a, const PreHit &b) { return a.score != b.score ? a.score > b.score : a.strand < b.strand; });
+                kept.resize(MAX_STRANDS);
+                std::sort(kept.begin(), kept.end(), [](const PreHit &a, const PreHit &b) { return a.strand < b.strand; });
+            }
+            out[r] = kept;
         }
     }
 

@@ -73,9 +73,13 @@ class EmulAligners:
         if rc != 0:
             raise EmulError(f"batch failed ({rc}): {self.e.emul_last_error(self._h).decode()}")
         try:
+            self.last_prealign_scores = _lib.read_prealign(self.e, "emul_", res, len(reads))
             return _lib.read_results(self.e, EMUL_RESULTS, res)
         finally:
             self.e.emul_free_results(res)
+
+    def prealign_batch(self, reads):
+        return _lib.prealign_batch(self.e, "emul_", self._h, reads, self.n_strands)
 
     def batch_sam(self, reads, headers, quals=None, sam_opts=None):
         """align_batch + the product's SAM record layer (host code shared with the CUDA library)."""
@@ -86,8 +90,10 @@ class EmulAligners:
             raise EmulError(f"batch failed ({rc}): {self.e.emul_last_error(self._h).decode()}")
         try:
             chains = _lib.read_results(self.e, EMUL_RESULTS, res)
+            pre = _lib.read_prealign(self.e, "emul_", res, len(reads))
+            self.last_prealign_scores = pre
             sam = [_lib.format_sam(self.e, "emul_", self._h, res, r, headers[r], bytes(reads[r]),
-                                   None if quals is None else quals[r], None, sam_opts) for r in range(len(reads))]
+                                   None if quals is None else quals[r], pre[r], sam_opts) for r in range(len(reads))]
             return chains, sam
         finally:
             self.e.emul_free_results(res)

@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.stitch_abi_version() == 2
+    assert lib.stitch_abi_version() == 3
 
 
 def test_no_cpu_fallback(lib):

@@ -25,7 +25,7 @@ def cli():
     import emul_lib
     emul_lib.build()
     if not os.path.exists(CLI) or os.path.getmtime(CLI) < os.path.getmtime(SRC):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", CLI, SRC, "-ldl", "-lz"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", CLI, SRC, "-ldl", "-lz"])
     env = dict(os.environ, STITCH_B200_LIB=os.path.join(ROOT, "tests", "emul", "libemul_s8.so"), STITCH_B200_PREFIX="emul_")
 
     def run(args):
@@ -153,8 +153,32 @@ def test_cli_sam_and_bam(cli, tmp_path):
 def test_cli_rejects_what_it_cannot_do(cli, tmp_path):
     p = subprocess.run([CLI, "align", "-r", "x.fa"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode != 0 and b"exactly one of --reads-fastq or --reads-fasta" in p.stderr
-    p = subprocess.run([CLI, "align", "-f", "a.fq", "-r", "x.fa", "-p"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert p.returncode != 0 and b"--pre-align is not supported" in p.stderr
+    p = subprocess.run([CLI, "align", "-f", "a.fq", "-r", "x.fa", "--bogus"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode != 0 and b"unknown option --bogus" in p.stderr
+
+
+def test_cli_pre_align(cli, tmp_path):
+    """-p -k -w -s -x (align.rs:119-146): reads below the pre-alignment score come out as unmapped records without `xs`, the others
+    carry the score in `xs`; same records as the library call with the same options."""
+    import emul_lib
+    rng = random.Random(91)
+    contigs = [gen.rand_seq(rng, rng.randint(300, 500)) for _ in range(6)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(150, 300), rng.randint(1, 2), strands=True) for _ in range(5)]
+    reads.insert(2, gen.rand_seq(rng, 120))          # matches nothing
+    heads = [f"q{k}" for k in range(len(reads))]
+    ref, fa = tmp_path / "ref.fa", tmp_path / "reads.fa"
+    ref.write_text("".join(f">c{k}\n{c.decode()}\n" for k, c in enumerate(contigs)))
+    fa.write_text("".join(f">{h}\n{r.decode()}\n" for h, r in zip(heads, reads)))
+    for x in ("true", "false"):
+        kw = dict(double_strand=True, pre_align=True, kmer_size=9, band_width=25, pre_align_min_score=45, pre_align_subset_contigs=(x == "true"))
+        e = emul_lib.EmulAligners(make_opts(**kw), [(f"c{k}", c) for k, c in enumerate(contigs)], strip=8)
+        _, exp = e.batch_sam(reads, heads, None, None)
+        e.close()
+        out = cli(["-a", str(fa), "-r", str(ref), "-d", "-p", "-k", "9", "-w", "25", "-s", "45", "-x", x, "--sam", "--batch", "2"]).decode().splitlines()
+        got = [l for l in out if not l.startswith("@")]
+        assert got == [l for per_read in exp for l in per_read]
+        assert got[2 if x == "true" else 2].split("\t")[0] != "" and any(l.split("\t")[1] == "4" and "xs:i:" not in l for l in got)
+        assert any("\txs:i:" in l for l in got)
 
 
 def test_cli_multi_context_order(cli, tmp_path):

@@ -346,7 +346,7 @@ def test_cli_on_gpu(oracle, tmp_path):
     import sam_oracle
     cli = os.path.join(root, "stitch_b200", "stitch-b200")
     if not os.path.exists(cli):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", cli, os.path.join(root, "stitch_b200", "csrc", "stitch_align_cli.cpp"), "-ldl", "-lz"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", cli, os.path.join(root, "stitch_b200", "csrc", "stitch_align_cli.cpp"), "-ldl", "-lz"])
     rng = random.Random(77)
     contigs = [gen.rand_seq(rng, rng.randint(400, 900)) for _ in range(4)]
     reads = [gen.chimeric_read(rng, contigs, rng.randint(200, 600), rng.randint(1, 4), strands=True, wrap=True) for _ in range(10)]
@@ -492,3 +492,79 @@ def test_contig_longer_than_the_staging_area(oracle):
     noisy = [gen.noisy(rng, reads[0][:400])]
     got, exp = run_both(oracle, dict(double_strand=False), contigs, noisy, raw=False)
     compare(got, exp, "long contig")
+
+
+class _GpuPre:
+    """The shape tests/test_prealign.py's checks expect, over the CUDA library."""
+    def __init__(self, kw, named):
+        self.al = gpu_aligners(kw, named)
+    def batch(self, reads):
+        out = self.al.align_batch(reads)
+        self.last_prealign_scores = self.al.last_prealign_scores
+        return out
+    def prealign_batch(self, reads):
+        return self.al.prealign_batch(reads)
+    def close(self):
+        self.al.close()
+
+
+def test_prealign_on_gpu(oracle):
+    """Pre-alignment contig selection on the CUDA kernel (kernels_prealign.cuh): the same selections and scores as the
+    sequential statement of prealign_core.h in the CPU emulator, chains equal to the oracle's on the selected subsets, a
+    600-strand contig table, direct (k <= 12) and hashed (k = 15) buckets."""
+    import emul_lib
+    import test_prealign as tp
+    for seed, kw, shape in ((11, dict(double_strand=True, pre_align=True, kmer_size=8, band_width=20, pre_align_min_score=40), (12, 300, 600, 6, 400, 3)),
+                            (13, dict(double_strand=True, pre_align=True, kmer_size=10, band_width=30, pre_align_min_score=50), (300, 120, 260, 5, 360, 3)),
+                            (14, dict(double_strand=True, circular=True, pre_align=True, kmer_size=15, band_width=50, pre_align_min_score=80), (40, 400, 900, 5, 900, 3))):
+        contigs, reads, truth = tp.make_case(seed, *shape)
+        sel, best = tp.check_subset_mode(oracle, _GpuPre, kw, contigs, reads, truth)
+        e = emul_lib.EmulAligners(make_opts(**kw), [(f"c{k}", s) for k, s in enumerate(contigs)], strip=8)
+        assert (sel, best) == e.prealign_batch(reads), kw
+        e.close()
+    # reads that reach the score nowhere come back unmapped
+    rng = random.Random(5)
+    contigs = [gen.rand_seq(rng, 400) for _ in range(4)]
+    al = gpu_aligners(dict(double_strand=True, pre_align=True), [(f"c{k}", s) for k, s in enumerate(contigs)])
+    chains = al.align_batch([contigs[2][50:350], gen.rand_seq(rng, 300), contigs[1][10:60]])
+    assert [len(c) for c in chains] == [1, 0, 0] and al.last_prealign_scores == [300, None, None]
+    al.close()
+
+
+def test_config3_full_table_with_prealign(oracle):
+    """BASELINE config 3 at its stated scale: 2 000 contigs of 5-10 kb x 2 strands = 4 000 contig-strands (15 Mb, 30 M indexed
+    k-mers), reads of 5-20 kb with 3-8 segments, `-d -p -x`.  Every contig-strand a read was drawn from is selected, the
+    selection stays far below 256 strands, and the chains of three reads equal the oracle's on the same subsets."""
+    import numpy as np
+    import test_prealign as tp
+    from stitch_b200 import synth
+    rng = np.random.default_rng(20243)
+    contigs = [c.tobytes() for c in synth.make_contigs(rng, 2000, 5000, 10000)]
+    reads, truth = [], []
+    for _ in range(48):
+        t = []
+        reads.append(synth.make_read(rng, [np.frombuffer(c, dtype=np.uint8) for c in contigs], int(rng.integers(5000, 20001)), 3, 8,
+                                     strands=True, truth=t).tobytes())
+        truth.append(sorted(set(t)))
+    kw = dict(double_strand=True, pre_align=True)
+    named = [(f"c{k}", s) for k, s in enumerate(contigs)]
+    al = gpu_aligners(kw, named)
+    got = al.align_batch(reads)
+    pre = al.last_prealign_scores
+    st = al.stats()
+    sel, best = al.prealign_batch(reads)
+    al.close()
+    assert st.prealign_reads == 48 and st.packed_cells == st.cells
+    for r in range(len(reads)):
+        # a segment shorter than ~150 bases may stay below the minimum score of 100, like in the reference
+        assert len(sel[r]) <= 32 and pre[r] == best[r] and len(got[r]) == 1
+        got[r][0].validate()
+    long_truth = sum(1 for r in range(len(reads)) for c in truth[r] if c in sel[r])
+    assert long_truth >= 0.9 * sum(len(t) for t in truth), (long_truth, sum(len(t) for t in truth))
+    for r in sorted(range(len(reads)), key=lambda r: (len(reads[r]) * len(sel[r]), r))[:3]:
+        oracle.set_checker_layout(True)
+        try:
+            exp = tp.reduced_oracle(oracle, kw, contigs, reads[r], sel[r])
+        finally:
+            oracle.set_checker_layout(False)
+        assert [a.key() for a in got[r]] == [a.key() for a in exp], r
