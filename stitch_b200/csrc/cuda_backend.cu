@@ -118,6 +118,8 @@ struct CudaBackend : host::Backend {
     uint32_t cluster_smem = 1;   // STITCH_CLUSTER_SMEM=0: clusters keep the rolling state in global memory
     uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
     uint32_t quiet_tail = 1;     // STITCH_QUIET_TAIL=0: the tail columns compute every tile
+    uint32_t cone_refill = 1;    // STITCH_CONE=0: the walk re-fills whole contigs (dp_packed.h: cone re-fill)
+    uint32_t stage_depth_pref = 4;   // STITCH_STAGE_DEPTH: slots of the cp.async staging ring per warp (2..4); reduced when shared memory is short
     uint32_t quiet_first = 1, quiet_edge = 1, quiet_last = 1;   // STITCH_QUIET_FIRST / _EDGE / _LAST = 0: those tiles are always computed
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
@@ -163,6 +165,8 @@ struct CudaBackend : host::Backend {
         cluster_min_tiles = env_u32("STITCH_CLUSTER_MIN_TILES", cluster_min_tiles);
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
         quiet_tiles = env_u32("STITCH_QUIET", quiet_tiles);
+        cone_refill = env_u32("STITCH_CONE", 1);
+        stage_depth_pref = std::min(4u, std::max(2u, env_u32("STITCH_STAGE_DEPTH", stage_depth_pref)));
         quiet_first = env_u32("STITCH_QUIET_FIRST", 1); quiet_edge = env_u32("STITCH_QUIET_EDGE", 1); quiet_last = env_u32("STITCH_QUIET_LAST", 1); quiet_tail = env_u32("STITCH_QUIET_TAIL", 1);
     }
     ~CudaBackend() override {
@@ -394,6 +398,14 @@ struct CudaBackend : host::Backend {
         }
         // shared memory of the packed fill, and of its walk phase (per-unit staging of K columns + the unit's contig bases) when
         // that fits beside it with the real K and the longest contig of this chunk; otherwise the separate walk kernel runs
+        // staging ring of the fill: as deep as shared memory allows (the walk phase's staging included when it would otherwise fit)
+        uint32_t depth = 2;
+        if (cluster == 1) {
+            const size_t walk_extra = (walk_in_kernel && cluster == 1 && n_packed > 0) ? UnitStage::bytes(K, max_ctiles, false) : 0;
+            for (depth = stage_depth_pref; depth > 2; --depth)
+                if ((PackSmem::bytes(cmax, ntmax, PACK_WARPS, PackSmem::default_stage(PACK_WARPS, depth)) + 15) / 16 * 16 + walk_extra <= SMEM_LIMIT) break;
+            pstage = PackSmem::default_stage(PACK_WARPS, depth);
+        }
         size_t psmem = (PackSmem::bytes(cmax, ntmax, PACK_WARPS, pstage) + 15) / 16 * 16;
         bool packed_walks_in_kernel = walk_in_kernel && cluster == 1 && n_packed > 0;
         bool pstage_bases = true;
@@ -446,7 +458,7 @@ struct CudaBackend : host::Backend {
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
-        P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1;
+        P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1; P.cone = cone_refill;
         if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
@@ -454,7 +466,7 @@ struct CudaBackend : host::Backend {
         mark(T_PACKED);
         if (n_packed) {
             Params Q = P; Q.order = d_order.p + nj; Q.n_jobs = n_packed; Q.counter = d_counter.p + 3;
-            Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes;
+            Q.cluster_size = cluster; Q.stage_bytes = (uint32_t)pstage; Q.cluster_state_smem = (uint32_t)cstate_bytes; Q.stage_depth = depth;
             Q.quiet = quiet_tiles; Q.quiet_first = quiet_first; Q.quiet_edge = quiet_edge; Q.quiet_last = quiet_last; Q.quiet_tail = quiet_tail;
             if (packed_walks_in_kernel) {   // second phase of the same kernel: fix-up + walk of the packed reads
                 d_done.reserve(nj);

@@ -648,12 +648,23 @@ enum : uint32_t { WALK_OK = 0, WALK_NONE = 1, WALK_OVERFLOW = 2, WALK_PANIC = 3 
 
 // The packed traceback bytes of ONE contig over one block of columns (jb, je], re-filled from
 // a column-state checkpoint when the walk needs them (checkpoint-and-recompute).
+//
+// A unit is re-filled for the cell (i_hi, je) the walk enters it at.  The walk only moves up and left from there, and a
+// cell depends only on cells above / left of it within `slope` rows per column (one row for the diagonal plus the reach of
+// the insertion chain, dp_packed.h), so a packed re-fill may restrict itself to the CONE of the entry cell: rows
+// [i_hi - slope * (je - j), i_hi] at column j.  Cells outside the cone hold stale values; the walk never reads them
+// (has() says "not loaded" for them and the unit is re-filled for the new entry cell).  Full units: i_hi = 0xffffffff.
 struct TbUnit {
     const uint8_t *bytes;   // column j (jb < j <= je), row i (1..m): bytes[(j - jb - 1) * pm + i - 1]
-    const ColRec *cr;       // per column of the unit: cr[j - jb - 1].lx = Lx[j] of this contig (SCA:407-429)
+    const ColRec *cr;       // per column of the unit: cr[j - jb - 1].lx = Lx[j] of this contig (SCA:407-429); full units only
     uint32_t a;             // layout position; 0xffffffff = nothing loaded
-    uint32_t jb, je, pm;
-    SHD bool has(uint32_t a_, uint32_t j) const { return a == a_ && j > jb && j <= je; }
+    uint32_t jb, je, pm;    // je: the last column filled (the column of the entry cell)
+    uint32_t i_hi, slope;   // cone (see above)
+    SHD bool has(uint32_t a_, uint32_t i, uint32_t j) const {
+        if (a != a_ || j <= jb || j > je) return false;
+        if (i_hi == 0xffffffffu) return true;
+        return i <= i_hi && (int64_t)i >= (int64_t)i_hi - (int64_t)slope * (int64_t)(je - j);
+    }
     SHD uint32_t at(uint32_t i, uint32_t j) const { return bytes[(uint64_t)(j - jb - 1) * pm + (i - 1)]; }
 };
 
@@ -750,7 +761,7 @@ SHD uint32_t walk_run(const ReadView &v, WalkState &st, ChainHdr &h) {
     uint32_t status = WALK_OK;
     for (;;) {
         if (w.overflow) { status = WALK_OVERFLOW; break; }
-        if (v.interior(i, j) && !v.unit.has(a, j) &&
+        if (v.interior(i, j) && !v.unit.has(a, i, j) &&
             (layer == WL_LOOKUP || layer == TB_INS || layer == TB_DEL || layer == TB_MATCH || layer == TB_SUBST ||
              layer == TB_XCLIP_SUFFIX)) {
             st.a = a; st.i = i; st.j = j; st.layer = layer; st.cur_idx = cur_idx;

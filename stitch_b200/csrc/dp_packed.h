@@ -430,6 +430,38 @@ SHD PkRowM pk_quiet_rowm(const PK &p, const PCol &c, const PkQuiet &qprev, int32
     return rm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cone re-fill of the walk (TbUnit, dp_core.h).  The walk enters a (contig, block of columns) unit at cell (i_entry, j)
+// and only moves up / left inside it.  A cell depends on the cell diagonally above-left, on D of the same row, and on the
+// insertion chain of at most R = band / |e| + 1 rows above it in its own column, so whatever the rows above
+// top(jj) = i_entry - slope * (j - jj), slope = R + 1, hold at column jj can only reach rows above top(jj + 1) at column
+// jj + 1 (any IN-BAND value: stale keys of an earlier column are in band, so the chain's reach bound applies to them).
+// The path itself stays inside the cone: one row per column on the diagonal, insertion runs no longer than R (a longer
+// one scores below the jump that is available everywhere).  Row m (it accumulates the x-suffix tracker over the WHOLE
+// column, SCA:407-429) and row 1 of a circular contig (it reads row m, SCA:258-289) need the full column.
+// Checked on the CPU emulator against full re-fills (tests/emul, EMUL_CONE_AUDIT) and against the oracle end to end.
+constexpr uint32_t PK_CONE_MAX_COLS = 384;   // columns of a cone unit (its window must fit one tile per warp)
+struct PkCone { bool on; uint32_t slope, win_lo, win_n; };
+SHD PkCone pk_cone_plan(const Scoring &sc, const ContigEntry &en, uint32_t i_entry, uint32_t j, uint32_t jb, uint32_t max_tiles) {
+    PkCone c; c.on = false; c.slope = 0; c.win_lo = 0; c.win_n = en.ntiles;
+    if (sc.e >= 0 || i_entry < 1 || i_entry >= en.m || j <= jb || j - jb > PK_CONE_MAX_COLS) return c;
+    c.slope = (uint32_t)(pk_band(sc) / -sc.e) + 2;
+    const int64_t top_first = (int64_t)i_entry - (int64_t)c.slope * (int64_t)(j - jb - 1);   // top row of the cone at column jb + 1
+    if (en.circular && top_first < 2) return c;
+    // the window starts `slope` rows higher: column jb + 1 reads the checkpointed column jb that far above its top row
+    const int64_t top_ck = top_first - (int64_t)c.slope;
+    const uint32_t r_top = top_ck < 1 ? 1u : (uint32_t)top_ck;
+    const uint32_t lo = (r_top - 1) / (uint32_t)TILE, hi = (i_entry - 1) / (uint32_t)TILE;
+    if (hi - lo + 1 > max_tiles) return c;
+    c.on = true; c.win_lo = lo; c.win_n = hi - lo + 1;
+    return c;
+}
+// First tile that is computed at column jj of a cone unit entered at (i_entry, j).
+SHD uint32_t pk_cone_top_tile(const PkCone &c, uint32_t i_entry, uint32_t j, uint32_t jj) {
+    const int64_t top = (int64_t)i_entry - (int64_t)c.slope * (int64_t)(j - jj);
+    return top < 1 ? 0u : (uint32_t)((top - 1) / TILE);
+}
+
 // Carry into a lane from the previous lane's exit (PP_INC -> PP_ICARRY).
 SHD int32_t pk_carry_from_exit(const PK &p, int32_t exit_key) { return exit_key + p.P1; }
 

@@ -58,15 +58,16 @@ struct PackSmem {
     static constexpr uint32_t TB_MASK = 31u, TB_Q = 32u;
     ContigEntry *ent_s;     // [cmax]: the layout's contig table (bulk pass: no global loads in the per-column serial phases)
     uint16_t *owner_s;      // [ntmax]: contig position of every tile
+    uint16_t *clist;        // [ntmax]: per warp chunk (slice [t_lo, t_hi)), the chunk-relative offsets of the tiles computed in this column
     uint32_t cmax;
-    unsigned char *stage;   // [W][2][STAGE_BYTES]: cp.async double buffer of the next tile (state in global memory only)
+    unsigned char *stage;   // [W][depth][STAGE_BYTES]: cp.async ring of the next tiles (state in global memory only)
     static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + TILE;   // S keys, D keys, bases of one tile
     // `stage_bytes`: the front area = cp.async double buffers (default_stage), or the cluster's slice of the rolling
     // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
-    static size_t default_stage(int W) { return (size_t)W * 2 * STAGE_BYTES; }
+    static size_t default_stage(int W, uint32_t depth = 2) { return (size_t)W * depth * STAGE_BYTES; }
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
         return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 9 + ntmax + 2 * W * 18) +
-               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 3 * (size_t)ntmax + 4 * 8 + 64;
+               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 5 * (size_t)ntmax + 4 * 8 + 64;
     }
     __device__ void carve(unsigned char *raw, uint32_t cmax_, uint32_t ntmax, int W, size_t stage_bytes) {
         const uint32_t cmax = cmax_;
@@ -86,7 +87,8 @@ struct PackSmem {
         Q = reinterpret_cast<PkQuiet *>(haloF + 2 * W + 2);
         ent_s = reinterpret_cast<ContigEntry *>(Q + 2 * cmax);
         owner_s = reinterpret_cast<uint16_t *>(ent_s + cmax);
-        tb = reinterpret_cast<uint8_t *>(owner_s + ntmax);
+        clist = owner_s + ntmax;
+        tb = reinterpret_cast<uint8_t *>(clist + ntmax);
     }
 };
 
@@ -106,12 +108,18 @@ struct PackCtx {            // uniform per (job, set of contigs)
     uint32_t n;
     bool yclip_mode;
     bool state_smem;        // the state arrays live in shared memory (walk kernel re-fills)
-    bool staged;            // cp.async double-buffering of tiles (state and bases both in global memory, stage buffers carved)
+    bool staged;            // cp.async staging of tiles (state and bases both in global memory, stage buffers carved)
+    uint32_t stage_depth;   // slots per warp of the staging ring (2..4): depth - 1 tiles are in flight ahead of the one computed
     Team team;
     // Tiles [own_lo, own_hi) are this CTA's (all tiles for a single-CTA team).  Sst/Dst address them as
     // Sst + tile * ST.  With cluster_smem the state of a tile lives in the shared memory of the CTA that owns it
     // (cstate = this CTA's block, same offset in every CTA of the cluster) and Sst = cstate - own_lo * ST.
     uint32_t own_lo, own_hi, warps;
+    // Cone re-fills of the walk (TbUnit, dp_core.h) run the columns over a WINDOW of the contig's tiles: tiles
+    // [win_lo, win_lo + NT), one per warp; tiles below `skip_below` are left stale in this column; no per-contig finish
+    // (row m is outside the window).  Everything else: win_lo = 0, skip_below = 0, no_finish = false.
+    uint32_t win_lo, skip_below;
+    bool no_finish;
     bool cluster_smem;
     bool quiet;             // the bulk pass may skip quiet tiles (single-CTA teams with the state in global memory)
     bool quiet_first, quiet_edge, quiet_last;   // the first / last tile of a contig, the first and last tile of a warp chunk may be skipped too
@@ -126,8 +134,8 @@ __device__ __forceinline__ uint32_t pk_chunk_lo(uint32_t NT, uint32_t Weff, uint
 __device__ __forceinline__ void pk_set_ownership(PackCtx &X, uint32_t W) {
     const uint32_t GW = X.team.size * W, Weff = X.NT < GW ? X.NT : GW;
     X.warps = W;
-    X.own_lo = pk_chunk_lo(X.NT, Weff, X.team.rank * W);
-    X.own_hi = pk_chunk_lo(X.NT, Weff, (X.team.rank + 1) * W);
+    X.own_lo = X.win_lo + pk_chunk_lo(X.NT, Weff, X.team.rank * W);
+    X.own_hi = X.win_lo + pk_chunk_lo(X.NT, Weff, (X.team.rank + 1) * W);
 }
 // The 512-key block of any tile of the read (possibly in another CTA's shared memory).
 __device__ __forceinline__ int32_t *pk_tile_ptr(const PackCtx &X, uint32_t tile) {
@@ -343,7 +351,7 @@ __device__ void pk_init_halos(const PackCtx &X, PackSmem &S, uint32_t slot) {
     const uint32_t GW = X.team.size * W, gw = X.team.rank * W + warp;
     const uint32_t Weff = X.NT < GW ? X.NT : GW;
     if (gw >= 1 && gw < Weff && lane < 9) {
-        const uint32_t t_lo = (uint32_t)((uint64_t)X.NT * gw / Weff);
+        const uint32_t t_lo = X.win_lo + (uint32_t)((uint64_t)X.NT * gw / Weff);
         const uint32_t hl = lane == 0 ? 30u : 31u, hk = lane == 0 ? (uint32_t)STRIP - 1 : lane - 1;
         const int32_t *tp = pk_tile_ptr(X, t_lo - 1) + (hk >> 2) * 128u + hl * 4u + (hk & 3u);
         S.haloS[(slot * W + warp) * 9 + lane] = tp[0];
@@ -368,14 +376,14 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const uint32_t Weff = NT < GW ? NT : GW;
     const PkQuiet *Qp = S.Q + (par ^ 1u) * S.cmax, *Qn = S.Q + par * S.cmax;
     const long long c0 = cs ? clock64() : 0;
-    if (gw < Weff) {
-        const uint32_t t_lo = (uint32_t)((uint64_t)NT * gw / Weff), t_hi = (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
+    if (gw < Weff && X.win_lo + (uint32_t)((uint64_t)NT * (gw + 1) / Weff) > X.skip_below) {
+        const uint32_t t_lo = X.win_lo + (uint32_t)((uint64_t)NT * gw / Weff), t_hi = X.win_lo + (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
         int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
-        // software pipeline: while tile t is computed, cp.async brings tile t+1 (S keys, D keys, bases) into this
-        // warp's shared-memory double buffer; each lane reads back exactly the bytes it copied (no warp sync needed)
+        // cp.async brings the next tiles (S keys, D keys, bases) into this warp's shared-memory ring while a tile is computed;
+        // each lane reads back exactly the bytes it copied (no warp sync needed)
         const bool staged = X.staged;
-        unsigned char *stg0 = S.stage + (size_t)warp * 2 * PackSmem::STAGE_BYTES;
+        unsigned char *stg0 = S.stage + (size_t)warp * X.stage_depth * PackSmem::STAGE_BYTES;
         // (`full` = the tile's state is loaded; a materialised tile only needs its bases)
         auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot, bool full) {
             unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
@@ -439,70 +447,63 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 __syncwarp();
             }
         }
+        // the tiles of this chunk that are computed in this column, in order (quiet tiles: the chunk-relative offsets, compacted
+        // into this warp's slice of S.clist)
+        uint16_t *cl = S.clist + t_lo;
+        uint32_t ncomp = t_hi - t_lo, nskipped = 0;
+        if (QUIET) {
+            ncomp = 0;
+            for (uint32_t base = t_lo; base < t_hi; base += 32) {
+                const bool comp = base + lane < t_hi && ((uint32_t)S.tb[base + lane] >> 6) != 0u;
+                const uint32_t m = __ballot_sync(FULL, comp);
+                if (comp) cl[ncomp + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base + lane - t_lo);
+                ncomp += __popc(m);
+            }
+            nskipped = (t_hi - t_lo) - ncomp;
+            __syncwarp();
+        }
+        auto tile_at = [&](uint32_t k) -> uint32_t { return QUIET ? t_lo + cl[k] : t_lo + k; };
         // contig of the current tile (reloaded only when the chunk crosses into the next contig)
         uint32_t a = X.owner ? X.owner[t_lo] : 0u;
         ContigEntry en = X.ent[a];
         int32_t Jc = S.Jc[a];
-        uint32_t nskipped = 0;
-        uint32_t pf_tile = 0xffffffffu, pf_slot = 1;   // the latest prefetch: tile and stage slot
-        bool last_skipped = false;                      // tile base-1 was skipped
-        for (uint32_t base = t_lo; base < t_hi; base += 32) {
-            const uint32_t nb = t_hi - base, validm = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-            // loadm: tiles whose state is loaded; compm / compm_next: tiles that are computed (each gets a stage slot: state + bases,
-            // or the bases alone when its state is materialised)
-            uint32_t skipm = 0, loadm = validm, compm = validm, compm_next = base + 32 < t_hi ? 1u : 0u, loadm_next = compm_next;
-            if (QUIET) {
-                const uint32_t m0 = base + lane < t_hi ? (uint32_t)S.tb[base + lane] >> 6 : 0u;
-                const uint32_t m1 = base + 32 + lane < t_hi ? (uint32_t)S.tb[base + 32 + lane] >> 6 : 0u;
-                skipm = __ballot_sync(FULL, m0 == 0u) & validm; loadm = __ballot_sync(FULL, m0 == 2u);
-                compm = ~skipm & validm; compm_next = __ballot_sync(FULL, m1 != 0u); loadm_next = __ballot_sync(FULL, m1 == 2u);
-                nskipped += __popc(skipm);
+        // software pipeline: a ring of `depth` stage slots per warp; while tile k is computed the next depth - 1 computed tiles are
+        // in flight (cp.async), so that a tile's HBM / L2 latency is covered by several tiles of arithmetic
+        const uint32_t depth = X.stage_depth;
+        uint32_t issued = 0;
+        auto issue = [&](uint32_t k) {
+            const uint32_t t = tile_at(k);
+            const bool full = !QUIET || ((uint32_t)S.tb[t] >> 6) == 2u;
+            if (t >= en.tile_start && t < en.tile_start + en.ntiles) prefetch(t, en, k % depth, full);
+            else { const ContigEntry e2 = X.ent[X.owner ? X.owner[t] : 0u]; prefetch(t, e2, k % depth, full); }
+        };
+        if (staged) for (; issued + 1u < depth && issued < ncomp; ++issued) issue(issued);
+        for (uint32_t k = 0; k < ncomp; ++k) {
+            const uint32_t tile = tile_at(k);
+            const bool is_load = !QUIET || ((uint32_t)S.tb[tile] >> 6) == 2u;
+            qz.prev_skipped = QUIET && tile != t_lo && (k == 0 || tile_at(k - 1) + 1u != tile);
+            if (tile >= en.tile_start + en.ntiles) { a = X.owner[tile]; en = X.ent[a]; Jc = S.Jc[a]; }
+            const unsigned char *stg = nullptr;
+            if (staged) {
+                if (issued < ncomp) { issue(issued); ++issued; }
+                switch (issued - 1u - k) {   // commits younger than tile k's may stay pending
+                case 0: __pipeline_wait_prior(0); break;
+                case 1: __pipeline_wait_prior(1); break;
+                case 2: __pipeline_wait_prior(2); break;
+                default: __pipeline_wait_prior(3); break;
+                }
+                stg = stg0 + (k % depth) * PackSmem::STAGE_BYTES;
             }
-            uint32_t dm = compm;
-            while (dm) {
-                const uint32_t b = __ffs(dm) - 1u;
-                dm &= dm - 1u;
-                const uint32_t tile = base + b;
-                const bool is_load = (loadm >> b) & 1u;
-                qz.prev_skipped = QUIET && (b ? ((skipm >> (b - 1u)) & 1u) != 0 : last_skipped);
-                if (tile >= en.tile_start + en.ntiles) { a = X.owner[tile]; en = X.ent[a]; Jc = S.Jc[a]; }
-                // software pipeline: the tile to load sits (or arrives) in a stage slot; the next tile that will be loaded
-                // is prefetched into the other slot while this one is computed
-                uint32_t cur_slot = 0;
-                if (staged) {
-                    if (pf_tile != tile) { pf_slot ^= 1u; prefetch(tile, en, pf_slot, is_load); pf_tile = tile; }
-                    cur_slot = pf_slot;
-                }
-                bool issued = false;
-                if (staged) {
-                    const uint32_t rest = b == 31u ? 0u : (compm & ~((2u << b) - 1u));
-                    uint32_t nl = 0xffffffffu; bool nfull = true;
-                    if (rest) { const uint32_t nb_ = (uint32_t)__ffs((int)rest) - 1u; nl = base + nb_; nfull = (loadm >> nb_) & 1u; }
-                    else if (compm_next) { const uint32_t nb_ = (uint32_t)__ffs((int)compm_next) - 1u; nl = base + 32u + nb_; nfull = (loadm_next >> nb_) & 1u; }
-                    if (nl != 0xffffffffu && nl != pf_tile) {
-                        pf_slot ^= 1u;
-                        if (nl < en.tile_start + en.ntiles) prefetch(nl, en, pf_slot, nfull);
-                        else { const ContigEntry e2 = X.ent[X.owner[nl]]; prefetch(nl, e2, pf_slot, nfull); }
-                        pf_tile = nl; issued = true;
-                    }
-                }
-                const unsigned char *stg = nullptr;
-                if (staged) {
-                    if (issued) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
-                    stg = stg0 + cur_slot * PackSmem::STAGE_BYTES;
-                }
-                qz.mat = QUIET && !is_load;
-                qz.Qp = Qp + a; qz.Qn = Qn + a;
-                const uint32_t tic = tile - en.tile_start;
-                bool qnow;
-                if (tic == 0 || tic + 1 == en.ntiles)
-                    qnow = pk_tile<true, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-                else
-                    qnow = pk_tile<false, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-                if (QUIET && lane == 0)
-                    S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && (tic + 1 != en.ntiles || (X.quiet_last && tic != 0))) ? PackSmem::TB_Q : 0u));
-            }
-            last_skipped = (skipm >> 31) != 0;
+            qz.mat = QUIET && !is_load;
+            qz.Qp = Qp + a; qz.Qn = Qn + a;
+            const uint32_t tic = tile - en.tile_start;
+            bool qnow;
+            if (tic == 0 || tic + 1 == en.ntiles)
+                qnow = pk_tile<true, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
+            else
+                qnow = pk_tile<false, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
+            if (QUIET && lane == 0)
+                S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && (tic + 1 != en.ntiles || (X.quiet_last && tic != 0))) ? PackSmem::TB_Q : 0u));
         }
         if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
         if (QUIET && gw + 1 < Weff && lane == 0) S.haloF[par * W + warp + 1] = (S.tb[t_hi - 1] & PackSmem::TB_Q) ? 1u : 0u;
@@ -525,6 +526,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         }
     }
     team.sync();
+    if (X.no_finish) return;   // cone re-fill: row m is outside the window, nothing reads the column best
 
     const long long c1 = cs ? clock64() : 0;
     // ---- per contig: tracker + row m + column best (contig a on CTA a % size) ----
@@ -932,6 +934,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         X.ent = S.ent_s; X.owner = S.owner_s;
         X.C = C; X.NT = ld.n_tiles; X.bases = P.contig_bases;
         X.n = n; X.yclip_mode = sc.yp != MIN_SCORE && sc.xp == MIN_SCORE;
+        X.win_lo = 0; X.skip_below = 0; X.no_finish = false;
         pk_set_ownership(X, W);
         if (tid <= team.size) {
             const uint32_t GW = team.size * W, Weff = X.NT < GW ? X.NT : GW;
@@ -941,9 +944,10 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         X.cluster_smem = P.cluster_state_smem != 0;
         X.cstate = reinterpret_cast<int32_t *>(S.stage);
         if (X.cluster_smem) {   // the rolling state lives in the cluster's shared memory: no HBM traffic per column
-            X.Sst = X.cstate - (size_t)X.own_lo * ST; X.state_smem = true; X.staged = false;
+            X.Sst = X.cstate - (size_t)X.own_lo * ST; X.state_smem = true; X.staged = false; X.stage_depth = 2;
         } else {
             X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.state_smem = false; X.staged = true;
+            X.stage_depth = P.stage_depth;
         }
         X.Dst = X.Sst + TILE;
         ColRec *colrec = P.colrec + jd.colrec_off;
@@ -1034,70 +1038,116 @@ struct UnitStage {
     int32_t *B;         // [K + 1]: B[t] = base of column jb + t  (B[0] = base of the checkpointed column jb)
     uint8_t *q;         // [K]
     uint8_t *bases;     // contig bases (+ 16 bytes of padding for the strip over-read); only when Params::unit_stage_bases
+    PkColConst *cc;     // [K] cone re-fills: the per-column constants of the whole unit (nullptr: not carved, no cone re-fills)
+    int32_t *Jc;        // [K]
     static __host__ __device__ size_t r16(size_t v) { return (v + 15) / 16 * 16; }
-    // `stage_bases` = false: the longest contig does not fit beside the rest; the re-fill reads bases from global memory
+    static bool cone_fits(uint32_t K) { return K <= PK_CONE_MAX_COLS; }
+    // `stage_bases` = false: the longest contig does not fit beside the rest; the re-fill reads bases from global memory.
+    // The cone area is carved whenever the checkpoint spacing allows cone re-fills at all (cone_fits).
     static size_t bytes(uint32_t K, uint32_t max_ctiles, bool stage_bases) {
-        return r16(sizeof(JumpInfo) * K) + r16(sizeof(int32_t) * (K + 1)) + r16(K) + (stage_bases ? r16((size_t)max_ctiles * TILE + 16) : 0);
+        return r16(sizeof(JumpInfo) * K) + r16(sizeof(int32_t) * (K + 1)) + r16(K) + (cone_fits(K) ? r16(sizeof(PkColConst) * K) + r16(sizeof(int32_t) * K) : 0) +
+               (stage_bases ? r16((size_t)max_ctiles * TILE + 16) : 0);
     }
     __device__ void carve(unsigned char *raw, uint32_t K) {   // raw is 16-byte aligned; every part stays 16-byte aligned
         J = reinterpret_cast<JumpInfo *>(raw);
         B = reinterpret_cast<int32_t *>(raw + r16(sizeof(JumpInfo) * K));
         q = reinterpret_cast<uint8_t *>(B) + r16(sizeof(int32_t) * (K + 1));
-        bases = q + r16(K);
+        unsigned char *p = q + r16(K);
+        cc = nullptr; Jc = nullptr;
+        if (K <= PK_CONE_MAX_COLS) { cc = reinterpret_cast<PkColConst *>(p); p += r16(sizeof(PkColConst) * K); Jc = reinterpret_cast<int32_t *>(p); p += r16(sizeof(int32_t) * K); }
+        bases = p;
     }
 };
 
 template <int W>
 __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc &ld, PackSmem &S, UnitStage &U, ContigEntry *s_en,
-                               PkColConst *s_cc, uint32_t a, uint32_t j, int32_t *pstate, uint64_t pstate_half, bool state_smem,
+                               PkColConst *s_cc, uint32_t a, uint32_t j, uint32_t i_entry, int32_t *pstate, uint64_t pstate_half, bool state_smem,
                                uint8_t *bytes, ColRec *ucr, TbUnit *unit_out) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
-    const uint32_t b = (j - 1) / K, jb = b * K, je = (jb + K < n) ? jb + K : n;
+    const uint32_t b = (j - 1) / K, jb = b * K;
+    const uint32_t ncols = j - jb;   // columns (jb, j]: the walk enters at column j and only moves left
     const ContigEntry gen = P.ents[ld.ent_off + a];
     const uint32_t pm = gen.ntiles * TILE, gbase = gen.tile_start * TILE;
     const int32_t *gcol = P.gcol + jd.gcol_off;
     const ColRec *colrec = P.colrec + jd.colrec_off;
     const uint8_t *read = P.reads + jd.read_off;
     const bool stage_bases = P.unit_stage_bases != 0;
+    // cone of the entry cell (dp_packed.h) when the staging area was carved for it, else the whole contig
+    PkCone cone; cone.on = false; cone.slope = 0; cone.win_lo = 0; cone.win_n = gen.ntiles;
+    if (P.cone && U.cc) cone = pk_cone_plan(P.sc, gen, i_entry, j, jb, (uint32_t)W);
+    const PK pk = pk_make(P.sc, jd.LB);
     if (tid == 0) { *s_en = gen; s_en->tile_start = 0; if (stage_bases) s_en->seq_off = 0; }
-    for (uint32_t t = tid; t < je - jb; t += T) {
+    for (uint32_t t = tid; t < ncols; t += T) {
         const ColRec cr = colrec[(uint64_t)(jb + 1 + t) * C + a];
         JumpInfo J; J.score = cr.jscore; J.len = cr.jlen; J.idx = cr.jidx; J.from = cr.jfrom;
         U.J[t] = J;
         U.q[t] = read[jb + t];
     }
-    for (uint32_t t = tid; t <= je - jb; t += T) U.B[t] = (jb + t >= 1) ? gcol[jb + t - 1] : 0;
-    if (stage_bases) for (uint32_t t = tid; t < pm + 16; t += T) U.bases[t] = t < gen.m ? P.contig_bases[gen.seq_off + t] : (uint8_t)0;
+    for (uint32_t t = tid; t <= ncols; t += T) U.B[t] = (jb + t >= 1) ? gcol[jb + t - 1] : 0;
+    if (stage_bases) {
+        const uint32_t lo = cone.on ? cone.win_lo * TILE : 0u, hi = cone.on ? (cone.win_lo + cone.win_n) * TILE + 16u : pm + 16u;
+        for (uint32_t t = (lo >= 16u ? lo - 16u : 0u) + tid; t < hi; t += T) U.bases[t] = t < gen.m ? P.contig_bases[gen.seq_off + t] : (uint8_t)0;
+    }
     __syncthreads();
     PackCtx X;
-    X.pk = pk_make(P.sc, jd.LB); X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.NT = gen.ntiles; X.bases = stage_bases ? U.bases : P.contig_bases;
+    X.pk = pk; X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.bases = stage_bases ? U.bases : P.contig_bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
-    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false;   // bases are staged in shared memory here
+    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false; X.stage_depth = 2;   // bases are staged in shared memory here
+    X.NT = cone.on ? cone.win_n : gen.ntiles; X.win_lo = cone.on ? cone.win_lo : 0u; X.skip_below = 0; X.no_finish = cone.on;
     pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);
     else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(b - 1) * 2 * PM + 2 * gbase, P.ck_sum + jd.cksum_off + (uint64_t)(b - 1) * C + a,
                              U.B[0]);
     pk_init_halos<W>(X, S, jb & 1u);
-    __syncthreads();
-    for (uint32_t jj = jb + 1; jj <= je; ++jj) {
-        const uint32_t t = jj - jb - 1;
-        if (tid == 0) {
+    PkColOut O; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false; O.track_thr = MIN_SCORE;
+    if (cone.on) {
+        // every per-column constant of the unit at once (one column per thread), so that a column is tiles + ONE barrier
+        for (uint32_t t = tid; t < ncols; t += T) {
             const int32_t B = U.B[t + 1], Bprev = U.B[t];   // B[t+1] = G(jj-1) = base of column jj
-            const JumpInfo J = U.J[t];
             PCol pcl; pcl.B = B; pcl.delta = B - Bprev;
-            S.Jw[0] = J;
-            S.Jc[0] = pk_jc(X.pk, pcl, J.score, J.len);
-            *s_cc = pk_col_const(X.pk, X.sc, B, Bprev, jj, n, U.q[t]);
+            U.Jc[t] = pk_jc(pk, pcl, U.J[t].score, U.J[t].len);
+            U.cc[t] = pk_col_const(pk, P.sc, B, Bprev, jb + 1 + t, n, U.q[t]);
         }
+        // the rows above the window are stale by construction: the halo of the window's first tile is any in-band value
+        if (cone.win_lo > 0 && tid < 17u)
+            for (uint32_t par = 0; par < 2; ++par) {
+                if (tid < 9u) S.haloS[(par * W) * 9 + tid] = pk.NEGKEY;
+                else S.haloD[(par * W) * 8 + tid - 9u] = pk.NEGKEY + pk.PD6;
+            }
         __syncthreads();
-        const PkColConst cc = *s_cc;
-        PkColOut O; O.tb_col = bytes + (uint64_t)t * pm; O.colrec_col = ucr + t; O.sn = nullptr; O.last = nullptr;
-        O.track = false; O.lastcol = false; O.track_thr = MIN_SCORE;
-        pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, jj, O);
+        PackSmem S2 = S;
+        for (uint32_t jj = jb + 1; jj <= j; ++jj) {
+            const uint32_t t = jj - jb - 1;
+            const PkColConst cc = U.cc[t];
+            S2.Jc = U.Jc + t;
+            X.skip_below = pk_cone_top_tile(cone, i_entry, j, jj);
+            O.tb_col = bytes + (uint64_t)t * pm; O.colrec_col = nullptr;
+            pk_column<W, true>(X, S2, cc.pc, cc.r0pkey, cc.cr1key, jj, O);   // (no per-contig finish: ends after its first barrier)
+        }
+    } else {
+        __syncthreads();
+        for (uint32_t jj = jb + 1; jj <= j; ++jj) {
+            const uint32_t t = jj - jb - 1;
+            if (tid == 0) {
+                const int32_t B = U.B[t + 1], Bprev = U.B[t];
+                const JumpInfo J = U.J[t];
+                PCol pcl; pcl.B = B; pcl.delta = B - Bprev;
+                S.Jw[0] = J;
+                S.Jc[0] = pk_jc(pk, pcl, J.score, J.len);
+                *s_cc = pk_col_const(pk, P.sc, B, Bprev, jj, n, U.q[t]);
+            }
+            __syncthreads();
+            const PkColConst cc = *s_cc;
+            O.tb_col = bytes + (uint64_t)t * pm; O.colrec_col = ucr + t;
+            pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, jj, O);
+        }
     }
-    if (tid == 0) { unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; }
+    if (tid == 0) {
+        unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = j; unit_out->pm = pm;
+        unit_out->i_hi = cone.on ? i_entry : 0xffffffffu; unit_out->slope = cone.slope;
+    }
     __syncthreads();
 }
 

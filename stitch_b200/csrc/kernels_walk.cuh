@@ -14,7 +14,7 @@ namespace stitch {
 namespace gpu {
 
 struct WalkShared {
-    uint32_t cmd, ua, uj;
+    uint32_t cmd, ua, uj, ui;
     ContigEntry en;
     TbUnit unit;
     PkColConst cc;
@@ -43,7 +43,7 @@ __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDe
         v.sc = P.sc; v.ent = P.ents + ld.ent_off; v.C = ld.C; v.n = jd.n;
         v.colrec = P.colrec + jd.colrec_off; v.last = P.last + jd.cell_off; v.sn = P.sn + jd.cell_off;
         v.contig_bases = P.contig_bases; v.read = P.reads + jd.read_off;
-        v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
+        v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0; v.unit.i_hi = 0xffffffffu; v.unit.slope = 0;
         if (jd.walk == host::WALK_ALL) for (uint32_t a = 0; a < ld.C; ++a) sh.seen[a] = 0;
     }
     for (;;) {
@@ -62,7 +62,7 @@ __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDe
                     walking = true;
                 }
                 const uint32_t s = walk_run(v, ws, h);
-                if (s == WALK_NEED_UNIT) { sh.cmd = WCMD_UNIT; sh.ua = ws.a; sh.uj = ws.j; break; }
+                if (s == WALK_NEED_UNIT) { sh.cmd = WCMD_UNIT; sh.ua = ws.a; sh.uj = ws.j; sh.ui = ws.i; break; }
                 walking = false;
                 auto mark = [&](uint32_t idx) {
                     const int p = v.pos_of(idx);
@@ -87,7 +87,7 @@ __device__ __noinline__ void walk_job(const Params &P, uint32_t job, const JobDe
         if (sh.cmd == WCMD_DONE) break;
         const long long t_r0 = clock64();
         if (PACKED_ONLY || jd.LB)
-            pk_refill_unit<W>(P, jd, ld, PS, US, &sh.en, &sh.cc, sh.ua, sh.uj, B.wps, P.wpstate_half, B.wps_smem, B.ubytes, B.ucr, &sh.unit);
+            pk_refill_unit<W>(P, jd, ld, PS, US, &sh.en, &sh.cc, sh.ua, sh.uj, sh.ui, B.wps, P.wpstate_half, B.wps_smem, B.ubytes, B.ucr, &sh.unit);
         else if (!PACKED_ONLY)
             refill_unit<W>(P, jd, ld, *WS, &sh.en, sh.ua, sh.uj, B.st0, B.st1, B.ubytes, B.ucr, &sh.unit);
         if (tid == 0) {

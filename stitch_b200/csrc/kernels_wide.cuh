@@ -72,6 +72,7 @@ struct Params {
     uint32_t ntmax;          // largest tile count among the packed jobs
     uint32_t cluster_size;   // packed kernel: CTAs per read (thread-block cluster), 1 = no cluster
     uint32_t stage_bytes;    // packed kernels: size of the front area of their dynamic shared memory (PackSmem)
+    uint32_t stage_depth;    // packed fill: slots per warp of the cp.async staging ring (2..4)
     uint32_t cluster_state_smem;   // the rolling state lives in the cluster's shared memory (bytes per CTA), 0 = global memory
     uint32_t quiet;          // packed bulk pass: skip quiet tiles (dp_packed.h), single-CTA teams only
     uint32_t quiet_tail;     // ... and in the tail columns (traceback variant), for tiles below the tracking threshold
@@ -86,6 +87,7 @@ struct Params {
     uint32_t *done;          // packed kernel with the in-kernel walk phase: per job, 1 once its fill and tail are complete
     uint32_t walk_stage_smem_off;   // walk kernel: byte offset of the per-unit staging area in dynamic shared memory
     uint32_t walk_state_smem_off;   // walk kernel: byte offset of the packed unit state in dynamic shared memory (0: global)
+    uint32_t cone;                  // walk: packed re-fills restricted to the cone of the entry cell (dp_packed.h); 0: whole contigs
     uint32_t unit_stage_bases;      // walk: the per-unit staging area holds the contig's bases (they fit); 0: read from global memory
     int32_t *gcol;
     OutOp *ops;
@@ -477,7 +479,7 @@ __device__ void refill_unit(const Params &P, const JobDesc &jd, const LayoutDesc
         A.track = false; A.lastcol = false;
         column_wide<W>(sc, A, S);
     }
-    if (tid == 0) { unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; }
+    if (tid == 0) { unit_out->bytes = bytes; unit_out->cr = ucr; unit_out->a = a; unit_out->jb = jb; unit_out->je = je; unit_out->pm = pm; unit_out->i_hi = 0xffffffffu; unit_out->slope = 0; }
     __syncthreads();
 }
 

@@ -138,7 +138,7 @@ static void emul_column(const ColumnArgs &A) {
 struct EmulBackend : Backend {
     Aligner &al;
     uint32_t dump_seq = 0;
-    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE, QUIET_LAST, CONE_AUDIT;
+    uint32_t K, WINDOW, PACKED, QUIET, QUIET_EDGE, QUIET_LAST, CONE_AUDIT, CONE;
     explicit EmulBackend(Aligner &a) : al(a) {
         K = std::max<uint32_t>(1, env_u32("EMUL_K", 7));          // checkpoint spacing (columns)
         WINDOW = std::max<uint32_t>(1, env_u32("EMUL_WINDOW", 6));  // columns at the end of the read filled by the wide path
@@ -146,6 +146,7 @@ struct EmulBackend : Backend {
         QUIET = env_u32("EMUL_QUIET", 1);                           // 0: the bulk pass never skips quiet tiles
         QUIET_EDGE = env_u32("EMUL_QUIET_EDGE", 1);                 // 0: the first and last tile of a warp chunk are always computed
         QUIET_LAST = env_u32("EMUL_QUIET_LAST", 1);                 // 0: the last tile of a contig (row m) is always computed
+        CONE = env_u32("EMUL_CONE", 1);                             // 0: the walk re-fills whole contigs
         CONE_AUDIT = env_u32("EMUL_CONE_AUDIT", 0);                 // 1: audit the dependency cone of the unit re-fills (experiment)
     }
     ~EmulBackend() {
@@ -666,66 +667,72 @@ struct EmulBackend : Backend {
         }
     }
 
-    // EMUL_CONE_AUDIT=1 (experiment for the next round): re-fill the unit a second time while rows above the
-    // dependency cone of the entry cell (i_entry, j) - rows < i_entry - slope * (j - jj) at column jj - are left stale, and check
-    // that the traceback bytes inside the cone do not change.
-    uint64_t cone_units = 0, cone_bad = 0, cone_cells = 0, cone_window_rows = 0, cone_full_rows = 0;
+    // The packed re-fill of the walk as the CUDA kernel does it (pk_refill_unit): columns (jb, j] only, and, when
+    // pk_cone_plan allows, restricted to the cone of the entry cell (i_entry, j): the tiles above the window hold the lowest
+    // in-band keys from the start, the tiles of the window above the cone's current top tile keep their stale values, and
+    // TbUnit::has() makes the walk ask for a new unit whenever it would read outside the cone.  EMUL_CONE=0: whole contigs.
+    // EMUL_CONE_AUDIT=1 additionally compares every traceback byte inside the cone with a full re-fill.
+    uint64_t cone_units = 0, cone_bad = 0, cone_cells = 0, cone_window_rows = 0, cone_full_rows = 0, full_units = 0;
     void load_unit_packed(const Job &job, const Layout &L, uint32_t LB, const Fill &F, uint32_t a, uint32_t j, std::vector<uint8_t> &bytes,
                           std::vector<ColRec> &ucr, TbUnit &u, uint32_t i_entry = 0) {
         const Scoring &sc = al.opts.sc;
         const uint32_t C = (uint32_t)L.ent.size(), PM = L.PM(), n = job.n;
-        const uint32_t b = (j - 1) / K, jb = b * K, je = std::min(jb + K, n);
+        const uint32_t b = (j - 1) / K, jb = b * K;
         const PK pk = pk_make(sc, LB);
         ContigEntry en = L.ent[a];
         const uint32_t pm = en.ntiles * TILE;
         const ContigEntry en_ck = en;
         en.tile_start = 0;
-        PkState st;
-        if (b == 0) pk_state_init0(pk, &en, 1, pm, st);
-        else pk_state_from_ck(pk, &en, &en_ck, 1, pm, jb, F.gcol[jb - 1], F.ck_state.data() + (size_t)(b - 1) * PM,
-                              F.ck_sum.data() + (size_t)(b - 1) * C + a, st);
-        bytes.assign((size_t)(je - jb) * pm, 0);
-        ucr.assign(je - jb, ColRec{});
-        stats.cells += (uint64_t)en.m * (je - jb);
+        PkCone cone; cone.on = false; cone.slope = 0; cone.win_lo = 0; cone.win_n = en.ntiles;
+        if (CONE && K <= PK_CONE_MAX_COLS) cone = pk_cone_plan(sc, en, i_entry, j, jb, 16);
         const std::vector<uint32_t> owner(en.ntiles, 0);
-        for (uint32_t jj = jb + 1; jj <= je; ++jj) {
-            const ColRec &cr = F.colrec[(size_t)jj * C + a];
-            JumpInfo J{cr.jscore, cr.jlen, cr.jidx, cr.jfrom};
-            PkCol A{};
-            A.ent = &en; A.C = 1; A.NT = en.ntiles; A.owner = owner.data(); A.read = job.read; A.j = jj; A.n = n;
-            A.B = F.gcol[jj - 1]; A.Bprev = jj >= 2 ? F.gcol[jj - 2] : 0; A.J = &J;
-            A.tb = true; A.tb_col = bytes.data() + (size_t)(jj - jb - 1) * pm; A.colrec_col = ucr.data() + (jj - jb - 1);
-            packed_column(pk, A, st);
-        }
-        u.bytes = bytes.data(); u.cr = ucr.data(); u.a = a; u.jb = jb; u.je = je; u.pm = pm;
-        if (CONE_AUDIT && i_entry >= 1 && i_entry < en.m && !(en.circular)) {
-            const uint32_t slope = (uint32_t)(pk_band(sc) / -sc.e) + 2;   // one row per column for the diagonal + the insertion chain's reach
-            PkState st2;
-            if (b == 0) pk_state_init0(pk, &en, 1, pm, st2);
+        auto run = [&](bool use_cone, std::vector<uint8_t> &out_bytes, std::vector<ColRec> &out_cr) {
+            PkState st;
+            if (b == 0) pk_state_init0(pk, &en, 1, pm, st);
             else pk_state_from_ck(pk, &en, &en_ck, 1, pm, jb, F.gcol[jb - 1], F.ck_state.data() + (size_t)(b - 1) * PM,
-                                  F.ck_sum.data() + (size_t)(b - 1) * C + a, st2);
-            std::vector<uint8_t> bytes2((size_t)(je - jb) * pm, 0);
-            std::vector<ColRec> ucr2(je - jb);
-            ++cone_units;
+                                  F.ck_sum.data() + (size_t)(b - 1) * C + a, st);
+            out_bytes.assign((size_t)(j - jb) * pm, 0);
+            out_cr.assign(j - jb, ColRec{});
+            const size_t above = use_cone ? (size_t)cone.win_lo * TILE : 0;   // rows (0-based) above the window
+            for (int par = 0; par < 2 && use_cone; ++par)
+                for (size_t r = 0; r < above; ++r) { st.S[par][r] = pk.NEGKEY; st.D[par][r] = pk.NEGKEY + pk.PD6; }
             for (uint32_t jj = jb + 1; jj <= j; ++jj) {
                 const ColRec &cr = F.colrec[(size_t)jj * C + a];
                 JumpInfo J{cr.jscore, cr.jlen, cr.jidx, cr.jfrom};
                 PkCol A{};
                 A.ent = &en; A.C = 1; A.NT = en.ntiles; A.owner = owner.data(); A.read = job.read; A.j = jj; A.n = n;
                 A.B = F.gcol[jj - 1]; A.Bprev = jj >= 2 ? F.gcol[jj - 2] : 0; A.J = &J;
-                A.tb = true; A.tb_col = bytes2.data() + (size_t)(jj - jb - 1) * pm; A.colrec_col = ucr2.data() + (jj - jb - 1);
-                packed_column(pk, A, st2);
-                const int64_t top = (int64_t)i_entry - (int64_t)slope * (int64_t)(j - jj);   // first row (1-based) of the cone at column jj
-                // rows above the cone are "not computed": they keep what they held one column earlier
-                for (int64_t r = 1; r < top && r <= (int64_t)en.m; ++r) {
-                    st2.S[jj & 1][(size_t)r - 1] = st2.S[(jj - 1) & 1][(size_t)r - 1];
-                    st2.D[jj & 1][(size_t)r - 1] = st2.D[(jj - 1) & 1][(size_t)r - 1];
+                A.tb = true; A.tb_col = out_bytes.data() + (size_t)(jj - jb - 1) * pm; A.colrec_col = out_cr.data() + (jj - jb - 1);
+                packed_column(pk, A, st);
+                if (use_cone) {   // the tiles above the cone's top tile are "not computed": they keep what they held
+                    const size_t stale = (size_t)pk_cone_top_tile(cone, i_entry, j, jj) * TILE;
+                    for (size_t r = 0; r < stale && r < (size_t)en.m; ++r) {
+                        st.S[jj & 1][r] = r < above ? pk.NEGKEY : st.S[(jj - 1) & 1][r];
+                        st.D[jj & 1][r] = r < above ? pk.NEGKEY + pk.PD6 : st.D[(jj - 1) & 1][r];
+                    }
                 }
+            }
+        };
+        run(cone.on, bytes, ucr);
+        stats.cells += (uint64_t)(cone.on ? cone.win_n * TILE : en.m) * (j - jb);
+        u.bytes = bytes.data(); u.cr = ucr.data(); u.a = a; u.jb = jb; u.je = j; u.pm = pm;
+        u.i_hi = cone.on ? i_entry : 0xffffffffu; u.slope = cone.slope;
+        if (cone.on) ++cone_units; else ++full_units;
+        if (CONE_AUDIT && cone.on) {
+            std::vector<uint8_t> bytes2; std::vector<ColRec> ucr2;
+            run(false, bytes2, ucr2);
+            for (uint32_t jj = jb + 1; jj <= j; ++jj) {
+                const int64_t top = (int64_t)i_entry - (int64_t)cone.slope * (int64_t)(j - jj);
                 const uint32_t lo = top < 1 ? 1u : (uint32_t)top;
                 cone_window_rows += i_entry - lo + 1; cone_full_rows += en.m;
                 for (uint32_t r = lo; r <= i_entry; ++r) {
                     ++cone_cells;
-                    if (bytes2[(size_t)(jj - jb - 1) * pm + r - 1] != bytes[(size_t)(jj - jb - 1) * pm + r - 1]) ++cone_bad;
+                    if (bytes2[(size_t)(jj - jb - 1) * pm + r - 1] != bytes[(size_t)(jj - jb - 1) * pm + r - 1]) {
+                        ++cone_bad;
+                        if (std::getenv("EMUL_CONE_DEBUG"))
+                            std::fprintf(stderr, "[cone diff] a %u m %u K %u jb %u j %u i_entry %u slope %u win %u+%u | cell (%u, %u): cone %u full %u\n", a, en.m, K, jb, j,
+                                         i_entry, cone.slope, cone.win_lo, cone.win_n, r, jj, bytes[(size_t)(jj - jb - 1) * pm + r - 1], bytes2[(size_t)(jj - jb - 1) * pm + r - 1]);
+                    }
                 }
             }
         }
@@ -788,7 +795,7 @@ struct EmulBackend : Backend {
             A.track = false; A.sn = nullptr; A.lastcol = false; A.last = nullptr;
             emul_column(A);
         }
-        u.bytes = bytes.data(); u.cr = ucr.data(); u.a = a; u.jb = jb; u.je = je; u.pm = pm;
+        u.bytes = bytes.data(); u.cr = ucr.data(); u.a = a; u.jb = jb; u.je = je; u.pm = pm; u.i_hi = 0xffffffffu; u.slope = 0;
     }
 
     void run_one(const Job &job, JobResult &res) {
@@ -807,7 +814,7 @@ struct EmulBackend : Backend {
         ReadView v;
         v.sc = sc; v.ent = L.ent.data(); v.C = C; v.n = n; v.colrec = F.colrec.data();
         v.last = F.last.data(); v.sn = F.sn.data(); v.contig_bases = al.contigs.blob.data(); v.read = job.read;
-        v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0;
+        v.unit.bytes = nullptr; v.unit.cr = nullptr; v.unit.a = 0xffffffffu; v.unit.jb = v.unit.je = v.unit.pm = 0; v.unit.i_hi = 0xffffffffu; v.unit.slope = 0;
         std::vector<uint8_t> unit_bytes; std::vector<ColRec> unit_cr;
         const uint32_t cap = 2 * n + 4 * C + 64;
         auto do_walk = [&](uint32_t a_end, RawChain &rc) -> uint32_t {
