@@ -94,43 +94,53 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-CPU_RATE_EST = 2.0e6   # cell updates / s / thread of the restated reference at n = 10 kb (measured: profiles/r02_cpu_port_vs_n.json)
-
-
 def cpu_baseline(kw, named, reads, truth, budget_s=30.0, max_threads=None):
     """Times the restated reference (oracle/, 16-byte cells in the reference's own matrix layout, one aligner per thread,
     as fg-stitch-cli/src/commands/align.rs:345-390 runs them) on host cores, on FULL-LENGTH reads of the workload.
 
-    What bounds the sample is the contig axis, not the read: every thread aligns one whole read against one contig-strand
-    it was drawn from (truncated to fewer rows only when even that exceeds the time budget).  The reference's cost per cell
-    update is set by the read length (it walks its (m+1) x (n+1) traceback matrix with a stride of 16 (n+1) bytes), hardly
-    by the number of contig rows, so CUPS measured this way stand for the whole workload; truncating the READS (round 1)
-    flattered the CPU by 3x (profiles/r02_cpu_port_vs_n.json)."""
+    What bounds the sample is the contig axis, not the read: every thread aligns one whole read against `s` contig-strands
+    (the ones it was drawn from first), s sized from a short calibration run so that the sample takes about `budget_s`
+    seconds (a single strand truncated to fewer rows only when even one whole strand exceeds the budget).  The reference
+    walks its (m+1) x (n+1) traceback matrix with a stride of 16 (n+1) bytes, so its cost per cell update depends on the
+    read length and the host's memory system, hardly on the number of contig rows (profiles/r02_cpu_port_vs_n.json)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from stitch_b200._abi import make_opts
     T = min(host_threads(), max_threads or 64, len(reads))
     n = max(len(r) for r in reads[:T])
+    ns = len(named) * (2 if kw.get("double_strand") else 1)
+    m_mean = sum(len(s) for _, s in named) / len(named)
     m_full = max(len(s) for _, s in named)
-    rows = int(min(m_full, max(256, budget_s * CPU_RATE_EST / n)))
-    try:   # 16 B x (n+1) x (rows+1) of traceback per thread (the reference's allocation)
+    oracle_lib.set_checker_layout(False)   # the reference's layout: this is the baseline, not a parity check
+    # calibration: every thread, its read against the first 256 rows of one strand
+    cal = oracle_lib.OracleAligners(make_opts(**kw), [(nm, s[:256]) for nm, s in named])
+    _, ci = cal.batch(reads[:T], subsets=[[truth[r][0]] for r in range(T)], raw=False, threads=T)
+    rate = max(1e5, ci["cells"] / max(ci["seconds"], 1e-3) / T)        # cell updates / s / thread
+    rows = budget_s * rate / n
+    try:   # 16 B x (n+1) x rows of traceback per thread (the reference's allocation)
         avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
-        T = max(1, min(T, int(avail * 0.5 // (16 * (n + 1) * (rows + 1)))))
+        rows = min(rows, avail * 0.5 / T / (16 * (n + 1)))
     except Exception:
         pass
-    sample = reads[:T]
-    use = named if rows >= m_full else [(nm, s[:rows]) for nm, s in named]
-    subsets = [[truth[r][0]] for r in range(T)]
+    if rows >= m_mean:
+        s_per = int(max(1, min(ns, rows // m_mean)))
+        use, what = named, f"{s_per} whole contig-strand(s)"
+    else:
+        s_per = 1
+        use, what = [(nm, s[:max(256, int(rows))]) for nm, s in named], f"the first {max(256, int(rows))} rows of one contig-strand"
+    subsets = []
+    for r in range(T):
+        mine = list(truth[r])[:s_per]
+        mine += [c for c in range(ns) if c not in mine][:s_per - len(mine)]
+        subsets.append(sorted(mine))
     o = oracle_lib.OracleAligners(make_opts(**kw), use)
-    oracle_lib.set_checker_layout(False)   # the reference's layout: this is the baseline, not a parity check
-    _, info = o.batch(sample, subsets=subsets, raw=False, threads=T)
+    _, info = o.batch(reads[:T], subsets=subsets, raw=False, threads=T)
     gcups = info["cells"] / info["seconds"] / 1e9
     return {"value": gcups, "unit": "GCUPS", "cores": T, "kind": "port",
-            "sample": f"{len(sample)} full-length reads ({n} b) of the workload, one per thread, each against one contig-strand it was "
-                      f"drawn from ({'whole, ' + str(m_full) if rows >= m_full else 'first ' + str(rows)} rows; same options; origin "
-                      f"re-alignment fills included): {info['fills']} fills, {info['cells']} cells in {info['seconds']:.1f} s; one "
-                      f"restated-reference aligner per thread, the reference's traceback layout; the Rust reference itself cannot be "
-                      f"built here (no cargo)",
+            "sample": f"{T} full-length reads ({n} b) of the workload, one per thread, each against {what} (the ones it was drawn from first; "
+                      f"same options; origin re-alignment fills included): {info['fills']} fills, {info['cells']} cells in {info['seconds']:.1f} s; "
+                      f"one restated-reference aligner per thread, the reference's traceback layout (calibrated at {rate / 1e6:.1f} M cell "
+                      f"updates/s/thread); the Rust reference itself cannot be built here (no cargo)",
             "seconds": info["seconds"], "cells": info["cells"]}
 
 
@@ -181,6 +191,46 @@ def parity_check(al, kw, named, reads, truth, e2e_chains, n_check=4, pool=32):
             "how": "GPU align_batch with per-read subset_words vs oracle/ on the same subsets, every field and operation of every chain"}
 
 
+def via_cli(args):
+    """The product's own multi-GPU path: ONE `stitch-b200 align --gpus N` process (a reader thread, one worker thread and one
+    device context per GPU pulling batches from a bounded queue, an ordered BAM writer), timed by wall clock from process
+    start to exit (context creation and file parsing included) on a synthetic FASTQ of the workload."""
+    import tempfile
+    from stitch_b200 import synth
+    kw, named, reads = synth.config(args.config, args.reads, args.read_len)
+    cli = os.path.join(ROOT, "stitch_b200", "stitch-b200")
+    with tempfile.TemporaryDirectory() as d:
+        ref, fq, out = os.path.join(d, "ref.fa"), os.path.join(d, "reads.fq"), os.path.join(d, "out.bam")
+        with open(ref, "wb") as f:
+            for n, sq in named:
+                f.write(b">" + n.encode() + b"\n" + sq + b"\n")
+        with open(fq, "wb") as f:
+            for k, r in enumerate(reads):
+                f.write(b"@r%d\n" % k + r + b"\n+\n" + b"I" * len(r) + b"\n")
+        cmd = [cli, "align", "-f", fq, "-r", ref, "--gpus", str(args.gpus), "--batch", str(args.cli_batch)]
+        if kw.get("double_strand"):
+            cmd.append("-d")
+        if kw.get("circular"):
+            cmd.append("-C")
+        walls = []
+        for _ in range(max(1, args.steps)):
+            t0 = time.perf_counter()
+            with open(out, "wb") as fo:
+                p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE)
+            walls.append(time.perf_counter() - t0)
+            if p.returncode != 0:
+                print(json.dumps({"error": p.stderr.decode()[-500:]}))
+                return 1
+        size = os.path.getsize(out)
+    cells = sum(len(s) for _, s in named) * (2 if kw.get("double_strand") else 1) * sum(len(r) for r in reads)
+    wall = min(walls)
+    print(json.dumps({"metric": "reads/s through `stitch-b200 align` (wall clock of the whole process)", "value": len(reads) / wall, "unit": "reads/s",
+                      "n_gpus": args.gpus, "reads": len(reads), "wall_s": wall, "walls_s": walls, "gcups_first_fills_only": cells / wall / 1e9,
+                      "bam_bytes": size, "batch": args.cli_batch, "config": {"workload": f"config {args.config}", "read_len": len(reads[0])},
+                      "stderr_tail": p.stderr.decode()[-200:]}))
+    return 0
+
+
 def workload_config(args, kw, named, world, read_len):
     """The `config` object of the JSON line: identical for both arms (the arms describe their own samples elsewhere)."""
     workload = {1: "config1: 10 kb chimeric reads vs 20 plasmids (7-9 kb), single strand, local",
@@ -206,14 +256,21 @@ def main():
     ap.add_argument("--impl", default="stitch_b200", choices=["stitch_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="diagnostic runs only: skip the end-to-end pass (the line is then not a bench line)")
     ap.add_argument("--cpu-budget-s", type=float, default=30.0, help="CPU seconds the cpu_baseline sample is sized for")
     ap.add_argument("--cpu-sweep", action="store_true", help="print the CPU port's CUPS against the read length and exit")
+    ap.add_argument("--via-cli", action="store_true", help="time the product's own command line (stitch-b200 align --gpus N) on a FASTQ of "
+                                                           "--reads reads: reader thread, one worker per GPU, ordered BAM writer")
+    ap.add_argument("--cli-batch", type=int, default=256)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from stitch_b200 import synth
+
+    if args.via_cli:
+        return via_cli(args)
 
     if args.cpu_sweep:
         truth = []
@@ -343,8 +400,12 @@ def main():
     dt, agg = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     # e2e: one warm-up, then the same number of steps
-    step_e2e()
-    dt_e, agg_e = timed(step_e2e, args.steps)
+    if args.no_e2e:
+        dt_e, agg_e = dt, dict(agg)
+        args.no_parity_check = True
+    else:
+        step_e2e()
+        dt_e, agg_e = timed(step_e2e, args.steps)
 
     if rank == 0:
         peaks, peak_src = read_peaks()

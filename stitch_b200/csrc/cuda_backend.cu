@@ -119,7 +119,10 @@ struct CudaBackend : host::Backend {
     uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
     uint32_t quiet_tail = 1;     // STITCH_QUIET_TAIL=0: the tail columns compute every tile
     uint32_t cone_refill = 1;    // STITCH_CONE=0: the walk re-fills whole contigs (dp_packed.h: cone re-fill)
-    uint32_t stage_depth_pref = 4;   // STITCH_STAGE_DEPTH: slots of the cp.async staging ring per warp (2..4); reduced when shared memory is short
+    // STITCH_STAGE_DEPTH: slots of the cp.async staging ring per warp (2 or 4).  Measured at 592 config-2 reads: 475 / 467 / 452 GCUPS
+    // at 2 / 3 / 4 slots: the ring's shared memory is taken from the L1 (184 KB instead of 110 KB per CTA), which costs more
+    // than the deeper prefetch brings; 2 is the default
+    uint32_t stage_depth_pref = 2;
     uint32_t quiet_first = 1, quiet_edge = 1, quiet_last = 1;   // STITCH_QUIET_FIRST / _EDGE / _LAST = 0: those tiles are always computed
     DevBuf<CkSum> d_cksum;
     DevBuf<int32_t> d_gcol;
@@ -166,7 +169,7 @@ struct CudaBackend : host::Backend {
         cluster_smem = env_u32("STITCH_CLUSTER_SMEM", 1);
         quiet_tiles = env_u32("STITCH_QUIET", quiet_tiles);
         cone_refill = env_u32("STITCH_CONE", 1);
-        stage_depth_pref = std::min(4u, std::max(2u, env_u32("STITCH_STAGE_DEPTH", stage_depth_pref)));
+        stage_depth_pref = env_u32("STITCH_STAGE_DEPTH", stage_depth_pref) >= 4 ? 4u : 2u;
         quiet_first = env_u32("STITCH_QUIET_FIRST", 1); quiet_edge = env_u32("STITCH_QUIET_EDGE", 1); quiet_last = env_u32("STITCH_QUIET_LAST", 1); quiet_tail = env_u32("STITCH_QUIET_TAIL", 1);
     }
     ~CudaBackend() override {
@@ -402,7 +405,7 @@ struct CudaBackend : host::Backend {
         uint32_t depth = 2;
         if (cluster == 1) {
             const size_t walk_extra = (walk_in_kernel && cluster == 1 && n_packed > 0) ? UnitStage::bytes(K, max_ctiles, false) : 0;
-            for (depth = stage_depth_pref; depth > 2; --depth)
+            for (depth = stage_depth_pref; depth > 2; depth /= 2)
                 if ((PackSmem::bytes(cmax, ntmax, PACK_WARPS, PackSmem::default_stage(PACK_WARPS, depth)) + 15) / 16 * 16 + walk_extra <= SMEM_LIMIT) break;
             pstage = PackSmem::default_stage(PACK_WARPS, depth);
         }

@@ -109,7 +109,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     bool yclip_mode;
     bool state_smem;        // the state arrays live in shared memory (walk kernel re-fills)
     bool staged;            // cp.async staging of tiles (state and bases both in global memory, stage buffers carved)
-    uint32_t stage_depth;   // slots per warp of the staging ring (2..4): depth - 1 tiles are in flight ahead of the one computed
+    uint32_t stage_depth;   // slots per warp of the staging ring (2 or 4): depth - 1 tiles are in flight ahead of the one computed
     Team team;
     // Tiles [own_lo, own_hi) are this CTA's (all tiles for a single-CTA team).  Sst/Dst address them as
     // Sst + tile * ST.  With cluster_smem the state of a tile lives in the shared memory of the CTA that owns it
@@ -469,30 +469,31 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         int32_t Jc = S.Jc[a];
         // software pipeline: a ring of `depth` stage slots per warp; while tile k is computed the next depth - 1 computed tiles are
         // in flight (cp.async), so that a tile's HBM / L2 latency is covered by several tiles of arithmetic
-        const uint32_t depth = X.stage_depth;
+        const uint32_t dmask = X.stage_depth - 1u;
         uint32_t issued = 0;
         auto issue = [&](uint32_t k) {
             const uint32_t t = tile_at(k);
             const bool full = !QUIET || ((uint32_t)S.tb[t] >> 6) == 2u;
-            if (t >= en.tile_start && t < en.tile_start + en.ntiles) prefetch(t, en, k % depth, full);
-            else { const ContigEntry e2 = X.ent[X.owner ? X.owner[t] : 0u]; prefetch(t, e2, k % depth, full); }
+            if (t >= en.tile_start && t < en.tile_start + en.ntiles) prefetch(t, en, k & dmask, full);
+            else { const ContigEntry e2 = X.ent[X.owner ? X.owner[t] : 0u]; prefetch(t, e2, k & dmask, full); }
         };
-        if (staged) for (; issued + 1u < depth && issued < ncomp; ++issued) issue(issued);
+        if (staged) for (; issued < dmask && issued < ncomp; ++issued) issue(issued);
+        uint32_t prev_tile = 0xfffffffeu;
         for (uint32_t k = 0; k < ncomp; ++k) {
             const uint32_t tile = tile_at(k);
             const bool is_load = !QUIET || ((uint32_t)S.tb[tile] >> 6) == 2u;
-            qz.prev_skipped = QUIET && tile != t_lo && (k == 0 || tile_at(k - 1) + 1u != tile);
+            qz.prev_skipped = QUIET && tile != t_lo && prev_tile + 1u != tile;
+            prev_tile = tile;
             if (tile >= en.tile_start + en.ntiles) { a = X.owner[tile]; en = X.ent[a]; Jc = S.Jc[a]; }
             const unsigned char *stg = nullptr;
             if (staged) {
                 if (issued < ncomp) { issue(issued); ++issued; }
-                switch (issued - 1u - k) {   // commits younger than tile k's may stay pending
-                case 0: __pipeline_wait_prior(0); break;
-                case 1: __pipeline_wait_prior(1); break;
-                case 2: __pipeline_wait_prior(2); break;
-                default: __pipeline_wait_prior(3); break;
-                }
-                stg = stg0 + (k % depth) * PackSmem::STAGE_BYTES;
+                const uint32_t pending = issued - 1u - k;   // commits younger than tile k's may stay pending
+                if (pending == 0u) __pipeline_wait_prior(0);
+                else if (pending == 1u) __pipeline_wait_prior(1);
+                else if (pending == 2u) __pipeline_wait_prior(2);
+                else __pipeline_wait_prior(3);
+                stg = stg0 + (k & dmask) * PackSmem::STAGE_BYTES;
             }
             qz.mat = QUIET && !is_load;
             qz.Qp = Qp + a; qz.Qn = Qn + a;
