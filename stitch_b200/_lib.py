@@ -9,7 +9,8 @@ import os
 from ._abi import StitchChain, StitchContig, StitchOp, StitchOpts, StitchStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstitch_b200.so")
+# (STITCH_B200_LIB selects another build of the same sources, e.g. a -DSTITCH_PACK_WARPS=12 variant; the CLI honours it too)
+LIB_PATH = os.environ.get("STITCH_B200_LIB") or os.path.join(_HERE, "libstitch_b200.so")
 
 # every symbol include/stitch_b200.h declares
 EXPORTED_SYMBOLS = [

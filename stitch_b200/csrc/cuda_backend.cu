@@ -37,7 +37,10 @@ using host::Error;
     } while (0)
 
 constexpr int FILL_WARPS = 8;
-constexpr int PACK_WARPS = 16;
+#ifndef STITCH_PACK_WARPS
+#define STITCH_PACK_WARPS 16
+#endif
+constexpr int PACK_WARPS = STITCH_PACK_WARPS;   // warps of a fill CTA (build-time: -DSTITCH_PACK_WARPS=12 trades four warps for 170 registers per thread)
 constexpr int WALK_WARPS = 16;
 
 // ---------------------------------------------------------------------------------------------
@@ -247,16 +250,6 @@ struct CudaBackend : host::Backend {
         const uint64_t held = d_ck.cap * sizeof(CellState) + d_colrec.cap * sizeof(ColRec) + d_last.cap * sizeof(LastCell) +
                               d_sn.cap * sizeof(SnRec) + d_ops.cap * sizeof(OutOp) + d_pck.cap * 4;
         mem_budget = (uint64_t)((double)((uint64_t)free_b + held) * 0.85);
-        // checkpoint spacing: K_base columns, widened so that no read holds more than ~512 MB of checkpoints
-        // (long reads against large references: config 4 is 100 kb x 2 M rows), up to K_MAX
-        K = K_base;
-        for (const auto &j : jobs) {
-            const uint64_t per_ck = (uint64_t)al.layouts.layouts[j.layout].PM() * 8;
-            const uint64_t max_cks = std::max<uint64_t>(1, (512ull << 20) / std::max<uint64_t>(per_ck, 1));
-            const uint64_t need_K = ((uint64_t)j.n + max_cks) / (max_cks + 1);
-            if (need_K > K) K = (uint32_t)((need_K + K_base - 1) / K_base * K_base);
-        }
-        if (K > K_MAX && K_base <= K_MAX) K = K_MAX / K_base * K_base;
         // equal-sized chunks (so that no chunk is a sliver) of per-read records + outputs
         std::vector<uint64_t> bytes(jobs.size());
         uint64_t total = 0;
@@ -268,13 +261,27 @@ struct CudaBackend : host::Backend {
                 total += bytes[k];
             }
         };
-        // a smaller checkpoint spacing (down to half) when the whole batch still fits in one launch: the tail and the unit re-fills of the
-        // walk (about a quarter of the kernel's time once quiet tiles made the bulk pass cheap) shrink with K; measured on
-        // config 2: 450 vs 431 GCUPS at 592 reads, but 390 vs 430 when the doubled checkpoints split 1000 reads into two launches
-        if (ck_auto && K == K_base && K >= 64) {
-            for (K = K_base / 2; K < K_base; K += K_base / 8) {   // the smallest spacing (in eighths of K_base) that keeps one launch
-                size_up();
-                if (total <= cap) break;
+        // Checkpoint spacing: the smallest spacing that still keeps the whole batch in ONE launch.  The tail and the unit
+        // re-fills of the walk shrink with K (a cone unit costs ~K^2), checkpoints grow with 1/K.  Measured on config 2: 450 vs
+        // 431 GCUPS at 592 reads with K_base / 2, but 390 vs 430 when the doubled checkpoints split 1000 reads into two
+        // launches; on config 4 (100 kb reads x 2 M rows, 16 MB per checkpoint) the spacing has to grow instead.  Candidates:
+        // K_base / 2 .. K_base in eighths (only without an explicit STITCH_CK_EVERY), then multiples of K_base up to K_MAX.
+        {
+            std::vector<uint32_t> cand;
+            if (ck_auto && K_base >= 64) for (uint32_t k = K_base / 2; k < K_base; k += K_base / 8) cand.push_back(k);
+            for (uint32_t q : {2u, 3u, 4u, 6u, 8u, 12u, 16u, 24u, 32u, 48u, 64u}) { const uint64_t k = (uint64_t)K_base * q / 2; if (k <= K_MAX || cand.empty()) cand.push_back((uint32_t)k); }
+            bool found = false;
+            for (uint32_t k : cand) { K = k; size_up(); if (total <= cap) { found = true; break; } }
+            if (!found) {
+                // several launches: K_base, widened so that no read holds more than ~512 MB of checkpoints
+                K = K_base;
+                for (const auto &j : jobs) {
+                    const uint64_t per_ck = (uint64_t)al.layouts.layouts[j.layout].PM() * 8;
+                    const uint64_t max_cks = std::max<uint64_t>(1, (512ull << 20) / std::max<uint64_t>(per_ck, 1));
+                    const uint64_t need_K = ((uint64_t)j.n + max_cks) / (max_cks + 1);
+                    if (need_K > K) K = (uint32_t)((need_K + K_base - 1) / K_base * K_base);
+                }
+                if (K > K_MAX && K_base <= K_MAX) K = K_MAX / K_base * K_base;
             }
         }
         size_up();

@@ -440,11 +440,11 @@ SHD PkRowM pk_quiet_rowm(const PK &p, const PCol &c, const PkQuiet &qprev, int32
 // one scores below the jump that is available everywhere).  Row m (it accumulates the x-suffix tracker over the WHOLE
 // column, SCA:407-429) and row 1 of a circular contig (it reads row m, SCA:258-289) need the full column.
 // Checked on the CPU emulator against full re-fills (tests/emul, EMUL_CONE_AUDIT) and against the oracle end to end.
-constexpr uint32_t PK_CONE_MAX_COLS = 384;   // columns of a cone unit (its window must fit one tile per warp)
+constexpr uint32_t PK_CONE_MAX_COLS = 384;   // cone units of up to this many columns get their per-column constants precomputed (shared memory)
 struct PkCone { bool on; uint32_t slope, win_lo, win_n; };
-SHD PkCone pk_cone_plan(const Scoring &sc, const ContigEntry &en, uint32_t i_entry, uint32_t j, uint32_t jb, uint32_t max_tiles) {
+SHD PkCone pk_cone_plan(const Scoring &sc, const ContigEntry &en, uint32_t i_entry, uint32_t j, uint32_t jb) {
     PkCone c; c.on = false; c.slope = 0; c.win_lo = 0; c.win_n = en.ntiles;
-    if (sc.e >= 0 || i_entry < 1 || i_entry >= en.m || j <= jb || j - jb > PK_CONE_MAX_COLS) return c;
+    if (sc.e >= 0 || i_entry < 1 || i_entry >= en.m || j <= jb) return c;
     c.slope = (uint32_t)(pk_band(sc) / -sc.e) + 2;
     const int64_t top_first = (int64_t)i_entry - (int64_t)c.slope * (int64_t)(j - jb - 1);   // top row of the cone at column jb + 1
     if (en.circular && top_first < 2) return c;
@@ -452,7 +452,6 @@ SHD PkCone pk_cone_plan(const Scoring &sc, const ContigEntry &en, uint32_t i_ent
     const int64_t top_ck = top_first - (int64_t)c.slope;
     const uint32_t r_top = top_ck < 1 ? 1u : (uint32_t)top_ck;
     const uint32_t lo = (r_top - 1) / (uint32_t)TILE, hi = (i_entry - 1) / (uint32_t)TILE;
-    if (hi - lo + 1 > max_tiles) return c;
     c.on = true; c.win_lo = lo; c.win_n = hi - lo + 1;
     return c;
 }

@@ -116,7 +116,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     // (cstate = this CTA's block, same offset in every CTA of the cluster) and Sst = cstate - own_lo * ST.
     uint32_t own_lo, own_hi, warps;
     // Cone re-fills of the walk (TbUnit, dp_core.h) run the columns over a WINDOW of the contig's tiles: tiles
-    // [win_lo, win_lo + NT), one per warp; tiles below `skip_below` are left stale in this column; no per-contig finish
+    // [win_lo, win_lo + NT), one fixed chunk per warp; chunks entirely below tile `skip_below` are left stale in this column; no per-contig finish
     // (row m is outside the window).  Everything else: win_lo = 0, skip_below = 0, no_finish = false.
     uint32_t win_lo, skip_below;
     bool no_finish;
@@ -1075,9 +1075,12 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     const ColRec *colrec = P.colrec + jd.colrec_off;
     const uint8_t *read = P.reads + jd.read_off;
     const bool stage_bases = P.unit_stage_bases != 0;
-    // cone of the entry cell (dp_packed.h) when the staging area was carved for it, else the whole contig
+    // cone of the entry cell (dp_packed.h): the columns run over the window of tiles the cone ever touches, split into one
+    // fixed chunk per warp; a chunk that lies entirely above the cone's top in a column is left stale.  Short units also get
+    // every per-column constant precomputed (one barrier per column).
     PkCone cone; cone.on = false; cone.slope = 0; cone.win_lo = 0; cone.win_n = gen.ntiles;
-    if (P.cone && U.cc) cone = pk_cone_plan(P.sc, gen, i_entry, j, jb, (uint32_t)W);
+    if (P.cone) cone = pk_cone_plan(P.sc, gen, i_entry, j, jb);
+    const bool pre = cone.on && U.cc != nullptr && ncols <= PK_CONE_MAX_COLS;
     const PK pk = pk_make(P.sc, jd.LB);
     if (tid == 0) { *s_en = gen; s_en->tile_start = 0; if (stage_bases) s_en->seq_off = 0; }
     for (uint32_t t = tid; t < ncols; t += T) {
@@ -1103,7 +1106,13 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
                              U.B[0]);
     pk_init_halos<W>(X, S, jb & 1u);
     PkColOut O; O.sn = nullptr; O.last = nullptr; O.track = false; O.lastcol = false; O.track_thr = MIN_SCORE;
-    if (cone.on) {
+    // the rows above the window are stale by construction: the halo of the window's first tile is any in-band value
+    if (cone.on && cone.win_lo > 0 && tid < 17u)
+        for (uint32_t par = 0; par < 2; ++par) {
+            if (tid < 9u) S.haloS[(par * W) * 9 + tid] = pk.NEGKEY;
+            else S.haloD[(par * W) * 8 + tid - 9u] = pk.NEGKEY + pk.PD6;
+        }
+    if (pre) {
         // every per-column constant of the unit at once (one column per thread), so that a column is tiles + ONE barrier
         for (uint32_t t = tid; t < ncols; t += T) {
             const int32_t B = U.B[t + 1], Bprev = U.B[t];   // B[t+1] = G(jj-1) = base of column jj
@@ -1111,12 +1120,6 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
             U.Jc[t] = pk_jc(pk, pcl, U.J[t].score, U.J[t].len);
             U.cc[t] = pk_col_const(pk, P.sc, B, Bprev, jb + 1 + t, n, U.q[t]);
         }
-        // the rows above the window are stale by construction: the halo of the window's first tile is any in-band value
-        if (cone.win_lo > 0 && tid < 17u)
-            for (uint32_t par = 0; par < 2; ++par) {
-                if (tid < 9u) S.haloS[(par * W) * 9 + tid] = pk.NEGKEY;
-                else S.haloD[(par * W) * 8 + tid - 9u] = pk.NEGKEY + pk.PD6;
-            }
         __syncthreads();
         PackSmem S2 = S;
         for (uint32_t jj = jb + 1; jj <= j; ++jj) {
@@ -1141,7 +1144,8 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
             }
             __syncthreads();
             const PkColConst cc = *s_cc;
-            O.tb_col = bytes + (uint64_t)t * pm; O.colrec_col = ucr + t;
+            if (cone.on) X.skip_below = pk_cone_top_tile(cone, i_entry, j, jj);
+            O.tb_col = bytes + (uint64_t)t * pm; O.colrec_col = cone.on ? nullptr : ucr + t;
             pk_column<W, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, jj, O);
         }
     }

@@ -150,6 +150,7 @@ struct EmulBackend : Backend {
         CONE_AUDIT = env_u32("EMUL_CONE_AUDIT", 0);                 // 1: audit the dependency cone of the unit re-fills (experiment)
     }
     ~EmulBackend() {
+        if (std::getenv("EMUL_UNIT_STATS")) std::fprintf(stderr, "[emul units] cone %llu full %llu\n", (unsigned long long)cone_units, (unsigned long long)full_units);
         if (CONE_AUDIT && cone_units)
             std::fprintf(stderr, "[emul cone] units %llu, cone cells %llu, differing bytes %llu, rows in the cone %.1f%% of the rows re-filled\n",
                          (unsigned long long)cone_units, (unsigned long long)cone_cells, (unsigned long long)cone_bad,
@@ -684,7 +685,7 @@ struct EmulBackend : Backend {
         const ContigEntry en_ck = en;
         en.tile_start = 0;
         PkCone cone; cone.on = false; cone.slope = 0; cone.win_lo = 0; cone.win_n = en.ntiles;
-        if (CONE && K <= PK_CONE_MAX_COLS) cone = pk_cone_plan(sc, en, i_entry, j, jb, 16);
+        if (CONE) cone = pk_cone_plan(sc, en, i_entry, j, jb);
         const std::vector<uint32_t> owner(en.ntiles, 0);
         auto run = [&](bool use_cone, std::vector<uint8_t> &out_bytes, std::vector<ColRec> &out_cr) {
             PkState st;
