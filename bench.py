@@ -197,7 +197,8 @@ def via_cli(args):
     start to exit (context creation and file parsing included) on a synthetic FASTQ of the workload."""
     import tempfile
     from stitch_b200 import synth
-    kw, named, reads = synth.config(args.config, args.reads, args.read_len)
+    kw, named, pool = synth.config(args.config, min(args.reads, args.cli_pool), args.read_len)
+    reads = [pool[k % len(pool)] for k in range(args.reads)]   # (the CLI only merges CONSECUTIVE identical reads, align.rs:364-375)
     cli = os.path.join(ROOT, "stitch_b200", "stitch-b200")
     with tempfile.TemporaryDirectory() as d:
         ref, fq, out = os.path.join(d, "ref.fa"), os.path.join(d, "reads.fq"), os.path.join(d, "out.bam")
@@ -262,6 +263,7 @@ def main():
     ap.add_argument("--via-cli", action="store_true", help="time the product's own command line (stitch-b200 align --gpus N) on a FASTQ of "
                                                            "--reads reads: reader thread, one worker per GPU, ordered BAM writer")
     ap.add_argument("--cli-batch", type=int, default=256)
+    ap.add_argument("--cli-pool", type=int, default=1000, help="--via-cli: distinct synthetic reads (cycled to --reads records)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -340,7 +340,7 @@ void usage() {
         "  -S, --soft-clip  -X, --use-eq-and-x  -P, --pick-primary <query-length|score>\n"
         "  --filter-secondary [--filter-secondary-pct <10>]  --suboptimal [--suboptimal-pct <20>]\n"
         "  -c, --compression <0>            BGZF level of the BAM written to stdout\n"
-        "  -t, --threads <2>                accepted for compatibility (alignment runs on the GPU)\n"
+        "  -t, --threads <2>                formatter threads (SAM records + BAM encoding; alignment runs on the GPU)\n"
         "  -p, --pre-align                  pre-align reads (k-mer seeding on the GPU) and align only those reaching the score\n"
         "  -k, --k <12>  -w, --w <50>  -s, --pre-align-min-score <100>  -x, --pre-align-subset-contigs <true>\n"
         "extras: --sam (SAM text instead of BAM)  --gpus <1>  --device <0>  --batch <2048>\n", stderr);
@@ -417,49 +417,69 @@ Args parse(int argc, char **argv) {
 }
 
 // One batch of input records on one device context: align the unique sequences, format every record.
-struct Batch { uint64_t seq_no = 0; std::vector<Record> recs; std::vector<std::string> lines; std::string error; };
+struct Batch {
+    uint64_t seq_no = 0;
+    std::vector<Record> recs;
+    std::vector<uint32_t> uniq_of;     // record -> aligned (de-duplicated) sequence
+    stitch_ctx *ctx = nullptr;         // the context that aligned it
+    stitch_results *res = nullptr;
+    std::vector<std::string> lines;    // SAM text lines (--sam)
+    std::vector<uint8_t> bam;          // encoded BAM records, back to back
+    uint64_t n_records = 0;
+    std::string error;
+};
 
-void run_batch(const Api &api, stitch_ctx *ctx, const stitch_sam_opts &so, Batch &b) {
+// Stage 2 (one thread per device context): align the unique sequences of the batch.
+void align_stage(const Api &api, stitch_ctx *ctx, Batch &b) {
     // a run of consecutive records with the same (upper-cased) sequence is aligned once (align.rs:364-375)
-    std::vector<uint32_t> uniq_of(b.recs.size());
+    b.uniq_of.resize(b.recs.size());
     std::vector<std::string> seqs;
     for (size_t k = 0; k < b.recs.size(); ++k) {
         std::string u = upper(b.recs[k].seq);
         if (seqs.empty() || seqs.back() != u) seqs.push_back(std::move(u));
-        uniq_of[k] = (uint32_t)seqs.size() - 1;
+        b.uniq_of[k] = (uint32_t)seqs.size() - 1;
     }
     std::string blob;
     std::vector<uint64_t> offs(seqs.size() + 1, 0);
     for (size_t k = 0; k < seqs.size(); ++k) { blob += seqs[k]; offs[k + 1] = blob.size(); }
-    stitch_results *res = nullptr;
-    if (api.align_batch(ctx, reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), (uint32_t)seqs.size(), nullptr, 0, &res) != STITCH_OK) {
+    b.ctx = ctx;
+    if (api.align_batch(ctx, reinterpret_cast<const uint8_t *>(blob.data()), offs.data(), (uint32_t)seqs.size(), nullptr, 0, &b.res) != STITCH_OK) {
         b.error = api.last_error(ctx);
-        return;
+        b.res = nullptr;
     }
-    for (size_t k = 0; k < b.recs.size(); ++k) {
+}
+
+// Stage 3 (--threads formatter threads): the SAM records of every read of the batch (host work: it overlaps the next
+// batch's alignment on the device), encoded as BAM unless --sam.
+void format_stage(const Api &api, const stitch_sam_opts &so, const std::vector<std::string> &names, bool sam, Batch &b) {
+    if (!b.res) return;
+    for (size_t k = 0; k < b.recs.size() && b.error.empty(); ++k) {
         const Record &r = b.recs[k];
         char *text = nullptr;
         int32_t pre_score = 0;
-        const int has_pre = api.results_prealign(res, uniq_of[k], &pre_score);   // the Option<i32> of Aligners::align (mod.rs:338-339)
+        const int has_pre = api.results_prealign(b.res, b.uniq_of[k], &pre_score);   // the Option<i32> of Aligners::align (mod.rs:338-339)
         // SEQ / QUAL of the records are the read as given (SamRecordFormatter::format uses fastq.seq(), mod.rs:630; only the
         // alignment sees the upper-cased copy, mod.rs:243)
-        if (api.format_sam(ctx, res, uniq_of[k], r.head.c_str(), reinterpret_cast<const uint8_t *>(r.seq.data()),
+        if (api.format_sam(b.ctx, b.res, b.uniq_of[k], r.head.c_str(), reinterpret_cast<const uint8_t *>(r.seq.data()),
                            r.has_qual ? reinterpret_cast<const uint8_t *>(r.qual.data()) : nullptr, (uint32_t)r.seq.size(), has_pre, pre_score, &so, &text) != STITCH_OK) {
-            b.error = api.last_error(ctx);
-            api.free_results(res);
-            return;
+            b.error = api.last_error(b.ctx);
+            break;
         }
-        const std::string t = text ? text : "";
-        api.free_text(text);
-        size_t p = 0;
-        while (p < t.size()) {
-            const size_t e = t.find('\n', p);
-            b.lines.push_back(t.substr(p, e == std::string::npos ? std::string::npos : e - p));
-            if (e == std::string::npos) break;
+        const char *p = text ? text : "";
+        while (*p) {
+            const char *e = std::strchr(p, '\n');
+            std::string line = e ? std::string(p, e) : std::string(p);
+            if (sam) b.lines.push_back(std::move(line));
+            else { const std::vector<uint8_t> rec = bam_record(line, names); b.bam.insert(b.bam.end(), rec.begin(), rec.end()); }
+            ++b.n_records;
+            if (!e) break;
             p = e + 1;
         }
+        api.free_text(text);
     }
-    api.free_results(res);
+    api.free_results(b.res);
+    b.res = nullptr;
+    std::vector<Record>().swap(b.recs);
 }
 
 // Bounded hand-over between the pipeline stages.
@@ -524,10 +544,19 @@ int main(int argc, char **argv) {
     so.soft_clip = a.soft_clip; so.use_eq_and_x = a.use_eq_and_x; so.pick_primary = (uint8_t)a.pick_primary;
     so.filter_secondary = a.filter_secondary; so.filter_secondary_pct = a.filter_secondary_pct;
 
+    // one context per device, created concurrently (driver initialisation and the contig upload of every device overlap)
     std::vector<stitch_ctx *> ctxs((size_t)a.gpus, nullptr);
-    for (int g = 0; g < a.gpus; ++g)
-        if (api.create(&o, contigs.data(), (uint32_t)contigs.size(), a.device + g, &ctxs[(size_t)g]) != STITCH_OK)
-            die(std::string("cannot create the aligner on device ") + std::to_string(a.device + g) + ": " + api.last_error(nullptr));
+    {
+        std::vector<std::string> errs((size_t)a.gpus);
+        std::vector<std::thread> th;
+        for (int g = 0; g < a.gpus; ++g)
+            th.emplace_back([&, g] {
+                if (api.create(&o, contigs.data(), (uint32_t)contigs.size(), a.device + g, &ctxs[(size_t)g]) != STITCH_OK)
+                    errs[(size_t)g] = std::string("cannot create the aligner on device ") + std::to_string(a.device + g) + ": " + api.last_error(nullptr);
+            });
+        for (auto &t : th) t.join();
+        for (const auto &e : errs) if (!e.empty()) die(e);
+    }
 
     // header: @HD, one @SQ per contig, @PG (align.rs:393-416)
     std::string header = "@HD\tVN:1.6\n";
@@ -546,7 +575,8 @@ int main(int argc, char **argv) {
         bg.write(h.data(), h.size());
     }
 
-    Channel<std::unique_ptr<Batch>> to_align((size_t)a.gpus * 2), to_write((size_t)a.gpus * 4 + 4);
+    const int n_fmt = std::max(std::max(1, a.threads), 2 * a.gpus);   // (two formatters keep up with one B200 on 10 kb reads)
+    Channel<std::unique_ptr<Batch>> to_align((size_t)a.gpus * 2), to_format((size_t)a.gpus * 2 + (size_t)n_fmt), to_write((size_t)a.gpus * 4 + 4);
     std::mutex err_m;
     std::string first_error;
     auto fail = [&](const std::string &e) { std::lock_guard<std::mutex> l(err_m); if (first_error.empty()) first_error = e; };
@@ -570,19 +600,29 @@ int main(int argc, char **argv) {
         }
         to_align.close();
     });
-    // workers: one per device context, each pulls the next batch as soon as it is free
+    // aligners: one per device context, each pulls the next batch as soon as it is free
     std::vector<std::thread> workers;
     for (int g = 0; g < a.gpus; ++g)
         workers.emplace_back([&, g] {
             std::unique_ptr<Batch> b;
             while (to_align.pop(b)) {
-                run_batch(api, ctxs[(size_t)g], so, *b);
+                align_stage(api, ctxs[(size_t)g], *b);
                 if (!b->error.empty()) fail(b->error);
-                std::vector<Record>().swap(b->recs);
+                to_format.push(std::move(b));
+            }
+        });
+    // formatters (-t): SAM records + BAM encoding, off the aligners' threads
+    std::vector<std::thread> formatters;
+    for (int t = 0; t < n_fmt; ++t)
+        formatters.emplace_back([&] {
+            std::unique_ptr<Batch> b;
+            while (to_format.pop(b)) {
+                format_stage(api, so, names, a.sam, *b);
+                if (!b->error.empty()) fail(b->error);
                 to_write.push(std::move(b));
             }
         });
-    // writer: input order restored, BAM encoding and BGZF off the aligners' threads
+    // writer: input order restored, BGZF and the output stream
     uint64_t n_lines = 0, n_batches = 0;
     std::thread writer([&] {
         std::map<uint64_t, std::unique_ptr<Batch>> pending;
@@ -591,17 +631,17 @@ int main(int argc, char **argv) {
         while (to_write.pop(b)) {
             pending[b->seq_no] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
-                for (const std::string &line : it->second->lines) {
-                    if (a.sam) { std::fputs(line.c_str(), stdout); std::fputc('\n', stdout); }
-                    else { const std::vector<uint8_t> rec = bam_record(line, names); bg.write(rec.data(), rec.size()); }
-                }
-                n_lines += it->second->lines.size(); ++n_batches;
+                if (a.sam) for (const std::string &line : it->second->lines) { std::fputs(line.c_str(), stdout); std::fputc('\n', stdout); }
+                else if (!it->second->bam.empty()) bg.write(it->second->bam.data(), it->second->bam.size());
+                n_lines += it->second->n_records; ++n_batches;
                 pending.erase(it); ++next;
             }
         }
     });
     reader.join();
     for (auto &t : workers) t.join();
+    to_format.close();
+    for (auto &t : formatters) t.join();
     to_write.close();
     writer.join();
     if (!first_error.empty()) die("alignment failed: " + first_error);
