@@ -169,7 +169,7 @@ __device__ __forceinline__ void unpack8(const uint2 xb, uint8_t *x) {
 // (its memory may be stale): materialise it instead of loading; `qz.prev_skipped` = the previous tile of this chunk
 // was skipped in this column (its last row and its chain exit come from the closed form).  Returns whether every
 // ordinary cell of the tile is in the closed form of column j.
-struct PkColStat { uint32_t skipped; unsigned long long t_tiles, t_finish, t_busy, t_select, t_f1, t_f2, t_fa; };   // per job, shared memory
+struct PkColStat { uint32_t skipped, timing; unsigned long long t_tiles, t_finish, t_busy, t_select, t_f1, t_f2, t_fa; };   // per job, shared memory
 struct PkQuietArgs {
     bool mat, prev_skipped;
     const PkQuiet *Qp, *Qn;     // closed forms of column j-1 / j of this tile's contig (shared memory)
@@ -326,8 +326,7 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
     *reinterpret_cast<int4 *>(X.Sst + tile * ST + 128 + lane * 4) = make_int4(Sn[4], Sn[5], Sn[6], Sn[7]);
     *reinterpret_cast<int4 *>(X.Dst + tile * ST + lane * 4) = make_int4(st.D6[0], st.D6[1], st.D6[2], st.D6[3]);
     *reinterpret_cast<int4 *>(X.Dst + tile * ST + 128 + lane * 4) = make_int4(st.D6[4], st.D6[5], st.D6[6], st.D6[7]);
-    STITCH_UNROLL
-    for (int d = 16; d >= 1; d >>= 1) colmax = pk_max(colmax, __shfl_xor_sync(FULL, colmax, d));
+    colmax = __reduce_max_sync(FULL, colmax);   // (REDUX.MAX: one instruction instead of a five-step shuffle butterfly on the tile's critical path)
     if (lane < X.team.size) X.team.peer(S.tilemax, lane)[tile] = colmax;   // every CTA of the team holds the whole tile table
     if (QUIET) {   // is the tile in the closed form of column j?  (S first: the cheap test, and the one that usually fails)
         const PkQuiet qn = *qz.Qn;
@@ -375,7 +374,8 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     const uint32_t GW = team.size * W, gw = team.rank * W + warp;
     const uint32_t Weff = NT < GW ? NT : GW;
     const PkQuiet *Qp = S.Q + (par ^ 1u) * S.cmax, *Qn = S.Q + par * S.cmax;
-    const long long c0 = cs ? clock64() : 0;
+    const bool cst = cs && cs->timing;   // per-phase cycle counters (STITCH_DEBUG_STATS only: 64-bit shared-memory atomics per warp and column)
+    const long long c0 = cst ? clock64() : 0;
     if (gw < Weff && X.win_lo + (uint32_t)((uint64_t)NT * (gw + 1) / Weff) > X.skip_below) {
         const uint32_t t_lo = X.win_lo + (uint32_t)((uint64_t)NT * gw / Weff), t_hi = X.win_lo + (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
@@ -506,7 +506,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             if (QUIET && lane == 0)
                 S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && (tic + 1 != en.ntiles || (X.quiet_last && tic != 0))) ? PackSmem::TB_Q : 0u));
         }
-        if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
+        if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); if (cst) atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
         if (QUIET && gw + 1 < Weff && lane == 0) S.haloF[par * W + warp + 1] = (S.tb[t_hi - 1] & PackSmem::TB_Q) ? 1u : 0u;
         if (gw + 1 < Weff && (!QUIET || ((uint32_t)S.tb[t_hi - 1] >> 6) != 0u)) {
             // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp); a skipped
@@ -529,7 +529,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
     team.sync();
     if (X.no_finish) return;   // cone re-fill: row m is outside the window, nothing reads the column best
 
-    const long long c1 = cs ? clock64() : 0;
+    const long long c1 = cst ? clock64() : 0;
     // ---- per contig: tracker + row m + column best (contig a on CTA a % size) ----
     const Row0 r0 = row0_at(sc, j, X.n);
     // Four contigs per warp at a time, one per group of 8 lanes (the groups' memory latencies overlap and the four
@@ -544,7 +544,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         STITCH_UNROLL
         for (int d = 4; d >= 1; d >>= 1) kmax = pk_max(kmax, __shfl_xor_sync(FULL, kmax, d));
         const int32_t smax = pk_rel(pk, kmax);
-        if (cs && tid == 0) cs->t_fa += (unsigned long long)(clock64() - c1);
+        if (cst && tid == 0) cs->t_fa += (unsigned long long)(clock64() - c1);
         // first row (< m) whose S has the best score (column best, SCA:680-687) / equals the best key (tracker, SCA:411-416)
         uint32_t frow = 0, trow = 0; int32_t fkey = 0;
         STITCH_UNROLL
@@ -593,7 +593,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             key = __shfl_sync(FULL, key, grp * 8u + (uint32_t)__ffs(hit) - 1u);
             if (en.m >= 2) { if (full) trow = best; else { frow = best; fkey = key; } }
         }
-        if (cs && tid == 0) cs->t_f1 += (unsigned long long)(clock64() - c1);
+        if (cst && tid == 0) cs->t_f1 += (unsigned long long)(clock64() - c1);
         if (gl == 0 && act) {
             CmPart rows; cm_init(rows);
             XsPart tr; xs_init(tr);
@@ -637,9 +637,9 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             }
         }
     }
-    if (cs && tid == 0) cs->t_f2 += (unsigned long long)(clock64() - c1);
+    if (cst && tid == 0) cs->t_f2 += (unsigned long long)(clock64() - c1);
     team.sync();
-    if (cs && tid == 0) { cs->t_tiles += (unsigned long long)(c1 - c0); cs->t_finish += (unsigned long long)(clock64() - c1); }
+    if (cst && tid == 0) { cs->t_tiles += (unsigned long long)(c1 - c0); cs->t_finish += (unsigned long long)(clock64() - c1); }
 }
 
 // Column 0 (SCA:97-186) of the contigs of X into the packed state (base B_0 = 0) + row-m summaries.
@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         X.quiet_first = X.quiet && P.quiet_first != 0; X.quiet_edge = X.quiet && P.quiet_edge != 0;
         X.quiet_last = X.quiet && P.quiet_last != 0;
         if (tid < 2 * W) S.haloF[tid] = 0;
-        if (tid == 0) { s_cs.skipped = 0; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
+        if (tid == 0) { s_cs.skipped = 0; s_cs.timing = P.dbg ? 1u : 0u; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
         if (X.quiet) {   // quiet tiles: no tile is quiet yet; base classes of every tile
             for (uint32_t a = tid; a < C; a += W * 32) S.Q[a] = pk_quiet_init(X.pk);
             const uint32_t lane = tid & 31u;
@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
             pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0, K);
             __syncthreads();
             const PkColConst cc = s_cc[par];
-            if (tid == 0) s_cs.t_select += (unsigned long long)(clock64() - cs0);
+            if (tid == 0 && P.dbg) s_cs.t_select += (unsigned long long)(clock64() - cs0);
             if (X.quiet) pk_column<W, false, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O, cc.yq, &s_cs);
             else pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
             if ((j % K == 0) && j < n)
