@@ -193,15 +193,15 @@ def parity_check(al, kw, named, reads, truth, e2e_chains, n_check=4, pool=32):
 
 def via_cli(args):
     """The product's own multi-GPU path: ONE `stitch-b200 align --gpus N` process (a reader thread, one worker thread and one
-    device context per GPU pulling batches from a bounded queue, an ordered BAM writer), timed by wall clock from process
-    start to exit (context creation and file parsing included) on a synthetic FASTQ of the workload."""
+    device context per GPU pulling batches from a bounded queue, formatter threads, an ordered BAM writer), timed by wall
+    clock from process start to exit (context creation and file parsing included) on a synthetic FASTQ of the workload."""
     import tempfile
     from stitch_b200 import synth
     kw, named, pool = synth.config(args.config, min(args.reads, args.cli_pool), args.read_len)
     reads = [pool[k % len(pool)] for k in range(args.reads)]   # (the CLI only merges CONSECUTIVE identical reads, align.rs:364-375)
     cli = os.path.join(ROOT, "stitch_b200", "stitch-b200")
     with tempfile.TemporaryDirectory() as d:
-        ref, fq, out = os.path.join(d, "ref.fa"), os.path.join(d, "reads.fq"), os.path.join(d, "out.bam")
+        ref, fq, out = os.path.join(d, "ref.fa"), os.path.join(d, "reads.fq"), (os.path.join(d, "out.bam") if args.cli_out == "tmp" else args.cli_out)
         with open(ref, "wb") as f:
             for n, sq in named:
                 f.write(b">" + n.encode() + b"\n" + sq + b"\n")
@@ -222,7 +222,7 @@ def via_cli(args):
             if p.returncode != 0:
                 print(json.dumps({"error": p.stderr.decode()[-500:]}))
                 return 1
-        size = os.path.getsize(out)
+        size = os.path.getsize(out) if os.path.isfile(out) else None
     cells = sum(len(s) for _, s in named) * (2 if kw.get("double_strand") else 1) * sum(len(r) for r in reads)
     wall = min(walls)
     print(json.dumps({"metric": "reads/s through `stitch-b200 align` (wall clock of the whole process)", "value": len(reads) / wall, "unit": "reads/s",
@@ -264,6 +264,7 @@ def main():
                                                            "--reads reads: reader thread, one worker per GPU, ordered BAM writer")
     ap.add_argument("--cli-batch", type=int, default=256)
     ap.add_argument("--cli-pool", type=int, default=1000, help="--via-cli: distinct synthetic reads (cycled to --reads records)")
+    ap.add_argument("--cli-out", default="/dev/null", help="--via-cli: where the BAM stream goes (default /dev/null: 650 KB per 10 kb read)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -149,49 +149,36 @@ std::string first_word(const std::string &s) {
 // ---------------------------------------------------------------------------------------------
 // BAM / BGZF
 // ---------------------------------------------------------------------------------------------
-class Bgzf {
-  public:
-    Bgzf(FILE *f, int level) : f_(f), level_(level) {}
-    void write(const void *p, size_t n) {
-        const uint8_t *b = static_cast<const uint8_t *>(p);
-        while (n) {
-            const size_t take = std::min(n, BLOCK - buf_.size());
-            buf_.insert(buf_.end(), b, b + take);
-            b += take; n -= take;
-            if (buf_.size() == BLOCK) flush_block();
-        }
-    }
-    void flush_block() {
-        if (buf_.empty()) return;
-        std::vector<uint8_t> out(BLOCK + 1024);
+// BGZF blocks (<= 0xff00 payload bytes each) of a byte range, appended to `out`.  Blocks are independent, so every batch is
+// compressed by the formatter thread that encoded it and the writer only copies bytes to the stream.
+void bgzf_compress(const uint8_t *p, size_t n, int level, std::vector<uint8_t> &out) {
+    constexpr size_t BLOCK = 0xff00;
+    while (n) {
+        const size_t take = std::min(n, BLOCK);
+        const size_t at = out.size();
+        out.resize(at + BLOCK + 1024);
         z_stream zs{};
-        if (deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib: deflateInit2 failed");
-        zs.next_in = buf_.data(); zs.avail_in = (uInt)buf_.size();
-        zs.next_out = out.data() + 18; zs.avail_out = (uInt)(out.size() - 18 - 8);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib: deflateInit2 failed");
+        zs.next_in = const_cast<uint8_t *>(p); zs.avail_in = (uInt)take;
+        zs.next_out = out.data() + at + 18; zs.avail_out = (uInt)(BLOCK + 1024 - 18 - 8);
         if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("zlib: deflate failed");
         const size_t clen = zs.total_out;
         deflateEnd(&zs);
         const size_t bsize = 18 + clen + 8;
         const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (uint8_t)((bsize - 1) & 255), (uint8_t)((bsize - 1) >> 8)};
-        std::memcpy(out.data(), hdr, 18);
-        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data(), (uInt)buf_.size()), isz = (uint32_t)buf_.size();
-        for (int k = 0; k < 4; ++k) { out[18 + clen + k] = (uint8_t)(crc >> (8 * k)); out[22 + clen + k] = (uint8_t)(isz >> (8 * k)); }
-        if (std::fwrite(out.data(), 1, bsize, f_) != bsize) die("write failed");
-        buf_.clear();
+        std::memcpy(out.data() + at, hdr, 18);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, (uInt)take), isz = (uint32_t)take;
+        for (int k = 0; k < 4; ++k) { out[at + 18 + clen + k] = (uint8_t)(crc >> (8 * k)); out[at + 22 + clen + k] = (uint8_t)(isz >> (8 * k)); }
+        out.resize(at + bsize);
+        p += take; n -= take;
     }
-    void finish() {
-        flush_block();
-        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (std::fwrite(eof, 1, 28, f_) != 28) die("write failed");
-        std::fflush(f_);
-    }
-    void flush() { flush_block(); std::fflush(f_); }   // the reference flushes stdout after every read (align.rs:436)
-
-  private:
-    static constexpr size_t BLOCK = 0xff00;
-    FILE *f_; int level_;
-    std::vector<uint8_t> buf_;
-};
+}
+void write_all(FILE *f, const uint8_t *p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) die("write failed"); }
+void bgzf_finish(FILE *f) {
+    static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    write_all(f, eof, 28);
+    std::fflush(f);
+}
 
 void put32(std::vector<uint8_t> &v, uint32_t x) { for (int k = 0; k < 4; ++k) v.push_back((uint8_t)(x >> (8 * k))); }
 void put16(std::vector<uint8_t> &v, uint32_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); }
@@ -451,7 +438,7 @@ void align_stage(const Api &api, stitch_ctx *ctx, Batch &b) {
 
 // Stage 3 (--threads formatter threads): the SAM records of every read of the batch (host work: it overlaps the next
 // batch's alignment on the device), encoded as BAM unless --sam.
-void format_stage(const Api &api, const stitch_sam_opts &so, const std::vector<std::string> &names, bool sam, Batch &b) {
+void format_stage(const Api &api, const stitch_sam_opts &so, const std::vector<std::string> &names, bool sam, int level, Batch &b) {
     if (!b.res) return;
     for (size_t k = 0; k < b.recs.size() && b.error.empty(); ++k) {
         const Record &r = b.recs[k];
@@ -480,6 +467,12 @@ void format_stage(const Api &api, const stitch_sam_opts &so, const std::vector<s
     api.free_results(b.res);
     b.res = nullptr;
     std::vector<Record>().swap(b.recs);
+    if (!sam && !b.bam.empty()) {   // BGZF here, in parallel: the writer only copies
+        std::vector<uint8_t> z;
+        z.reserve(b.bam.size() + b.bam.size() / 512 + 64);
+        bgzf_compress(b.bam.data(), b.bam.size(), level, z);
+        b.bam.swap(z);
+    }
 }
 
 // Bounded hand-over between the pipeline stages.
@@ -562,7 +555,7 @@ int main(int argc, char **argv) {
     std::string header = "@HD\tVN:1.6\n";
     for (size_t k = 0; k < names.size(); ++k) header += "@SQ\tSN:" + names[k] + "\tLN:" + std::to_string(seqs[k].size()) + "\n";
     header += "@PG\tID:stitch\tPN:stitch\tVN:b200-0.1.0\tCL:" + a.command_line + "\n";
-    Bgzf bg(stdout, a.compression);
+    std::setvbuf(stdout, nullptr, _IOFBF, 8u << 20);
     if (a.sam) std::fputs(header.c_str(), stdout);
     else {
         std::vector<uint8_t> h = {'B', 'A', 'M', 1};
@@ -572,7 +565,9 @@ int main(int argc, char **argv) {
             put32(h, (uint32_t)names[k].size() + 1); h.insert(h.end(), names[k].begin(), names[k].end()); h.push_back(0);
             put32(h, (uint32_t)seqs[k].size());
         }
-        bg.write(h.data(), h.size());
+        std::vector<uint8_t> z;
+        bgzf_compress(h.data(), h.size(), a.compression, z);
+        write_all(stdout, z.data(), z.size());
     }
 
     const int n_fmt = std::max(std::max(1, a.threads), 2 * a.gpus);   // (two formatters keep up with one B200 on 10 kb reads)
@@ -617,7 +612,7 @@ int main(int argc, char **argv) {
         formatters.emplace_back([&] {
             std::unique_ptr<Batch> b;
             while (to_format.pop(b)) {
-                format_stage(api, so, names, a.sam, *b);
+                format_stage(api, so, names, a.sam, a.compression, *b);
                 if (!b->error.empty()) fail(b->error);
                 to_write.push(std::move(b));
             }
@@ -632,7 +627,7 @@ int main(int argc, char **argv) {
             pending[b->seq_no] = std::move(b);
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
                 if (a.sam) for (const std::string &line : it->second->lines) { std::fputs(line.c_str(), stdout); std::fputc('\n', stdout); }
-                else if (!it->second->bam.empty()) bg.write(it->second->bam.data(), it->second->bam.size());
+                else write_all(stdout, it->second->bam.data(), it->second->bam.size());
                 n_lines += it->second->n_records; ++n_batches;
                 pending.erase(it); ++next;
             }
@@ -645,7 +640,7 @@ int main(int argc, char **argv) {
     to_write.close();
     writer.join();
     if (!first_error.empty()) die("alignment failed: " + first_error);
-    if (a.sam) std::fflush(stdout); else bg.finish();
+    if (a.sam) std::fflush(stdout); else bgzf_finish(stdout);
     for (stitch_ctx *c : ctxs) api.destroy(c);
     std::fprintf(stderr, "stitch-b200: wrote %llu records of %llu batches\n", (unsigned long long)n_lines, (unsigned long long)n_batches);
     return 0;
