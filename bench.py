@@ -217,7 +217,7 @@ def via_cli(args):
         for _ in range(max(1, args.steps)):
             t0 = time.perf_counter()
             with open(out, "wb") as fo:
-                p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE)
+                p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE, env=dict(os.environ, STITCH_CLI_TIMING="1"))
             walls.append(time.perf_counter() - t0)
             if p.returncode != 0:
                 print(json.dumps({"error": p.stderr.decode()[-500:]}))
@@ -225,7 +225,12 @@ def via_cli(args):
         size = os.path.getsize(out) if os.path.isfile(out) else None
     cells = sum(len(s) for _, s in named) * (2 if kw.get("double_strand") else 1) * sum(len(r) for r in reads)
     wall = min(walls)
+    stages = None   # the CLI's own account of its last run: start-up, the span in which the devices aligned, busy time per stage
+    for line in p.stderr.decode().splitlines():
+        if line.startswith("stitch-b200 timing: "):
+            stages = json.loads(line[len("stitch-b200 timing: "):])
     print(json.dumps({"metric": "reads/s through `stitch-b200 align` (wall clock of the whole process)", "value": len(reads) / wall, "unit": "reads/s",
+                      "stages": stages,
                       "n_gpus": args.gpus, "reads": len(reads), "wall_s": wall, "walls_s": walls, "gcups_first_fills_only": cells / wall / 1e9,
                       "bam_bytes": size, "batch": args.cli_batch, "config": {"workload": f"config {args.config}", "read_len": len(reads[0])},
                       "stderr_tail": p.stderr.decode()[-200:]}))

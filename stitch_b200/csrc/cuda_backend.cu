@@ -98,7 +98,7 @@ struct CudaBackend : host::Backend {
     uint32_t WINDOW = 64;    // columns at the end of the read with y-suffix tracking; STITCH_TRACK_WINDOW
     const uint8_t *device_reads = nullptr;   // set for run_device()
 
-    DevBuf<uint8_t> d_contigs, d_reads, d_unit;
+    DevBuf<uint8_t> d_contigs, d_reads, d_unit, d_ptbases;
     DevBuf<ContigEntry> d_ents;
     DevBuf<uint16_t> d_owners;
     DevBuf<LayoutDesc> d_layouts;
@@ -328,6 +328,12 @@ struct CudaBackend : host::Backend {
             if (big == nj || PackSmem::bytes(cmax, nt, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) <= SMEM_LIMIT) break;
             LBs[big] = 0;
         }
+        // one key layout per launch: every packed job takes the largest LB any of them needs (more length bits are always valid:
+        // pk_plan's score-range test depends on the scoring alone and has passed for that LB), so that the kernels read the PK
+        // constants from the constant bank (Params::pk) instead of rebuilding them from a per-job LB
+        uint32_t LBu = 0;
+        for (uint32_t k = 0; k < nj; ++k) LBu = std::max(LBu, LBs[k]);
+        for (uint32_t k = 0; k < nj; ++k) if (LBs[k]) LBs[k] = LBu;
         for (uint32_t k = 0; k < nj; ++k) {
             const host::Job &j = jobs[begin + k];
             const host::Layout &L = Ls[j.layout];
@@ -435,6 +441,8 @@ struct CudaBackend : host::Backend {
         d_state.reserve((uint64_t)std::max(wide_grid, n_wide ? wgrid : 0u) * 2 * pm_max + 64);
         d_hand.reserve(64); d_handsum.reserve(handsum_n + 64);   // (hand-over buffers of the retired packed -> wide tail)
         d_pstate.reserve((uint64_t)pteams * 2 * ppm_max + 64);
+        const uint64_t tb_stride = round_up(ppm_max + 2 * PackSmem::STAGE_PRE, 256);   // tile-ordered bases per team (+ the 16 bytes before tile 0)
+        d_ptbases.reserve((uint64_t)pteams * tb_stride + 256);
         d_tailj0.reserve(nj);
         const uint64_t wps_half = (uint64_t)max_ctiles * TILE;
         d_wpstate.reserve((uint64_t)bufgrid * 2 * wps_half + 64);
@@ -457,6 +465,7 @@ struct CudaBackend : host::Backend {
         CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 8 * sizeof(uint32_t), stream));
 
         Params P{};
+        if (LBu) P.pk = pk_make(al.opts.sc, LBu);
         P.sc = al.opts.sc; P.jobs = d_jobs.p; P.order = d_order.p; P.n_jobs = nj; P.cmax = cmax;
         P.layouts = d_layouts.p; P.ents = d_ents.p; P.owners = d_owners.p;
         P.contig_bases = d_contigs.p; P.reads = device_reads ? device_reads : d_reads.p;
@@ -467,6 +476,7 @@ struct CudaBackend : host::Backend {
         d_qstats.reserve(2); CUDA_CHECK(cudaMemsetAsync(d_qstats.p, 0, 2 * sizeof(unsigned long long), stream)); P.qstats = d_qstats.p;
         P.K = K; P.tracked_mode = tracked ? 1 : 0; P.force_full = 0;
         P.hand_state = d_hand.p; P.hand_sum = d_handsum.p; P.pstate = d_pstate.p; P.pstate_stride = 2 * ppm_max; P.pstate_half = ppm_max;
+        P.ptbases = d_ptbases.p; P.ptbases_stride = tb_stride;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
         P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1; P.cone = cone_refill;
         if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
@@ -485,6 +495,7 @@ struct CudaBackend : host::Backend {
                 Q.walk_stage_smem_off = (uint32_t)psmem; Q.unit_stage_bases = pstage_bases ? 1u : 0u;
                 psmem += UnitStage::bytes(K, max_ctiles, pstage_bases);
             }
+            Q.pso = PackSmem::layout(cmax, ntmax, PACK_WARPS, pstage);
             set_smem(fill_packed_kernel<PACK_WARPS>, psmem);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(pteams * cluster); cfg.blockDim = dim3(PACK_WARPS * 32); cfg.dynamicSmemBytes = psmem; cfg.stream = stream;

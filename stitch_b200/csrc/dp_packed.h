@@ -104,6 +104,12 @@ SHD int32_t pk_rel(const PK &p, int32_t key) { return key >> p.SH; }
 SHD uint32_t pk_len(const PK &p, int32_t key) { return (uint32_t)(key & p.LMASK); }
 SHD uint32_t pk_prio(const PK &p, int32_t key) { return (uint32_t)(key >> p.LB) & 15u; }
 SHD int32_t pk_max(int32_t a, int32_t b) { return a > b ? a : b; }
+#ifdef STITCH_PK_FLOORS   // (build variant for A/B measurements: floors in the bulk pass too)
+constexpr bool PK_FLOORS = true;
+#else
+constexpr bool PK_FLOORS = false;
+#endif
+SHD int32_t pk_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 #if defined(__CUDA_ARCH__)
 // DPX instructions of sm_90+/sm_100: VIMNMX3 and VIADDMNMX (one issue slot each)
 SHD int32_t pk_max3(int32_t a, int32_t b, int32_t c) { return __vimax3_s32(a, b, c); }
@@ -182,7 +188,9 @@ SHD void pk_pass1(const PK &p, const PCol &c, const int32_t *Sup, const int32_t 
         const bool rowm = SPECIAL && has_m && k == nv;
         if (ordinary || rowm) {
             const int32_t cc = (x[k] == c.q) ? c.cM : c.cX;
-            const int32_t ext = pk_addmax(Dup[k], c.cE, p.NEGKEY);
+            // (the floors at NEG keep the traceback variant's I / D pointers canonical; the bulk pass only needs the values that
+            // can still win, and an unfloored value stays within (STRIP + 1) extensions of NEG, which pk_plan's range covers)
+            const int32_t ext = (TB || PK_FLOORS) ? pk_addmax(Dup[k], c.cE, p.NEGKEY) : pk_add(Dup[k], c.cE);
             const int32_t Dp = pk_addmax(Sup[k], c.cOE, ext);
             const int32_t D6 = (Dp & p.NPM) | p.PD6;
             int32_t jp = Jc + cc;
@@ -201,7 +209,7 @@ SHD void pk_pass1(const PK &p, const PCol &c, const int32_t *Sup, const int32_t 
                 int32_t H = pk_max3(A, jp | (A & p.PB8), c.XC);
                 if (SPECIAL) H = pk_max(H, o.YC[k]);
                 const int32_t Hc = H & p.NPM;
-                const int32_t exti = pk_addmax(Iacc, c.cEi, p.NEGKEY + p.PI4);
+                const int32_t exti = (TB || PK_FLOORS) ? pk_addmax(Iacc, c.cEi, p.NEGKEY + p.PI4) : pk_add(Iacc, c.cEi);
                 const int32_t Ip = pk_addmax(Hc, c.cOEi, exti);
                 if (TB) iacc_ext = ((Ip >> p.LB) & 15) == PP_INC ? 1u : 0u;
                 Iacc = (Ip & p.NPM) | p.PI4;
@@ -219,9 +227,12 @@ SHD void pk_pass1(const PK &p, const PCol &c, const int32_t *Sup, const int32_t 
 // (PP_ICARRY), `cin_open` = it opens from the row just before (traceback variant).
 // Outputs: S[k] clean keys of the ordinary rows, their running max in `colmax`, packed traceback
 // bytes (TB), and for row m the insertion candidate arriving at it.
+// `notq` (ordinary tiles of the bulk pass): accumulates (S ^ jump candidate) over the strip; the closed form of a quiet
+// cell is the jump candidate with its priority cleared (PkQuiet::bk[s] == (Jc + cM|cX) & NPM == jp & NPM), so the strip's
+// S keys are all in the closed form iff (notq & NPM) == 0.
 template <bool SPECIAL, bool TB>
 SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint32_t cin_open, int nv, bool has_m,
-                  int32_t *S, int32_t &colmax, uint8_t *tb, int32_t *Iarr, int32_t &I_m, uint32_t &iext_m) {
+                  int32_t *S, int32_t &colmax, uint8_t *tb, int32_t *Iarr, int32_t &I_m, uint32_t &iext_m, int32_t *notq = nullptr) {
     int32_t cx = cin;
     STITCH_UNROLL
     for (int k = 0; k < STRIP; ++k) {
@@ -235,6 +246,7 @@ SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint
             const int32_t Sc = Sp & p.NPM;
             S[k] = Sc;
             colmax = pk_max(colmax, Sc);
+            if (!SPECIAL && !TB && notq) *notq |= Sp ^ s.jp[k];
             if (TB) {
                 const uint32_t pr = (uint32_t)(Sp >> p.LB) & 15u;
                 uint32_t mv;
@@ -255,7 +267,7 @@ SHD void pk_pass2(const PK &p, const PCol &c, const PStrip &s, int32_t cin, uint
             I_m = from_carry ? cx : s.Inc[k];
             iext_m = from_carry ? ((k == 0) ? (cin_open ? 0u : 1u) : 1u) : ((s.fl[k] & 2u) ? 1u : 0u);
         }
-        cx = pk_addmax(cx, c.cEi, p.NEGKEY + p.PI5);
+        cx = (TB || PK_FLOORS) ? pk_addmax(cx, c.cEi, p.NEGKEY + p.PI5) : pk_add(cx, c.cEi);
     }
 }
 

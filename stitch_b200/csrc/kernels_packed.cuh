@@ -36,6 +36,35 @@ namespace gpu {
 
 namespace cg = cooperative_groups;
 
+// Bulk asynchronous copies (cp.async.bulk, the TMA engine without a tensor map: SASS UBLKCP) completing on an mbarrier
+// (SYNCS).  One elected lane issues a whole tile; the copy engine works beside the LSU pipe, no per-lane address arithmetic.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// Orders this thread's earlier generic-proxy writes (st.global of the rolling state) before later async-proxy reads of the
+// same bytes (the bulk copy of the tile in the next column); executed by every writer before the CTA barrier.
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // The CTAs that share one read: a thread-block cluster (size > 1) or a single CTA.  A cluster splits the tiles
 // of every column over its CTAs; the small per-contig tables live in every CTA's shared memory and are kept
 // identical through distributed-shared-memory stores, ordered by two cluster barriers per column.
@@ -52,43 +81,72 @@ struct PackSmem {
     PkRowM *stash;
     JumpInfo *Jw;
     PkQuiet *Q;             // [2][cmax]: closed form of a quiet tile per contig, by column parity (dp_packed.h)
-    // per tile, one byte: bits 0..4 base classes present (A C G T other), bit 5 quiet flag of the latest column,
-    // bits 6..7 what the tile does in the current column (0 skip, 1 materialise, 2 load); owned by the tile's warp
+    // per tile, one byte: bits 0..4 base classes present (A C G T other), bit 5 quiet flag of the latest column, bit 6 the
+    // tile may turn quiet at all (static: not the last tile of its contig, or last tiles may); owned by the tile's warp
     uint8_t *tb;
-    static constexpr uint32_t TB_MASK = 31u, TB_Q = 32u;
+    static constexpr uint32_t TB_MASK = 31u, TB_Q = 32u, TB_CANQ = 64u;
     ContigEntry *ent_s;     // [cmax]: the layout's contig table (bulk pass: no global loads in the per-column serial phases)
     uint16_t *owner_s;      // [ntmax]: contig position of every tile
     uint16_t *clist;        // [ntmax]: per warp chunk (slice [t_lo, t_hi)), the chunk-relative offsets of the tiles computed in this column
     uint32_t cmax;
-    unsigned char *stage;   // [W][depth][STAGE_BYTES]: cp.async ring of the next tiles (state in global memory only)
-    static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + TILE;   // S keys, D keys, bases of one tile
+    unsigned char *stage;   // [W][depth][STAGE_BYTES]: bulk-copy ring of the next tiles (state in global memory only)
+    unsigned long long *mbar;   // [W][4]: one mbarrier per ring slot
+    uint32_t *mphase;       // [W]: phase parity of every slot's mbarrier (bit = slot), kept across columns and reads
+    // one slot: S keys, D keys, the 16 bases before the tile (its upper neighbour's last rows: diagonal source of a skipped
+    // neighbour, halo strip of a chunk's first tile), the tile's bases
+    static constexpr uint32_t STAGE_PRE = 16, STAGE_BASES = 2 * TILE * 4 + STAGE_PRE;
+    static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + STAGE_PRE + TILE;
     // `stage_bytes`: the front area = cp.async double buffers (default_stage), or the cluster's slice of the rolling
     // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
     static size_t default_stage(int W, uint32_t depth = 2) { return (size_t)W * depth * STAGE_BYTES; }
+    // One definition of the layout for the host (sizes, Params::pso) and the device (carve).
+    static __host__ __device__ PackSmemOff layout(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
+        PackSmemOff o;
+        uint32_t p = (uint32_t)stage_bytes;
+        o.Jw = p; p += (uint32_t)sizeof(JumpInfo) * cmax;
+        o.stash = p; p += (uint32_t)sizeof(PkRowM) * cmax;
+        o.Jc = p; p += 4u * cmax; o.cm = p; p += 4u * cmax; o.Sm = p; p += 4u * cmax; o.SmKey = p; p += 4u * cmax;
+        o.cml = p; p += 4u * cmax; o.cmk = p; p += 4u * cmax; o.slm = p; p += 4u * cmax; o.tbm = p; p += 4u * cmax;
+        o.DmKey = p; p += 4u * cmax;
+        o.tilemax = p; p += 4u * ntmax;
+        o.haloS = p; p += 4u * 2u * (uint32_t)W * 9u;            // [2][W][9]
+        o.haloD = p; p += 4u * 2u * (uint32_t)W * 8u;            // [2][W][8]
+        o.haloF = p; p += 4u * (2u * (uint32_t)W + 2u);          // [2][W]: quiet flag of the last tile of the previous chunk
+        o.Q = p; p += (uint32_t)sizeof(PkQuiet) * 2u * cmax;
+        o.ent_s = p; p += (uint32_t)sizeof(ContigEntry) * cmax;
+        o.owner_s = p; p += 2u * ntmax;
+        o.clist = p; p += 2u * ntmax;
+        o.tb = p; p += ntmax;
+        p = (p + 7u) & ~7u;
+        o.mbar = p; p += 8u * 4u * (uint32_t)W;
+        o.mphase = p; p += 4u * (uint32_t)W;
+        o.end = p;
+        return o;
+    }
     static size_t bytes(uint32_t cmax, uint32_t ntmax, int W, size_t stage_bytes) {
         return stage_bytes + sizeof(int32_t) * ((size_t)cmax * 9 + ntmax + 2 * W * 18) +
-               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 5 * (size_t)ntmax + 4 * 8 + 64;
+               (sizeof(PkRowM) + sizeof(JumpInfo) + 2 * sizeof(PkQuiet) + sizeof(ContigEntry)) * cmax + 5 * (size_t)ntmax + 4 * 8 + 64 + 36 * (size_t)W + 8;
     }
-    __device__ void carve(unsigned char *raw, uint32_t cmax_, uint32_t ntmax, int W, size_t stage_bytes) {
-        const uint32_t cmax = cmax_;
-        this->cmax = cmax_;
+    __device__ __forceinline__ void carve(unsigned char *raw, const PackSmemOff &o, uint32_t cmax_) {
+        cmax = cmax_;
         stage = raw;
-        raw += stage_bytes;
-        Jw = reinterpret_cast<JumpInfo *>(raw);
-        stash = reinterpret_cast<PkRowM *>(Jw + cmax);
-        Jc = reinterpret_cast<int32_t *>(stash + cmax);
-        cm = Jc + cmax; Sm = cm + cmax; SmKey = Sm + cmax;
-        cml = reinterpret_cast<uint32_t *>(SmKey + cmax); cmk = cml + cmax; slm = cmk + cmax; tbm = slm + cmax;
-        DmKey = reinterpret_cast<int32_t *>(tbm + cmax);
-        tilemax = DmKey + cmax;
-        haloS = tilemax + ntmax;                             // [2][W][9]
-        haloD = haloS + 2 * W * 9;                           // [2][W][8]
-        haloF = reinterpret_cast<uint32_t *>(haloD + 2 * W * 8);   // [2][W]: quiet flag of the last tile of the previous chunk
-        Q = reinterpret_cast<PkQuiet *>(haloF + 2 * W + 2);
-        ent_s = reinterpret_cast<ContigEntry *>(Q + 2 * cmax);
-        owner_s = reinterpret_cast<uint16_t *>(ent_s + cmax);
-        clist = owner_s + ntmax;
-        tb = reinterpret_cast<uint8_t *>(clist + ntmax);
+        Jw = reinterpret_cast<JumpInfo *>(raw + o.Jw);
+        stash = reinterpret_cast<PkRowM *>(raw + o.stash);
+        Jc = reinterpret_cast<int32_t *>(raw + o.Jc); cm = reinterpret_cast<int32_t *>(raw + o.cm);
+        Sm = reinterpret_cast<int32_t *>(raw + o.Sm); SmKey = reinterpret_cast<int32_t *>(raw + o.SmKey);
+        cml = reinterpret_cast<uint32_t *>(raw + o.cml); cmk = reinterpret_cast<uint32_t *>(raw + o.cmk);
+        slm = reinterpret_cast<uint32_t *>(raw + o.slm); tbm = reinterpret_cast<uint32_t *>(raw + o.tbm);
+        DmKey = reinterpret_cast<int32_t *>(raw + o.DmKey);
+        tilemax = reinterpret_cast<int32_t *>(raw + o.tilemax);
+        haloS = reinterpret_cast<int32_t *>(raw + o.haloS); haloD = reinterpret_cast<int32_t *>(raw + o.haloD);
+        haloF = reinterpret_cast<uint32_t *>(raw + o.haloF);
+        Q = reinterpret_cast<PkQuiet *>(raw + o.Q);
+        ent_s = reinterpret_cast<ContigEntry *>(raw + o.ent_s);
+        owner_s = reinterpret_cast<uint16_t *>(raw + o.owner_s);
+        clist = reinterpret_cast<uint16_t *>(raw + o.clist);
+        tb = raw + o.tb;
+        mbar = reinterpret_cast<unsigned long long *>(raw + o.mbar);
+        mphase = reinterpret_cast<uint32_t *>(raw + o.mphase);
     }
 };
 
@@ -104,6 +162,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     const ContigEntry *ent; const uint16_t *owner;   // owner == nullptr: a single contig (position 0)
     uint32_t C, NT;
     const uint8_t *bases;
+    const uint8_t *tbases;  // staged fills: the layout's bases in tile order (tile t at tbases + t * TILE, 16 readable bytes before tile 0)
     int32_t *Sst, *Dst;
     uint32_t n;
     bool yclip_mode;
@@ -195,7 +254,7 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
     int32_t Sup[STRIP], Dup[STRIP];
     uint2 xb;
     if (QUIET && qz.mat) {
-        xb = stg ? reinterpret_cast<const uint2 *>(stg + 2 * TILE * 4)[lane] : *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
+        xb = stg ? reinterpret_cast<const uint2 *>(stg + PackSmem::STAGE_BASES)[lane] : *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (row0 - 1));
         uint8_t xm[STRIP];
         unpack8(xb, xm);
         const PkQuiet qp = *qz.Qp;
@@ -208,10 +267,10 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
         }
     } else {
         int4 s0, s1, d0, d1;
-        if (stg) {   // this tile was staged in shared memory by cp.async while the previous tile was computed
+        if (stg) {   // this tile was staged in shared memory by a bulk copy while the previous tile was computed
             const int4 *q = reinterpret_cast<const int4 *>(stg);
             s0 = q[lane]; s1 = q[32 + lane]; d0 = q[64 + lane]; d1 = q[96 + lane];
-            xb = reinterpret_cast<const uint2 *>(stg + 2 * TILE * 4)[lane];
+            xb = reinterpret_cast<const uint2 *>(stg + PackSmem::STAGE_BASES)[lane];
         } else {
             s0 = pk_ld_state(X, X.Sst + tile * ST + lane * 4);
             s1 = pk_ld_state(X, X.Sst + tile * ST + 128 + lane * 4);
@@ -229,7 +288,8 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
     if (lane == 0) {
         if (first) Sdg0 = r0pkey;
         else if (chunk_start) Sdg0 = hS[8];
-        else if (QUIET && qz.prev_skipped) Sdg0 = X.bases[en.seq_off + row0 - 2] == qz.yq[1] ? qz.Qp->bk[0] : qz.Qp->bk[1];   // last row of a quiet tile
+        else if (QUIET && qz.prev_skipped)   // last row of a quiet tile (its base: the byte before this tile's bases)
+            Sdg0 = (stg ? stg[PackSmem::STAGE_BASES - 1] : X.bases[en.seq_off + row0 - 2]) == qz.yq[1] ? qz.Qp->bk[0] : qz.Qp->bk[1];
         else Sdg0 = prev_s7;
     }
     PStrip st;
@@ -260,7 +320,7 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
         PStrip h;
         uint8_t hx[STRIP];
         const uint32_t hrow0 = tic * TILE - STRIP + 1;
-        unpack8(*reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (hrow0 - 1)), hx);
+        unpack8(stg ? *reinterpret_cast<const uint2 *>(stg + PackSmem::STAGE_BASES - STRIP) : *reinterpret_cast<const uint2 *>(X.bases + en.seq_off + (hrow0 - 1)), hx);
         int32_t hs[STRIP], hd[STRIP];
         STITCH_UNROLL
         for (int k = 0; k < STRIP; ++k) {
@@ -278,8 +338,9 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
 
     int32_t Sn[STRIP], Iarr[STRIP]; uint8_t tbb[STRIP];
     int32_t colmax = pk.NEGKEY; int32_t I_m = pk.NEGKEY; uint32_t iext_m = 0;
+    int32_t notq = 0;   // ordinary tiles of the bulk pass: the S half of the closed-form test rides along in pass 2
     if (SPECIAL) pk_pass2<true, TB>(pk, pc, st, cin, cin_open, nv, has_m, Sn, colmax, tbb, Iarr, I_m, iext_m);
-    else pk_pass2<false, TB>(pk, pc, st, cin, cin_open, STRIP, false, Sn, colmax, tbb, Iarr, I_m, iext_m);
+    else pk_pass2<false, TB>(pk, pc, st, cin, cin_open, STRIP, false, Sn, colmax, tbb, Iarr, I_m, iext_m, (QUIET && !TB) ? &notq : nullptr);
 
     // what the next tile of this chunk needs (before the in-place stores)
     prev_s7 = __shfl_sync(FULL, Sup[STRIP - 1], 31);
@@ -331,9 +392,12 @@ __device__ __forceinline__ bool pk_tile(const PackCtx &X, const PCol &pc, PackSm
     if (QUIET) {   // is the tile in the closed form of column j?  (S first: the cheap test, and the one that usually fails)
         const PkQuiet qn = *qz.Qn;
         bool ok = true;
-        STITCH_UNROLL
-        for (int k = 0; k < STRIP; ++k)
-            if (!SPECIAL || k < nv) ok = ok && Sn[k] == (x[k] == pc.q ? qn.bk[0] : qn.bk[1]);
+        if (!SPECIAL && !TB) ok = (notq & pk.NPM) == 0;   // jp & NPM is the closed form's key of the cell (pk_quiet_next)
+        else {
+            STITCH_UNROLL
+            for (int k = 0; k < STRIP; ++k)
+                if (!SPECIAL || k < nv) ok = ok && Sn[k] == (x[k] == pc.q ? qn.bk[0] : qn.bk[1]);
+        }
         if (!__all_sync(FULL, ok)) return false;
         STITCH_UNROLL
         for (int k = 0; k < STRIP; ++k)
@@ -366,7 +430,7 @@ __device__ __forceinline__ uint32_t pk_base_bit(uint8_t b) { return b == 'A' ? 1
 template <int W, bool TB, bool QUIET = false>
 __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t r0pkey, int32_t cr1key, uint32_t j,
                           const PkColOut &O, const uint8_t *yq = nullptr, PkColStat *cs = nullptr) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = __shfl_sync(FULL, tid >> 5, 0);   // (a shuffle from lane 0: the compiler then treats the warp index and what derives from it as warp-uniform)
     const PK &pk = X.pk;
     const Scoring &sc = X.sc;
     const uint32_t NT = X.NT, C = X.C, par = j & 1u;
@@ -380,60 +444,62 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         const uint32_t t_lo = X.win_lo + (uint32_t)((uint64_t)NT * gw / Weff), t_hi = X.win_lo + (uint32_t)((uint64_t)NT * (gw + 1) / Weff);
         const int32_t *hS = S.haloS + ((par ^ 1u) * W + warp) * 9, *hD = S.haloD + ((par ^ 1u) * W + warp) * 8;
         int32_t prev_exit = 0, prev_s7 = 0; uint32_t prev_exit_open = 0;
-        // cp.async brings the next tiles (S keys, D keys, bases) into this warp's shared-memory ring while a tile is computed;
-        // each lane reads back exactly the bytes it copied (no warp sync needed)
+        // bulk copies bring the next tiles (S keys, D keys, bases) into this warp's shared-memory ring while a tile is computed:
+        // one elected lane issues a tile (cp.async.bulk: the state and the bases are contiguous), every lane waits on the slot's
+        // mbarrier
         const bool staged = X.staged;
-        unsigned char *stg0 = S.stage + (size_t)warp * X.stage_depth * PackSmem::STAGE_BYTES;
-        // (`full` = the tile's state is loaded; a materialised tile only needs its bases)
-        auto prefetch = [&](uint32_t t, const ContigEntry &e, uint32_t slot, bool full) {
-            unsigned char *d = stg0 + slot * PackSmem::STAGE_BYTES;
-            if (full) {
-                __pipeline_memcpy_async(d + lane * 16, X.Sst + t * ST + lane * 4, 16);
-                __pipeline_memcpy_async(d + 512 + lane * 16, X.Sst + t * ST + 128 + lane * 4, 16);
-                __pipeline_memcpy_async(d + 1024 + lane * 16, X.Dst + t * ST + lane * 4, 16);
-                __pipeline_memcpy_async(d + 1536 + lane * 16, X.Dst + t * ST + 128 + lane * 4, 16);
-            }
-            __pipeline_memcpy_async(d + 2048 + lane * 8, X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP, 8);
-            __pipeline_commit();
-        };
         PkQuietArgs qz; qz.mat = false; qz.prev_skipped = false; qz.Qp = Qp; qz.Qn = Qn; qz.yq = yq; qz.deadrel = QUIET ? pk_deadrel(sc) : 0;
         // quiet tiles: the plan of this warp's chunk for this column, from the flags of column j-1 (a warp owns the flags
         // of its chunk), one tile per lane: 0 = skip, 1 = compute from the materialised closed form, 2 = load + compute.
         // The first and last tile of a chunk and of a contig are always computed (halos, row 1, row m).  A skipped tile
-        // only contributes its best key (the better of the closed form's two keys among the bases it holds).
+        // only contributes its best key (the better of the closed form's two keys among the bases it holds).  The tiles that
+        // are computed go, in order, into this warp's slice of S.clist as descriptors: bits 0..12 chunk-relative tile, bit 13
+        // the tile may turn quiet, bits 14..15 the mode.
         const bool edge = QUIET && X.quiet_edge;
         const uint32_t lq0 = (edge && gw > 0) ? S.haloF[(par ^ 1u) * W + warp] : 0u;   // last tile of the previous chunk was quiet at column j-1
+        uint16_t *cl = S.clist + t_lo;
+        uint32_t ncomp = t_hi - t_lo, nskipped = 0, mode_first = 2u, mode_last = 2u;
         if (QUIET) {
             const uint32_t mb = pk_base_bit(pc.q);
-            for (uint32_t t = t_lo + lane; t < t_hi; t += 32) {
-                uint32_t mode = 2;
-                const uint32_t tbv = S.tb[t];
-                if (tbv & PackSmem::TB_Q) {
-                    const uint32_t a_t = X.owner[t];
-                    const uint32_t tic = t - X.ent[a_t].tile_start;
-                    const PkQuiet &qn = Qn[a_t];
-                    // (the first tile of a contig has no upper neighbour but four more conditions: stay_first; the first tile
-                    // of a chunk reads the flag its neighbour chunk's owner published with the halo)
-                    const bool left_ok = t != t_lo ? (S.tb[t - 1] & PackSmem::TB_Q) != 0 : lq0 != 0u;
-                    const bool lastt = tic + 1 == X.ent[a_t].ntiles;
-                    mode = ((!lastt || (X.quiet_last && tic != 0)) && (edge || (t != t_lo && t + 1 != t_hi)) &&
-                            (tic == 0 ? qn.stay_first != 0 : (left_ok && qn.stay))) ? 0u : 1u;
-                    if (mode == 0) {
-                        const uint32_t tm = tbv & PackSmem::TB_MASK;
-                        S.tilemax[t] = tm == 0u ? pk.NEGKEY : ((tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1]);
-                        if (lastt) {   // row m: the candidates the tile would have stashed for the per-contig finish
-                            const ContigEntry &e = X.ent[a_t];
-                            int32_t dmn;
-                            S.stash[a_t] = pk_quiet_rowm(pk, pc, Qp[a_t], S.Jc[a_t], S.SmKey[a_t], S.DmKey[a_t],
-                                                         X.bases[e.seq_off + e.m - 2] == yq[1] ? 0 : 1, X.bases[e.seq_off + e.m - 1] == pc.q, &dmn);
-                            S.DmKey[a_t] = dmn;
+            ncomp = 0;
+            for (uint32_t base = t_lo; base < t_hi; base += 32) {
+                const uint32_t t = base + lane;
+                uint32_t mode = 2, tbv = 0;
+                if (t < t_hi) {
+                    tbv = S.tb[t];
+                    if (tbv & PackSmem::TB_Q) {
+                        const uint32_t a_t = X.owner[t];
+                        const uint32_t tic = t - X.ent[a_t].tile_start;
+                        const PkQuiet &qn = Qn[a_t];
+                        // (the first tile of a contig has no upper neighbour but four more conditions: stay_first; the first tile
+                        // of a chunk reads the flag its neighbour chunk's owner published with the halo)
+                        const bool left_ok = t != t_lo ? (S.tb[t - 1] & PackSmem::TB_Q) != 0 : lq0 != 0u;
+                        const bool lastt = tic + 1 == X.ent[a_t].ntiles;
+                        mode = ((!lastt || (X.quiet_last && tic != 0)) && (edge || (t != t_lo && t + 1 != t_hi)) &&
+                                (tic == 0 ? qn.stay_first != 0 : (left_ok && qn.stay))) ? 0u : 1u;
+                        if (mode == 0) {
+                            const uint32_t tm = tbv & PackSmem::TB_MASK;
+                            S.tilemax[t] = tm == 0u ? pk.NEGKEY : ((tm & mb) ? ((tm & ~mb) ? pk_max(qn.bk[0], qn.bk[1]) : qn.bk[0]) : qn.bk[1]);
+                            if (lastt) {   // row m: the candidates the tile would have stashed for the per-contig finish
+                                const ContigEntry &e = X.ent[a_t];
+                                int32_t dmn;
+                                S.stash[a_t] = pk_quiet_rowm(pk, pc, Qp[a_t], S.Jc[a_t], S.SmKey[a_t], S.DmKey[a_t],
+                                                             X.bases[e.seq_off + e.m - 2] == yq[1] ? 0 : 1, X.bases[e.seq_off + e.m - 1] == pc.q, &dmn);
+                                S.DmKey[a_t] = dmn;
+                            }
                         }
                     }
                 }
-                S.tb[t] = (uint8_t)((tbv & 63u) | (mode << 6));
+                const bool comp = t < t_hi && mode != 0u;
+                const uint32_t m = __ballot_sync(FULL, comp);
+                if (comp) cl[ncomp + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((t - t_lo) | ((tbv & PackSmem::TB_CANQ) ? 0x2000u : 0u) | (mode << 14));
+                ncomp += __popc(m);
+                if (base == t_lo) mode_first = __shfl_sync(FULL, mode, 0);
+                if (t_hi - 1u - base < 32u) mode_last = __shfl_sync(FULL, mode, (int)(t_hi - 1u - base));
             }
+            nskipped = (t_hi - t_lo) - ncomp;
             __syncwarp();
-            if (lq0 && ((uint32_t)S.tb[t_lo] >> 6) != 0u) {
+            if (lq0 && mode_first != 0u) {
                 // the chunk's first tile is computed and its upper neighbour (another warp's tile) is quiet, its memory possibly
                 // stale: the 17-key halo of column j-1 comes from the closed form instead of the published copy
                 const uint32_t a0 = X.owner[t_lo];
@@ -447,53 +513,46 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 __syncwarp();
             }
         }
-        // the tiles of this chunk that are computed in this column, in order (quiet tiles: the chunk-relative offsets, compacted
-        // into this warp's slice of S.clist)
-        uint16_t *cl = S.clist + t_lo;
-        uint32_t ncomp = t_hi - t_lo, nskipped = 0;
-        if (QUIET) {
-            ncomp = 0;
-            for (uint32_t base = t_lo; base < t_hi; base += 32) {
-                const bool comp = base + lane < t_hi && ((uint32_t)S.tb[base + lane] >> 6) != 0u;
-                const uint32_t m = __ballot_sync(FULL, comp);
-                if (comp) cl[ncomp + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base + lane - t_lo);
-                ncomp += __popc(m);
-            }
-            nskipped = (t_hi - t_lo) - ncomp;
-            __syncwarp();
-        }
-        auto tile_at = [&](uint32_t k) -> uint32_t { return QUIET ? t_lo + cl[k] : t_lo + k; };
+        auto desc_at = [&](uint32_t k) -> uint32_t { return QUIET ? (uint32_t)cl[k] : (k | (2u << 14)); };
         // contig of the current tile (reloaded only when the chunk crosses into the next contig)
         uint32_t a = X.owner ? X.owner[t_lo] : 0u;
         ContigEntry en = X.ent[a];
         int32_t Jc = S.Jc[a];
         // software pipeline: a ring of `depth` stage slots per warp; while tile k is computed the next depth - 1 computed tiles are
-        // in flight (cp.async), so that a tile's HBM / L2 latency is covered by several tiles of arithmetic
+        // in flight, so that a tile's HBM / L2 latency is covered by several tiles of arithmetic
         const uint32_t dmask = X.stage_depth - 1u;
+        unsigned char *stgw = S.stage + (size_t)warp * X.stage_depth * PackSmem::STAGE_BYTES;
+        const uint32_t stg_s = smem_u32(stgw), bar_s = smem_u32(S.mbar + warp * 4u);
+        uint32_t phase = staged ? S.mphase[warp] : 0u;
         uint32_t issued = 0;
         auto issue = [&](uint32_t k) {
-            const uint32_t t = tile_at(k);
-            const bool full = !QUIET || ((uint32_t)S.tb[t] >> 6) == 2u;
-            if (t >= en.tile_start && t < en.tile_start + en.ntiles) prefetch(t, en, k & dmask, full);
-            else { const ContigEntry e2 = X.ent[X.owner ? X.owner[t] : 0u]; prefetch(t, e2, k & dmask, full); }
+            if (lane == 0) {
+                const uint32_t d = desc_at(k), t = t_lo + (d & 0x1fffu), slot = k & dmask;
+                const uint32_t dst = stg_s + slot * PackSmem::STAGE_BYTES, bar = bar_s + slot * 8u;
+                const bool full = (d >> 14) == 2u;   // (a materialised tile only needs its bases)
+                mbar_expect_tx(bar, full ? PackSmem::STAGE_BYTES : PackSmem::STAGE_PRE + (uint32_t)TILE);
+                if (full) bulk_g2s(dst, X.Sst + (size_t)t * ST, 2 * TILE * 4, bar);
+                bulk_g2s(dst + 2 * TILE * 4, X.tbases + (size_t)t * TILE - PackSmem::STAGE_PRE, PackSmem::STAGE_PRE + (uint32_t)TILE, bar);
+            }
         };
         if (staged) for (; issued < dmask && issued < ncomp; ++issued) issue(issued);
         uint32_t prev_tile = 0xfffffffeu;
         for (uint32_t k = 0; k < ncomp; ++k) {
-            const uint32_t tile = tile_at(k);
-            const bool is_load = !QUIET || ((uint32_t)S.tb[tile] >> 6) == 2u;
+            const uint32_t d = desc_at(k);
+            const uint32_t tile = t_lo + (d & 0x1fffu);
+            const bool is_load = (d >> 14) == 2u;
             qz.prev_skipped = QUIET && tile != t_lo && prev_tile + 1u != tile;
             prev_tile = tile;
             if (tile >= en.tile_start + en.ntiles) { a = X.owner[tile]; en = X.ent[a]; Jc = S.Jc[a]; }
             const unsigned char *stg = nullptr;
             if (staged) {
+                // (the slot tile k + depth - 1 goes into was read by tile k - 1: every lane is past those reads, the tile ends in
+                // warp-wide votes)
                 if (issued < ncomp) { issue(issued); ++issued; }
-                const uint32_t pending = issued - 1u - k;   // commits younger than tile k's may stay pending
-                if (pending == 0u) __pipeline_wait_prior(0);
-                else if (pending == 1u) __pipeline_wait_prior(1);
-                else if (pending == 2u) __pipeline_wait_prior(2);
-                else __pipeline_wait_prior(3);
-                stg = stg0 + (k & dmask) * PackSmem::STAGE_BYTES;
+                const uint32_t slot = k & dmask;
+                mbar_wait(bar_s + slot * 8u, (phase >> slot) & 1u);
+                phase ^= 1u << slot;
+                stg = stgw + slot * PackSmem::STAGE_BYTES;
             }
             qz.mat = QUIET && !is_load;
             qz.Qp = Qp + a; qz.Qn = Qn + a;
@@ -503,12 +562,16 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
                 qnow = pk_tile<true, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
             else
                 qnow = pk_tile<false, TB, QUIET>(X, pc, S, O, j, tile, lane, r0pkey, cr1key, tile == t_lo, hS, hD, prev_exit, prev_exit_open, prev_s7, stg, a, en, Jc, qz);
-            if (QUIET && lane == 0)
-                S.tb[tile] = (uint8_t)((S.tb[tile] & ~PackSmem::TB_Q) | ((qnow && (tic + 1 != en.ntiles || (X.quiet_last && tic != 0))) ? PackSmem::TB_Q : 0u));
+            if (QUIET && lane == 0) {
+                const uint32_t tbv = S.tb[tile];
+                S.tb[tile] = (uint8_t)((tbv & ~PackSmem::TB_Q) | ((qnow && (d & 0x2000u)) ? PackSmem::TB_Q : 0u));
+            }
         }
+        if (staged && lane == 0) S.mphase[warp] = phase;
         if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); if (cst) atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
+        if (QUIET) __syncwarp();   // (lane 0's flag of the last tile)
         if (QUIET && gw + 1 < Weff && lane == 0) S.haloF[par * W + warp + 1] = (S.tb[t_hi - 1] & PackSmem::TB_Q) ? 1u : 0u;
-        if (gw + 1 < Weff && (!QUIET || ((uint32_t)S.tb[t_hi - 1] >> 6) != 0u)) {
+        if (gw + 1 < Weff && (!QUIET || mode_last != 0u)) {
             // publish the halo of the next chunk for the next column (the next CTA's warp 0 after our last warp); a skipped
             // last tile publishes only its flag (above): its memory is stale and the consumer uses the closed form
             const bool local = warp + 1 < (uint32_t)W;
@@ -526,6 +589,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             if (lane == 30) nS[0] = tp[128 + 30 * 4 + 3];
         }
     }
+    if (X.staged) fence_async_proxy();   // this column's state stores before the next column's bulk copies of the same tiles
     team.sync();
     if (X.no_finish) return;   // cone re-fill: row m is outside the window, nothing reads the column best
 
@@ -638,6 +702,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
         }
     }
     if (cst && tid == 0) cs->t_f2 += (unsigned long long)(clock64() - c1);
+    if (X.staged) fence_async_proxy();   // (row m's key)
     team.sync();
     if (cst && tid == 0) { cs->t_tiles += (unsigned long long)(c1 - c0); cs->t_finish += (unsigned long long)(clock64() - c1); }
 }
@@ -670,6 +735,7 @@ __device__ void pk_state_init0(const PackCtx &X, PackSmem &S) {
         S.SmKey[a] = pk_from_wide(pk, 0, cmm.S, cmm.sl, 0);
         S.DmKey[a] = pk.NEGKEY + pk.PD6;
     }
+    if (X.staged) fence_async_proxy();
     X.team.sync();
 }
 
@@ -689,6 +755,7 @@ __device__ void pk_state_from_ck(const PackCtx &X, PackSmem &S, const int32_t *c
         S.Sm[a] = cs.Sm; S.slm[a] = cs.slm; S.tbm[a] = cs.tbm;
         S.SmKey[a] = pk_from_wide(pk, Bj0, cs.Sm, cs.slm, 0);
     }
+    if (X.staged) fence_async_proxy();
     X.team.sync();
 }
 
@@ -709,6 +776,8 @@ __device__ void pk_write_ck(const PackCtx &X, PackSmem &S, int32_t *dck, CkSum *
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tail: columns (j0, n] again in the traceback variant
 struct PkColConst { PCol pc; int32_t r0pkey, cr1key; uint8_t yq[PKQ_L + 2]; };   // yq[k] = y_{j-k} (bulk pass), 0 = none
 __device__ __forceinline__ PkColConst pk_col_const(const PK &pk, const Scoring &sc, int32_t B, int32_t Bprev, uint32_t j, uint32_t n, uint8_t q) {
     PkColConst c;
@@ -720,19 +789,15 @@ __device__ __forceinline__ PkColConst pk_col_const(const PK &pk, const Scoring &
 }
 
 // ---------------------------------------------------------------------------------------------
-// tail: columns (j0, n] again in the traceback variant
-// ---------------------------------------------------------------------------------------------
 // Closed form of a quiet tile of contig `a` in column j (dp_packed.h) and whether quiet tiles of that contig stay quiet;
 // S.Jc / S.SmKey / S.tbm of the contig are up to date.  `allow` = the column may skip tiles at all.
-__device__ __forceinline__ void pk_quiet_contig(const PackCtx &X, PackSmem &S, uint32_t a, uint32_t j, int32_t B, int32_t Bprev, uint8_t q,
-                                                bool allow) {
+__device__ __forceinline__ void pk_quiet_contig(const PackCtx &X, PackSmem &S, uint32_t a, uint32_t j, const PkColConst &ccl, bool allow) {
     const uint32_t par = j & 1u;
-    const PkColConst ccl = pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, q);
     PkFirstIn fi;   // what row 1 of this contig sees beyond an ordinary row
     fi.r0pkey = ccl.r0pkey; fi.cr1key = ccl.cr1key; fi.wbase = pk_wbase(X.pk, S.SmKey[a]);
     fi.wrap = X.ent[a].circular && S.tbm[a] != TB_XCLIP_SUFFIX;
-    fi.yc1 = X.yclip_mode ? pk_key(X.pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e - B, PP_YC, col0_slen(X.sc, 1, X.ent[a].m)) : X.pk.NEGKEY;
-    S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, ccl.pc, S.Jc[a], S.Q[(par ^ 1u) * S.cmax + a], allow && pk_base_bit(q) != 16u,
+    fi.yc1 = X.yclip_mode ? pk_key(X.pk, (int64_t)X.sc.yp + X.sc.o + (int64_t)X.sc.e - ccl.pc.B, PP_YC, col0_slen(X.sc, 1, X.ent[a].m)) : X.pk.NEGKEY;
+    S.Q[par * S.cmax + a] = pk_quiet_next(X.pk, X.sc, ccl.pc, S.Jc[a], S.Q[(par ^ 1u) * S.cmax + a], allow && pk_base_bit(ccl.pc.q) != 16u,
                                           X.quiet_first ? &fi : nullptr);
 }
 
@@ -753,7 +818,7 @@ __device__ __forceinline__ void pk_replay_consts(const PackCtx &X, PackSmem &S, 
         if (tail_quiet) {
             // quiet tiles in the tail: a skipped tile must not hold a cell that can still set a final y-suffix tracker
             // (SCA:432-447), and column n leaves the records of every cell for the end-of-read fix-up
-            pk_quiet_contig(X, S, a, j, B, Bprev, read[j - 1], j != X.n);
+            pk_quiet_contig(X, S, a, j, pk_col_const(X.pk, X.sc, B, Bprev, j, X.n, read[j - 1]), j != X.n);
             PkQuiet &qn = S.Q[(j & 1u) * S.cmax + a];
             if (track && pk_abs(X.pk, B, pk_max(qn.bk[0], qn.bk[1])) >= track_thr) { qn.stay = 0; qn.stay_first = 0; }
         }
@@ -805,7 +870,7 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
             S.DmKey[a] = X.Dst[mt * ST + (mk >> 2) * 128u + ml * 4u + (mk & 3u)];
             S.Q[a] = pk_quiet_init(X.pk); S.Q[S.cmax + a] = pk_quiet_init(X.pk);
         }
-        for (uint32_t t = tid; t < X.NT; t += W * 32) S.tb[t] = (uint8_t)(S.tb[t] & PackSmem::TB_MASK);
+        for (uint32_t t = tid; t < X.NT; t += W * 32) S.tb[t] = (uint8_t)(S.tb[t] & (PackSmem::TB_MASK | PackSmem::TB_CANQ));
         if (tid < 2 * W) S.haloF[tid] = 0;
     }
     X.team.sync();   // trackers of every row initialised before any CTA updates them
@@ -822,34 +887,101 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
 
 // Base of column j, jump selection for every contig (MCA:279-331), per-column constants (the CTA must synchronise
 // before using them).  s_cc[(j-1)&1].pc.B holds the base of column j-1.
+// One inter-contig jump source: column best (score without the jump cost), its length, layout position.
+struct PkSrc { int32_t s; uint32_t l, b; };
+__device__ __forceinline__ bool pk_src_before(const PkSrc &x, const PkSrc &y) {   // x is preferred to y: (score, length, position) lexicographic
+    return x.s != y.s ? x.s > y.s : (x.l != y.l ? x.l > y.l : x.b > y.b);
+}
+#ifndef STITCH_SELECT_TOP3
+#define STITCH_SELECT_TOP3 0
+#endif
 template <int W>
 __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, ColRec *colrec, int32_t *gcol, const uint8_t *read,
                                                  uint32_t j, PkColConst *s_cc, bool writer, uint32_t K) {
-    const uint32_t tid = threadIdx.x, par = j & 1u, C = X.C;
-    constexpr uint32_t T = W * 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, par = j & 1u, C = X.C;
     const int32_t Bprev = s_cc[par ^ 1u].pc.B;
-    if (tid < C || tid == 0) {
+#if !STITCH_SELECT_TOP3
+    (void)lane;
+    if (tid < C || tid == 0) {   // every thread scans all contigs (select_jump, dp_core.h)
         int32_t g = S.cm[0];
         for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-        PCol pcl; pcl.B = g; pcl.delta = g - Bprev;
-        for (uint32_t a = tid; a < C; a += T) {
+        const PkColConst ccl = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, read[j - 1]);
+        for (uint32_t a = tid; a < C; a += W * 32) {
             const JumpInfo J = select_jump(X.sc, X.ent, C, a, S.cm, S.cml, S.cmk);
             if (writer) {
                 ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
                 cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
                 colrec[(uint64_t)j * C + a] = cr;
             }
-            const int32_t Jc = pk_jc(X.pk, pcl, J.score, J.len);
-            S.Jc[a] = Jc;
-            if (X.quiet) pk_quiet_contig(X, S, a, j, g, Bprev, read[j - 1], !((j % K == 0) && j < X.n));   // (not at checkpoint columns)
+            S.Jc[a] = pk_jc(X.pk, ccl.pc, J.score, J.len);
+            if (X.quiet) pk_quiet_contig(X, S, a, j, ccl, !((j % K == 0) && j < X.n));   // (not at checkpoint columns)
         }
         if (tid == 0) {
             if (writer) gcol[j - 1] = g;
-            s_cc[par] = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, read[j - 1]);
+            s_cc[par] = ccl;
             STITCH_UNROLL
             for (int k = 0; k < PKQ_L + 2; ++k) s_cc[par].yq[k] = j >= 1u + (uint32_t)k ? read[j - 1 - (uint32_t)k] : (uint8_t)0;
         }
     }
+#else
+    if (tid < ((C + 31u) & ~31u)) {   // whole warps: one thread per contig
+        const uint8_t q = read[j - 1];
+        // The three best sources over ALL contigs in the order select_jump's scan prefers (it keeps the last of the longest of
+        // the best-scoring candidates: the lexicographic maximum of (score, length, position)); the inter-contig source of a
+        // contig is the first of them that is neither the contig nor its opposite strand.  Per lane a sorted top 3 of its own
+        // contigs, then three warp-wide pops (REDUX); every participating warp computes the same list.
+        constexpr uint32_t NONE = 0xffffffffu;
+        PkSrc t0{INT32_MIN, 0u, NONE}, t1 = t0, t2 = t0;
+        for (uint32_t b = lane; b < C; b += 32) {
+            PkSrc c{S.cm[b], S.cml[b], b};
+            if (pk_src_before(c, t0)) { t2 = t1; t1 = t0; t0 = c; }
+            else if (pk_src_before(c, t1)) { t2 = t1; t1 = c; }
+            else if (pk_src_before(c, t2)) t2 = c;
+        }
+        PkSrc top[3];
+        STITCH_UNROLL
+        for (int r = 0; r < 3; ++r) {
+            const int32_t ms = __reduce_max_sync(FULL, t0.s);
+            const bool c1 = t0.s == ms && t0.b != NONE;
+            const uint32_t ml = __reduce_max_sync(FULL, c1 ? t0.l : 0u);
+            const bool c2 = c1 && t0.l == ml;
+            const int32_t mb = __reduce_max_sync(FULL, c2 ? (int32_t)t0.b : -1);
+            top[r].s = ms; top[r].l = ml; top[r].b = mb < 0 ? NONE : (uint32_t)mb;
+            if (c2 && (int32_t)t0.b == mb) { t0 = t1; t1 = t2; t2.s = INT32_MIN; t2.l = 0u; t2.b = NONE; }
+        }
+        const int32_t g = top[0].s;   // best cell of column j-1 over all contigs: the base of column j
+        const PkColConst ccl = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, q);
+        const uint32_t a = tid;
+        if (a < C) {
+            // MCA:279-331, as select_jump (dp_core.h) with the scan over the other contigs replaced by the list above
+            JumpInfo J;
+            J.score = S.cm[a] + X.sc.g_same; J.len = S.cml[a] + 1; J.idx = X.ent[a].contig_idx; J.from = S.cmk[a];
+            const int32_t opp = X.ent[a].opp;
+            if (opp >= 0) {
+                const int32_t so = S.cm[opp] + X.sc.g_opp;
+                if (so > J.score) { J.score = so; J.len = S.cml[opp] + 1; J.idx = X.ent[opp].contig_idx; J.from = S.cmk[opp]; }
+            }
+            PkSrc it = top[0];
+            if (it.b == a || (int32_t)it.b == opp) { it = top[1]; if (it.b == a || (int32_t)it.b == opp) it = top[2]; }
+            if (it.b != NONE && it.s + X.sc.g_inter > J.score) {
+                J.score = it.s + X.sc.g_inter; J.len = it.l + 1; J.idx = X.ent[it.b].contig_idx; J.from = S.cmk[it.b];
+            }
+            if (writer) {
+                ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
+                cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
+                colrec[(uint64_t)j * C + a] = cr;
+            }
+            S.Jc[a] = pk_jc(X.pk, ccl.pc, J.score, J.len);
+            if (X.quiet) pk_quiet_contig(X, S, a, j, ccl, !((j % K == 0) && j < X.n));   // (not at checkpoint columns)
+        }
+        if (tid == 0) {
+            if (writer) gcol[j - 1] = g;
+            s_cc[par] = ccl;
+            STITCH_UNROLL
+            for (int k = 0; k < PKQ_L + 2; ++k) s_cc[par].yq[k] = j >= 1u + (uint32_t)k ? read[j - 1 - (uint32_t)k] : (uint8_t)0;
+        }
+    }
+#endif
 }
 
 // After the bulk pass: best score of column n, and the column the tail restarts from: the last checkpoint before
@@ -900,7 +1032,7 @@ template <int W> __device__ __noinline__ void pk_walk_phase(const Params P, unsi
 template <int W>
 __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PackSmem S; S.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
+    PackSmem S; S.carve(smem_raw, P.pso, P.cmax);
     __shared__ uint32_t sJob;
     __shared__ PkColConst s_cc[2];
     __shared__ int32_t s_gmax;
@@ -912,6 +1044,10 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
 
     Team team; team.rank = 0; team.size = P.cluster_size;
     if (team.size > 1) team.rank = cg::this_cluster().block_rank();
+    if (tid < (uint32_t)W * 4u) mbar_init(smem_u32(S.mbar + tid), 1u);   // staging ring: one mbarrier per (warp, slot)
+    if (tid < (uint32_t)W) S.mphase[tid] = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
     const uint32_t team_id = blockIdx.x / team.size;
 
     for (;;) {
@@ -928,7 +1064,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         const uint32_t C = ld.C, PM = ld.PM, n = jd.n, K = P.K;
         PackCtx X;
         X.team = team;
-        X.pk = pk_make(sc, jd.LB); X.sc = sc;
+        X.pk = P.pk; X.sc = sc;   // (jd.LB is the launch's LB for every packed job)
         // the layout's contig and tile-owner tables are staged in shared memory (every CTA of a team holds its own copy)
         for (uint32_t a = tid; a < C; a += W * 32) S.ent_s[a] = P.ents[ld.ent_off + a];
         for (uint32_t t = tid; t < ld.n_tiles; t += W * 32) S.owner_s[t] = P.owners[ld.owner_off + t];
@@ -949,6 +1085,20 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         } else {
             X.Sst = P.pstate + (uint64_t)team_id * P.pstate_stride; X.state_smem = false; X.staged = true;
             X.stage_depth = P.stage_depth;
+        }
+        X.tbases = nullptr;
+        if (X.staged) {   // the bases of this CTA's tiles in tile order (one bulk copy per tile whatever its contig)
+            uint8_t *tbw = P.ptbases + (uint64_t)team_id * P.ptbases_stride + PackSmem::STAGE_PRE;
+            X.tbases = tbw;
+            const uint32_t lane = tid & 31u;
+            __syncthreads();   // S.ent_s / S.owner_s
+            for (uint32_t t = X.own_lo + (tid >> 5); t < X.own_hi; t += W) {
+                const ContigEntry e = X.ent[X.owner[t]];
+                // (a strip starts at a multiple of 8 and contigs are 16-byte aligned: over-reads stay inside the blob's padding)
+                *reinterpret_cast<uint2 *>(tbw + (size_t)t * TILE + lane * STRIP) =
+                    *reinterpret_cast<const uint2 *>(X.bases + e.seq_off + (t - e.tile_start) * TILE + lane * STRIP);
+            }
+            fence_async_proxy();
         }
         X.Dst = X.Sst + TILE;
         ColRec *colrec = P.colrec + jd.colrec_off;
@@ -978,6 +1128,8 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
                 STITCH_UNROLL
                 for (int k = 0; k < STRIP; ++k) if (r0 + (uint32_t)k + 1 < e.m) bits |= pk_base_bit(xq[k]);   // ordinary rows (i < m) only
                 bits = __reduce_or_sync(FULL, bits);
+                const uint32_t tic = t - e.tile_start;
+                if (tic + 1 != e.ntiles || (X.quiet_last && tic != 0)) bits |= PackSmem::TB_CANQ;
                 if (lane == 0) S.tb[t] = (uint8_t)bits;
             }
         }
@@ -1081,7 +1233,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     PkCone cone; cone.on = false; cone.slope = 0; cone.win_lo = 0; cone.win_n = gen.ntiles;
     if (P.cone) cone = pk_cone_plan(P.sc, gen, i_entry, j, jb);
     const bool pre = cone.on && U.cc != nullptr && ncols <= PK_CONE_MAX_COLS;
-    const PK pk = pk_make(P.sc, jd.LB);
+    const PK pk = P.pk;
     if (tid == 0) { *s_en = gen; s_en->tile_start = 0; if (stage_bases) s_en->seq_off = 0; }
     for (uint32_t t = tid; t < ncols; t += T) {
         const ColRec cr = colrec[(uint64_t)(jb + 1 + t) * C + a];
@@ -1098,7 +1250,7 @@ __device__ void pk_refill_unit(const Params &P, const JobDesc &jd, const LayoutD
     PackCtx X;
     X.pk = pk; X.sc = P.sc; X.ent = s_en; X.owner = nullptr; X.C = 1; X.bases = stage_bases ? U.bases : P.contig_bases;
     X.Sst = pstate; X.Dst = pstate + TILE; X.n = n; X.yclip_mode = P.sc.yp != MIN_SCORE && P.sc.xp == MIN_SCORE;
-    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false; X.stage_depth = 2;   // bases are staged in shared memory here
+    X.team.rank = 0; X.team.size = 1; X.state_smem = state_smem; X.staged = false; X.stage_depth = 2; X.tbases = nullptr;   // bases are staged in shared memory here
     X.NT = cone.on ? cone.win_n : gen.ntiles; X.win_lo = cone.on ? cone.win_lo : 0u; X.skip_below = 0; X.no_finish = cone.on;
     pk_set_ownership(X, W); X.cluster_smem = false; X.quiet = false; X.quiet_first = false; X.quiet_edge = false; X.quiet_last = false; X.cstate = nullptr; X.cta_lo = nullptr;
     if (b == 0) pk_state_init0<W>(X, S);

@@ -110,7 +110,7 @@ template <int W>
 __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WideSmem<W> S; S.carve(smem_raw, 1);
-    PackSmem PS; PS.carve(smem_raw, 1, P.max_ctiles, W, 0);   // same bytes: a job uses one of the two
+    PackSmem PS; PS.carve(smem_raw, PackSmem::layout(1, P.max_ctiles, W, 0), 1);   // same bytes: a job uses one of the two
     UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
     __shared__ uint32_t sJob;
     __shared__ WalkShared sh;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
 // per-unit staging area after them, and the re-fill state of one contig in the (now idle) cp.async stage buffers.
 template <int W>
 __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_raw) {   // by value: the caller's P stays in the constant bank
-    PackSmem PS; PS.carve(smem_raw, P.cmax, P.ntmax, W, P.stage_bytes);
+    PackSmem PS; PS.carve(smem_raw, P.pso, P.cmax);
     UnitStage US; US.carve(smem_raw + P.walk_stage_smem_off, P.K);
     __shared__ uint32_t sJob;
     __shared__ WalkShared sh;

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "dp_core.h"
+#include "dp_packed.h"
 #include "host_common.hpp"
 
 namespace stitch {
@@ -44,8 +45,18 @@ struct LayoutDesc { uint32_t ent_off, C, n_tiles, owner_off, pad0, PM, max_ctile
 enum : uint32_t { JOB_OK = 0, JOB_NEED_FULL_TRACK = 100 };
 struct JobOut { uint32_t n_chains, status; };
 
+// Byte offsets of the tables of PackSmem (kernels_packed.cuh) inside the dynamic shared memory of a launch.  The host
+// computes them once per launch (PackSmem::layout) so that a table address is one constant-bank value added to the base:
+// the packed kernels have no registers to spare for ~20 table pointers, and re-deriving them from cmax / ntmax inside the
+// tile loop cost ~40 instructions per tile.
+struct PackSmemOff {
+    uint32_t Jw, stash, Jc, cm, Sm, SmKey, cml, cmk, slm, tbm, DmKey, tilemax, haloS, haloD, haloF, Q, ent_s, owner_s, clist, tb, mbar, mphase, end;
+};
+
 struct Params {
     Scoring sc;
+    PK pk;                   // packed kernels: the key layout of the launch (one LB for every packed job: the largest any of them needs)
+    PackSmemOff pso;         // packed kernels: table offsets in dynamic shared memory
     const JobDesc *jobs;
     const uint32_t *order;
     uint32_t n_jobs, cmax;
@@ -69,6 +80,8 @@ struct Params {
     CkSum *hand_sum;
     int32_t *pstate;         // packed kernel, per CTA: S keys then D keys
     uint64_t pstate_stride, pstate_half;
+    uint8_t *ptbases;        // packed kernel, per team: the contig bases of the read's layout in TILE order (tile t at 16 + t * TILE),
+    uint64_t ptbases_stride; // so that a tile's bases are one bulk copy away whatever contig it belongs to
     uint32_t ntmax;          // largest tile count among the packed jobs
     uint32_t cluster_size;   // packed kernel: CTAs per read (thread-block cluster), 1 = no cluster
     uint32_t stage_bytes;    // packed kernels: size of the front area of their dynamic shared memory (PackSmem)

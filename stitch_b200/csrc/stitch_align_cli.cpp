@@ -23,6 +23,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -507,9 +509,17 @@ class Channel {
 }  // namespace
 
 int main(int argc, char **argv) {
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since_start = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     const Args a = parse(argc, argv);
     Api api;
     api.load(argv[0]);
+    // STITCH_CLI_TIMING=1: one JSON line on stderr at exit (where the wall clock of the process goes: start-up, the span
+    // in which the devices align, the busy time of every stage)
+    const bool timing = std::getenv("STITCH_CLI_TIMING") != nullptr;
+    std::atomic<uint64_t> align_busy_us{0}, format_busy_us{0}, write_busy_us{0}, reads_aligned{0};
+    std::mutex span_m;
+    double t_ctx_ready = 0, t_first_align = -1, t_last_align = 0;
 
     // reference contigs: upper-cased, name = first word of the header (target_seq.rs:99-121)
     std::vector<std::string> names, seqs;
@@ -550,6 +560,7 @@ int main(int argc, char **argv) {
         for (auto &t : th) t.join();
         for (const auto &e : errs) if (!e.empty()) die(e);
     }
+    t_ctx_ready = since_start();
 
     // header: @HD, one @SQ per contig, @PG (align.rs:393-416)
     std::string header = "@HD\tVN:1.6\n";
@@ -601,7 +612,11 @@ int main(int argc, char **argv) {
         workers.emplace_back([&, g] {
             std::unique_ptr<Batch> b;
             while (to_align.pop(b)) {
+                const double t0 = since_start();
                 align_stage(api, ctxs[(size_t)g], *b);
+                const double t1 = since_start();
+                align_busy_us += (uint64_t)((t1 - t0) * 1e6); reads_aligned += b->recs.size();
+                { std::lock_guard<std::mutex> l(span_m); if (t_first_align < 0 || t0 < t_first_align) t_first_align = t0; if (t1 > t_last_align) t_last_align = t1; }
                 if (!b->error.empty()) fail(b->error);
                 to_format.push(std::move(b));
             }
@@ -612,7 +627,9 @@ int main(int argc, char **argv) {
         formatters.emplace_back([&] {
             std::unique_ptr<Batch> b;
             while (to_format.pop(b)) {
+                const double t0 = since_start();
                 format_stage(api, so, names, a.sam, a.compression, *b);
+                format_busy_us += (uint64_t)((since_start() - t0) * 1e6);
                 if (!b->error.empty()) fail(b->error);
                 to_write.push(std::move(b));
             }
@@ -625,12 +642,14 @@ int main(int argc, char **argv) {
         std::unique_ptr<Batch> b;
         while (to_write.pop(b)) {
             pending[b->seq_no] = std::move(b);
+            const double t0 = since_start();
             for (auto it = pending.find(next); it != pending.end(); it = pending.find(next)) {
                 if (a.sam) for (const std::string &line : it->second->lines) { std::fputs(line.c_str(), stdout); std::fputc('\n', stdout); }
                 else write_all(stdout, it->second->bam.data(), it->second->bam.size());
                 n_lines += it->second->n_records; ++n_batches;
                 pending.erase(it); ++next;
             }
+            write_busy_us += (uint64_t)((since_start() - t0) * 1e6);
         }
     });
     reader.join();
@@ -642,6 +661,15 @@ int main(int argc, char **argv) {
     if (!first_error.empty()) die("alignment failed: " + first_error);
     if (a.sam) std::fflush(stdout); else bgzf_finish(stdout);
     for (stitch_ctx *c : ctxs) api.destroy(c);
+    if (timing) {
+        const double span = t_last_align - t_first_align, wall = since_start();
+        std::fprintf(stderr, "stitch-b200 timing: {\"wall_s\": %.3f, \"contexts_ready_s\": %.3f, \"first_align_s\": %.3f, \"last_align_s\": %.3f, "
+                             "\"align_span_s\": %.3f, \"reads\": %llu, \"reads_per_s_in_align_span\": %.1f, \"gpus\": %d, \"align_busy_s\": %.3f, "
+                             "\"format_threads\": %d, \"format_busy_s\": %.3f, \"write_busy_s\": %.3f}\n",
+                     wall, t_ctx_ready, t_first_align, t_last_align, span, (unsigned long long)reads_aligned.load(),
+                     span > 0 ? (double)reads_aligned.load() / span : 0.0, a.gpus, align_busy_us.load() * 1e-6, n_fmt, format_busy_us.load() * 1e-6,
+                     write_busy_us.load() * 1e-6);
+    }
     std::fprintf(stderr, "stitch-b200: wrote %llu records of %llu batches\n", (unsigned long long)n_lines, (unsigned long long)n_batches);
     return 0;
 }
