@@ -227,7 +227,8 @@ struct CudaBackend : host::Backend {
     Need need_of(const host::Job &j, bool packed) const {
         const host::Layout &L = al.layouts.layouts[j.layout];
         const uint64_t C = L.ent.size(), PM = L.PM(), nb = blocks_of(j.n);
-        return Need{(uint64_t)(j.n + 1) * C, PM, packed ? 0 : (nb - 1) * PM, (nb - 1) * C, (uint64_t)j.n + 1, packed ? (nb - 1) * 2 * PM : 0};
+        const uint64_t late = packed ? PK_LATE_CKS : 0;   // late checkpoints of the packed fill (kernels_packed.cuh)
+        return Need{(uint64_t)(j.n + 1) * C, PM, packed ? 0 : (nb - 1) * PM, (nb - 1 + late) * C, (uint64_t)j.n + 1, packed ? (nb - 1 + late) * 2 * PM : 0};
     }
     static uint64_t need_bytes(const Need &n) {
         return n.colrec * sizeof(ColRec) + n.cell * (sizeof(LastCell) + sizeof(SnRec)) + n.ck * sizeof(CellState) + n.pck * 4 +
@@ -479,7 +480,7 @@ struct CudaBackend : host::Backend {
         P.ptbases = d_ptbases.p; P.ptbases_stride = tb_stride;
         P.ntmax = ntmax; P.tail_j0 = d_tailj0.p; P.wpstate = d_wpstate.p; P.wpstate_stride = 2 * wps_half; P.wpstate_half = wps_half;
         P.unit_cr = d_ucr.p; P.max_ctiles = max_ctiles; P.cluster_size = 1; P.cone = cone_refill;
-        if (debug_stats) { d_dbg.reserve(16); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 16 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
+        if (debug_stats) { d_dbg.reserve(80); CUDA_CHECK(cudaMemsetAsync(d_dbg.p, 0, 80 * sizeof(unsigned long long), stream)); P.dbg = d_dbg.p; }
 
         const size_t smem = WideSmem<FILL_WARPS>::bytes(cmax);
         set_smem(fill_wide_kernel<FILL_WARPS>, smem);
@@ -588,13 +589,16 @@ struct CudaBackend : host::Backend {
             stats.tile_columns += hq[0]; stats.quiet_tile_columns += hq[1];
         }
         if (debug_stats) {
-            unsigned long long h[16];
+            unsigned long long h[80];
             cudaMemcpy(h, d_dbg.p, sizeof(h), cudaMemcpyDeviceToHost);
             std::fprintf(stderr, "[stitch dbg] jobs %u (K %u): tail columns %llu, tail Mcycles %.1f, bulk Mcycles %.1f | walk units %llu, "
                          "refill columns %llu, refill Mcycles %.1f, walk-job Mcycles %.1f\n", nj, K, h[0], h[1] * 1e-6, h[2] * 1e-6, h[3], h[6],
                          h[4] * 1e-6, h[5] * 1e-6);
             std::fprintf(stderr, "[stitch dbg] bulk columns, Mcycles summed over reads: select %.1f, tile phase %.1f (mean warp busy %.1f), per-contig finish %.1f (warp 0: tile maxima reduced at %.1f, look-ups done at %.1f, row m done at %.1f)\n",
                          h[7] * 1e-6, h[8] * 1e-6, h[10] * 1e-6, h[9] * 1e-6, h[13] * 1e-6, h[11] * 1e-6, h[12] * 1e-6);
+            std::fprintf(stderr, "[stitch dbg] tile phase per warp, Gcycles busy / M tiles computed:");
+            for (int w = 0; w < PACK_WARPS; ++w) std::fprintf(stderr, " %.1f/%.1f", h[16 + w] * 1e-9, h[48 + w] * 1e-6);
+            std::fprintf(stderr, "\n");
         }
         stats.tb_bytes += tot.ck * sizeof(CellState) + tot.pck * 4 + tot.colrec * sizeof(ColRec);
         stats.d2h += nj * sizeof(JobOut) + chains_n * sizeof(ChainHdr) + ops_n * sizeof(OutOp);

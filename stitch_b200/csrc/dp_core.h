@@ -352,15 +352,31 @@ SHD SnRec sn_init(const Scoring &sc, int32_t S0, uint32_t sl0, uint32_t self_idx
 // score - min(match, mismatch), because every cell of column j+1 can be entered by a jump from the
 // best cell of column j.  Columns with G(j) < Gmax - W' therefore never hold the final (Sn, Ly) of any
 // row; the trackers only need the columns from the first candidate on (column 0 is their start value).
-SHD uint32_t first_candidate_column(const Scoring &sc, const int32_t *gcol, uint32_t n) {
-    int32_t gmax = gcol[0];
-    for (uint32_t j = 1; j <= n; ++j) gmax = gcol[j] > gmax ? gcol[j] : gmax;
+//
+// `best_only` (reads walked with `traceback`, TB:129-150, i.e. only from the best end) with an x-suffix clip
+// (xs finite and <= 0: the local mode): the margin is -xs.  The end of the read (SCA:453-555) folds the rows of a
+// contig into its row m by "replace if greater, or equal and longer" scans in row order, and `traceback`
+// compares the row-m cells of the contigs the same way: the outcome is decided by the rows whose final value is
+// the maximum, in the contigs that reach the best final value V.  A row's tracker reaches row m through the
+// x-suffix clip (+ xs; the x-jump reads the cell before its y-clip), row m's own tracker directly, the
+// insertion re-computation with o + e < 0 on top.  The row of the best cell gives V >= Gmax + ys + xs, so a row
+// that decides anything through its tracker has Sn(i) - ys >= Gmax + xs: its tracker is set by cells within -xs
+// of the best score of the whole matrix, and those are tracked.  Every other row keeps a tracker that is too
+// low (never too high), loses the same scans it loses with the exact value, and is never walked.  (Without an
+// x-suffix clip the trackers of the rows below m never reach row m and V has no such bound: full margin.)
+SHD int32_t track_margin(const Scoring &sc, bool best_only) {
+    if (best_only && sc.xs != MIN_SCORE && sc.xs <= 0) return -sc.xs;
     int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
     if (submax < 0) submax = 0;
     const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
     int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
     gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
-    const int32_t thr = gmax - (submax - gmin - submin);
+    return submax - gmin - submin;
+}
+SHD uint32_t first_candidate_column(const Scoring &sc, const int32_t *gcol, uint32_t n, bool best_only = false) {
+    int32_t gmax = gcol[0];
+    for (uint32_t j = 1; j <= n; ++j) gmax = gcol[j] > gmax ? gcol[j] : gmax;
+    const int32_t thr = gmax - track_margin(sc, best_only);
     for (uint32_t j = 1; j <= n; ++j) if (gcol[j] >= thr) return j;
     return n + 1;
 }

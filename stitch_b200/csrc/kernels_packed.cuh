@@ -228,7 +228,7 @@ __device__ __forceinline__ void unpack8(const uint2 xb, uint8_t *x) {
 // (its memory may be stale): materialise it instead of loading; `qz.prev_skipped` = the previous tile of this chunk
 // was skipped in this column (its last row and its chain exit come from the closed form).  Returns whether every
 // ordinary cell of the tile is in the closed form of column j.
-struct PkColStat { uint32_t skipped, timing; unsigned long long t_tiles, t_finish, t_busy, t_select, t_f1, t_f2, t_fa; };   // per job, shared memory
+struct PkColStat { uint32_t skipped, timing; unsigned long long t_tiles, t_finish, t_busy, t_select, t_f1, t_f2, t_fa, t_warp[32], n_warp[32]; };   // per job, shared memory
 struct PkQuietArgs {
     bool mat, prev_skipped;
     const PkQuiet *Qp, *Qn;     // closed forms of column j-1 / j of this tile's contig (shared memory)
@@ -568,7 +568,7 @@ __device__ void pk_column(const PackCtx &X, PackSmem &S, const PCol &pc, int32_t
             }
         }
         if (staged && lane == 0) S.mphase[warp] = phase;
-        if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); if (cst) atomicAdd(&cs->t_busy, (unsigned long long)(clock64() - c0)); }
+        if (cs && lane == 0) { if (nskipped) atomicAdd(&cs->skipped, nskipped); if (cst) { const unsigned long long dt = (unsigned long long)(clock64() - c0); atomicAdd(&cs->t_busy, dt); cs->t_warp[warp] += dt; cs->n_warp[warp] += ncomp; } }
         if (QUIET) __syncwarp();   // (lane 0's flag of the last tile)
         if (QUIET && gw + 1 < Weff && lane == 0) S.haloF[par * W + warp + 1] = (S.tb[t_hi - 1] & PackSmem::TB_Q) ? 1u : 0u;
         if (gw + 1 < Weff && (!QUIET || mode_last != 0u)) {
@@ -830,6 +830,23 @@ __device__ __forceinline__ void pk_replay_consts(const PackCtx &X, PackSmem &S, 
     }
 }
 
+// Late checkpoints.  The tail restarts from the last checkpoint before the first column that can hold a final y-suffix
+// tracker, typically a few tens of columns before the end of the read; with regular checkpoints alone it re-runs up to K more
+// columns in the (slower) traceback variant.  PK_LATE_CKS extra checkpoints at columns n - PK_LATE_STEP * k (k = 1 ..
+// PK_LATE_CKS, unless that is a regular checkpoint column) are stored after the regular ones.
+constexpr uint32_t PK_LATE_CKS = 3, PK_LATE_STEP = 32;
+__host__ __device__ inline uint32_t pk_regular_cks(uint32_t n, uint32_t K) { return (n - 1) / K; }   // columns K, 2K, ... < n
+// k (1 .. PK_LATE_CKS) when column j is a late checkpoint column of a read of n columns, else 0
+__device__ __forceinline__ uint32_t pk_late_ck(uint32_t j, uint32_t n, uint32_t K) {
+    if (j >= n || j % K == 0u) return 0u;
+    const uint32_t d = n - j;
+    return (d % PK_LATE_STEP == 0u && d / PK_LATE_STEP <= PK_LATE_CKS) ? d / PK_LATE_STEP : 0u;
+}
+// index (among the read's checkpoints) of the one at column j0 > 0
+__device__ __forceinline__ uint32_t pk_ck_index(uint32_t j0, uint32_t n, uint32_t K) {
+    return j0 % K == 0u ? j0 / K - 1u : pk_regular_cks(n, K) + (n - j0) / PK_LATE_STEP - 1u;
+}
+
 // The tail of one job on the CTA that ran its bulk pass (s_cc: one shared PkColConst slot).
 template <int W>
 __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld, PackCtx &X, PackSmem &S, PkColConst *s_cc, uint32_t j0,
@@ -843,8 +860,8 @@ __device__ void pk_tail(const Params &P, const JobDesc &jd, const LayoutDesc &ld
     SnRec *sn = P.sn + jd.cell_off;
     const bool tracked = P.tracked_mode != 0;
     if (j0 == 0) pk_state_init0<W>(X, S);
-    else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j0 / K - 1) * 2 * PM,
-                             P.ck_sum + jd.cksum_off + (uint64_t)(j0 / K - 1) * C, gcol[j0 - 1]);
+    else pk_state_from_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)pk_ck_index(j0, n, K) * 2 * PM,
+                             P.ck_sum + jd.cksum_off + (uint64_t)pk_ck_index(j0, n, K) * C, gcol[j0 - 1]);
     if (tracked) {   // trackers start from column 0 (SCA:179-183)
         for (uint32_t tile = X.team.rank * W + warp; tile < X.NT; tile += X.team.size * W) {
             const ContigEntry en = X.ent[X.owner[tile]];
@@ -892,38 +909,11 @@ struct PkSrc { int32_t s; uint32_t l, b; };
 __device__ __forceinline__ bool pk_src_before(const PkSrc &x, const PkSrc &y) {   // x is preferred to y: (score, length, position) lexicographic
     return x.s != y.s ? x.s > y.s : (x.l != y.l ? x.l > y.l : x.b > y.b);
 }
-#ifndef STITCH_SELECT_TOP3
-#define STITCH_SELECT_TOP3 0
-#endif
 template <int W>
 __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, ColRec *colrec, int32_t *gcol, const uint8_t *read,
-                                                 uint32_t j, PkColConst *s_cc, bool writer, uint32_t K) {
+                                                 uint32_t j, PkColConst *s_cc, bool writer, bool ck_col) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, par = j & 1u, C = X.C;
     const int32_t Bprev = s_cc[par ^ 1u].pc.B;
-#if !STITCH_SELECT_TOP3
-    (void)lane;
-    if (tid < C || tid == 0) {   // every thread scans all contigs (select_jump, dp_core.h)
-        int32_t g = S.cm[0];
-        for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g;
-        const PkColConst ccl = pk_col_const(X.pk, X.sc, g, Bprev, j, X.n, read[j - 1]);
-        for (uint32_t a = tid; a < C; a += W * 32) {
-            const JumpInfo J = select_jump(X.sc, X.ent, C, a, S.cm, S.cml, S.cmk);
-            if (writer) {
-                ColRec cr; cr.jscore = J.score; cr.jlen = J.len; cr.jidx = J.idx; cr.jfrom = J.from;
-                cr.lx = 0; cr.pad0 = cr.pad1 = cr.pad2 = 0;
-                colrec[(uint64_t)j * C + a] = cr;
-            }
-            S.Jc[a] = pk_jc(X.pk, ccl.pc, J.score, J.len);
-            if (X.quiet) pk_quiet_contig(X, S, a, j, ccl, !((j % K == 0) && j < X.n));   // (not at checkpoint columns)
-        }
-        if (tid == 0) {
-            if (writer) gcol[j - 1] = g;
-            s_cc[par] = ccl;
-            STITCH_UNROLL
-            for (int k = 0; k < PKQ_L + 2; ++k) s_cc[par].yq[k] = j >= 1u + (uint32_t)k ? read[j - 1 - (uint32_t)k] : (uint8_t)0;
-        }
-    }
-#else
     if (tid < ((C + 31u) & ~31u)) {   // whole warps: one thread per contig
         const uint8_t q = read[j - 1];
         // The three best sources over ALL contigs in the order select_jump's scan prefers (it keeps the last of the longest of
@@ -972,7 +962,7 @@ __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, 
                 colrec[(uint64_t)j * C + a] = cr;
             }
             S.Jc[a] = pk_jc(X.pk, ccl.pc, J.score, J.len);
-            if (X.quiet) pk_quiet_contig(X, S, a, j, ccl, !((j % K == 0) && j < X.n));   // (not at checkpoint columns)
+            if (X.quiet) pk_quiet_contig(X, S, a, j, ccl, !ck_col);   // (every tile is computed and stored in a checkpoint column)
         }
         if (tid == 0) {
             if (writer) gcol[j - 1] = g;
@@ -981,7 +971,6 @@ __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, 
             for (int k = 0; k < PKQ_L + 2; ++k) s_cc[par].yq[k] = j >= 1u + (uint32_t)k ? read[j - 1 - (uint32_t)k] : (uint8_t)0;
         }
     }
-#endif
 }
 
 // After the bulk pass: best score of column n, and the column the tail restarts from: the last checkpoint before
@@ -989,7 +978,7 @@ __device__ __forceinline__ void pk_select_consts(const PackCtx &X, PackSmem &S, 
 // part of the tail.  Also the score below which a cell cannot hold a final tracker value.
 template <int W>
 __device__ uint32_t pk_tail_start(const Params &P, PackSmem &S, const Scoring &sc, int32_t *gcol, uint32_t n, uint32_t C, uint32_t K,
-                                  int32_t *s_gmax, uint32_t *s_first, int32_t &track_thr, bool writer) {
+                                  int32_t *s_gmax, uint32_t *s_first, int32_t &track_thr, bool writer, bool best_only) {
     const uint32_t tid = threadIdx.x;
     constexpr uint32_t T = W * 32;
     __syncthreads();
@@ -1006,20 +995,21 @@ __device__ uint32_t pk_tail_start(const Params &P, PackSmem &S, const Scoring &s
         for (uint32_t jj = tid; jj < n; jj += T) g = gcol[jj] > g ? gcol[jj] : g;
         atomicMax(s_gmax, g);
         __syncthreads();
-        int32_t submax = sc.match > sc.mismatch ? sc.match : sc.mismatch;
-        if (submax < 0) submax = 0;
-        const int32_t submin = sc.match < sc.mismatch ? sc.match : sc.mismatch;
-        int32_t gmin = sc.g_same < sc.g_opp ? sc.g_same : sc.g_opp;
-        gmin = gmin < sc.g_inter ? gmin : sc.g_inter;
         const int32_t gmax = *s_gmax;
-        const int32_t thr = gmax - (submax - gmin - submin);
+        const int32_t thr = gmax - track_margin(sc, best_only);   // (dp_core.h: reads walked from the best end only need the cells that hold the best score)
         track_thr = thr;
         uint32_t first = n;
         for (uint32_t jj = 1 + tid; jj < n; jj += T) if (gcol[jj] >= thr) { first = jj; break; }
         atomicMin(s_first, first);
         __syncthreads();
     }
-    const uint32_t j0 = ((*s_first - 1) / K) * K;
+    uint32_t j0 = ((*s_first - 1) / K) * K;
+    for (uint32_t k = 1; k <= PK_LATE_CKS; ++k) {   // the latest late checkpoint that is still before the first candidate column
+        if (n <= PK_LATE_STEP * k) break;
+        const uint32_t jl = n - PK_LATE_STEP * k;
+        if (jl % K == 0u) continue;   // (a regular checkpoint column: j0 already covers it)
+        if (jl < *s_first) { if (jl > j0) j0 = jl; break; }
+    }
     __syncthreads();
     return j0;
 }
@@ -1115,7 +1105,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         X.quiet_first = X.quiet && P.quiet_first != 0; X.quiet_edge = X.quiet && P.quiet_edge != 0;
         X.quiet_last = X.quiet && P.quiet_last != 0;
         if (tid < 2 * W) S.haloF[tid] = 0;
-        if (tid == 0) { s_cs.skipped = 0; s_cs.timing = P.dbg ? 1u : 0u; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; }
+        if (tid == 0) { s_cs.skipped = 0; s_cs.timing = P.dbg ? 1u : 0u; s_cs.t_tiles = s_cs.t_finish = s_cs.t_busy = s_cs.t_select = s_cs.t_f1 = s_cs.t_f2 = s_cs.t_fa = 0; for (int w = 0; w < 32; ++w) { s_cs.t_warp[w] = 0; s_cs.n_warp[w] = 0; } }
         if (X.quiet) {   // quiet tiles: no tile is quiet yet; base classes of every tile
             for (uint32_t a = tid; a < C; a += W * 32) S.Q[a] = pk_quiet_init(X.pk);
             const uint32_t lane = tid & 31u;
@@ -1138,14 +1128,18 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
         for (uint32_t j = 1; j <= n; ++j) {
             const uint32_t par = j & 1u;
             const long long cs0 = clock64();
-            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0, K);
+            const uint32_t late = pk_late_ck(j, n, K);
+            const bool ck_col = ((j % K == 0) && j < n) || late != 0u;
+            pk_select_consts<W>(X, S, colrec, gcol, read, j, s_cc, team.rank == 0, ck_col);
             __syncthreads();
             const PkColConst cc = s_cc[par];
             if (tid == 0 && P.dbg) s_cs.t_select += (unsigned long long)(clock64() - cs0);
             if (X.quiet) pk_column<W, false, true>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O, cc.yq, &s_cs);
             else pk_column<W, false>(X, S, cc.pc, cc.r0pkey, cc.cr1key, j, O);
-            if ((j % K == 0) && j < n)
-                pk_write_ck<W>(X, S, P.pck + jd.ck_off + (uint64_t)(j / K - 1) * 2 * PM, P.ck_sum + jd.cksum_off + (uint64_t)(j / K - 1) * C);
+            if (ck_col) {
+                const uint64_t ci = pk_ck_index(j, n, K);
+                pk_write_ck<W>(X, S, P.pck + jd.ck_off + ci * 2 * PM, P.ck_sum + jd.cksum_off + ci * C);
+            }
         }
         if (tid == 0 && team.rank == 0 && P.qstats) {
             atomicAdd(P.qstats + 0, (unsigned long long)X.NT * n);
@@ -1153,6 +1147,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
             if (P.dbg) {
                 atomicAdd(P.dbg + 7, s_cs.t_select); atomicAdd(P.dbg + 8, s_cs.t_tiles); atomicAdd(P.dbg + 9, s_cs.t_finish);
                 atomicAdd(P.dbg + 10, s_cs.t_busy / W); atomicAdd(P.dbg + 11, s_cs.t_f1); atomicAdd(P.dbg + 12, s_cs.t_f2); atomicAdd(P.dbg + 13, s_cs.t_fa);
+                for (int w = 0; w < W; ++w) { atomicAdd(P.dbg + 16 + w, s_cs.t_warp[w]); atomicAdd(P.dbg + 48 + w, s_cs.n_warp[w]); }
             }
         }
         int32_t track_thr = MIN_SCORE;
@@ -1160,7 +1155,7 @@ __global__ void __launch_bounds__(W * 32, 1) fill_packed_kernel(const Params P) 
             if (tid == 0 && team.rank == 0) { int32_t g = S.cm[0]; for (uint32_t a = 1; a < C; ++a) g = S.cm[a] > g ? S.cm[a] : g; gcol[n] = g; }
             team.sync();
         }
-        const uint32_t j0 = pk_tail_start<W>(P, S, sc, gcol, n, C, K, &s_gmax, &s_first, track_thr, team.rank == 0);
+        const uint32_t j0 = pk_tail_start<W>(P, S, sc, gcol, n, C, K, &s_gmax, &s_first, track_thr, team.rank == 0, jd.walk == host::WALK_BEST);
         if (tid == 0 && team.rank == 0) P.tail_j0[job] = j0;
         __syncthreads();
         const long long t_tail0 = clock64();

@@ -652,9 +652,7 @@ struct EmulBackend : Backend {
         // every row ends with a tracker value >= max_j G(j) - W' (dp_core.h: first_candidate_column): cells below can be skipped
         int32_t thr = MIN_SCORE;
         if (tracked) {
-            int32_t submax = std::max(std::max(sc.match, sc.mismatch), 0), submin = std::min(sc.match, sc.mismatch);
-            int32_t gmin = std::min(sc.g_same, std::min(sc.g_opp, sc.g_inter));
-            thr = max_of(F.gcol) - (submax - gmin - submin);
+            thr = max_of(F.gcol) - track_margin(sc, job.walk == WALK_BEST);
         }
         for (uint32_t j = j0 + 1; j <= n; ++j) {
             for (uint32_t a = 0; a < C; ++a) { const ColRec &cr = F.colrec[(size_t)j * C + a]; J[a] = JumpInfo{cr.jscore, cr.jlen, cr.jidx, cr.jfrom}; }
@@ -752,7 +750,7 @@ struct EmulBackend : Backend {
         // the tail restarts at the last checkpoint before the first column that can hold a final y-suffix
         // tracker (dp_core.h: first_candidate_column); column n is always part of it
         const bool tracked = sc.ys != MIN_SCORE;
-        const uint32_t jc = tracked ? std::min(first_candidate_column(sc, F.gcol.data(), n), n) : n;
+        const uint32_t jc = tracked ? std::min(first_candidate_column(sc, F.gcol.data(), n, job.walk == WALK_BEST), n) : n;
         const uint32_t j0 = ((jc - 1) / K) * K;
         fill_packed_tail(job, L, LB, j0, tracked, F);
         F.need_full_track = false;
