@@ -170,6 +170,7 @@ struct EmulBackend : Backend {
         if (std::getenv("EMUL_QUIET_STATS") && q_tiles)
             std::fprintf(stderr, "[emul quiet] tile-columns %llu skipped %llu (%.1f%%) materialised %llu\n", (unsigned long long)q_tiles,
                          (unsigned long long)q_skipped, 100.0 * (double)q_skipped / (double)q_tiles, (unsigned long long)q_mat),
+            std::fprintf(stderr, "   skipped share by class: first tiles %.1f%% (of %llu), last tiles %.1f%% (of %llu), others %.1f%%\n", 100.0 * q_cls[0][1] / std::max<uint64_t>(q_cls[0][0], 1), (unsigned long long)q_cls[0][0], 100.0 * q_cls[1][1] / std::max<uint64_t>(q_cls[1][0], 1), (unsigned long long)q_cls[1][0], 100.0 * q_cls[2][1] / std::max<uint64_t>(q_cls[2][0], 1)),
             std::fprintf(stderr, "   dense because: special %.1f%% boundary %.1f%% !stay %.1f%% !self %.1f%% !left %.1f%%\n", 100.0 * q_special / q_tiles,
                          100.0 * q_boundary / q_tiles, 100.0 * q_nostay / q_tiles, 100.0 * q_noself / q_tiles, 100.0 * q_noleft / q_tiles);
     }
@@ -267,7 +268,7 @@ struct EmulBackend : Backend {
     };
     static uint32_t base_bit(uint8_t b) { return b == 'A' ? 1u : b == 'C' ? 2u : b == 'G' ? 4u : b == 'T' ? 8u : 16u; }
     static const int32_t POISON = 0x7f7f7f7f;   // what a skipped tile leaves in the state arrays (nobody may read it)
-    uint64_t q_hist[6] = {0}; uint64_t q_agehist[12] = {0}; std::vector<uint32_t> q_age; uint64_t q_failS = 0, q_failD = 0, q_failcells[2] = {0, 0}; uint64_t q_why[64] = {0}, q_delta[64] = {0}; uint64_t q_tiles = 0, q_skipped = 0, q_mat = 0, q_special = 0, q_boundary = 0, q_nostay = 0, q_noself = 0, q_noleft = 0;
+    uint64_t q_hist[6] = {0}; uint64_t q_agehist[12] = {0}; std::vector<uint32_t> q_age; uint64_t q_failS = 0, q_failD = 0, q_failcells[2] = {0, 0}; uint64_t q_why[64] = {0}, q_delta[64] = {0}; uint64_t q_cls[3][2] = {{0,0},{0,0},{0,0}}; uint64_t q_tiles = 0, q_skipped = 0, q_mat = 0, q_special = 0, q_boundary = 0, q_nostay = 0, q_noself = 0, q_noleft = 0;
     void pk_quiet_setup(const PK &pk, const ContigEntry *ent, uint32_t C, uint32_t NT, PkState &st) {
         const uint8_t *bases = al.contigs.blob.data();
         st.quiet_on = QUIET != 0;
@@ -371,7 +372,7 @@ struct EmulBackend : Backend {
                 const uint8_t qleft = first ? 0 : (tile > t_lo ? qold_left : (edge_on ? quiet_old[tile - 1] : 0));
                 qold_left = qold;
                 if (quiet_on) {
-                    ++q_tiles;
+                    ++q_tiles; ++q_cls[first ? 0 : (lastt ? 1 : 2)][0];
                     if ((lastt && !(last_on && !first)) || (first && !Qn[a].stay_first && Qn[a].stay)) ++q_special; else if (!edge_on && (tile == t_lo || tile + 1 == t_hi)) ++q_boundary; else if (!Qn[a].stay) ++q_nostay;
                     else if (!qold) ++q_noself; else if (!qleft) ++q_noleft;
                 }
@@ -387,7 +388,7 @@ struct EmulBackend : Backend {
                         st.DmKey[a] = dm_new;
                     }
                     for (uint32_t r = 0; r < (uint32_t)TILE; ++r) { Sc[tile * TILE + r] = POISON; Dc[tile * TILE + r] = POISON; }
-                    prev_skipped = true; ++q_skipped;
+                    prev_skipped = true; ++q_skipped; ++q_cls[first ? 0 : (lastt ? 1 : 2)][1];
                     continue;   // stays quiet
                 }
                 const int32_t *SpT = Sp, *DpT = Dp;   // state of column j-1 as this tile reads it (own rows: base .. base+TILE)

@@ -195,3 +195,28 @@ def test_cli_multi_context_order(cli, tmp_path):
     assert one == many
     names = [l.split("\t")[0] for l in one if not l.startswith("@")]
     assert [n for k, n in enumerate(names) if k == 0 or names[k - 1] != n] == [f"q{k}" for k in range(len(reads))]
+
+
+def test_cli_timing_line(cli, tmp_path):
+    """STITCH_CLI_TIMING=1: one JSON line on stderr accounts for the stages of the pipeline (what `bench.py --via-cli` reads);
+    without the variable stderr carries no such line and stdout is the same either way."""
+    import json
+    rng = random.Random(91)
+    contigs = [gen.rand_seq(rng, rng.randint(150, 300)) for _ in range(2)]
+    reads = [gen.chimeric_read(rng, contigs, rng.randint(50, 150), 2, strands=True, wrap=False) for _ in range(9)]
+    ref, fa = tmp_path / "ref.fa", tmp_path / "reads.fa"
+    ref.write_text("".join(f">c{k}\n{c.decode()}\n" for k, c in enumerate(contigs)))
+    fa.write_text("".join(f">q{k}\n{r.decode()}\n" for k, r in enumerate(reads)))
+    env = dict(os.environ, STITCH_B200_LIB=os.path.join(ROOT, "tests", "emul", "libemul_s8.so"), STITCH_B200_PREFIX="emul_")
+    args = [CLI, "align", "-a", str(fa), "-r", str(ref), "-d", "--sam", "--gpus", "2", "--batch", "4"]
+    quiet = subprocess.run(args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    timed = subprocess.run(args, env=dict(env, STITCH_CLI_TIMING="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert quiet.returncode == 0 and timed.returncode == 0, timed.stderr.decode()
+    assert quiet.stdout == timed.stdout
+    assert b"stitch-b200 timing:" not in quiet.stderr
+    lines = [l for l in timed.stderr.decode().splitlines() if l.startswith("stitch-b200 timing: ")]
+    assert len(lines) == 1
+    t = json.loads(lines[0][len("stitch-b200 timing: "):])
+    assert t["reads"] == len(reads) and t["gpus"] == 2
+    assert 0 <= t["contexts_ready_s"] <= t["first_align_s"] <= t["last_align_s"] <= t["wall_s"]
+    assert t["align_span_s"] > 0 and t["reads_per_s_in_align_span"] > 0 and t["format_threads"] >= 1
