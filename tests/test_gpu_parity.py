@@ -219,6 +219,28 @@ def test_fuzz_packed_multi_tile(oracle, block):
         compare(got, exp, f"seed {seed} {kw}")
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tail_restart_columns(oracle, mode):
+    """The tail of the packed fill restarts from a regular checkpoint (every K columns) or from one of the late ones at
+    n - 32, n - 64, n - 96 (kernels_packed.cuh): read lengths on both sides of every such column, with K = 64 so that late
+    checkpoints coincide with regular ones for some lengths, exist only in part for short reads, and are the restart column for
+    others; local mode (tracking threshold of the best-end walk, dp_core.h track_margin) and query-local mode (full margin)."""
+    rng = random.Random(4242 + mode)
+    contigs = [gen.rand_seq(rng, rng.randint(300, 700)) for _ in range(3)]
+    lengths = [1, 20, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 159, 160, 161, 191, 192, 193, 224, 250, 256, 257, 300]
+    reads = []
+    for n in lengths:
+        r = gen.chimeric_read(rng, contigs, n, 1 + n // 120, strands=True, wrap=True, noise=True)
+        r = (r + gen.rand_seq(rng, n))[:n]   # exactly n columns (the noise changes the length)
+        reads.append(r)
+    kw = dict(mode=mode, double_strand=True, circular=True)
+    for tuning in ({"STITCH_CK_EVERY": "64"}, {"STITCH_CK_EVERY": "64", "STITCH_QUIET": "0"}, {"STITCH_CK_EVERY": "96", "STITCH_WALK_IN_KERNEL": "0"}):
+        got, exp = run_both(oracle, kw, contigs, reads, raw=False, tuning=tuning)
+        compare(got, exp, f"mode {mode} {tuning}")
+        got, exp = run_both(oracle, kw, contigs, reads, raw=True, tuning=tuning)
+        compare(got, exp, f"mode {mode} raw {tuning}")
+
+
 def test_config3_config4_shapes_downscaled(oracle):
     """BASELINE config 3 (many contigs: the reference's limit of 256 contig-strands) and config 4 (reads several
     times longer than the contigs, many segments) down-scaled so the oracle finishes in seconds."""
