@@ -122,7 +122,7 @@ struct CudaBackend : host::Backend {
     uint32_t quiet_tiles = 1;    // STITCH_QUIET=0: the packed bulk pass computes every tile of every column
     uint32_t quiet_tail = 1;     // STITCH_QUIET_TAIL=0: the tail columns compute every tile
     uint32_t cone_refill = 1;    // STITCH_CONE=0: the walk re-fills whole contigs (dp_packed.h: cone re-fill)
-    // STITCH_STAGE_DEPTH: slots of the cp.async staging ring per warp (2 or 4).  Measured at 592 config-2 reads: 475 / 467 / 452 GCUPS
+    // STITCH_STAGE_DEPTH: slots of the staging ring per warp (2 or 4).  Measured at 592 config-2 reads: 475 / 467 / 452 GCUPS
     // at 2 / 3 / 4 slots: the ring's shared memory is taken from the L1 (184 KB instead of 110 KB per CTA), which costs more
     // than the deeper prefetch brings; 2 is the default
     uint32_t stage_depth_pref = 2;
@@ -215,7 +215,7 @@ struct CudaBackend : host::Backend {
         uint32_t m_max = 0;
         for (const auto &e : L.ent) m_max = std::max(m_max, e.m);
         const uint32_t LB = pk_plan(al.opts.sc, j.n, m_max);
-        // shared memory of the packed fill: per-contig / per-tile tables + cp.async stage buffers; otherwise the read takes the
+        // shared memory of the packed fill: per-contig / per-tile tables + the stage ring; otherwise the read takes the
         // (slow, exact) wide path.  The walk phase's staging is optional: run_chunk sizes it with the real K and falls back
         // to the separate walk kernel (or to unstaged contig bases) when it does not fit.
         if (LB && PackSmem::bytes((uint32_t)L.ent.size(), L.n_tiles, PACK_WARPS, PackSmem::default_stage(PACK_WARPS)) > SMEM_LIMIT) return 0;

@@ -96,7 +96,7 @@ struct PackSmem {
     // neighbour, halo strip of a chunk's first tile), the tile's bases
     static constexpr uint32_t STAGE_PRE = 16, STAGE_BASES = 2 * TILE * 4 + STAGE_PRE;
     static constexpr uint32_t STAGE_BYTES = 2 * TILE * 4 + STAGE_PRE + TILE;
-    // `stage_bytes`: the front area = cp.async double buffers (default_stage), or the cluster's slice of the rolling
+    // `stage_bytes`: the front area = bulk-copy ring of the tiles (default_stage), or the cluster's slice of the rolling
     // state when that lives in shared memory, or the walk phase's re-fill state; 0 = none (walk kernel)
     static size_t default_stage(int W, uint32_t depth = 2) { return (size_t)W * depth * STAGE_BYTES; }
     // One definition of the layout for the host (sizes, Params::pso) and the device (carve).
@@ -167,7 +167,7 @@ struct PackCtx {            // uniform per (job, set of contigs)
     uint32_t n;
     bool yclip_mode;
     bool state_smem;        // the state arrays live in shared memory (walk kernel re-fills)
-    bool staged;            // cp.async staging of tiles (state and bases both in global memory, stage buffers carved)
+    bool staged;            // tiles staged by bulk copies (state and bases both in global memory, stage buffers carved)
     uint32_t stage_depth;   // slots per warp of the staging ring (2 or 4): depth - 1 tiles are in flight ahead of the one computed
     Team team;
     // Tiles [own_lo, own_hi) are this CTA's (all tiles for a single-CTA team).  Sst/Dst address them as

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(W * 32) walk_kernel(const Params P) {
 }
 
 // Walk phase of fill_packed_kernel (see there).  Shared memory: the tables of PackSmem as carved by the kernel, the
-// per-unit staging area after them, and the re-fill state of one contig in the (now idle) cp.async stage buffers.
+// per-unit staging area after them, and the re-fill state of one contig in the (now idle) stage ring.
 template <int W>
 __device__ __noinline__ void pk_walk_phase(const Params P, unsigned char *smem_raw) {   // by value: the caller's P stays in the constant bank
     PackSmem PS; PS.carve(smem_raw, P.pso, P.cmax);

@@ -85,7 +85,7 @@ struct Params {
     uint32_t ntmax;          // largest tile count among the packed jobs
     uint32_t cluster_size;   // packed kernel: CTAs per read (thread-block cluster), 1 = no cluster
     uint32_t stage_bytes;    // packed kernels: size of the front area of their dynamic shared memory (PackSmem)
-    uint32_t stage_depth;    // packed fill: slots per warp of the cp.async staging ring (2 or 4)
+    uint32_t stage_depth;    // packed fill: slots per warp of the bulk-copy staging ring (2 or 4)
     uint32_t cluster_state_smem;   // the rolling state lives in the cluster's shared memory (bytes per CTA), 0 = global memory
     uint32_t quiet;          // packed bulk pass: skip quiet tiles (dp_packed.h), single-CTA teams only
     uint32_t quiet_tail;     // ... and in the tail columns (traceback variant), for tiles below the tracking threshold
